@@ -1,0 +1,183 @@
+/*
+ * tssep_b200 — C ABI of the B200 (sm_100a) TS-SEP inference hot path.
+ *
+ * The reference (merlresearch/tssep) is pure Python and has no FFI of its own;
+ * its plug-in boundary is the `factory:` key of its config dicts
+ * (tssep/exp/init_cfg_common.yaml:7-83, README.md:98-99).  The Python classes
+ * in tssep_b200/ mirror those factories and call the functions below through
+ * ctypes.  Every function states the reference operator (file:line) it replaces.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller unless said otherwise;
+ *     the library never allocates, frees or retains caller memory;
+ *   - work is enqueued on `stream` (a cudaStream_t); no implicit device sync;
+ *   - return 0 on success, negative on error; message via tssep_last_error()
+ *     (thread-local, valid until the next failing call on the same thread);
+ *   - no exceptions cross this boundary, there is no CPU fallback;
+ *   - "bf16" pointers are raw uint16 bfloat16 bit patterns; cfloat = float[2].
+ */
+#ifndef TSSEP_B200_H_
+#define TSSEP_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* tssep_stream_t; /* cudaStream_t */
+
+const char* tssep_last_error(void);
+int tssep_abi_version(void);
+/* Fills SM count and compute capability of the current device. */
+int tssep_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------
+ * (1) Feature front end
+ * ---------------------------------------------------------------------- */
+
+/* fe.stft(signal): padertorch STFT, call site tssep/train/model.py:504,
+ * parameters tssep/exp/init_cfg_common.yaml:45-50.
+ * audio (n_signals, num_samples) f32 -> X (n_signals, T, size/2+1) cfloat.
+ * window: (window_length) f32 analysis window; twiddle: (size/2) cfloat,
+ * twiddle[k] = exp(-2*pi*i*k/size).  size must be a power of two in [8, 4096],
+ * window_length <= size.  T must equal the reference frame count. */
+int tssep_stft(const float* audio, int64_t n_signals, int64_t num_samples, const float* window,
+               const float* twiddle, int size, int shift, int window_length, int fading, int64_t T,
+               float* X, tssep_stream_t stream);
+
+/* First pass of stft_to_feature: global statistics.
+ * TorchMFCC.stft_to_feature   tssep/train/feature_extractor_torchaudio.py:93-106
+ * Log1pMaxNormAbsSTFT         tssep/train/feature_extractor.py:233-248
+ * X (n_items, T, F) cfloat (item stride x_item_stride cfloats, so the reference
+ * channel of a multi-channel STFT can be addressed in place).
+ * absmax_key / maxdb_key: (n_items) u32 order-preserving keys, ZEROED by this call.
+ * mel_t (n_mels, F) f32 transposed filterbank with support [mel_lo, mel_hi) per
+ * filter; meldb (n_items, T, n_mels) f32 out.  n_mels == 0 skips the mel part. */
+int tssep_feature_stats(const float* X, int64_t n_items, int64_t x_item_stride, int64_t T, int F,
+                        const float* mel_t, const int32_t* mel_lo, const int32_t* mel_hi, int n_mels,
+                        uint32_t* absmax_key, uint32_t* maxdb_key, float* meldb, tssep_stream_t stream);
+
+/* Second pass: writes feature rows [mfcc(n_mfcc) | log1p spectrum(F if with_log1p)].
+ * ConcaternatedSTFTFeatures.stft_to_feature tssep/train/feature_extractor.py:352-360.
+ * couple_batch != 0 reproduces torchaudio's batch-coupled top_db cut-off (one max
+ * over the whole batched tensor).  feat_f32 (n_items, T, Din) and/or feat_bf16
+ * (n_items*T, ld_bf16) may be NULL. */
+int tssep_feature_write(const float* X, int64_t n_items, int64_t x_item_stride, int64_t T, int F,
+                        const uint32_t* absmax_key, const uint32_t* maxdb_key, const float* meldb,
+                        const float* dct, int n_mels, int n_mfcc, int with_log1p, float top_db,
+                        int couple_batch, float* feat_f32, uint16_t* feat_bf16, int64_t ld_bf16,
+                        tssep_stream_t stream);
+
+/* f32 (rows, cols) -> bf16 (rows, ld) conversion (zero padded columns). */
+int tssep_cast_bf16(const float* src, int64_t rows, int64_t cols, int64_t ld_src, uint16_t* dst,
+                    int64_t ld_dst, tssep_stream_t stream);
+
+/* InstanceNorm over the last axis (tssep/train/net.py:250-285), rows of `cols`. */
+int tssep_instance_norm(const float* src, int64_t rows, int64_t cols, int unbiased, float* dst,
+                        tssep_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * (2) Conditioning + bulk contractions (torch.nn.Linear / LSTM input GEMMs,
+ *     tssep/train/rnnp.py:87-96, tssep/train/net.py:663-666, :871-894)
+ * ---------------------------------------------------------------------- */
+
+/* Speaker-embedding conditioning folded into the first post_net projection.
+ * mode 0 ('mul', net.py:871-874):  Wk[z,n,f] = bf16(W[n,f] * e[z,f]),  bias_k[z,n] = b[n]
+ * mode 1 ('cat', net.py:879-894):  bias_k[z,n] = b[n] + sum_a W[n,F+a] * e[z,a]
+ *                                  (Wk is not written; the GEMM uses the shared W[:, :F])
+ * W (N, ldw) f32 packed input weights, e (Z, A) f32 embeddings already in slot order. */
+int tssep_fold_embedding(int mode, const float* W, int64_t ldw, const float* b, const float* e,
+                         int64_t Z, int N, int F, int A, uint16_t* Wk, int64_t ld_wk, float* bias_k,
+                         tssep_stream_t stream);
+
+/* Batched contraction on tcgen05/TMEM tensor cores:
+ *   out[z] = act(alpha * A[z / a_div] . B[z % b_mod]^T + bias[z % b_mod])      z in [0, batch)
+ * A (rows, K) bf16 row-major (lda), B (N, K) bf16 row-major (ldb); lda, ldb multiples
+ * of 8 elements, base pointers 16-byte aligned, batch strides whole rows.
+ * Offsets in elements:  A += (z / a_div) * a_stride,  B += (z % b_mod) * b_stride,
+ * bias += (z % b_mod) * bias_stride,
+ * out += (z / out_div) * out_stride_hi + (z % out_div) * out_stride.
+ * mode TSSEP_EPI_F32 / TSSEP_EPI_BF16: out[m * ldo + n] (act: 0 none, 1 tanh).
+ * mode TSSEP_EPI_HEAD (TS-VAD/TS-SEP output head, net.py:629-668, :928-986): column
+ *   n = q * row_len + f of item z goes to plane p = plane_map[z * n_blocks + q]:
+ *   logit[(p * M + m) * row_len + f] = v and mask[...] = sigmoid(v); either may be NULL.
+ *   The caller folds the speaker rotation / trial mean into B and bias (K = trials*projs)
+ *   and the un-permutation into plane_map.
+ * impl: 0 = tcgen05 (product path), 1 = plain SIMT kernel (debug / bisecting only). */
+enum { TSSEP_EPI_F32 = 0, TSSEP_EPI_BF16 = 1, TSSEP_EPI_HEAD = 2 };
+
+typedef struct tssep_gemm_desc {
+  const uint16_t* A; int64_t lda; int64_t a_stride; int32_t a_div;
+  const uint16_t* B; int64_t ldb; int64_t b_stride; int32_t b_mod;
+  const float* bias; int64_t bias_stride;
+  int64_t M; int32_t N; int32_t K; int32_t batch;
+  float alpha; int32_t act; int32_t mode;
+  void* out; int64_t ldo; int64_t out_stride; int32_t out_div; int64_t out_stride_hi;
+  float* mask; const int32_t* plane_map; int32_t n_blocks; int32_t row_len;
+  int32_t impl;
+} tssep_gemm_desc;
+
+int tssep_gemm(const tssep_gemm_desc* desc, tssep_stream_t stream);
+
+/* output_resolution 't' (net.py:653-659): logits (Z, T, n_blocks) f32 -> logit/mask
+ * planes (P, T, F) broadcast over frequency; block q of item z goes to plane
+ * plane_map[z * n_blocks + q] (speakers un-permuted by the map). */
+int tssep_head_expand_t(const float* small, int64_t Z, int64_t T, int n_blocks, int F,
+                        const int32_t* plane_map, float* logit, float* mask, tssep_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * (3) BLSTM recurrence (torch.nn.LSTM inside RNNP_packed, rnnp.py:87-95, :143-159)
+ * ---------------------------------------------------------------------- */
+
+/* Persistent cluster kernel: recurrent weights register/SM resident, h exchanged
+ * through distributed shared memory, both directions concurrently.
+ * G    (rows, T, 2, 4, Up) f32  input projections + both biases, gate order i,f,g,o
+ * Wfrag packed recurrent weights from tssep_pack_whh (2 * Up/4 * Up/16 * 128 u32)
+ * H    (rows, T, 2*Up) bf16 out: [h_fwd(Up) | h_bwd(Up)]
+ * Up = hidden units rounded up to a multiple of 16 (<= 320); padded units stay 0.
+ * cluster: CTAs per cluster (1,2,4,8), 0 = choose.  fast_math: 0 accurate
+ * exp-based gates, 1 tanh.approx. */
+int tssep_blstm_recurrence(const float* G, const uint32_t* Wfrag, uint16_t* H, int64_t rows, int64_t T,
+                           int Up, int cluster, int fast_math, tssep_stream_t stream);
+
+/* weight_hh_l0 / weight_hh_l0_reverse (4U, U) f32 -> mma fragment order. */
+int tssep_pack_whh(const float* whh_fwd, const float* whh_bwd, int U, int Up, uint32_t* Wfrag,
+                   tssep_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * (4) Enhancement: mask x mixture STFT, iSTFT overlap-add
+ *     Masking.__call__ tssep/train/enhancer.py:73-100; fe.istft model.py:661-664
+ * ---------------------------------------------------------------------- */
+
+/* If mask != NULL:  Y[z,k] = X[z] * mask[z,k]  (X (Z,T,F) cfloat with item stride,
+ * mask (Z,K,T,F) f32) else Y = X viewed as (Z*K, T, F) cfloat.
+ * stft_estimate (Z,K,T,F) cfloat and time (Z,K,num_samples) f32 are optional outputs.
+ * synwin (window_length) f32 synthesis window, twiddle as in tssep_stft. */
+int tssep_mask_istft(const float* X, int64_t x_item_stride, const float* mask, int64_t Z, int n_spk,
+                     int64_t T, int size, int shift, int window_length, int fading,
+                     const float* synwin, const float* twiddle, float* stft_estimate, float* time,
+                     int64_t num_samples, tssep_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * (5) Diarization post-processing (no reference implementation; anchors
+ *     tssep/util/utils.py:11-129, tssep/train/loss.py:343)
+ * ---------------------------------------------------------------------- */
+
+/* activity[n,t] = mean_f mask[n,t,f]. */
+int tssep_activity(const float* mask, int64_t n, int64_t T, int F, float* activity, tssep_stream_t stream);
+
+/* smooth = running median (odd width <= 63, edges replicated); active = smooth > thr. */
+int tssep_median_threshold(const float* activity, int64_t n, int64_t T, int width, float threshold,
+                           float* smooth, uint8_t* active, tssep_stream_t stream);
+
+/* Maximal runs of active frames -> sample intervals.  segments (n, max_segments, 2)
+ * i32, counts (n) i32 (the true number of runs, may exceed max_segments). */
+int tssep_segments(const uint8_t* active, int64_t n, int64_t T, int window_length, int shift, int fading,
+                   int64_t num_samples, int32_t* segments, int32_t* counts, int max_segments,
+                   tssep_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TSSEP_B200_H_ */

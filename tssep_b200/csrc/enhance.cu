@@ -1,0 +1,242 @@
+// Conditioning fold, 't'-resolution head expansion, and enhancement
+// (mask x mixture STFT -> iSTFT overlap-add).
+//
+// Reference operators: MaskEstimator_v2 conditioning tssep/train/net.py:862-896,
+// final einops Reduce('repeat') net.py:653-659, Masking.__call__
+// tssep/train/enhancer.py:73-100, fe.istft (padertorch) called at
+// tssep/train/model.py:661-664.
+#include "../../include/tssep_b200.h"
+#include "common.cuh"
+#include "fft.cuh"
+
+namespace tssep {
+
+// ---------------------------------------------------------------------------
+// Conditioning folded into the first post_net input projection
+// ---------------------------------------------------------------------------
+__global__ void fold_mul_kernel(const float* __restrict__ W, int64_t ldw, const float* __restrict__ b,
+                                const float* __restrict__ e, int64_t Z, int N, int F, int A,
+                                __nv_bfloat16* __restrict__ Wk, int64_t ld_wk, float* __restrict__ bias_k) {
+  const int64_t total = Z * N * ld_wk;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t f = i % ld_wk;
+    const int64_t zn = i / ld_wk;
+    const int64_t n = zn % N, z = zn / N;
+    float v = 0.f;
+    if (f < F) v = W[n * ldw + f] * e[z * A + f];
+    Wk[i] = __float2bfloat16_rn(v);
+    if (f == 0) bias_k[zn] = b[n];
+  }
+}
+
+__global__ void fold_cat_kernel(const float* __restrict__ W, int64_t ldw, const float* __restrict__ b,
+                                const float* __restrict__ e, int64_t Z, int N, int F, int A,
+                                float* __restrict__ bias_k) {
+  const int lane = threadIdx.x & 31;
+  const int64_t zn = blockIdx.x * static_cast<int64_t>(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (zn >= Z * N) return;
+  const int64_t n = zn % N, z = zn / N;
+  const float* w = W + n * ldw + F;
+  const float* ez = e + z * A;
+  float acc = 0.f;
+  for (int a = lane; a < A; a += 32) acc = fmaf(w[a], ez[a], acc);
+  acc = warp_sum(acc);
+  if (lane == 0) bias_k[zn] = b[n] + acc;
+}
+
+// ---------------------------------------------------------------------------
+// output_resolution 't': broadcast (Z, T, K) logits over frequency
+// ---------------------------------------------------------------------------
+__global__ void head_expand_t_kernel(const float* __restrict__ small, int64_t Z, int64_t T, int K, int F,
+                                     const int* __restrict__ perm, float* __restrict__ logit,
+                                     float* __restrict__ mask) {
+  const int lane = threadIdx.x & 31;
+  const int64_t total = Z * K * T;
+  for (int64_t r = blockIdx.x * static_cast<int64_t>(blockDim.x >> 5) + (threadIdx.x >> 5); r < total;
+       r += static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5)) {
+    const int64_t t = r % T;
+    const int64_t zq = r / T;
+    const int q = static_cast<int>(zq % K);
+    const int64_t z = zq / K;
+    const int64_t plane = perm[z * K + q];
+    const float v = small[(z * T + t) * K + q];
+    const float m = sigmoid_acc(v);
+    const int64_t o = (plane * T + t) * F;
+    for (int f = lane; f < F; f += 32) {
+      if (logit) logit[o + f] = v;
+      if (mask) mask[o + f] = m;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// mask x X  ->  (stft_estimate)  ->  iSTFT overlap-add
+// One CTA produces `hops` output hops of all speakers of one item; the frames
+// it needs (hops + OV - 1) are inverse-transformed into shared memory and
+// overlap-added in gather form, so there are no atomics and every output sample
+// is written exactly once.  The mixture STFT tile is staged once per CTA and
+// reused for all speakers.
+// ---------------------------------------------------------------------------
+constexpr int kEWarps = 8;
+constexpr int kEThreads = kEWarps * 32;
+
+__global__ void __launch_bounds__(kEThreads)
+mask_istft_kernel(const float2* __restrict__ X, int64_t x_item_stride, const float* __restrict__ mask, int n_spk,
+                  int64_t T, int S, int log2m, int R, int wl, int trim, const float* __restrict__ synwin,
+                  const float2* __restrict__ twiddle, float2* __restrict__ est, float* __restrict__ time_out,
+                  int64_t num_samples, int hops) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int M = S >> 1, F = M + 1, OV = wl / R;
+  const int nslots = hops + OV - 1;
+  float2* tw = reinterpret_cast<float2*>(smem_raw);       // M
+  float2* Xs = tw + M;                                     // nslots * F (only when mask != nullptr)
+  float* fbuf = reinterpret_cast<float*>(Xs + (mask ? nslots * F : 0));  // nslots * S
+  float* syn = fbuf + nslots * S;                          // wl
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t z = blockIdx.y;
+  const int64_t j0 = static_cast<int64_t>(blockIdx.x) * hops;
+  const int64_t tfirst = j0 - (OV - 1);
+  const int64_t J = T + OV - 1;
+  const float inv_m = 1.0f / static_cast<float>(M);
+
+  for (int i = threadIdx.x; i < M; i += kEThreads) tw[i] = twiddle[i];
+  for (int i = threadIdx.x; i < wl; i += kEThreads) syn[i] = synwin[i] * inv_m;
+  if (mask) {
+    for (int i = threadIdx.x; i < nslots * F; i += kEThreads) {
+      const int fl = i / F, f = i - fl * F;
+      const int64_t t = tfirst + fl;
+      Xs[i] = (t >= 0 && t < T) ? X[z * x_item_stride + t * F + f] : make_float2(0.f, 0.f);
+    }
+  }
+  __syncthreads();
+
+  for (int k = 0; k < n_spk; ++k) {
+    const int64_t sig = z * n_spk + k;
+    for (int fl = warp; fl < nslots; fl += kEWarps) {
+      const int64_t t = tfirst + fl;
+      float* fr = fbuf + fl * S;
+      if (t < 0 || t >= T) {
+        for (int i = lane; i < wl; i += 32) fr[i] = 0.f;
+        continue;
+      }
+      float2* zb = reinterpret_cast<float2*>(fr);
+      const int64_t row = (sig * T + t) * F;
+      const bool own = est != nullptr && t >= j0;
+      for (int kk = lane; kk < M; kk += 32) {
+        float2 yk, ym;
+        if (mask) {
+          const float mk = mask[row + kk], mm = mask[row + M - kk];
+          const float2 xk = Xs[fl * F + kk], xm = Xs[fl * F + M - kk];
+          yk = make_float2(xk.x * mk, xk.y * mk);
+          ym = make_float2(xm.x * mm, xm.y * mm);
+        } else {
+          yk = X[row + kk];
+          ym = X[row + M - kk];
+        }
+        if (own) {
+          est[row + kk] = yk;
+          if (kk == 0) est[row + M] = ym;
+        }
+        if (kk == 0) {
+          yk.y = 0.f;  // c2r ignores the imaginary parts of DC and Nyquist
+          ym.y = 0.f;
+        }
+        zb[bitrev(kk, log2m)] = irfft_pack(yk, ym, kk, tw);
+      }
+      __syncwarp();
+      warp_fft_inplace<true>(zb, log2m, tw, S, lane);
+      for (int i = lane; i < wl; i += 32) fr[i] *= syn[i];
+    }
+    __syncthreads();
+    if (time_out) {
+      for (int idx = threadIdx.x; idx < hops * R; idx += kEThreads) {
+        const int hj = idx / R, i = idx - hj * R;
+        const int64_t j = j0 + hj;
+        const int64_t n = j * R + i - trim;
+        if (j < J && n >= 0 && n < num_samples) {
+          float acc = 0.f;
+          for (int o = 0; o < OV; ++o) acc += fbuf[(hj + OV - 1 - o) * S + o * R + i];
+          time_out[sig * num_samples + n] = acc;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+static int ilog2_exact(int v) {
+  int l = 0;
+  while ((1 << l) < v) ++l;
+  return (1 << l) == v ? l : -1;
+}
+
+}  // namespace tssep
+
+using namespace tssep;
+
+extern "C" {
+
+int tssep_fold_embedding(int mode, const float* W, int64_t ldw, const float* b, const float* e, int64_t Z, int N,
+                         int F, int A, uint16_t* Wk, int64_t ld_wk, float* bias_k, tssep_stream_t stream) {
+  TSSEP_REQUIRE(W && b && e && bias_k, "tssep_fold_embedding: null pointer");
+  TSSEP_REQUIRE(mode == 0 || mode == 1, "tssep_fold_embedding: mode must be 0 (mul) or 1 (cat)");
+  if (Z == 0) return 0;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (mode == 0) {
+    TSSEP_REQUIRE(Wk && ld_wk >= F && A == F && ldw >= F, "tssep_fold_embedding(mul): need Wk, ld_wk >= F, A == F");
+    const int64_t total = Z * N * ld_wk;
+    const int blocks = static_cast<int>(imin64((total + 255) / 256, 148 * 16));
+    fold_mul_kernel<<<blocks, 256, 0, s>>>(W, ldw, b, e, Z, N, F, A, reinterpret_cast<__nv_bfloat16*>(Wk), ld_wk,
+                                           bias_k);
+  } else {
+    TSSEP_REQUIRE(ldw >= F + A, "tssep_fold_embedding(cat): ldw < F + A");
+    const int64_t rows = Z * N;
+    fold_cat_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, s>>>(W, ldw, b, e, Z, N, F, A, bias_k);
+  }
+  return check_launch("tssep_fold_embedding");
+}
+
+int tssep_head_expand_t(const float* small, int64_t Z, int64_t T, int n_spk, int F, const int32_t* perm,
+                        float* logit, float* mask, tssep_stream_t stream) {
+  TSSEP_REQUIRE(small && perm && (logit || mask), "tssep_head_expand_t: null pointer");
+  if (Z == 0 || T == 0) return 0;
+  const int64_t rows = Z * n_spk * T;
+  const int blocks = static_cast<int>(imin64((rows + 7) / 8, 148 * 16));
+  head_expand_t_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(small, Z, T, n_spk, F, perm, logit, mask);
+  return check_launch("tssep_head_expand_t");
+}
+
+int tssep_mask_istft(const float* X, int64_t x_item_stride, const float* mask, int64_t Z, int n_spk, int64_t T,
+                     int size, int shift, int window_length, int fading, const float* synwin, const float* twiddle,
+                     float* stft_estimate, float* time, int64_t num_samples, tssep_stream_t stream) {
+  TSSEP_REQUIRE(X && synwin && twiddle, "tssep_mask_istft: null pointer");
+  TSSEP_REQUIRE(stft_estimate || time, "tssep_mask_istft: no output requested");
+  const int l2 = ilog2_exact(size);
+  TSSEP_REQUIRE(l2 >= 3 && size <= 4096, "tssep_mask_istft: size must be a power of two in [8, 4096], got %d", size);
+  TSSEP_REQUIRE(window_length <= size && shift >= 1 && window_length % shift == 0,
+                "tssep_mask_istft: need window_length <= size and window_length %% shift == 0");
+  TSSEP_REQUIRE(Z >= 0 && Z < 65536 && n_spk >= 1 && T >= 0, "tssep_mask_istft: bad extent");
+  if (Z == 0 || T == 0) return 0;
+  const int M = size / 2, F = M + 1, OV = window_length / shift;
+  int hops = 16;
+  auto smem_for = [&](int h) {
+    const size_t ns = h + OV - 1;
+    return sizeof(float2) * M + (mask ? sizeof(float2) * ns * F : 0) + sizeof(float) * ns * size +
+           sizeof(float) * window_length;
+  };
+  while (hops > 1 && smem_for(hops) > 200 * 1024) hops /= 2;
+  const size_t smem = smem_for(hops);
+  TSSEP_REQUIRE(smem <= 227 * 1024, "tssep_mask_istft: frame geometry does not fit shared memory");
+  TSSEP_CUDA(cudaFuncSetAttribute(mask_istft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  const int64_t J = T + OV - 1;
+  dim3 grid(static_cast<unsigned>((J + hops - 1) / hops), static_cast<unsigned>(Z));
+  mask_istft_kernel<<<grid, kEThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float2*>(X), x_item_stride, mask, n_spk, T, size, l2 - 1, shift, window_length,
+      fading ? window_length - shift : 0, synwin, reinterpret_cast<const float2*>(twiddle),
+      reinterpret_cast<float2*>(stft_estimate), time, num_samples, hops);
+  return check_launch("tssep_mask_istft");
+}
+
+}  // extern "C"

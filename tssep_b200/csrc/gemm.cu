@@ -1,0 +1,410 @@
+// Bulk contractions of the RNNP stack on 5th-gen tensor cores.
+//
+//   out[z] = act(alpha * A[z / a_div] . B[z]^T + bias[z])
+//
+// A (rows, K) and B (N, K) are bf16, K-major.  One persistent CTA per SM:
+// warp 0 streams 128 x 64 (A) and BN x 64 (B) tiles with TMA (128-byte swizzle)
+// through a 4-stage mbarrier ring, one elected thread of warp 1 issues
+// tcgen05.mma (M=128, N=BN, K=16) into a double-buffered TMEM accumulator,
+// warps 2-5 drain TMEM with tcgen05.ld and run the fused epilogue (bias, tanh,
+// cast, or the un-permuting sigmoid head) while the next tile is multiplied.
+//
+// Replaces torch.nn.Linear / the input half of torch.nn.LSTM in the reference
+// (tssep/train/rnnp.py:87-96, tssep/train/net.py:663-666) and the final
+// rearrange + trial mean + un-permute + sigmoid (net.py:629-661, :928-986).
+#include "../../include/tssep_b200.h"
+#include "common.cuh"
+
+#include <cstdlib>
+
+namespace tssep {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int kStages = 4;
+constexpr int kGemmThreads = 192;
+constexpr int kTmemCols = 512;
+constexpr int kAccCols = 256;
+
+enum EpiMode { EPI_F32 = 0, EPI_BF16 = 1, EPI_HEAD = 2 };
+
+struct GemmArgs {
+  int64_t M;
+  int N, K, batch, a_div, b_mod;
+  int64_t a_row_stride;  // rows of A per (z / a_div)
+  int64_t b_row_stride;  // rows of B per (z % b_mod)
+  const float* bias;
+  int64_t bias_stride;
+  float alpha;
+  int act;
+  int mode;
+  void* out;
+  int64_t ldo, out_stride, out_stride_hi;
+  int out_div;
+  // head
+  float* mask;
+  const int* plane_map;
+  int n_blocks, row_len;
+  // tiling
+  int bn, m_tiles, n_tiles, k_blocks;
+  int64_t total_tiles;
+  // simt only
+  const __nv_bfloat16* A;
+  const __nv_bfloat16* B;
+  int64_t lda, ldb;
+};
+
+__device__ __forceinline__ float apply_act(float v, int act) { return act == 1 ? tanh_acc(v) : v; }
+
+// Stores up to 32 consecutive columns [n0, n0+32) of row m of batch z.
+__device__ __forceinline__ void epilogue_store(const GemmArgs& g, int z, int64_t m, int n0, const float* acc) {
+  const int nvalid = min(32, g.N - n0);
+  if (nvalid <= 0) return;
+  const float* bias = g.bias ? g.bias + static_cast<int64_t>(z % g.b_mod) * g.bias_stride + n0 : nullptr;
+  const int64_t zoff = static_cast<int64_t>(z / g.out_div) * g.out_stride_hi + static_cast<int64_t>(z % g.out_div) * g.out_stride;
+  if (g.mode == EPI_F32) {
+    float* o = static_cast<float*>(g.out) + zoff + m * g.ldo + n0;
+    if (nvalid == 32 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        float4 v;
+        v.x = apply_act(g.alpha * acc[i + 0] + (bias ? bias[i + 0] : 0.f), g.act);
+        v.y = apply_act(g.alpha * acc[i + 1] + (bias ? bias[i + 1] : 0.f), g.act);
+        v.z = apply_act(g.alpha * acc[i + 2] + (bias ? bias[i + 2] : 0.f), g.act);
+        v.w = apply_act(g.alpha * acc[i + 3] + (bias ? bias[i + 3] : 0.f), g.act);
+        *reinterpret_cast<float4*>(o + i) = v;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (i < nvalid) o[i] = apply_act(g.alpha * acc[i] + (bias ? bias[i] : 0.f), g.act);
+    }
+  } else if (g.mode == EPI_BF16) {
+    __nv_bfloat16* o = static_cast<__nv_bfloat16*>(g.out) + zoff + m * g.ldo + n0;
+    if (nvalid == 32 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        uint4 v;
+        uint32_t* pv = reinterpret_cast<uint32_t*>(&v);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float a = apply_act(g.alpha * acc[i + 2 * j] + (bias ? bias[i + 2 * j] : 0.f), g.act);
+          const float b = apply_act(g.alpha * acc[i + 2 * j + 1] + (bias ? bias[i + 2 * j + 1] : 0.f), g.act);
+          pv[j] = pack_bf16x2(a, b);
+        }
+        *reinterpret_cast<uint4*>(o + i) = v;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (i < nvalid) o[i] = __float2bfloat16_rn(apply_act(g.alpha * acc[i] + (bias ? bias[i] : 0.f), g.act));
+    }
+  } else {  // EPI_HEAD
+    int q = n0 / g.row_len;
+    int f = n0 - q * g.row_len;
+    int64_t plane = g.plane_map[z * g.n_blocks + q];
+    float* lo = static_cast<float*>(g.out);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      if (i >= nvalid) break;
+      const float v = g.alpha * acc[i] + (bias ? bias[i] : 0.f);
+      const int64_t idx = (plane * g.M + m) * g.row_len + f;
+      if (lo) lo[idx] = v;
+      if (g.mask) g.mask[idx] = sigmoid_acc(v);
+      if (++f == g.row_len) {
+        f = 0;
+        ++q;
+        if (q < g.n_blocks) plane = g.plane_map[z * g.n_blocks + q];
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  // K-major, 128-byte swizzle: LBO (ignored) = 1, SBO = 1024 B, version 1, layout type 2
+  return static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t a_bytes = BM * BK * 2;
+  const uint32_t b_bytes = static_cast<uint32_t>(g.bn) * BK * 2;
+  const uint32_t sA = base;
+  const uint32_t sB = base + kStages * a_bytes;
+  const uint32_t sBar = sB + kStages * b_bytes;  // 8-byte aligned (multiples of 1024 before it)
+  const uint32_t full0 = sBar, empty0 = sBar + 8 * kStages, tfull0 = sBar + 16 * kStages,
+                 tempty0 = tfull0 + 16, tptr = tempty0 + 16;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < kStages; ++s) {
+        mbar_init(full0 + 8 * s, 1);
+        mbar_init(empty0 + 8 * s, 1);
+      }
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(tfull0 + 8 * s, 1);
+        mbar_init(tempty0 + 8 * s, 4);
+      }
+      mbar_fence_init();
+    }
+    __syncwarp();
+    tc_alloc(tptr, kTmemCols);
+    tc_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tptr));
+
+  const int64_t tiles_per_z = static_cast<int64_t>(g.m_tiles) * g.n_tiles;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int64_t tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+        const int z = static_cast<int>(tile / tiles_per_z);
+        const int64_t rem = tile - z * tiles_per_z;
+        const int mt = static_cast<int>(rem / g.n_tiles), nt = static_cast<int>(rem - static_cast<int64_t>(mt) * g.n_tiles);
+        const int a_row = static_cast<int>((z / g.a_div) * g.a_row_stride + static_cast<int64_t>(mt) * BM);
+        const int b_row = static_cast<int>((z % g.b_mod) * g.b_row_stride + static_cast<int64_t>(nt) * g.bn);
+        for (int kb = 0; kb < g.k_blocks; ++kb) {
+          mbar_wait(empty0 + 8 * s, ph ^ 1);
+          mbar_arrive_expect_tx(full0 + 8 * s, a_bytes + b_bytes);
+          tma_load_2d(sA + s * a_bytes, &tmA, full0 + 8 * s, kb * BK, a_row);
+          tma_load_2d(sB + s * b_bytes, &tmB, full0 + 8 * s, kb * BK, b_row);
+          if (++s == kStages) {
+            s = 0;
+            ph ^= 1;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(g.bn >> 3) << 17) |
+                             (static_cast<uint32_t>(BM >> 4) << 24);
+      int s = 0;
+      uint32_t ph = 0;
+      uint32_t it = 0;
+      for (int64_t tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++it) {
+        const uint32_t as = it & 1, aph = (it >> 1) & 1;
+        mbar_wait(tempty0 + 8 * as, aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * kAccCols;
+        for (int kb = 0; kb < g.k_blocks; ++kb) {
+          mbar_wait(full0 + 8 * s, ph);
+          tc_fence_after();
+          const uint32_t a0 = sA + s * a_bytes, b0 = sB + s * b_bytes;
+#pragma unroll
+          for (int k4 = 0; k4 < BK / 16; ++k4) {
+            tc_mma_bf16(d_tmem, make_smem_desc(a0 + k4 * 32), make_smem_desc(b0 + k4 * 32), idesc,
+                        (kb | k4) != 0 ? 1u : 0u);
+          }
+          tc_commit(empty0 + 8 * s);
+          if (++s == kStages) {
+            s = 0;
+            ph ^= 1;
+          }
+        }
+        tc_commit(tfull0 + 8 * as);
+      }
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3;  // TMEM lane quarter this warp may touch
+    uint32_t it = 0;
+    for (int64_t tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++it) {
+      const uint32_t as = it & 1, aph = (it >> 1) & 1;
+      const int z = static_cast<int>(tile / tiles_per_z);
+      const int64_t rem = tile - z * tiles_per_z;
+      const int mt = static_cast<int>(rem / g.n_tiles), nt = static_cast<int>(rem - static_cast<int64_t>(mt) * g.n_tiles);
+      const int64_t m = static_cast<int64_t>(mt) * BM + q * 32 + lane;
+      mbar_wait(tfull0 + 8 * as, aph);
+      tc_fence_after();
+      const uint32_t t0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kAccCols;
+      for (int c0 = 0; c0 < g.bn; c0 += 32) {
+        uint32_t v[32];
+        tc_ld32(t0 + c0, v);
+        tc_wait_ld();
+        if (m < g.M) epilogue_store(g, z, m, nt * g.bn + c0, reinterpret_cast<const float*>(v));
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty0 + 8 * as);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tc_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// Debug / bisecting reference: one thread per 32-column strip, plain FMAs.
+__global__ void gemm_simt_kernel(const GemmArgs g) {
+  const int64_t strips = (g.N + 31) / 32;
+  const int64_t total = static_cast<int64_t>(g.batch) * g.M * strips;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int strip = static_cast<int>(i % strips);
+    const int64_t rest = i / strips;
+    const int64_t m = rest % g.M;
+    const int z = static_cast<int>(rest / g.M);
+    const __nv_bfloat16* a = g.A + ((z / g.a_div) * g.a_row_stride + m) * g.lda;
+    float acc[32];
+    for (int j = 0; j < 32; ++j) {
+      const int n = strip * 32 + j;
+      float s = 0.f;
+      if (n < g.N) {
+        const __nv_bfloat16* b = g.B + ((z % g.b_mod) * g.b_row_stride + n) * g.ldb;
+        for (int k = 0; k < g.K; ++k) s = fmaf(__bfloat162float(a[k]), __bfloat162float(b[k]), s);
+      }
+      acc[j] = s;
+    }
+    epilogue_store(g, z, m, strip * 32, acc);
+  }
+}
+
+static int make_map_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t rows, uint64_t ld_elems,
+                       uint32_t box_rows) {
+  EncodeTiledFn enc = get_encode_tiled();
+  TSSEP_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[2] = {inner, rows};
+  cuuint64_t strides[1] = {ld_elems * 2};
+  cuuint32_t box[2] = {BK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  TSSEP_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code %d (inner=%llu rows=%llu ld=%llu box_rows=%u)",
+                static_cast<int>(r), (unsigned long long)inner, (unsigned long long)rows, (unsigned long long)ld_elems,
+                box_rows);
+  return 0;
+}
+
+static int choose_bn(int N) {
+  if (const char* e = getenv("TSSEP_GEMM_BN")) {
+    const int v = atoi(e);
+    if (v >= 16 && v <= 256 && v % 16 == 0) return v;
+  }
+  if (N <= 256) return ((N + 15) / 16) * 16;
+  int best = 256;
+  double best_score = 1e9;
+  for (int bn = 256; bn >= 128; bn -= 16) {
+    const int tiles = (N + bn - 1) / bn;
+    const double waste = static_cast<double>(tiles) * bn / N - 1.0;
+    const double score = waste + 0.0002 * (256 - bn);
+    if (score < best_score) {
+      best_score = score;
+      best = bn;
+    }
+  }
+  return best;
+}
+
+static int launch_gemm(GemmArgs g, const uint16_t* A, int64_t lda, int64_t a_stride, const uint16_t* B, int64_t ldb,
+                       int64_t b_stride, int impl, cudaStream_t stream) {
+  TSSEP_REQUIRE(A && B, "gemm: null operand");
+  TSSEP_REQUIRE(g.M >= 0 && g.N >= 1 && g.K >= 1 && g.batch >= 1 && g.a_div >= 1 && g.b_mod >= 1 && g.out_div >= 1,
+                "gemm: bad extent");
+  TSSEP_REQUIRE(lda >= g.K && ldb >= g.K, "gemm: leading dimension smaller than K");
+  TSSEP_REQUIRE(a_stride % lda == 0 && b_stride % ldb == 0, "gemm: batch strides must be whole rows");
+  if (g.M == 0) return 0;
+  g.a_row_stride = a_stride / lda;
+  g.b_row_stride = b_stride / ldb;
+  g.A = reinterpret_cast<const __nv_bfloat16*>(A);
+  g.B = reinterpret_cast<const __nv_bfloat16*>(B);
+  g.lda = lda;
+  g.ldb = ldb;
+  if (impl == 1) {
+    const int64_t total = static_cast<int64_t>(g.batch) * g.M * ((g.N + 31) / 32);
+    const int blocks = static_cast<int>(imin64((total + 127) / 128, 148 * 32));
+    gemm_simt_kernel<<<blocks, 128, 0, stream>>>(g);
+    return check_launch("gemm_simt");
+  }
+  TSSEP_REQUIRE(impl == 0, "gemm: unknown impl %d", impl);
+  TSSEP_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "gemm: lda/ldb must be multiples of 8 (got %lld, %lld)", (long long)lda,
+                (long long)ldb);
+  TSSEP_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0,
+                "gemm: operands must be 16-byte aligned");
+  g.bn = choose_bn(g.N);
+  g.m_tiles = static_cast<int>((g.M + BM - 1) / BM);
+  g.n_tiles = (g.N + g.bn - 1) / g.bn;
+  g.k_blocks = (g.K + BK - 1) / BK;
+  g.total_tiles = static_cast<int64_t>(g.batch) * g.m_tiles * g.n_tiles;
+  const int64_t a_rows = ((g.batch - 1) / g.a_div) * g.a_row_stride + g.M;
+  const int64_t b_rows = static_cast<int64_t>((g.batch < g.b_mod ? g.batch : g.b_mod) - 1) * g.b_row_stride + g.N;
+  TSSEP_REQUIRE(a_rows < (1ll << 31) && b_rows < (1ll << 31), "gemm: too many rows for 32-bit TMA coordinates");
+  CUtensorMap tmA, tmB;
+  if (int r = make_map_2d(&tmA, A, g.K, a_rows, lda, BM)) return r;
+  if (int r = make_map_2d(&tmB, B, g.K, b_rows, ldb, g.bn)) return r;
+  int dev = 0, sms = 148;
+  TSSEP_CUDA(cudaGetDevice(&dev));
+  TSSEP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const size_t smem = 1024 + kStages * (BM * BK * 2 + static_cast<size_t>(g.bn) * BK * 2) + 256;
+  TSSEP_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  const int grid = static_cast<int>(imin64(g.total_tiles, sms));
+  gemm_tc_kernel<<<grid, kGemmThreads, smem, stream>>>(tmA, tmB, g);
+  return check_launch("gemm_tc");
+}
+
+}  // namespace tssep
+
+using namespace tssep;
+
+extern "C" {
+
+int tssep_gemm(const tssep_gemm_desc* d, tssep_stream_t stream) {
+  TSSEP_REQUIRE(d != nullptr, "tssep_gemm: null descriptor");
+  TSSEP_REQUIRE(d->mode == TSSEP_EPI_F32 || d->mode == TSSEP_EPI_BF16 || d->mode == TSSEP_EPI_HEAD,
+                "tssep_gemm: unknown epilogue mode %d", d->mode);
+  TSSEP_REQUIRE(d->act == 0 || d->act == 1, "tssep_gemm: act must be 0 (none) or 1 (tanh)");
+  GemmArgs g{};
+  g.M = d->M;
+  g.N = d->N;
+  g.K = d->K;
+  g.batch = d->batch;
+  g.a_div = d->a_div;
+  g.b_mod = d->b_mod;
+  g.bias = d->bias;
+  g.bias_stride = d->bias_stride;
+  g.alpha = d->alpha;
+  g.act = d->act;
+  g.mode = d->mode;
+  g.out = d->out;
+  g.ldo = d->ldo;
+  g.out_stride = d->out_stride;
+  g.out_stride_hi = d->out_stride_hi;
+  g.out_div = d->out_div;
+  g.mask = d->mask;
+  g.plane_map = d->plane_map;
+  g.n_blocks = d->n_blocks;
+  g.row_len = d->row_len;
+  if (d->mode == TSSEP_EPI_HEAD) {
+    TSSEP_REQUIRE(d->out || d->mask, "tssep_gemm(head): no output");
+    TSSEP_REQUIRE(d->plane_map && d->n_blocks >= 1 && d->row_len >= 1 && d->N == d->n_blocks * d->row_len,
+                  "tssep_gemm(head): need plane_map and N == n_blocks * row_len");
+    TSSEP_REQUIRE(d->act == 0, "tssep_gemm(head): act must be 0");
+  } else {
+    TSSEP_REQUIRE(d->out != nullptr, "tssep_gemm: null output");
+    TSSEP_REQUIRE(d->ldo >= d->N, "tssep_gemm: ldo < N");
+  }
+  return launch_gemm(g, d->A, d->lda, d->a_stride, d->B, d->ldb, d->b_stride, d->impl,
+                     static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"
