@@ -1,0 +1,113 @@
+"""ctypes binding of ``libtssep_b200.so`` (include/tssep_b200.h).
+
+The shared library is the product: if it is missing the import of any
+``tssep_b200`` operator fails loudly -- there is no CPU or PyTorch fallback.
+PyTorch is used for device memory, streams and ``torch.distributed`` only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import torch
+
+_LIB_PATH = Path(__file__).resolve().parent / "_lib" / "libtssep_b200.so"
+_lib = None
+
+c_i64, c_i32, c_f32, c_vp = C.c_int64, C.c_int32, C.c_float, C.c_void_p
+
+
+class GemmDesc(C.Structure):
+    """Mirror of ``tssep_gemm_desc``."""
+
+    _fields_ = [
+        ("A", c_vp), ("lda", c_i64), ("a_stride", c_i64), ("a_div", c_i32),
+        ("B", c_vp), ("ldb", c_i64), ("b_stride", c_i64), ("b_mod", c_i32),
+        ("bias", c_vp), ("bias_stride", c_i64),
+        ("M", c_i64), ("N", c_i32), ("K", c_i32), ("batch", c_i32),
+        ("alpha", c_f32), ("act", c_i32), ("mode", c_i32),
+        ("out", c_vp), ("ldo", c_i64), ("out_stride", c_i64), ("out_div", c_i32), ("out_stride_hi", c_i64),
+        ("mask", c_vp), ("plane_map", c_vp), ("n_blocks", c_i32), ("row_len", c_i32),
+        ("impl", c_i32),
+    ]
+
+
+EPI_F32, EPI_BF16, EPI_HEAD = 0, 1, 2
+
+_SIGNATURES = {
+    "tssep_abi_version": ([], C.c_int),
+    "tssep_device_info": ([C.POINTER(C.c_int)] * 3, C.c_int),
+    "tssep_stft": ([c_vp, c_i64, c_i64, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i64, c_vp, c_vp], C.c_int),
+    "tssep_feature_stats": ([c_vp, c_i64, c_i64, c_i64, c_i32, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp],
+                            C.c_int),
+    "tssep_feature_write": ([c_vp, c_i64, c_i64, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_f32,
+                             c_i32, c_vp, c_vp, c_i64, c_vp], C.c_int),
+    "tssep_cast_bf16": ([c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp], C.c_int),
+    "tssep_instance_norm": ([c_vp, c_i64, c_i64, c_i32, c_vp, c_vp], C.c_int),
+    "tssep_fold_embedding": ([c_i32, c_vp, c_i64, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_vp, c_i64, c_vp, c_vp],
+                             C.c_int),
+    "tssep_gemm": ([C.POINTER(GemmDesc), c_vp], C.c_int),
+    "tssep_head_expand_t": ([c_vp, c_i64, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp], C.c_int),
+    "tssep_blstm_recurrence": ([c_vp, c_vp, c_vp, c_i64, c_i64, c_i32, c_i32, c_i32, c_vp], C.c_int),
+    "tssep_pack_whh": ([c_vp, c_vp, c_i32, c_i32, c_vp, c_vp], C.c_int),
+    "tssep_mask_istft": ([c_vp, c_i64, c_vp, c_i64, c_i32, c_i64, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp,
+                          c_i64, c_vp], C.c_int),
+    "tssep_activity": ([c_vp, c_i64, c_i64, c_i32, c_vp, c_vp], C.c_int),
+    "tssep_median_threshold": ([c_vp, c_i64, c_i64, c_i32, c_f32, c_vp, c_vp, c_vp], C.c_int),
+    "tssep_segments": ([c_vp, c_i64, c_i64, c_i32, c_i32, c_i32, c_i64, c_vp, c_vp, c_i32, c_vp], C.c_int),
+}
+
+EXPORTED_SYMBOLS = ["tssep_last_error", *_SIGNATURES]
+
+
+def lib_path() -> Path:
+    return _LIB_PATH
+
+
+def load():
+    """Loads the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not _LIB_PATH.exists():
+        raise RuntimeError(
+            f"{_LIB_PATH} is missing: build it with `python -m tssep_b200.build` "
+            "(tssep_b200 has no CPU / PyTorch fallback)."
+        )
+    lib = C.CDLL(os.fspath(_LIB_PATH))
+    lib.tssep_last_error.restype = C.c_char_p
+    lib.tssep_last_error.argtypes = []
+    for name, (argtypes, restype) in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = restype
+    _lib = lib
+    return lib
+
+
+def check(code: int, what: str):
+    if code != 0:
+        msg = load().tssep_last_error().decode(errors="replace")
+        raise RuntimeError(f"{what} failed ({code}): {msg}")
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream_of(t: torch.Tensor = None):
+    return torch.cuda.current_stream(t.device if t is not None else None).cuda_stream
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError(
+                "tssep_b200 operators run on CUDA tensors only (no CPU fallback); got a tensor on " f"{t.device}"
+            )
+
+
+def call(name: str, *args):
+    check(getattr(load(), name)(*args), name)

@@ -1,0 +1,62 @@
+"""Drop-in ``Masking`` enhancer (tssep/train/enhancer.py:21-32, :73-100).
+
+``stft_estimate = Observation[..., ref, None, :, :] * squeeze(mask, -3)`` computed by
+``tssep_mask_istft``; ``apply`` can also return the iSTFT of the product from the
+same kernel launch (mask x X -> irfft -> synthesis window -> overlap-add).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib
+from .configurable import Configurable
+
+
+class ABC(Configurable, torch.nn.Module):
+    @property
+    def name(self):
+        return self.__class__.__name__
+
+    def __call__(self, masks, ex, model):
+        raise NotImplementedError()
+
+
+class Masking(ABC):
+    def __call__(self, masks: torch.Tensor, ex, model):
+        return self.apply(masks, ex["Observation"], ex["reference_channel"], fe=model.fe)[0]
+
+    @staticmethod
+    def apply(masks, Observation, reference_channel, fe, want_estimate=True, want_time=False, num_samples=None):
+        """masks (K,1,T,F) or (B,K,1,T,F) f32; Observation ([B,] C, T, F) complex64 (or without the channel
+        axis when ``reference_channel`` is None).  Returns (stft_estimate | None, time_estimate | None)."""
+        batched = {4: False, 5: True}[masks.dim()]
+        if isinstance(Observation, np.ndarray):
+            Observation = torch.as_tensor(Observation, device=masks.device)
+        _lib.require_cuda(masks, Observation)
+        if reference_channel is None:
+            assert Observation.dim() == (3 if batched else 2), Observation.shape
+            obs = Observation
+        else:
+            assert Observation.dim() == (4 if batched else 3), Observation.shape
+            obs = Observation[..., reference_channel, :, :]
+        if masks.shape[-3] != 1:
+            raise ValueError(f"Masking needs nmask == 1, got mask shape {tuple(masks.shape)}")
+        obs = obs.to(torch.complex64).contiguous()
+        m = masks.float().contiguous()
+        T, F = m.shape[-2:]
+        K = m.shape[-4]
+        Z = m.shape[0] if batched else 1
+        assert obs.shape[-2:] == (T, F), (obs.shape, m.shape)
+        lead = (Z, K) if batched else (K,)
+        est = torch.empty((*lead, T, F), dtype=torch.complex64, device=m.device) if want_estimate else None
+        time = None
+        if want_time:
+            total = (T - 1) * fe.shift + fe.window_length - (2 * (fe.window_length - fe.shift) if fe.fading else 0)
+            n = total if num_samples is None else min(int(num_samples), total)
+            time = torch.empty((*lead, n), dtype=torch.float32, device=m.device)
+        tab = fe._device_tables(m.device)
+        _lib.call("tssep_mask_istft", obs.data_ptr(), T * F, m.data_ptr(), Z, K, T, fe.size, fe.shift,
+                  fe.window_length, int(bool(fe.fading)), tab["synwin"].data_ptr(), tab["twiddle"].data_ptr(),
+                  _lib.ptr(est), _lib.ptr(time), time.shape[-1] if time is not None else 0, _lib.stream_of(m))
+        return est, time

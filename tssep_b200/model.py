@@ -1,0 +1,144 @@
+"""Drop-in ``Model`` glue for the inference path (tssep/train/model.py:70-164, :454-536, :661-664).
+
+``Model.forward(ex)`` keeps the reference's call contract (same ``ex`` keys in,
+``ForwardOutput`` out, ``ex['Observation']`` / ``ex['Input']`` / ``ex['AuxInput']``
+filled in).  ``Model.separate`` is the throughput entry point: a batch of
+independent meetings in, every output of the path (mask, logit, stft_estimate,
+time_estimate and optionally diarization segments) out, all on the device.
+Dataset plumbing, review summaries and the trainer are out of scope.
+"""
+from __future__ import annotations
+
+import dataclasses
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from .configurable import Configurable, import_class
+from .enhancer import Masking
+from .feature_extractor import _compute_features
+
+
+@dataclasses.dataclass
+class ForwardOutput:
+    mask: torch.Tensor
+    logit: torch.Tensor
+    embedding: torch.Tensor = None
+    stft_estimate: torch.Tensor = None
+    time_estimate: torch.Tensor = None
+
+    vad_mask: torch.Tensor = None
+    vad_logit: torch.Tensor = None
+
+
+class Model(Configurable, torch.nn.Module):
+    ForwardOutput = ForwardOutput
+
+    @classmethod
+    def finalize_dogmatic_config(cls, config):
+        # same defaults as tssep/train/model.py:119-149
+        config["fe"] = dict(factory="tssep_b200.feature_extractor.Log1pMaxNormAbsSTFT", size=1024, shift=256,
+                            window="hann")
+        config["reader"] = dict(factory="tssep_b200.data.DummyReader")
+        config["enhancer"] = dict(factory="tssep_b200.enhancer.Masking")
+        fe = Configurable.from_config(config["fe"])
+        is_masking = issubclass(import_class(config["enhancer"]["factory"]), Masking)
+        config["mask_estimator"] = dict(factory="tssep_b200.net.MaskEstimator_v2", idim=fe.output_size,
+                                        odim=fe.frequencies, nmask=1 if is_masking else 2)
+        config["loss"] = dict(factory="tssep_b200.loss.LogMAE")
+
+    def __init__(self, fe=None, reader=None, mask_estimator=None, enhancer=None, loss=None):
+        super().__init__()
+        self.fe = fe
+        self.reader = reader
+        self.mask_estimator = mask_estimator
+        self.enhancer = enhancer
+        self.loss = loss
+
+    # -- helpers -----------------------------------------------------------------
+    def example_to_device(self, ex, device):
+        """numpy / CPU example -> tensors on ``device`` (tssep/train/model.py:166-180)."""
+        out = dict(ex)
+        if "audio_data" in ex:
+            out["observation"] = ex["audio_data"]["observation"]
+            for k, v in ex["audio_data"].items():
+                if k != "observation":
+                    out.setdefault(k, v)
+        out.setdefault("reference_channel", 0)
+        targets = self.loss.targets() + self.loss.targets(lower=True) if self.loss is not None else []
+        for k in ["observation", "auxInput", "Input", *targets]:
+            if k in out and not isinstance(out[k], (str, int)):
+                out[k] = torch.as_tensor(np.asarray(out[k]) if not torch.is_tensor(out[k]) else out[k]).to(device)
+        return out
+
+    def _features(self, ex, couple=None):
+        ref = ex["reference_channel"]
+        if not isinstance(ref, int):
+            raise NotImplementedError(type(ref), ref)
+        if "Observation" not in ex:
+            ex["Observation"] = self.fe.stft(ex["observation"])
+        Xr = ex["Observation"][..., ref, :, :]
+        feats = _compute_features(self.fe, Xr, want_f32=True, want_bf16=True, couple=couple)
+        return feats
+
+    # -- reference contract --------------------------------------------------------
+    def forward(self, ex, feature_transform=None, with_time_estimate=False) -> ForwardOutput:
+        """tssep/train/model.py:465-536.  ``with_time_estimate=True`` additionally runs the iSTFT of
+        ``Model.review`` (model.py:661-664) in the same enhancement kernel."""
+        ex["AuxInput"] = [a for a in ex["auxInput"]]
+        bf16 = None
+        if "Input" not in ex:
+            feats = self._features(ex)
+            ex["Input"] = feats["f32"]
+            bf16 = (feats["bf16"], feats["ld"])
+        if feature_transform is not None:
+            ex["Input"] = feature_transform(ex["Input"])
+            bf16 = None
+        ex = self.reader.data_hooks.pre_net(ex) if self.reader is not None else ex
+        me_out = self.mask_estimator(ex["Input"], ex["AuxInput"], _features_bf16=bf16)
+        stft_estimate = time_estimate = None
+        if "Observation" in ex:
+            if isinstance(self.enhancer, Masking):
+                n = ex["observation"].shape[-1] if "observation" in ex else None
+                stft_estimate, time_estimate = Masking.apply(
+                    me_out.mask, ex["Observation"], ex["reference_channel"], self.fe, want_estimate=True,
+                    want_time=with_time_estimate and n is not None, num_samples=n)
+            else:
+                stft_estimate = self.enhancer(me_out.mask, ex, self)
+        return ForwardOutput(mask=me_out.mask, logit=me_out.logit, vad_mask=me_out.vad_mask,
+                             vad_logit=me_out.vad_logit, embedding=me_out.embedding, stft_estimate=stft_estimate,
+                             time_estimate=time_estimate)
+
+    def istft(self, out: ForwardOutput, num_samples: Optional[int]):
+        """The time-domain step of ``Model.review`` (tssep/train/model.py:661-664)."""
+        out.time_estimate = self.fe.istft(out.stft_estimate, num_samples=num_samples)
+        return out
+
+    # -- throughput entry point ------------------------------------------------------
+    @torch.no_grad()
+    def separate(self, observation: torch.Tensor, aux: torch.Tensor, *, want_estimate=True, want_time=True,
+                 diarize: Optional[dict] = None) -> ForwardOutput:
+        """A batch of independent single-channel meetings.
+
+        observation (M, N) or (M, 1, N) float32, aux (M, K, A) float32, both on the device.  Each
+        meeting is processed exactly as a separate unbatched ``forward`` call would (own feature
+        statistics, one ``np.random.permutation`` draw per meeting, in order).
+        ``diarize`` = dict(threshold=, median_width=, max_segments=) adds ``.segments``.
+        """
+        _lib.require_cuda(observation, aux)
+        if observation.dim() == 2:
+            observation = observation[:, None, :]
+        ex = {"observation": observation, "reference_channel": 0}
+        feats = self._features(ex, couple=False)
+        me_out = self.mask_estimator(feats["f32"], [a for a in aux], _features_bf16=(feats["bf16"], feats["ld"]))
+        est, time = Masking.apply(me_out.mask, ex["Observation"], 0, self.fe, want_estimate=want_estimate,
+                                  want_time=want_time, num_samples=observation.shape[-1])
+        out = ForwardOutput(mask=me_out.mask, logit=me_out.logit, embedding=me_out.embedding, stft_estimate=est,
+                            time_estimate=time, vad_mask=me_out.vad_mask, vad_logit=me_out.vad_logit)
+        if diarize is not None:
+            from .postprocess import diarize as run_diarize
+
+            out.segments = run_diarize(me_out.mask, self.fe, num_samples=observation.shape[-1], **diarize)
+        return out

@@ -1,0 +1,365 @@
+"""Drop-in ``MaskEstimator_v2`` (tssep/train/net.py:333-986) and its helper modules.
+
+Constructor keywords, attribute names, module tree (hence ``repr`` and ``state_dict``
+keys ``pre_net.net.0.weight_ih_l0`` ... ``post_net.linear2.bias``) and the
+``forward(xs, aux) -> Output`` contract equal the reference's.  ``forward`` never
+materialises the reference's intermediate tensors:
+
+* conditioning (net.py:862-896) is folded into the first post_net input
+  projection (``tssep_fold_embedding``): 'mul' scales the weight columns per
+  speaker, 'cat' turns the embedding half of the weight into a per-speaker bias;
+* the permutation-averaging trials (net.py:900-924) are de-duplicated: birnn0 /
+  birnn1 are speaker-independent, so they run once for the K speakers and the R
+  cyclic speaker orders only enter through R column-rotated copies of the
+  speaker-concat layer's input weights (net.py:606-612);
+* the trial mean, the inverse rotation, the speaker un-permutation and the
+  sigmoid (net.py:928-986) live in the head GEMM: rotated head weights are
+  concatenated along K, the mean is the fp32 accumulation, the un-permutation
+  is the epilogue's plane map.
+"""
+from __future__ import annotations
+
+import collections
+import dataclasses
+
+import numpy as np
+import torch
+
+from . import _lib, ops
+from .configurable import Configurable
+from .rnnp import RNNP_packed, param_key
+
+
+@dataclasses.dataclass
+class Output:
+    mask: torch.Tensor
+    logit: torch.Tensor
+    embedding: torch.Tensor = None
+
+    vad_mask: torch.Tensor = None
+    vad_logit: torch.Tensor = None
+
+
+class InstanceNorm(torch.nn.Module):
+    """``(x - mean) / std`` over ``dim`` (tssep/train/net.py:250-285); CUDA path: last axis."""
+
+    def __init__(self, dim=-1, unbiased=False):
+        super().__init__()
+        self.dim = dim
+        self.unbiased = unbiased
+
+    def extra_repr(self):
+        return f"dim={self.dim!r}, unbiased={self.unbiased!r}"
+
+    def forward(self, x):
+        if self.dim not in (-1, x.dim() - 1):
+            raise NotImplementedError("InstanceNorm on the CUDA path normalises the last axis only")
+        return ops.instance_norm(x, self.unbiased)
+
+
+class _Einop(torch.nn.Module):
+    """Placeholder keeping the reference's layer names; the rearrangement itself is fused."""
+
+    def __init__(self, pattern, **axes):
+        super().__init__()
+        self.pattern, self.axes = pattern, axes
+
+    def extra_repr(self):
+        return ", ".join([repr(self.pattern)] + [f"{k}={v}" for k, v in self.axes.items()])
+
+
+class Sequential(torch.nn.Sequential):
+    """Container only (tssep/train/net.py:190-237); ``MaskEstimator_v2.forward`` drives the kernels."""
+
+
+class _SequentialDict:
+    """Names layers ``<key><idx>`` with a non-decreasing index (tssep/train/net.py:572-587)."""
+
+    def __init__(self):
+        self.data = collections.OrderedDict()
+        self.idx = 0
+
+    def add(self, key, value):
+        for self.idx in range(self.idx, 100):
+            k = f"{key}{self.idx}"
+            if k not in self.data:
+                self.data[k] = value
+                return
+        raise RuntimeError(key)
+
+
+class MaskEstimator_v2(Configurable, torch.nn.Module):
+    @classmethod
+    def finalize_dogmatic_config(cls, config):
+        config["aux_net"] = None
+        if config["aux_net_output_size"] is None:
+            config["aux_net_output_size"] = 100  # I-vectors by default (net.py:488-490)
+
+    def __init__(self, *, idim=80, odim=None, layers=3, units=300, projs=320, dropout=0, nmask=1, pre_net="RNNP",
+                 aux_net=None, aux_net_output_size=None, combination: str = "cat", ts_vad=False,
+                 output_resolution: str = "tf", random_speaker_order=True, num_averaged_permutations=1,
+                 input_normalizer=None, aux_normalizer=None, explicit_vad=False):
+        super().__init__()
+        if aux_net is not None:
+            raise NotImplementedError("aux_net is forced to None by the reference (net.py:487)")
+        if odim is None:
+            odim = idim
+        self.odim, self.nmask = odim, nmask
+        self.output_resolution = output_resolution
+        self.random_speaker_order = random_speaker_order
+        self.num_averaged_permutations = num_averaged_permutations
+        self.ts_vad = ts_vad
+        self.input_normalizer, self.aux_normalizer = input_normalizer, aux_normalizer
+        self.explicit_vad = explicit_vad
+        self.layers, self.units, self.projs = layers, units, projs
+        if not ts_vad:
+            assert num_averaged_permutations == 1, (ts_vad, num_averaged_permutations)
+        if pre_net == "RNNP":
+            self.pre_net = RNNP_packed(idim=idim, elayers=1, cdim=units, hdim=odim, dropout=dropout, typ="blstm")
+        elif pre_net in [None, False]:
+            self.pre_net = torch.nn.Identity()
+        else:
+            raise ValueError(pre_net)
+        self.aux_net = aux_net
+        self.combination = combination
+        if combination == "cat":
+            assert aux_net_output_size is not None, (combination, aux_net_output_size)
+            first = odim + aux_net_output_size
+        elif combination == "mul":
+            first = odim
+        else:
+            raise NotImplementedError(combination) if combination == "film" else ValueError(combination)
+        self.aux_size = aux_net_output_size
+        post = _SequentialDict()
+        ts_factor = 1
+        for l in range(layers):
+            if l == layers - 1 and ts_vad is not False:
+                assert 2 < ts_vad < 20, ts_vad
+                post.add("rearrange", _Einop("... spk time feature -> ... 1 time (spk feature)", spk=ts_vad))
+                ts_factor = ts_vad
+            post.add("birnn", RNNP_packed(idim=(first if l == 0 else projs) * ts_factor, elayers=1, cdim=units,
+                                          hdim=projs, dropout=dropout, typ="blstm"))
+            if l < layers - 1:
+                post.add("dropout", torch.nn.Dropout(p=dropout))
+                post.add("activation", torch.nn.Tanh())
+        if output_resolution == "tf":
+            out_features = (odim + int(explicit_vad)) * nmask * ts_factor
+            pattern = ("... spk time (mask freq) -> ... spk mask time freq" if ts_vad is False
+                       else "... 1 time (spk mask freq) -> ... spk mask time freq")
+        elif output_resolution == "t":
+            assert explicit_vad is False, explicit_vad
+            out_features = nmask * ts_factor
+            pattern = ("... spk time mask -> ... spk mask time freq" if ts_vad is False
+                       else "... 1 time (spk mask) -> ... spk mask time freq")
+        else:
+            raise ValueError(output_resolution)
+        post.add("linear", torch.nn.Linear(in_features=projs, out_features=out_features))
+        post.add("rearrange", _Einop(pattern, mask=nmask))
+        self.post_net = Sequential(post.data)
+        self.final_activation = torch.nn.Sigmoid()
+        self._head_cache = None
+        self._rot_cache = None
+
+    def extra_repr(self) -> str:
+        return f"combination={self.combination!r},"
+
+    # -- derived weight caches -------------------------------------------------
+    def _birnns(self):
+        return [m for n, m in self.post_net.named_children() if n.startswith("birnn")]
+
+    def _head_linear(self):
+        return [m for n, m in self.post_net.named_children() if n.startswith("linear")][0]
+
+    def _head_pack(self, K, R, row_len):
+        lin = self._head_linear()
+        key = (param_key(lin), K, R, row_len)
+        if self._head_cache is None or self._head_cache[0] != key:
+            with torch.no_grad():
+                P = lin.in_features
+                W = lin.weight.detach().float()
+                b = lin.bias.detach().float()
+                if self.ts_vad is not False:
+                    Wv = W.view(K, -1, P)
+                    bv = b.view(K, -1)
+                    q = torch.arange(K, device=W.device)
+                    Wr = torch.cat([Wv[(q - r) % K] for r in range(R)], dim=-1)  # (K, blk, R*P)
+                    W2 = Wr.reshape(-1, R * P)
+                    b2 = torch.stack([bv[(q - r) % K] for r in range(R)], 0).mean(0).reshape(-1)
+                else:
+                    W2, b2 = W, b
+                pack = {"w": ops.cast_bf16(W2.contiguous()), "ld": ops.round_up(W2.shape[1], 8),
+                        "b": b2.contiguous(), "kdim": W2.shape[1], "n": W2.shape[0]}
+            self._head_cache = (key, pack)
+        return self._head_cache[1]
+
+    def _rotated_input_weights(self, pk, K, R):
+        """R column-rotated copies of the speaker-concat layer's W_ih, stacked on rows."""
+        key = (id(pk), K, R)
+        if self._rot_cache is None or self._rot_cache[0] != key:
+            with torch.no_grad():
+                P = pk.I // K
+                Wv = pk.w_ih_f32.view(8 * pk.Up, K, P)
+                q = torch.arange(K, device=Wv.device)
+                Wr = torch.stack([Wv[:, (q - r) % K] for r in range(R)], 0).reshape(R * 8 * pk.Up, K * P)
+                ld = ops.round_up(K * P, 8)
+                self._rot_cache = (key, {"w": ops.cast_bf16(Wr.contiguous(), ld), "ld": ld})
+        return self._rot_cache[1]
+
+    # -- forward ---------------------------------------------------------------
+    def forward(self, xs, aux=None, _features_bf16=None) -> Output:
+        """xs (T, idim) or (B, T, idim) float32; aux list of K (A,) tensors / list of B (K, A).
+
+        ``_features_bf16=(tensor, ld)`` lets ``Model.forward`` hand over the bf16 feature rows the
+        feature kernel already produced.
+        """
+        _lib.require_cuda(xs)
+        dev = xs.device
+        if xs.dim() == 2:
+            batched, B = False, 1
+            K = len(aux)
+            perms = [np.random.permutation(K) if self.random_speaker_order else np.arange(K)]
+            aux_t = torch.stack([a for a in aux], dim=0)[None]
+        elif xs.dim() == 3:
+            batched, B = True, xs.shape[0]
+            K = len(aux[0])
+            perms = [np.random.permutation(K) if self.random_speaker_order else np.arange(K) for _ in range(len(aux))]
+            aux_t = torch.stack([torch.stack([x for x in a], 0) if isinstance(a, (tuple, list)) else a for a in aux], 0)
+        else:
+            raise RuntimeError(xs.shape)
+        _lib.require_cuda(aux_t)
+        perm_t = torch.as_tensor(np.stack(perms), device=dev, dtype=torch.long)
+        aux_p = torch.gather(aux_t.float(), 1, perm_t[:, :, None].expand(B, K, aux_t.shape[-1]))  # slot order
+        if batched and self.aux_normalizer is not None:
+            aux_p = self.aux_normalizer(aux_p)
+        A = aux_p.shape[-1]
+        T, Din = xs.shape[-2:]
+        R = self.num_averaged_permutations
+        L = self.layers
+        if self.ts_vad is not False:
+            assert self.ts_vad == K, (self.ts_vad, K)
+            if L < 2:
+                raise NotImplementedError("ts_vad with layers == 1 is not implemented")
+
+        # features -> bf16 rows
+        if self.input_normalizer is not None:
+            xs = self.input_normalizer(xs)
+            _features_bf16 = None
+        if _features_bf16 is not None:
+            xb, ld = _features_bf16
+        else:
+            xb = ops.cast_bf16(xs.reshape(B * T, Din).float())
+            ld = ops.round_up(Din, 8)
+
+        # pre_net on the mixture (net.py:860)
+        if isinstance(self.pre_net, RNNP_packed):
+            for pk in self.pre_net.layer_packs():
+                G = pk.input_gemm(xb, ld, B * T)
+                H = pk.recurrence(G, B, T)
+                del G
+                ld = ops.round_up(pk.hdim, 8)
+                xb = torch.empty((B * T, ld), dtype=torch.bfloat16, device=dev)
+                pk.projection(H, B * T, xb, mode=ops.EPI_BF16, ldo=ld, act=0)
+                del H
+                F = pk.hdim
+        else:
+            F = Din
+
+        # conditioning folded into birnn0's input projection (net.py:862-896)
+        birnns = self._birnns()
+        pk0 = birnns[0].layer_packs()[0]
+        Up = pk0.Up
+        e = aux_p.reshape(B * K, A).contiguous()
+        bias_k = torch.empty((B * K, 8 * Up), dtype=torch.float32, device=dev)
+        G = torch.empty((B * K * T, 8 * Up), dtype=torch.float32, device=dev)
+        stream = _lib.stream_of(xs)
+        if self.combination == "mul":
+            assert A == F, ("combination='mul' needs aux_size == odim", A, F)
+            ldk = ops.round_up(F, 8)
+            Wk = torch.empty((B * K * 8 * Up, ldk), dtype=torch.bfloat16, device=dev)
+            _lib.call("tssep_fold_embedding", 0, pk0.w_ih_f32.data_ptr(), pk0.I, pk0.bias.data_ptr(), e.data_ptr(),
+                      B * K, 8 * Up, F, A, Wk.data_ptr(), ldk, bias_k.data_ptr(), stream)
+            ops.gemm(xb, ld, Wk, ldk, T, 8 * Up, F, G, mode=ops.EPI_F32, ldo=8 * Up, batch=B * K, a_stride=T * ld,
+                     a_div=K, b_stride=8 * Up * ldk, bias=bias_k, bias_stride=8 * Up, out_stride=T * 8 * Up)
+            del Wk
+        else:  # cat
+            assert pk0.I == F + A, (pk0.I, F, A)
+            _lib.call("tssep_fold_embedding", 1, pk0.w_ih_f32.data_ptr(), pk0.I, pk0.bias.data_ptr(), e.data_ptr(),
+                      B * K, 8 * Up, F, A, None, 0, bias_k.data_ptr(), stream)
+            ops.gemm(xb, ld, pk0.w_ih, pk0.ld_in, T, 8 * Up, F, G, mode=ops.EPI_F32, ldo=8 * Up, batch=B * K,
+                     a_stride=T * ld, a_div=K, b_stride=0, bias=bias_k, bias_stride=8 * Up, out_stride=T * 8 * Up)
+        del xb
+
+        P = self.projs
+        ldp = ops.round_up(P, 8)
+        rows = B * K
+        y, y_ld = None, None
+        for l in range(L):
+            pk = birnns[l].layer_packs()[0]
+            last = l == L - 1
+            tsv_last = last and self.ts_vad is not False
+            if l > 0:
+                if tsv_last:
+                    rot = self._rotated_input_weights(pk, K, R)
+                    rows = B * R
+                    G = torch.empty((rows * T, 8 * pk.Up), dtype=torch.float32, device=dev)
+                    ops.gemm(y, y_ld, rot["w"], rot["ld"], T, 8 * pk.Up, K * P, G, mode=ops.EPI_F32, ldo=8 * pk.Up,
+                             batch=rows, a_stride=T * y_ld, a_div=R, b_stride=8 * pk.Up * rot["ld"], b_mod=R,
+                             bias=pk.bias, bias_stride=0, out_stride=T * 8 * pk.Up)
+                else:
+                    G = pk.input_gemm(y, y_ld, rows * T)
+            H = pk.recurrence(G, rows, T)
+            del G
+            if not last and l == L - 2 and self.ts_vad is not False:
+                # write tanh(proj) straight into the speaker-concat layout (B, T, K*P)   net.py:606-612
+                y_ld = ops.round_up(K * P, 8)
+                y = torch.empty((B * T, y_ld), dtype=torch.bfloat16, device=dev)
+                pk.projection(H, 0, y, mode=ops.EPI_BF16, ldo=y_ld, act=1, batch=rows, a_stride=T * 2 * pk.Up, M=T,
+                              out_stride=P, out_div=K, out_stride_hi=T * y_ld)
+            elif tsv_last:
+                # trial-concat layout (B, T, R*P) feeding the averaged head
+                y_ld = ops.round_up(R * P, 8)
+                y = torch.empty((B * T, y_ld), dtype=torch.bfloat16, device=dev)
+                pk.projection(H, 0, y, mode=ops.EPI_BF16, ldo=y_ld, act=0, batch=rows, a_stride=T * 2 * pk.Up, M=T,
+                              out_stride=P, out_div=R, out_stride_hi=T * y_ld)
+            else:
+                y_ld = ldp
+                y = torch.empty((rows * T, y_ld), dtype=torch.bfloat16, device=dev)
+                pk.projection(H, rows * T, y, mode=ops.EPI_BF16, ldo=y_ld, act=0 if last else 1)
+            del H
+
+        # head: Linear + rearrange + trial mean + un-permute + sigmoid (net.py:629-668, :928-986)
+        nmask, odim = self.nmask, self.odim
+        fh = odim + int(self.explicit_vad)
+        tf = self.output_resolution == "tf"
+        row_len = fh if tf else 1
+        hp = self._head_pack(K, R, row_len)
+        perm_np = np.stack(perms)  # (B, K)
+        if self.ts_vad is not False:
+            items, nb = B, K * nmask
+            planes = (np.arange(B)[:, None, None] * K + perm_np[:, :, None]) * nmask + np.arange(nmask)[None, None, :]
+        else:
+            items, nb = B * K, nmask
+            planes = ((np.arange(B)[:, None] * K + perm_np)[:, :, None]) * nmask + np.arange(nmask)[None, None, :]
+        plane_map = torch.as_tensor(planes.reshape(-1).astype(np.int32), device=dev)
+        shape = (B, K, nmask, T, fh if tf else odim)
+        logit = torch.empty(shape, dtype=torch.float32, device=dev)
+        mask = torch.empty(shape, dtype=torch.float32, device=dev)
+        if tf:
+            ops.gemm(y, y_ld, hp["w"], hp["ld"], T, hp["n"], hp["kdim"], logit, mode=ops.EPI_HEAD, batch=items,
+                     a_stride=T * y_ld, b_stride=0, b_mod=1, bias=hp["b"], alpha=1.0 / R, mask=mask,
+                     plane_map=plane_map, n_blocks=nb, row_len=row_len)
+        else:
+            small = torch.empty((items * T, nb), dtype=torch.float32, device=dev)
+            ops.gemm(y, y_ld, hp["w"], hp["ld"], items * T, hp["n"], hp["kdim"], small, mode=ops.EPI_F32, ldo=nb,
+                     b_mod=1, bias=hp["b"], alpha=1.0 / R)
+            _lib.call("tssep_head_expand_t", small.data_ptr(), items, T, nb, odim, plane_map.data_ptr(),
+                      logit.data_ptr(), mask.data_ptr(), stream)
+        del y
+        embedding = aux_p.unsqueeze(-2)
+        if not batched:
+            logit, mask, embedding = logit[0], mask[0], embedding[0]
+        if self.explicit_vad:
+            vad_mask = mask[..., 0]
+            return Output(mask=mask[..., 1:] * vad_mask[..., None], logit=None, vad_mask=vad_mask,
+                          vad_logit=logit[..., 0], embedding=embedding)
+        return Output(mask=mask, logit=logit, embedding=embedding)

@@ -1,0 +1,88 @@
+"""Thin typed wrappers around the C-ABI calls shared by several modules.
+
+Nothing here computes on the host: each function validates, allocates the
+output with torch (device memory only) and enqueues one kernel from
+``libtssep_b200.so`` on the current CUDA stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+from . import _lib
+from ._lib import EPI_BF16, EPI_F32, EPI_HEAD, GemmDesc
+
+
+def round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+def _gemm_impl() -> int:
+    return 1 if os.environ.get("TSSEP_GEMM_IMPL", "tcgen05") == "simt" else 0
+
+
+def gemm(A, lda, B, ldb, M, N, K, out, *, mode, ldo=0, batch=1, a_stride=0, a_div=1, b_stride=0, b_mod=None,
+         bias=None, bias_stride=0, alpha=1.0, act=0, out_stride=0, out_div=1, out_stride_hi=0, mask=None,
+         plane_map=None, n_blocks=0, row_len=0, impl=None):
+    """``tssep_gemm``: out[z] = act(alpha * A[z / a_div] . B[z % b_mod]^T + bias[z % b_mod])."""
+    _lib.require_cuda(A, B, out, bias, mask, plane_map)
+    d = GemmDesc()
+    d.A, d.lda, d.a_stride, d.a_div = A.data_ptr(), lda, a_stride, a_div
+    d.B, d.ldb, d.b_stride, d.b_mod = B.data_ptr(), ldb, b_stride, batch if b_mod is None else b_mod
+    d.bias, d.bias_stride = _lib.ptr(bias), bias_stride
+    d.M, d.N, d.K, d.batch = M, N, K, batch
+    d.alpha, d.act, d.mode = alpha, act, mode
+    d.out, d.ldo, d.out_stride, d.out_div, d.out_stride_hi = _lib.ptr(out), ldo, out_stride, out_div, out_stride_hi
+    d.mask, d.plane_map, d.n_blocks, d.row_len = _lib.ptr(mask), _lib.ptr(plane_map), n_blocks, row_len
+    d.impl = _gemm_impl() if impl is None else impl
+    _lib.call("tssep_gemm", C.byref(d), _lib.stream_of(A))
+
+
+def cast_bf16(src: torch.Tensor, ld_dst: int = None) -> torch.Tensor:
+    """(rows, cols) f32 -> (rows, ld_dst) bf16 with zero padded columns."""
+    _lib.require_cuda(src)
+    src = src.contiguous()
+    rows, cols = src.shape
+    ld_dst = round_up(cols, 8) if ld_dst is None else ld_dst
+    dst = torch.empty((rows, ld_dst), dtype=torch.bfloat16, device=src.device)
+    _lib.call("tssep_cast_bf16", src.data_ptr(), rows, cols, cols, dst.data_ptr(), ld_dst, _lib.stream_of(src))
+    return dst
+
+
+def pack_whh(w_fwd: torch.Tensor, w_bwd: torch.Tensor, U: int, Up: int) -> torch.Tensor:
+    _lib.require_cuda(w_fwd, w_bwd)
+    n = 2 * (Up // 4) * (Up // 16) * 128
+    out = torch.empty(n, dtype=torch.int32, device=w_fwd.device)
+    _lib.call("tssep_pack_whh", w_fwd.contiguous().data_ptr(), w_bwd.contiguous().data_ptr(), U, Up, out.data_ptr(),
+              _lib.stream_of(w_fwd))
+    return out
+
+
+def blstm_recurrence(G: torch.Tensor, wfrag: torch.Tensor, rows: int, T: int, Up: int, cluster: int = None,
+                     fast_math: bool = None) -> torch.Tensor:
+    """G (rows, T, 2, 4, Up) f32 -> H (rows, T, 2*Up) bf16."""
+    _lib.require_cuda(G, wfrag)
+    if cluster is None:
+        cluster = int(os.environ.get("TSSEP_LSTM_CLUSTER", "0"))
+    if fast_math is None:
+        fast_math = os.environ.get("TSSEP_LSTM_FAST_MATH", "0") == "1"
+    H = torch.empty((rows, T, 2 * Up), dtype=torch.bfloat16, device=G.device)
+    _lib.call("tssep_blstm_recurrence", G.data_ptr(), wfrag.data_ptr(), H.data_ptr(), rows, T, Up, cluster,
+              int(fast_math), _lib.stream_of(G))
+    return H
+
+
+def instance_norm(x: torch.Tensor, unbiased=False) -> torch.Tensor:
+    _lib.require_cuda(x)
+    x = x.contiguous().float()
+    cols = x.shape[-1]
+    rows = x.numel() // cols
+    out = torch.empty_like(x)
+    _lib.call("tssep_instance_norm", x.data_ptr(), rows, cols, int(bool(unbiased)), out.data_ptr(), _lib.stream_of(x))
+    return out
+
+
+__all__ = ["gemm", "cast_bf16", "pack_whh", "blstm_recurrence", "instance_norm", "round_up", "EPI_F32", "EPI_BF16",
+           "EPI_HEAD"]

@@ -1,0 +1,52 @@
+"""Diarization post-processing on the device: frame activity (frequency mean of the
+mask), running-median smoothing, thresholding and run-length segment extraction.
+
+The reference has no implementation of this stage (it lives in fgnt/tssep_data;
+anchors: tssep/util/utils.py:11-129, tssep/train/loss.py:343); the behaviour is
+specified by ``oracle/tssep_oracle.py::diarize_reference`` (parity unpinned).
+"""
+from __future__ import annotations
+
+import dataclasses
+
+import torch
+
+from . import _lib
+
+
+@dataclasses.dataclass
+class Diarization:
+    activity: torch.Tensor   # (..., K, T) float32  mean_f mask
+    smooth: torch.Tensor     # (..., K, T) float32  running median
+    active: torch.Tensor     # (..., K, T) uint8
+    segments: torch.Tensor   # (..., K, max_segments, 2) int32 sample intervals [start, end)
+    counts: torch.Tensor     # (..., K) int32 number of runs (may exceed max_segments)
+
+    def to_lists(self):
+        """Host copy: list (per leading index) of lists of (start, end) tuples."""
+        seg = self.segments.cpu().numpy().reshape(-1, *self.segments.shape[-2:])
+        cnt = self.counts.cpu().numpy().reshape(-1)
+        return [[(int(a), int(b)) for a, b in s[: min(c, s.shape[0])]] for s, c in zip(seg, cnt)]
+
+
+def diarize(mask: torch.Tensor, fe, *, num_samples=None, threshold=0.5, median_width=1, max_segments=256) -> Diarization:
+    """mask (..., K, 1, T, F) float32 on the device."""
+    _lib.require_cuda(mask)
+    if mask.shape[-3] != 1:
+        raise ValueError(f"expected nmask == 1, got {tuple(mask.shape)}")
+    m = mask.float().contiguous()
+    lead = m.shape[:-3]
+    T, F = m.shape[-2:]
+    n = m.numel() // (T * F)
+    dev, stream = m.device, _lib.stream_of(m)
+    act = torch.empty((*lead, T), dtype=torch.float32, device=dev)
+    smooth = torch.empty_like(act)
+    active = torch.empty((*lead, T), dtype=torch.uint8, device=dev)
+    seg = torch.zeros((*lead, max_segments, 2), dtype=torch.int32, device=dev)
+    cnt = torch.empty(lead, dtype=torch.int32, device=dev)
+    _lib.call("tssep_activity", m.data_ptr(), n, T, F, act.data_ptr(), stream)
+    _lib.call("tssep_median_threshold", act.data_ptr(), n, T, int(median_width), float(threshold), smooth.data_ptr(),
+              active.data_ptr(), stream)
+    _lib.call("tssep_segments", active.data_ptr(), n, T, fe.window_length, fe.shift, int(bool(fe.fading)),
+              -1 if num_samples is None else int(num_samples), seg.data_ptr(), cnt.data_ptr(), max_segments, stream)
+    return Diarization(act, smooth, active, seg, cnt)

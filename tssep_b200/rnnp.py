@@ -1,0 +1,152 @@
+"""Drop-in ``RNNP_packed`` (tssep/train/rnnp.py:12-173): projected BLSTM stack.
+
+Same constructor arguments, module list (so ``repr`` and ``state_dict`` keys
+``net.0.weight_ih_l0`` ... match the reference) and ``forward`` contract for
+2-/3-/4-D inputs.  The ``torch.nn.LSTM`` / ``Linear`` children only hold the
+parameters; ``forward`` runs
+
+    x . W_ih^T (+ b_ih + b_hh)      tcgen05 GEMM, both directions at once
+    time recurrence                 persistent cluster kernel (csrc/lstm.cu)
+    [h_fwd | h_bwd] . W_proj^T + b  tcgen05 GEMM with fused bias (+ tanh)
+
+on bf16 operands with fp32 accumulation and fp32 cell state.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib, ops
+
+
+class LayerPack:
+    """Device-resident, kernel-ready copies of one BLSTM + projection layer (a derived cache)."""
+
+    def __init__(self, lstm: torch.nn.LSTM, linear: torch.nn.Linear):
+        U, I = lstm.hidden_size, lstm.input_size
+        Up = ops.round_up(U, 16)
+        if Up > 320:
+            raise NotImplementedError(f"hidden size {U} > 320 is not supported by the recurrence kernel yet")
+        dev = lstm.weight_ih_l0.device
+        _lib.require_cuda(lstm.weight_ih_l0)
+        self.U, self.Up, self.I = U, Up, I
+        self.hdim = linear.out_features
+        with torch.no_grad():
+            w = torch.zeros((2, 4, Up, I), dtype=torch.float32, device=dev)
+            w[0, :, :U] = lstm.weight_ih_l0.detach().float().view(4, U, I)
+            w[1, :, :U] = lstm.weight_ih_l0_reverse.detach().float().view(4, U, I)
+            self.w_ih_f32 = w.view(8 * Up, I)  # rows [dir][gate][unit]
+            b = torch.zeros((2, 4, Up), dtype=torch.float32, device=dev)
+            b[0, :, :U] = (lstm.bias_ih_l0 + lstm.bias_hh_l0).detach().float().view(4, U)
+            b[1, :, :U] = (lstm.bias_ih_l0_reverse + lstm.bias_hh_l0_reverse).detach().float().view(4, U)
+            self.bias = b.view(8 * Up).contiguous()
+            self.ld_in = ops.round_up(I, 8)
+            self.w_ih = ops.cast_bf16(self.w_ih_f32, self.ld_in)
+            self.whh = ops.pack_whh(lstm.weight_hh_l0.detach().float(), lstm.weight_hh_l0_reverse.detach().float(),
+                                    U, Up)
+            wp = torch.zeros((self.hdim, 2 * Up), dtype=torch.float32, device=dev)
+            wp[:, :U] = linear.weight.detach().float()[:, :U]
+            wp[:, Up:Up + U] = linear.weight.detach().float()[:, U:]
+            self.w_proj = ops.cast_bf16(wp, 2 * Up)
+            self.b_proj = linear.bias.detach().float().contiguous()
+
+    # -- the three stages ------------------------------------------------------
+    def input_gemm(self, xb: torch.Tensor, ld: int, rows_t: int) -> torch.Tensor:
+        """xb (rows*T, ld) bf16 -> G (rows*T, 8*Up) f32."""
+        G = torch.empty((rows_t, 8 * self.Up), dtype=torch.float32, device=xb.device)
+        ops.gemm(xb, ld, self.w_ih, self.ld_in, rows_t, 8 * self.Up, self.I, G, mode=ops.EPI_F32, ldo=8 * self.Up,
+                 bias=self.bias)
+        return G
+
+    def recurrence(self, G: torch.Tensor, rows: int, T: int) -> torch.Tensor:
+        return ops.blstm_recurrence(G, self.whh, rows, T, self.Up)
+
+    def projection(self, H: torch.Tensor, rows_t: int, out: torch.Tensor, *, mode: int, ldo: int, act: int,
+                   batch=1, a_stride=0, M=None, out_stride=0, out_div=1, out_stride_hi=0):
+        """H (rows*T, 2*Up) bf16 -> out (bias and optional tanh fused)."""
+        ops.gemm(H, 2 * self.Up, self.w_proj, 2 * self.Up, rows_t if M is None else M, self.hdim, 2 * self.Up, out,
+                 mode=mode, ldo=ldo, bias=self.b_proj, act=act, batch=batch, a_stride=a_stride, b_mod=1,
+                 out_stride=out_stride, out_div=out_div, out_stride_hi=out_stride_hi)
+
+
+def param_key(module: torch.nn.Module):
+    return tuple((id(p), p._version, p.data_ptr()) for p in module.parameters())
+
+
+class RNNP_packed(torch.nn.Module):
+    """RNN with projection layers; see the module docstring.
+
+    >>> RNNP_packed(512, 2, 300, 320, 0)  # doctest: +NORMALIZE_WHITESPACE
+    RNNP_packed(
+      (net): ModuleList(
+        (0): LSTM(512, 300, batch_first=True, bidirectional=True)
+        (1): Linear(in_features=600, out_features=320, bias=True)
+        (2): Dropout(p=0, inplace=False)
+        (3): Tanh()
+        (4): LSTM(320, 300, batch_first=True, bidirectional=True)
+        (5): Linear(in_features=600, out_features=320, bias=True)
+      )
+    )
+    """
+
+    def __init__(self, idim, elayers, cdim, hdim, dropout, typ="blstm", return_states=False):
+        super().__init__()
+        if typ != "blstm":
+            raise NotImplementedError(f"typ={typ!r}: only 'blstm' (the value used by MaskEstimator_v2, "
+                                      "tssep/train/net.py:545-552) is implemented")
+        net = []
+        for i in range(elayers):
+            net.append(torch.nn.LSTM(idim if i == 0 else hdim, cdim, num_layers=1, bidirectional=True,
+                                     batch_first=True))
+            net.append(torch.nn.Linear(2 * cdim, hdim))
+            if i < elayers - 1:
+                net.append(torch.nn.Dropout(p=dropout))
+                net.append(torch.nn.Tanh())
+        self.net = torch.nn.ModuleList(net)
+        self.elayers, self.cdim, self.typ, self.bidir = elayers, cdim, typ, True
+        self.idim, self.hdim = idim, hdim
+        self.dropout, self.return_states = dropout, return_states
+        self._packs, self._packs_key = None, None
+
+    def layer_packs(self):
+        """Kernel-ready weights; rebuilt whenever a parameter was modified, moved or reloaded."""
+        key = param_key(self)
+        if self._packs is None or self._packs_key != key:
+            mods = list(self.net)
+            pairs = [(m, mods[i + 1]) for i, m in enumerate(mods) if isinstance(m, torch.nn.LSTM)]
+            self._packs = [LayerPack(lstm, lin) for lstm, lin in pairs]
+            self._packs_key = key
+        return self._packs
+
+    def forward(self, xs_pack, prev_state=None):
+        assert prev_state is None, prev_state
+        if self.return_states:
+            raise NotImplementedError("return_states=True is not implemented (unused by the reference configs)")
+        if self.training and self.dropout:
+            raise NotImplementedError("dropout > 0 in training mode is not implemented on the CUDA path")
+        if isinstance(xs_pack, torch.nn.utils.rnn.PackedSequence):
+            raise NotImplementedError("PackedSequence input (unsupported by the reference too, rnnp.py:29-31)")
+        _lib.require_cuda(xs_pack)
+        shape = xs_pack.shape
+        if len(shape) not in (2, 3, 4):
+            raise KeyError(len(shape))
+        T, D = shape[-2:]
+        rows = 1
+        for s in shape[:-2]:
+            rows *= s
+        x = xs_pack.reshape(rows * T, D).float()
+        packs = self.layer_packs()
+        xb, ld = ops.cast_bf16(x), ops.round_up(D, 8)
+        out = None
+        for li, pk in enumerate(packs):
+            G = pk.input_gemm(xb, ld, rows * T)
+            H = pk.recurrence(G, rows, T)
+            del G
+            if li == len(packs) - 1:
+                out = torch.empty((rows * T, pk.hdim), dtype=torch.float32, device=x.device)
+                pk.projection(H, rows * T, out, mode=ops.EPI_F32, ldo=pk.hdim, act=0)
+            else:
+                ld = ops.round_up(pk.hdim, 8)
+                xb = torch.empty((rows * T, ld), dtype=torch.bfloat16, device=x.device)
+                pk.projection(H, rows * T, xb, mode=ops.EPI_BF16, ldo=ld, act=1)
+            del H
+        return out.reshape(*shape[:-1], packs[-1].hdim)
