@@ -97,7 +97,8 @@ int tssep_fold_embedding(int mode, const float* W, int64_t ldw, const float* b, 
  * of 8 elements, base pointers 16-byte aligned, batch strides whole rows.
  * Offsets in elements:  A += (z / a_div) * a_stride,  B += (z % b_mod) * b_stride,
  * bias += (z % b_mod) * bias_stride,
- * out += (z / out_div) * out_stride_hi + (z % out_div) * out_stride.
+ * out += (z / out_div) * out_stride_hi + (z % out_div) * out_stride  (plain batching:
+ * out_div = batch, out_stride_hi = 0).
  * mode TSSEP_EPI_F32 / TSSEP_EPI_BF16: out[m * ldo + n] (act: 0 none, 1 tanh).
  * mode TSSEP_EPI_HEAD (TS-VAD/TS-SEP output head, net.py:629-668, :928-986): column
  *   n = q * row_len + f of item z goes to plane p = plane_map[z * n_blocks + q]:

@@ -57,8 +57,8 @@ struct GemmArgs {
 __device__ __forceinline__ float apply_act(float v, int act) { return act == 1 ? tanh_acc(v) : v; }
 
 // Stores up to 32 consecutive columns [n0, n0+32) of row m of batch z.
-__device__ __forceinline__ void epilogue_store(const GemmArgs& g, int z, int64_t m, int n0, const float* acc) {
-  const int nvalid = min(32, g.N - n0);
+__device__ __forceinline__ void epilogue_store(const GemmArgs& g, int z, int64_t m, int n0, int limit, const float* acc) {
+  const int nvalid = min(limit, g.N - n0);
   if (nvalid <= 0) return;
   const float* bias = g.bias ? g.bias + static_cast<int64_t>(z % g.b_mod) * g.bias_stride + n0 : nullptr;
   const int64_t zoff = static_cast<int64_t>(z / g.out_div) * g.out_stride_hi + static_cast<int64_t>(z % g.out_div) * g.out_stride;
@@ -238,7 +238,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint32_t v[32];
         tc_ld32(t0 + c0, v);
         tc_wait_ld();
-        if (m < g.M) epilogue_store(g, z, m, nt * g.bn + c0, reinterpret_cast<const float*>(v));
+        if (m < g.M) epilogue_store(g, z, m, nt * g.bn + c0, min(32, g.bn - c0), reinterpret_cast<const float*>(v));
       }
       tc_fence_before();
       __syncwarp();
@@ -275,7 +275,7 @@ __global__ void gemm_simt_kernel(const GemmArgs g) {
       }
       acc[j] = s;
     }
-    epilogue_store(g, z, m, strip * 32, acc);
+    epilogue_store(g, z, m, strip * 32, 32, acc);
   }
 }
 

@@ -24,7 +24,7 @@ def _gemm_impl() -> int:
 
 
 def gemm(A, lda, B, ldb, M, N, K, out, *, mode, ldo=0, batch=1, a_stride=0, a_div=1, b_stride=0, b_mod=None,
-         bias=None, bias_stride=0, alpha=1.0, act=0, out_stride=0, out_div=1, out_stride_hi=0, mask=None,
+         bias=None, bias_stride=0, alpha=1.0, act=0, out_stride=0, out_div=None, out_stride_hi=0, mask=None,
          plane_map=None, n_blocks=0, row_len=0, impl=None):
     """``tssep_gemm``: out[z] = act(alpha * A[z / a_div] . B[z % b_mod]^T + bias[z % b_mod])."""
     _lib.require_cuda(A, B, out, bias, mask, plane_map)
@@ -34,7 +34,8 @@ def gemm(A, lda, B, ldb, M, N, K, out, *, mode, ldo=0, batch=1, a_stride=0, a_di
     d.bias, d.bias_stride = _lib.ptr(bias), bias_stride
     d.M, d.N, d.K, d.batch = M, N, K, batch
     d.alpha, d.act, d.mode = alpha, act, mode
-    d.out, d.ldo, d.out_stride, d.out_div, d.out_stride_hi = _lib.ptr(out), ldo, out_stride, out_div, out_stride_hi
+    d.out, d.ldo, d.out_stride, d.out_stride_hi = _lib.ptr(out), ldo, out_stride, out_stride_hi
+    d.out_div = batch if out_div is None else out_div
     d.mask, d.plane_map, d.n_blocks, d.row_len = _lib.ptr(mask), _lib.ptr(plane_map), n_blocks, row_len
     d.impl = _gemm_impl() if impl is None else impl
     _lib.call("tssep_gemm", C.byref(d), _lib.stream_of(A))

@@ -61,7 +61,7 @@ class LayerPack:
         return ops.blstm_recurrence(G, self.whh, rows, T, self.Up)
 
     def projection(self, H: torch.Tensor, rows_t: int, out: torch.Tensor, *, mode: int, ldo: int, act: int,
-                   batch=1, a_stride=0, M=None, out_stride=0, out_div=1, out_stride_hi=0):
+                   batch=1, a_stride=0, M=None, out_stride=0, out_div=None, out_stride_hi=0):
         """H (rows*T, 2*Up) bf16 -> out (bias and optional tanh fused)."""
         ops.gemm(H, 2 * self.Up, self.w_proj, 2 * self.Up, rows_t if M is None else M, self.hdim, 2 * self.Up, out,
                  mode=mode, ldo=ldo, bias=self.b_proj, act=act, batch=batch, a_stride=a_stride, b_mod=1,
