@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""Throughput benchmark of the B200 TS-SEP inference hot path.
+
+    python bench.py --gpus N --steps K --warmup W          # product arm (this repo's CUDA path)
+    python bench.py --impl reference ...                    # the reference's CPU arithmetic (oracle) on host cores
+
+Metric (BASELINE.json): audio-seconds processed per wall-second (RTF^-1), TS-SEP 8-speaker
+inference.  One "step" = one pass of the whole path (STFT -> features -> RNNP mask estimator ->
+mask x STFT -> iSTFT -> diarization) over the rank's batch of synthetic LibriCSS-shaped 10-min
+meetings; every output of the reference's ForwardOutput is materialised in HBM.  Scaling is weak
+(meetings are independent; each rank processes --meetings-per-gpu of them, no data-path collective,
+one NCCL gather of the segment tables per step).  Rank 0 prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SAMPLE_RATE = 16000
+MODEL_KW = dict(idim=553, odim=513, layers=3, units=300, projs=320, combination="mul", ts_vad=8,
+                aux_net_output_size=513, num_averaged_permutations=2, output_resolution="tf",
+                random_speaker_order=True)
+FE_CFG = {
+    "fe1": {"factory": "tssep_b200.feature_extractor_torchaudio.TorchMFCC"},
+    "fe2": {"factory": "tssep_b200.feature_extractor.Log1pMaxNormAbsSTFT"},
+    "size": 1024, "shift": 256, "window": "hann",
+}
+# deduplicated algorithmic work of one 10-min meeting
+GFLOP_PER_AUDIO_S = 6.21
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--meetings-per-gpu", type=int, default=int(os.environ.get("TSSEP_BENCH_MEETINGS", 8)))
+    ap.add_argument("--seconds", type=float, default=600.0, help="length of every synthetic meeting")
+    ap.add_argument("--cpu-sample-seconds", type=float, default=60.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-json", default=None, help="also write the per-kernel breakdown to this file")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------
+def synth_meeting(seed: int, num_samples: int, aux_size=513):
+    """tssep/data.py:75-139 generator at arbitrary length (product-side restatement)."""
+    from tssep_b200.data import DummyReader
+
+    ex = DummyReader(sample_rate=SAMPLE_RATE, aux_size=aux_size).get_example(seed, num_samples=num_samples,
+                                                                           with_targets=False)
+    return ex["audio_data"]["observation"][0].astype(np.float32), ex["auxInput"]
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower() == "active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+# ----------------------------------------------------------------------------------------------
+def oracle_setup(units, projs):
+    from oracle import tssep_oracle as O
+
+    torch.manual_seed(0)
+    kw = {k: v for k, v in MODEL_KW.items() if k != "layers"}
+    kw.update(units=units, projs=projs)
+    net = O.OracleMaskEstimator(**kw).eval()
+    return O, net, O.MFCCTables()
+
+
+def time_oracle(sample_seconds: float, reps: int, warmup: int = 1):
+    """The reference's CPU arithmetic (oracle restatement: torch.nn.LSTM/Linear, torchaudio, torch.fft)
+    on all host cores, on a bounded sample of the workload (the path is linear in the audio length)."""
+    O, net, tables = oracle_setup(MODEL_KW["units"], MODEL_KW["projs"])
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    n = int(sample_seconds * SAMPLE_RATE)
+    obs, aux = synth_meeting(0, n)
+    obs_t, aux_t = torch.tensor(obs)[None], torch.tensor(aux)
+    times = []
+    for i in range(warmup + reps):
+        np.random.seed(0)
+        t0 = time.perf_counter()
+        O.forward_path(obs_t, aux_t, net, feature="concat", tables=tables, window="hann")
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return sample_seconds / float(np.median(times)), cores, times
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    value, cores, times = time_oracle(args.cpu_sample_seconds, reps=max(1, args.steps), warmup=max(1, min(args.warmup, 1)))
+    sample = (f"oracle restatement of the reference CPU path on one {args.cpu_sample_seconds:.0f}-s slice of a synthetic "
+              f"8-speaker meeting per step (cost is linear in audio length), torch threads={cores}")
+    line = {
+        "impl": "reference", "metric": "audio_seconds_per_second", "value": value, "unit": "audio-s/s",
+        "n_gpus": args.gpus, "steps": len(times), "warmup": 1, "ms_per_step": float(np.median(times)) * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "TS-SEP 8-speaker inference, LibriCSS-shaped synthetic meeting, U=300 P=320 mul ts_vad=8 R=2",
+                   "sample_seconds": args.cpu_sample_seconds},
+        "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------
+def build_product_model(device):
+    from tssep_b200.data import DummyReader
+    from tssep_b200.enhancer import Masking
+    from tssep_b200.feature_extractor import ConcaternatedSTFTFeatures
+    from tssep_b200.loss import LogMAE
+    from tssep_b200.model import Model
+    from tssep_b200.net import MaskEstimator_v2
+
+    torch.manual_seed(0)
+    me = MaskEstimator_v2.new(dict(MODEL_KW)).eval()
+    fe = ConcaternatedSTFTFeatures.new(FE_CFG)
+    model = Model(fe=fe, reader=DummyReader(aux_size=513), mask_estimator=me, enhancer=Masking(), loss=LogMAE())
+    return model.eval().to(device)
+
+
+def kernel_breakdown(timeline, steps):
+    agg = {}
+    for name, s, e in timeline:
+        ms = s.elapsed_time(e)
+        a = agg.setdefault(name, [0.0, 0])
+        a[0] += ms
+        a[1] += 1
+    return {k: {"ms_per_step": v[0] / steps, "launches_per_step": v[1] / steps} for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])}
+
+
+def run_b200(args):
+    from tssep_b200 import _lib
+    from tssep_b200 import dist as tdist
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torch.distributed.run)"
+    assert torch.cuda.is_available(), "bench.py needs CUDA (the product has no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    _lib.load()
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.distributed.init_process_group("nccl", device_id=dev)
+
+    M = args.meetings_per_gpu
+    n = int(args.seconds * SAMPLE_RATE)
+    model = build_product_model(dev)
+    meetings = [synth_meeting(rank * M + i, n) for i in range(M)]
+    obs_host = torch.tensor(np.stack([m[0] for m in meetings])).pin_memory()
+    aux_host = torch.tensor(np.stack([m[1] for m in meetings])).pin_memory()
+    obs_dev, aux_dev = obs_host.to(dev), aux_host.to(dev)
+    diar = dict(threshold=0.5, median_width=11, max_segments=256)
+    global_ids = list(range(rank * M, rank * M + M))
+
+    def step(obs, aux):
+        np.random.seed(0)
+        out = model.separate(obs, aux, diarize=diar)
+        seg = out.segments
+        if world > 1:
+            tdist.gather_segments(global_ids, seg.segments, seg.counts, world * M)
+        return out
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        out = step(obs_dev, aux_dev)
+        del out
+    barrier()
+
+    # ---- device-resident timed region -----------------------------------------------------
+    timeline = []
+    _lib.set_timeline(timeline)
+    l0 = _lib.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        barrier()
+        ev0.record()
+        for _ in range(args.steps):
+            out = step(obs_dev, aux_dev)
+            del out
+        ev1.record()
+        barrier()
+    _lib.set_timeline(None)
+    launches = _lib.launch_count - l0
+    ms = ev0.elapsed_time(ev1)
+    breakdown = kernel_breakdown(timeline, args.steps)
+
+    # ---- end-to-end: pinned host buffers in, separated audio + segments back on the host ----
+    k = 8
+    time_host = torch.empty((M, k, n), dtype=torch.float32).pin_memory()
+    seg_host = torch.empty((M, k, diar["max_segments"], 2), dtype=torch.int32).pin_memory()
+    cnt_host = torch.empty((M, k), dtype=torch.int32).pin_memory()
+
+    def e2e_step():
+        o = obs_host.to(dev, non_blocking=True)
+        a = aux_host.to(dev, non_blocking=True)
+        out = step(o, a)
+        time_host.copy_(out.time_estimate, non_blocking=True)
+        seg_host.copy_(out.segments.segments, non_blocking=True)
+        cnt_host.copy_(out.segments.counts, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    e2e_step()
+    barrier()
+    ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ee0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    ee1.record()
+    barrier()
+    e2e_ms = ee0.elapsed_time(ee1)
+
+    if world > 1:
+        t = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms, e2e_ms = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return
+
+    audio_s = world * M * args.seconds * args.steps
+    value = audio_s / (ms / 1e3)
+    e2e_value = audio_s / (e2e_ms / 1e3)
+    peaks = measured_peaks()
+    T = model.fe.num_frames(n)
+    Up = 304
+    # dominant kernel: the BLSTM recurrence (latency bound; expressed against the tensor peak as asked)
+    rec = breakdown.get("tssep_blstm_recurrence", {"ms_per_step": 0.0, "launches_per_step": 1})
+    rec_rows = M * (1 + 8 + 8 + 2)  # pre_net, birnn0, birnn1, birnn2 (R=2) batch rows
+    rec_flops = 2.0 * rec_rows * T * 2 * (4 * 300 * 300)
+    rec_tflops = rec_flops / (rec["ms_per_step"] / 1e3) / 1e12 if rec["ms_per_step"] else 0.0
+    gemm = breakdown.get("tssep_gemm", {"ms_per_step": 0.0})
+    gemm_flops = M * (3.726e12 - 2.0 * 19 * T * 2 * 4 * 300 * 300)
+    gemm_tflops = gemm_flops / (gemm["ms_per_step"] / 1e3) / 1e12 if gemm["ms_per_step"] else 0.0
+    top = max(breakdown.items(), key=lambda kv: kv[1]["ms_per_step"])[0] if breakdown else None
+    roofline = {
+        "kernel": "blstm_rec_kernel", "bound": "tensor", "achieved": rec_tflops, "peak": peaks["bf16_tflops_sustained"],
+        "unit": "TFLOP/s", "frac": rec_tflops / peaks["bf16_tflops_sustained"], "traffic": None,
+        "peak_source": peaks["source"] + " (sustained)",
+        "note": "recurrence is bound by the latency of T dependent steps, not by the tensor pipe",
+        "us_per_recurrent_step": rec["ms_per_step"] * 1e3 / (4 * T) if rec["ms_per_step"] else None,
+        "share_of_step": rec["ms_per_step"] / (ms / args.steps),
+        "top_kernel_by_time": top,
+    }
+    roofline_gemm = {"kernel": "gemm_tc_kernel", "bound": "tensor", "achieved": gemm_tflops,
+                     "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                     "frac": gemm_tflops / peaks["bf16_tflops_sustained"],
+                     "share_of_step": gemm["ms_per_step"] / (ms / args.steps)}
+    F = 513
+    hbm = {}
+    for name, nbytes in {
+        "tssep_stft": M * (4 * n + 8 * T * F),
+        "tssep_feature_stats": M * (8 * T * F + 4 * T * 40),
+        "tssep_feature_write": M * (8 * T * F + 4 * T * 40 + 6 * T * 553),
+        "tssep_mask_istft": M * (8 * T * F + 4 * 8 * T * F + 8 * 8 * T * F + 4 * 8 * n),
+    }.items():
+        if name in breakdown and breakdown[name]["ms_per_step"] > 0:
+            gbs = nbytes / (breakdown[name]["ms_per_step"] / 1e3) / 1e9
+            hbm[name] = {"achieved_GBps": gbs, "frac": gbs / peaks["hbm_gbs"], "algorithmic_bytes": nbytes}
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        v, cores, times = time_oracle(args.cpu_sample_seconds, reps=2)
+        cpu = {"value": v, "unit": "audio-s/s", "cores": cores, "kind": "port",
+               "sample": f"oracle (reference CPU arithmetic) on a {args.cpu_sample_seconds:.0f}-s slice of meeting 0, "
+                         f"median of 2 after 1 warm-up, torch threads={cores}; cost is linear in audio length"}
+
+    line = {
+        "metric": "audio_seconds_per_second", "value": value, "unit": "audio-s/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16 operands, f32 accumulate/state/FFT", "data": "synthetic",
+        "config": {"workload": f"{M} LibriCSS-shaped synthetic {args.seconds:.0f}-s 16 kHz meetings per GPU per step, "
+                               "8 speakers, TS-SEP (U=300, P=320, mul, ts_vad=8, 2 averaged permutations), "
+                               "random-init weights; all ForwardOutput fields + time_estimate + segments materialised",
+                   "meetings_per_gpu": M, "meeting_seconds": args.seconds, "frames": T,
+                   "l2": "inputs and intermediates (GBs per step) far exceed the 126 MB L2; no explicit flush",
+                   "parallelism": f"dp{world} over meetings"},
+        "clocks": clocks.summary(),
+        "e2e": {"value": e2e_value, "unit": "audio-s/s", "ms_per_step": e2e_ms / args.steps,
+                "h2d_bytes_per_step": int(obs_host.numel() * 4 + aux_host.numel() * 4),
+                "d2h_bytes_per_step": int(time_host.numel() * 4 + seg_host.numel() * 4 + cnt_host.numel() * 4)},
+        "gpu_launches": launches,
+        "roofline": roofline, "roofline_gemm": roofline_gemm, "hbm_kernels": hbm,
+        "cpu_baseline": cpu,
+        "kernels": breakdown,
+    }
+    print(json.dumps(line))
+    if args.profile_json:
+        os.makedirs(os.path.dirname(os.path.abspath(args.profile_json)), exist_ok=True)
+        json.dump(line, open(args.profile_json, "w"), indent=1)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

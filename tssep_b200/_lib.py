@@ -109,5 +109,26 @@ def require_cuda(*tensors):
             )
 
 
+# Optional per-call device timing (bench.py): when a list is installed here every C-ABI call is
+# bracketed by CUDA events recorded on the current stream; `launch_count` counts kernel launches.
+_timeline = None
+launch_count = 0
+
+
+def set_timeline(timeline):
+    global _timeline
+    _timeline = timeline
+
+
 def call(name: str, *args):
-    check(getattr(load(), name)(*args), name)
+    global launch_count
+    fn = getattr(load(), name)
+    launch_count += 1
+    if _timeline is None:
+        check(fn(*args), name)
+        return
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    check(fn(*args), name)
+    end.record()
+    _timeline.append((name, start, end))
