@@ -1,0 +1,48 @@
+#!/usr/bin/env python
+"""Micro-benchmark of the BLSTM recurrence kernel: microseconds per recurrent step for a few
+batch sizes / cluster sizes / math modes, timed with CUDA events (also the ncu target)."""
+import argparse
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from tssep_b200 import _lib, ops  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--units", type=int, default=300)
+    ap.add_argument("--frames", type=int, default=4000)
+    ap.add_argument("--rows", type=int, nargs="+", default=[1, 8, 16, 64, 128])
+    ap.add_argument("--clusters", type=int, nargs="+", default=[0])
+    ap.add_argument("--fast", type=int, nargs="+", default=[0, 1])
+    ap.add_argument("--reps", type=int, default=3)
+    a = ap.parse_args()
+    dev = torch.device("cuda:0")
+    U = a.units
+    Up = ops.round_up(U, 16)
+    torch.manual_seed(0)
+    w = (torch.rand((2, 4 * U, U), device=dev) - 0.5) * (2 / U ** 0.5)
+    whh = ops.pack_whh(w[0], w[1], U, Up)
+    for rows in a.rows:
+        G = torch.randn((rows, a.frames, 8 * Up), device=dev) * 0.3
+        for C in a.clusters:
+            for fast in a.fast:
+                for _ in range(2):
+                    ops.blstm_recurrence(G, whh, rows, a.frames, Up, cluster=C, fast_math=bool(fast))
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(a.reps):
+                    ops.blstm_recurrence(G, whh, rows, a.frames, Up, cluster=C, fast_math=bool(fast))
+                e1.record()
+                torch.cuda.synchronize()
+                us = e0.elapsed_time(e1) * 1e3 / a.reps / a.frames
+                print(f"U={U} rows={rows:4d} cluster={C} fast={fast}: {us:.3f} us/step", flush=True)
+        del G
+
+
+if __name__ == "__main__":
+    main()
