@@ -40,7 +40,14 @@ def main():
                 e1.record()
                 torch.cuda.synchronize()
                 us = e0.elapsed_time(e1) * 1e3 / a.reps / a.frames
-                print(f"U={U} rows={rows:4d} cluster={C} fast={fast}: {us:.3f} us/step", flush=True)
+                prof = torch.zeros(6, dtype=torch.int32, device=dev)
+                os.environ["TSSEP_REC_PROF"] = str(prof.data_ptr())
+                ops.blstm_recurrence(G, whh, rows, a.frames, Up, cluster=C, fast_math=bool(fast))
+                torch.cuda.synchronize()
+                del os.environ["TSSEP_REC_PROF"]
+                pc = prof.cpu().numpy().astype(float)
+                ph = " ".join(f"{n}={v / max(pc[5], 1):.0f}" for n, v in zip(["gwait", "hwait", "mma", "gates", "send"], pc[:5]))
+                print(f"U={U} rows={rows:4d} cluster={C} fast={fast}: {us:.3f} us/step | cycles/step {ph}", flush=True)
         del G
 
 

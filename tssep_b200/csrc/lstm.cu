@@ -22,6 +22,8 @@
 #include "../../include/tssep_b200.h"
 #include "common.cuh"
 
+#include <cstdlib>
+
 namespace tssep {
 
 constexpr int kGStages = 4;
@@ -43,21 +45,28 @@ __device__ __forceinline__ void ldmatrix_x2(uint32_t addr, uint32_t& r0, uint32_
   asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr) : "memory");
 }
 
-template <int KT>
-__global__ void __launch_bounds__(32 * (kMaxWarpsCompute + 1), 1)
+// compute warps per CTA: large hidden sizes hold many weight fragments per thread and are limited to
+// 10 warps (+1 producer) so that ptxas may use up to 184 registers
+constexpr int max_compute_warps(int kt) { return kt >= 13 ? 10 : kMaxWarpsCompute; }
+
+template <int KT, int NB>
+__global__ void __launch_bounds__(32 * (max_compute_warps(KT) + 1), 1)
 blstm_rec_kernel(const __grid_constant__ CUtensorMap gmap, const uint4* __restrict__ Wfrag,
-                 __nv_bfloat16* __restrict__ H, int rows, int T, int NT, int fast) {
+                 __nv_bfloat16* __restrict__ H, int rows, int T, int NT, int fast, int* __restrict__ prof) {
   constexpr int Up = 16 * KT;
   constexpr int LDH = Up + 8;          // bf16 elements per h row (+8 keeps ldmatrix conflict free)
   constexpr int n_tiles = Up / 4;      // unit tiles per direction
+  constexpr int BR = 8 * NB;           // batch rows per cluster
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const uint32_t sbase = smem_u32(smem_raw);
-  const uint32_t g_stage_bytes = static_cast<uint32_t>(4 * 8 * 4 * NT) * 4;  // [gate][b][unit] f32
-  const uint32_t s_gring = sbase;                                            // kGStages stages
-  const uint32_t s_hbuf = s_gring + kGStages * g_stage_bytes;                // 2 x 8 x LDH bf16
-  const uint32_t h_buf_bytes = 8 * LDH * 2;
-  const uint32_t s_bar = s_hbuf + 2 * h_buf_bytes;
-  const uint32_t hfull0 = s_bar, gfull0 = s_bar + 16, gempty0 = gfull0 + 8 * kGStages;
+  const uint32_t g_stage_bytes = static_cast<uint32_t>(4 * BR * 4 * NT) * 4;  // [gate][b][unit] f32
+  const uint32_t s_gring = sbase;                                             // kGStages stages
+  const uint32_t s_hbuf = s_gring + kGStages * g_stage_bytes;                 // [NB][2][8][LDH] bf16
+  constexpr uint32_t h_buf_bytes = 8 * LDH * 2;
+  const uint32_t s_bar = s_hbuf + NB * 2 * h_buf_bytes;
+  const uint32_t hfull0 = s_bar;                    // [NB][2]
+  const uint32_t gfull0 = hfull0 + 16 * NB;         // [kGStages]
+  const uint32_t gempty0 = gfull0 + 8 * kGStages;   // [kGStages]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t crank = cluster_ctarank();
@@ -67,19 +76,17 @@ blstm_rec_kernel(const __grid_constant__ CUtensorMap gmap, const uint4* __restri
   nvalid = nvalid < 0 ? 0 : (nvalid > NT ? NT : nvalid);
   const uint32_t tx_bytes = n_tiles * 64u;  // all unit tiles x (8 rows x 4 units x bf16)
 
-  // zero both h buffers (h_{-1} = 0, padded units stay 0)
-  for (uint32_t i = threadIdx.x; i < 2 * h_buf_bytes / 4; i += blockDim.x)
+  // zero all h buffers (h_{-1} = 0, padded units stay 0)
+  for (uint32_t i = threadIdx.x; i < NB * 2 * h_buf_bytes / 4; i += blockDim.x)
     asm volatile("st.shared.u32 [%0], %1;" ::"r"(s_hbuf + 4 * i), "r"(0u) : "memory");
   if (threadIdx.x == 0) {
-    mbar_init(hfull0, 1);
-    mbar_init(hfull0 + 8, 1);
+    for (int i = 0; i < 2 * NB; ++i) mbar_init(hfull0 + 8 * i, 1);
     for (int i = 0; i < kGStages; ++i) {
       mbar_init(gfull0 + 8 * i, 1);
       mbar_init(gempty0 + 8 * i, nvalid > 0 ? nvalid : 1);
     }
     mbar_fence_init();
-    mbar_arrive_expect_tx(hfull0, tx_bytes);
-    mbar_arrive_expect_tx(hfull0 + 8, tx_bytes);
+    for (int i = 0; i < 2 * NB; ++i) mbar_arrive_expect_tx(hfull0 + 8 * i, tx_bytes);
     tma_prefetch_desc(&gmap);
   }
   __syncthreads();
@@ -94,10 +101,11 @@ blstm_rec_kernel(const __grid_constant__ CUtensorMap gmap, const uint4* __restri
         const int t = dir ? T - 1 - s : s;
         mbar_wait(gempty0 + 8 * gs, gph ^ 1);
         mbar_arrive_expect_tx(gfull0 + 8 * gs, g_stage_bytes);
-        tma_load_5d(s_gring + gs * g_stage_bytes, &gmap, gfull0 + 8 * gs, static_cast<int>(crank) * 4 * NT, bt * 8, 0,
+        tma_load_5d(s_gring + gs * g_stage_bytes, &gmap, gfull0 + 8 * gs, static_cast<int>(crank) * 4 * NT, bt * BR, 0,
                     dir, t);
       }
     }
+    __syncwarp();
   } else if (warp < nvalid) {
     // ---- compute warp: one unit tile ---------------------------------------
     const int gt = static_cast<int>(crank) * NT + warp;
@@ -110,12 +118,12 @@ blstm_rec_kernel(const __grid_constant__ CUtensorMap gmap, const uint4* __restri
     const bool upper = lane >= 16;
     const int u = (lane >> 2) & 3;
     const int n0 = 2 * (lane & 3);
-    // G offsets (floats) inside a ring stage: [gate][b][unit]
+    // G offsets (floats) inside a ring stage: [gate][BR rows][unit]
     const int gA = upper ? 1 : 0, gB = upper ? 3 : 2;
     const int unit_local = warp * 4 + u;
     const int ld_u = 4 * NT;
-    const int offA0 = (gA * 8 + n0) * ld_u + unit_local, offA1 = offA0 + ld_u;
-    const int offB0 = (gB * 8 + n0) * ld_u + unit_local, offB1 = offB0 + ld_u;
+    const int offA = (gA * BR + n0) * ld_u + unit_local;
+    const int offB = (gB * BR + n0) * ld_u + unit_local;
     // ldmatrix row address: matrix (lane>>3) covers k offset 8*(lane>>3), row (lane&7)
     const uint32_t ldm_off = static_cast<uint32_t>(((lane & 7) * LDH + (lane >> 3) * 8) * 2);
     // transposed send: this lane ships batch row nn, 4 units, to CTAs dg, dg+4
@@ -129,98 +137,141 @@ blstm_rec_kernel(const __grid_constant__ CUtensorMap gmap, const uint4* __restri
       r_hbuf[j] = dst < C ? mapa(s_hbuf, dst) : 0;
       r_bar[j] = dst < C ? mapa(hfull0, dst) : 0;
     }
-    const int64_t brow = static_cast<int64_t>(bt) * 8 + nn;
-    __nv_bfloat16* hout = H + (brow * T) * (2 * Up) + dir * Up + gt * 4;
-    const bool store_h = (dg == 0) && (brow < rows);
+    const int64_t brow0 = static_cast<int64_t>(bt) * BR + nn;
+    __nv_bfloat16* hout = H + (brow0 * T) * (2 * Up) + dir * Up + gt * 4;
     const float kB = upper ? 1.0f : 2.0f;
 
-    float c_state = 0.f;
-    for (int s = 0; s < T; ++s) {
-      const int t = dir ? T - 1 - s : s;
-      // input projection for this step (prefetched by the producer warp)
+    float c_state[NB];
+    float g_cur[NB][4], g_nxt[NB][4];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) c_state[b] = 0.f;
+    auto load_g = [&](int s, float (*g)[4]) {
       const int gs = s % kGStages;
       mbar_wait(gfull0 + 8 * gs, (s / kGStages) & 1);
       const uint32_t gp = s_gring + gs * g_stage_bytes;
-      float gA0, gA1, gB0, gB1;
-      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(gA0) : "r"(gp + 4 * offA0));
-      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(gA1) : "r"(gp + 4 * offA1));
-      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(gB0) : "r"(gp + 4 * offB0));
-      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(gB1) : "r"(gp + 4 * offB1));
-      __syncwarp();
-      if (lane == 0) mbar_arrive(gempty0 + 8 * gs);
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(g[b][0]) : "r"(gp + 4 * (offA + b * 8 * ld_u)));
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(g[b][1]) : "r"(gp + 4 * (offA + (b * 8 + 1) * ld_u)));
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(g[b][2]) : "r"(gp + 4 * (offB + b * 8 * ld_u)));
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(g[b][3]) : "r"(gp + 4 * (offB + (b * 8 + 1) * ld_u)));
+      }
+    };
+    load_g(0, g_cur);
 
-      // h_{t-1} from every CTA of the cluster
+    const bool do_prof = prof != nullptr && blockIdx.y == 0 && blockIdx.z == 0 && crank == 0 && warp == 0;
+    int pc[6] = {0, 0, 0, 0, 0, 0};
+    for (int s = 0; s < T; ++s) {
+      const int t = dir ? T - 1 - s : s;
+      int c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0;
+      if (do_prof) c0 = clock();
+      // prefetch the next step's input projection into registers; its latency hides in the h wait
+      if (s + 1 < T) load_g(s + 1, g_nxt);
+      if (do_prof) c1 = clock();
       const int rb = (s & 1) ^ 1;
-      if (s > 0) {
-        mbar_wait_cluster(hfull0 + 8 * rb, ((s - 1) >> 1) & 1);
-        if (warp == 0 && lane == 0) mbar_arrive_expect_tx(hfull0 + 8 * rb, tx_bytes);
-      }
-      float acc[4][4];
+      // The batch tiles are independent recurrences: while the new h of one tile travels through
+      // DSMEM, the warp already works on the other tile.
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int b = 0; b < NB; ++b) {
+        if (do_prof) c1 = clock();
+        // h_{t-1} of batch tile b from every CTA of the cluster.  st.async completes bytes on OUR
+        // mbarrier after the data landed in OUR shared memory, so the default (CTA-scope) wait
+        // suffices (as for multicast TMA); a cluster-scope acquire costs a CCTL.IVALL per step.
+        const uint32_t hbar = hfull0 + 8 * (b * 2 + rb);
+        if (s > 0) {
+          mbar_wait(hbar, ((s - 1) >> 1) & 1);
+          if (warp == 0 && lane == 0) mbar_arrive_expect_tx(hbar, tx_bytes);
+        }
+        if (do_prof) c2 = clock();
+        float acc[4][4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-      const uint32_t hb = s_hbuf + rb * h_buf_bytes + ldm_off;
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int kt = 0; kt < KT; kt += 2) {
-        if (kt + 1 < KT) {
-          uint32_t b0, b1, b2, b3;
-          ldmatrix_x4(hb + kt * 32, b0, b1, b2, b3);
-          mma_bf16_16816(acc[kt & 3], a[kt], b0, b1);
-          mma_bf16_16816(acc[(kt + 1) & 3], a[kt + 1], b2, b3);
+          for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        const uint32_t hb = s_hbuf + (b * 2 + rb) * h_buf_bytes + ldm_off;
+#pragma unroll
+        for (int kt = 0; kt < KT; kt += 2) {
+          if (kt + 1 < KT) {
+            uint32_t b0, b1, b2, b3;
+            ldmatrix_x4(hb + kt * 32, b0, b1, b2, b3);
+            mma_bf16_16816(acc[kt & 3], a[kt], b0, b1);
+            mma_bf16_16816(acc[(kt + 1) & 3], a[kt + 1], b2, b3);
+          } else {
+            uint32_t b0, b1;
+            ldmatrix_x2(hb + kt * 32, b0, b1);
+            mma_bf16_16816(acc[kt & 3], a[kt], b0, b1);
+          }
+        }
+        const float pA0 = (acc[0][0] + acc[1][0]) + (acc[2][0] + acc[3][0]) + g_cur[b][0];  // row r,   col n0
+        const float pA1 = (acc[0][1] + acc[1][1]) + (acc[2][1] + acc[3][1]) + g_cur[b][1];  // row r,   col n0+1
+        const float pB0 = (acc[0][2] + acc[1][2]) + (acc[2][2] + acc[3][2]) + g_cur[b][2];  // row r+8, col n0
+        const float pB1 = (acc[0][3] + acc[1][3]) + (acc[2][3] + acc[3][3]) + g_cur[b][3];  // row r+8, col n0+1
+        if (do_prof) c3 = clock() + (__float_as_int(pA0 + pA1 + pB0 + pB1) & 0);
+
+        // lower half-warp holds (i, g), upper half-warp holds (f, o) of unit u, columns n0, n0+1
+        float sA0, sA1, sB0, sB1;
+        if (fast) {
+          sA0 = fmaf(0.5f, tanh_fast(0.5f * pA0), 0.5f);
+          sA1 = fmaf(0.5f, tanh_fast(0.5f * pA1), 0.5f);
+          sB0 = upper ? fmaf(0.5f, tanh_fast(0.5f * pB0), 0.5f) : tanh_fast(pB0);
+          sB1 = upper ? fmaf(0.5f, tanh_fast(0.5f * pB1), 0.5f) : tanh_fast(pB1);
         } else {
-          uint32_t b0, b1;
-          ldmatrix_x2(hb + kt * 32, b0, b1);
-          mma_bf16_16816(acc[kt & 3], a[kt], b0, b1);
+          sA0 = sigmoid_acc(pA0);
+          sA1 = sigmoid_acc(pA1);
+          sB0 = sigmoid_acc(kB * pB0);
+          sB1 = sigmoid_acc(kB * pB1);
+          if (!upper) {
+            sB0 = fmaf(2.0f, sB0, -1.0f);  // tanh(g)
+            sB1 = fmaf(2.0f, sB1, -1.0f);
+          }
         }
-      }
-      const float pA0 = (acc[0][0] + acc[1][0]) + (acc[2][0] + acc[3][0]) + gA0;  // row r,   col n0
-      const float pA1 = (acc[0][1] + acc[1][1]) + (acc[2][1] + acc[3][1]) + gA1;  // row r,   col n0+1
-      const float pB0 = (acc[0][2] + acc[1][2]) + (acc[2][2] + acc[3][2]) + gB0;  // row r+8, col n0
-      const float pB1 = (acc[0][3] + acc[1][3]) + (acc[2][3] + acc[3][3]) + gB1;  // row r+8, col n0+1
+        // lower owns column n0, upper owns column n0+1
+        const float ig0 = sA0 * sB0, ig1 = sA1 * sB1;  // meaningful on lower lanes only
+        const float x1 = __shfl_xor_sync(0xffffffffu, upper ? sA0 : ig1, 16);  // lower gets s(f0), upper gets ig1
+        const float x2 = __shfl_xor_sync(0xffffffffu, sB0, 16);                // lower gets s(o0)
+        const float fgate = upper ? sA1 : x1;
+        const float inew = upper ? x1 : ig0;
+        const float ogate = upper ? sB1 : x2;
+        c_state[b] = fmaf(fgate, c_state[b], inew);
+        const float hval = ogate * (fast ? tanh_fast(c_state[b]) : tanh_acc(c_state[b]));
 
-      // lower half-warp holds (i, g), upper half-warp holds (f, o) of unit u, columns n0, n0+1
-      float sA0, sA1, sB0, sB1;
-      if (fast) {
-        sA0 = fmaf(0.5f, tanh_fast(0.5f * pA0), 0.5f);
-        sA1 = fmaf(0.5f, tanh_fast(0.5f * pA1), 0.5f);
-        sB0 = upper ? fmaf(0.5f, tanh_fast(0.5f * pB0), 0.5f) : tanh_fast(pB0);
-        sB1 = upper ? fmaf(0.5f, tanh_fast(0.5f * pB1), 0.5f) : tanh_fast(pB1);
-      } else {
-        sA0 = sigmoid_acc(pA0);
-        sA1 = sigmoid_acc(pA1);
-        sB0 = sigmoid_acc(kB * pB0);
-        sB1 = sigmoid_acc(kB * pB1);
-        if (!upper) {
-          sB0 = fmaf(2.0f, sB0, -1.0f);  // tanh(g)
-          sB1 = fmaf(2.0f, sB1, -1.0f);
-        }
-      }
-      // lower owns column n0, upper owns column n0+1
-      const float ig0 = sA0 * sB0, ig1 = sA1 * sB1;  // meaningful on lower lanes only
-      const float x1 = __shfl_xor_sync(0xffffffffu, upper ? sA0 : ig1, 16);  // lower gets s(f0), upper gets ig1
-      const float x2 = __shfl_xor_sync(0xffffffffu, sB0, 16);                // lower gets s(o0)
-      const float fgate = upper ? sA1 : x1;
-      const float inew = upper ? x1 : ig0;
-      const float ogate = upper ? sB1 : x2;
-      c_state = fmaf(fgate, c_state, inew);
-      const float hval = ogate * (fast ? tanh_fast(c_state) : tanh_acc(c_state));
-
-      // transpose: lane (nn, dg) gathers units 0..3 of batch column nn
-      const float v0 = __shfl_sync(0xffffffffu, hval, src_base + 0);
-      const float v1 = __shfl_sync(0xffffffffu, hval, src_base + 4);
-      const float v2 = __shfl_sync(0xffffffffu, hval, src_base + 8);
-      const float v3 = __shfl_sync(0xffffffffu, hval, src_base + 12);
-      const uint32_t lo = pack_bf16x2(v0, v1), hi = pack_bf16x2(v2, v3);
-      if (s + 1 < T) {
-        const uint32_t wb_off = static_cast<uint32_t>(s & 1) * h_buf_bytes + send_off;
-        const uint32_t bar_off = static_cast<uint32_t>(s & 1) * 8;
+        // transpose: lane (nn, dg) gathers units 0..3 of batch column nn
+        const float v0 = __shfl_sync(0xffffffffu, hval, src_base + 0);
+        const float v1 = __shfl_sync(0xffffffffu, hval, src_base + 4);
+        const float v2 = __shfl_sync(0xffffffffu, hval, src_base + 8);
+        const float v3 = __shfl_sync(0xffffffffu, hval, src_base + 12);
+        const uint32_t lo = pack_bf16x2(v0, v1), hi = pack_bf16x2(v2, v3);
+        if (do_prof) c4 = clock() + (lo & hi & 0);
+        if (s + 1 < T) {
+          const uint32_t wb_off = static_cast<uint32_t>(b * 2 + (s & 1)) * h_buf_bytes + send_off;
+          const uint32_t bar_off = static_cast<uint32_t>(b * 2 + (s & 1)) * 8;
 #pragma unroll
-        for (int j = 0; j < 2; ++j)
-          if (dg + 4 * j < static_cast<int>(C)) st_async_v2(r_hbuf[j] + wb_off, lo, hi, r_bar[j] + bar_off);
+          for (int j = 0; j < 2; ++j)
+            if (dg + 4 * j < static_cast<int>(C)) st_async_v2(r_hbuf[j] + wb_off, lo, hi, r_bar[j] + bar_off);
+        }
+        if (dg == 0 && brow0 + b * 8 < rows)
+          *reinterpret_cast<uint2*>(hout + (static_cast<int64_t>(b) * 8 * T + t) * (2 * Up)) = make_uint2(lo, hi);
+        if (do_prof) {
+          const int c5 = clock();
+          pc[0] += (b == 0) ? c1 - c0 : 0;  // G prefetch
+          pc[1] += c2 - c1;                 // h wait
+          pc[2] += c3 - c2;                 // ldmatrix + mma
+          pc[3] += c4 - c3;                 // gates + shuffles
+          pc[4] += c5 - c4;                 // sends + store
+          c0 = c1 = c5;
+        }
       }
-      if (store_h) *reinterpret_cast<uint2*>(hout + static_cast<int64_t>(t) * (2 * Up)) = make_uint2(lo, hi);
+      // the values of stage s were consumed by the gates above: hand the slot back to the producer
+      __syncwarp();
+      if (lane == 0) mbar_arrive(gempty0 + 8 * (s % kGStages));
+#pragma unroll
+      for (int b = 0; b < NB; ++b)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) g_cur[b][i] = g_nxt[b][i];
+      if (do_prof) pc[5] += 1;
     }
+    if (do_prof && lane == 0)
+      for (int i = 0; i < 6; ++i) prof[i] = pc[i];
   }
   __syncthreads();
   cluster_sync_all();
@@ -252,15 +303,16 @@ __global__ void pack_whh_kernel(const float* __restrict__ w_fwd, const float* __
   }
 }
 
-template <int KT>
+template <int KT, int NB>
 static int launch_rec(const CUtensorMap& gmap, const uint32_t* Wfrag, uint16_t* H, int64_t rows, int64_t T, int C,
-                      int NT, int fast, cudaStream_t stream) {
+                      int NT, int fast, int* prof, cudaStream_t stream) {
   constexpr int Up = 16 * KT;
-  const size_t smem = static_cast<size_t>(kGStages) * (4 * 8 * 4 * NT) * 4 + 2 * 8 * (Up + 8) * 2 + 16 + 16 * kGStages + 128;
-  TSSEP_CUDA(cudaFuncSetAttribute(blstm_rec_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  const size_t smem = static_cast<size_t>(kGStages) * (4 * 8 * NB * 4 * NT) * 4 + NB * 2 * 8 * (Up + 8) * 2 + 16 * NB +
+                      16 * kGStages + 128;
+  TSSEP_CUDA(cudaFuncSetAttribute(blstm_rec_kernel<KT, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(smem)));
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(C, static_cast<unsigned>((rows + 7) / 8), 2);
+  cfg.gridDim = dim3(C, static_cast<unsigned>((rows + 8 * NB - 1) / (8 * NB)), 2);
   cfg.blockDim = dim3(32 * (NT + 1));
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
@@ -271,9 +323,9 @@ static int launch_rec(const CUtensorMap& gmap, const uint32_t* Wfrag, uint16_t* 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  TSSEP_CUDA(cudaLaunchKernelEx(&cfg, blstm_rec_kernel<KT>, gmap, reinterpret_cast<const uint4*>(Wfrag),
+  TSSEP_CUDA(cudaLaunchKernelEx(&cfg, blstm_rec_kernel<KT, NB>, gmap, reinterpret_cast<const uint4*>(Wfrag),
                                 reinterpret_cast<__nv_bfloat16*>(H), static_cast<int>(rows), static_cast<int>(T), NT,
-                                fast));
+                                fast, prof));
   return check_launch("blstm_rec");
 }
 
@@ -308,8 +360,12 @@ int tssep_blstm_recurrence(const float* G, const uint32_t* Wfrag, uint16_t* H, i
   }
   TSSEP_REQUIRE(C == 1 || C == 2 || C == 4 || C == 8, "tssep_blstm_recurrence: cluster must be 0, 1, 2, 4 or 8");
   const int NT = (tiles + C - 1) / C;
-  TSSEP_REQUIRE(NT <= kMaxWarpsCompute, "tssep_blstm_recurrence: %d unit tiles per CTA exceed %d (raise cluster)", NT,
-                kMaxWarpsCompute);
+  // two batch tiles per cluster (interleaved, so one tile's DSMEM hop hides behind the other's math)
+  // as soon as there is more than one tile of rows; TSSEP_LSTM_NB overrides
+  int NB = rows > 8 ? 2 : 1;
+  if (const char* e = getenv("TSSEP_LSTM_NB")) NB = atoi(e) == 2 ? 2 : 1;
+  TSSEP_REQUIRE(NT <= max_compute_warps(Up / 16), "tssep_blstm_recurrence: %d unit tiles per CTA exceed %d (raise cluster)",
+                NT, max_compute_warps(Up / 16));
   TSSEP_REQUIRE((C - 1) * NT < tiles, "tssep_blstm_recurrence: cluster %d leaves an empty CTA for Up=%d", C, Up);
 
   // G viewed as (unit, b, gate, dir, t)
@@ -319,7 +375,7 @@ int tssep_blstm_recurrence(const float* G, const uint32_t* Wfrag, uint16_t* H, i
   const cuuint64_t up = static_cast<cuuint64_t>(Up);
   cuuint64_t dims[5] = {up, static_cast<cuuint64_t>(rows), 4, 2, static_cast<cuuint64_t>(T)};
   cuuint64_t strides[4] = {static_cast<cuuint64_t>(T) * 8 * up * 4, up * 4, 4 * up * 4, 8 * up * 4};
-  cuuint32_t box[5] = {static_cast<cuuint32_t>(4 * NT), 8, 4, 1, 1};
+  cuuint32_t box[5] = {static_cast<cuuint32_t>(4 * NT), static_cast<cuuint32_t>(8 * NB), 4, 1, 1};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = enc(&gmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(G), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -327,10 +383,14 @@ int tssep_blstm_recurrence(const float* G, const uint32_t* Wfrag, uint16_t* H, i
   TSSEP_REQUIRE(r == CUDA_SUCCESS, "tssep_blstm_recurrence: cuTensorMapEncodeTiled failed with code %d", static_cast<int>(r));
 
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // debugging aid: TSSEP_REC_PROF=<device pointer to 6 ints> makes one warp record per-phase cycle counts
+  int* prof = nullptr;
+  if (const char* e = getenv("TSSEP_REC_PROF")) prof = reinterpret_cast<int*>(strtoull(e, nullptr, 0));
   switch (Up / 16) {
-#define TSSEP_CASE(kt) \
-  case kt:             \
-    return launch_rec<kt>(gmap, Wfrag, H, rows, T, C, NT, fast_math, s);
+#define TSSEP_CASE(kt)                                                                                  \
+  case kt:                                                                                              \
+    return NB == 2 ? launch_rec<kt, 2>(gmap, Wfrag, H, rows, T, C, NT, fast_math & 1, prof, s)          \
+                   : launch_rec<kt, 1>(gmap, Wfrag, H, rows, T, C, NT, fast_math & 1, prof, s);
     TSSEP_CASE(1) TSSEP_CASE(2) TSSEP_CASE(3) TSSEP_CASE(4) TSSEP_CASE(5) TSSEP_CASE(6) TSSEP_CASE(7) TSSEP_CASE(8)
     TSSEP_CASE(9) TSSEP_CASE(10) TSSEP_CASE(11) TSSEP_CASE(12) TSSEP_CASE(13) TSSEP_CASE(14) TSSEP_CASE(15)
     TSSEP_CASE(16) TSSEP_CASE(17) TSSEP_CASE(18) TSSEP_CASE(19) TSSEP_CASE(20)
