@@ -1,0 +1,68 @@
+"""World-size-2 gloo tests (CPU) of the multi-GPU host logic: meeting assignment and the
+end-of-path gather of segment tables."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def test_assign_meetings_is_balanced_and_deterministic():
+    from tssep_b200.dist import assign_meetings
+
+    lengths = [600, 30, 590, 45, 300, 310, 10, 5]
+    plan = assign_meetings(lengths, 3)
+    assert sorted(i for p in plan for i in p) == list(range(8))
+    loads = [sum(lengths[i] for i in p) for p in plan]
+    assert max(loads) - min(loads) <= 45
+    assert plan == assign_meetings(lengths, 3)
+    assert assign_meetings([600] * 64, 8) == [list(range(r, 64, 8)) for r in range(8)]
+
+
+def _worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from tssep_b200.dist import assign_meetings, gather_segments
+
+    lengths = [100, 90, 80, 70, 60]
+    mine = assign_meetings(lengths, world)[rank]
+    K, S = 2, 4
+    seg = torch.zeros((len(mine), K, S, 2), dtype=torch.int32)
+    cnt = torch.zeros((len(mine), K), dtype=torch.int32)
+    for j, m in enumerate(mine):
+        seg[j, :, 0, 0] = m * 10
+        seg[j, :, 0, 1] = m * 10 + 5
+        cnt[j] = m + 1
+    out_s, out_c = gather_segments(mine, seg, cnt, len(lengths))
+    ok = all(int(out_s[m, 0, 0, 0]) == m * 10 and int(out_s[m, 1, 0, 1]) == m * 10 + 5 and int(out_c[m, 0]) == m + 1
+             for m in range(len(lengths)))
+    ret[rank] = bool(ok) and len(mine) in (2, 3)
+    dist.destroy_process_group()
+
+
+def test_gather_segments_world_size_2():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert ret[0] and ret[1]
+
+
+def test_gather_segments_single_process():
+    from tssep_b200.dist import gather_segments
+
+    seg = torch.arange(2 * 2 * 3 * 2, dtype=torch.int32).reshape(2, 2, 3, 2)
+    cnt = torch.tensor([[1, 2], [3, 0]], dtype=torch.int32)
+    out_s, out_c = gather_segments([2, 0], seg, cnt, 3)
+    assert torch.equal(out_s[2], seg[0]) and torch.equal(out_s[0], seg[1]) and int(out_s[1].abs().sum()) == 0
+    assert out_c.tolist() == [[3, 0], [0, 0], [1, 2]]

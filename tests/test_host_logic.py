@@ -1,0 +1,169 @@
+"""CPU tests of the host-side mirror of the reference interface: config protocol, factory
+remapping, module tree / state_dict contract, error behaviour without a GPU."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import tssep_oracle as O
+
+REF = "/root/reference/tssep/exp"
+
+
+def test_get_config_layout_matches_reference_doctest():
+    """Dict layout pinned by tssep/train/net.py:345-365."""
+    from tssep_b200.net import MaskEstimator_v2
+
+    cfg = MaskEstimator_v2.get_config({"combination": "cat"})
+    assert list(cfg.items()) == [
+        ("factory", "tssep_b200.net.MaskEstimator_v2"), ("idim", 80), ("odim", None), ("layers", 3), ("units", 300),
+        ("projs", 320), ("dropout", 0), ("nmask", 1), ("pre_net", "RNNP"), ("aux_net", None),
+        ("aux_net_output_size", 100), ("combination", "cat"), ("ts_vad", False), ("output_resolution", "tf"),
+        ("random_speaker_order", True), ("num_averaged_permutations", 1), ("input_normalizer", None),
+        ("aux_normalizer", None), ("explicit_vad", False)]
+
+
+def test_model_default_config_and_param_count():
+    """tssep/train/model.py:74-115 (defaults) and :553-554 (114038 parameters)."""
+    from tssep_b200.model import Model
+
+    cfg = Model.get_config()
+    assert cfg["fe"] == {"factory": "tssep_b200.feature_extractor.Log1pMaxNormAbsSTFT", "size": 1024, "shift": 256,
+                         "window_length": 1024, "pad": True, "fading": True, "output_size": 513, "window": "hann",
+                         "statistics_axis": "tf"}
+    assert cfg["mask_estimator"]["idim"] == 513 and cfg["mask_estimator"]["odim"] == 513
+    assert cfg["mask_estimator"]["nmask"] == 1 and cfg["loss"]["target"] == "speaker_reverberation_early_ch0"
+    torch.manual_seed(0)
+    model = Model.new({"mask_estimator": {"units": 10, "projs": 12}})
+    assert sum(p.numel() for p in model.parameters()) == 114038
+
+
+def test_same_random_init_and_state_dict_keys_as_oracle():
+    """Modules are created in the reference's order, so torch.manual_seed reproduces its init."""
+    from tssep_b200.net import MaskEstimator_v2
+
+    kw = dict(idim=553, odim=513, units=8, projs=6, combination="mul", ts_vad=8, aux_net_output_size=513,
+              num_averaged_permutations=2)
+    torch.manual_seed(3)
+    ref = O.OracleMaskEstimator(**kw)
+    torch.manual_seed(3)
+    me = MaskEstimator_v2.new(kw)
+    a, b = ref.state_dict(), me.state_dict()
+    assert list(a.keys()) == list(b.keys())
+    assert all(torch.equal(a[k], b[k]) for k in a)
+
+
+def test_repr_matches_reference_layout():
+    """tssep/train/net.py:403-440 (mul, ts_vad=4, idim=513)."""
+    from tssep_b200.net import MaskEstimator_v2
+
+    r = repr(MaskEstimator_v2.new({"combination": "mul", "ts_vad": 4, "idim": 513}))
+    for line in ["combination='mul',", "(0): LSTM(513, 300, batch_first=True, bidirectional=True)",
+                 "(1): Linear(in_features=600, out_features=513, bias=True)", "(dropout0): Dropout(p=0, inplace=False)",
+                 "(activation1): Tanh()", "(rearrange1):", "(0): LSTM(1280, 300, batch_first=True, bidirectional=True)",
+                 "(linear2): Linear(in_features=320, out_features=2052, bias=True)", "(rearrange2):",
+                 "(final_activation): Sigmoid()"]:
+        assert line in r, line
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="reference checkout not present (GPU box)")
+@pytest.mark.parametrize("variant,resolution", [("init_cfg_tssep.yaml", "tf"), ("init_cfg_tsvad.yaml", "t")])
+def test_reference_yaml_loads_with_only_factories_swapped(variant, resolution):
+    import yaml
+
+    from tssep_b200.configurable import import_class, remap_factories
+
+    def merge(a, b):
+        for k, v in b.items():
+            if isinstance(v, dict) and isinstance(a.get(k), dict):
+                merge(a[k], v)
+            else:
+                a[k] = v
+
+    cfg = yaml.safe_load(open(f"{REF}/init_cfg_common.yaml"))["eg"]["trainer"]["model"]
+    merge(cfg, yaml.safe_load(open(f"{REF}/{variant}"))["eg"]["trainer"]["model"])
+    cfg = remap_factories(cfg)
+    cls = import_class(cfg.pop("factory"))
+    model = cls.from_config(cls.get_config(cfg))
+    me = model.mask_estimator
+    assert me.output_resolution == resolution and me.ts_vad == 8 and me.num_averaged_permutations == 2
+    assert model.fe.output_size == 553 and model.fe.frequencies == 513
+    assert me.pre_net.net[0].input_size == 553 and me.post_net.birnn2.net[0].input_size == 42 * 8
+    keys = list(model.state_dict().keys())
+    assert "fe.fe1.dct_mat" in keys and "mask_estimator.post_net.linear2.weight" in keys
+    assert model.mask_estimator.post_net.linear2.out_features == (4104 if resolution == "tf" else 8)
+
+
+def test_vad2sep_broadcast_relies_on_speaker_major_head_rows():
+    """InitCheckPointVAD2Sep (tssep/train/init_ckpt.py:62-83): repeat_interleave of the 't' head gives
+    a 'tf' head whose logits are the 't' logits broadcast over frequency."""
+    kw = dict(idim=40, odim=33, units=4, projs=5, combination="mul", ts_vad=3, aux_net_output_size=33,
+              random_speaker_order=False)
+    torch.manual_seed(0)
+    vad = O.OracleMaskEstimator(output_resolution="t", **kw)
+    sep = O.OracleMaskEstimator(output_resolution="tf", **kw)
+    sd = vad.state_dict()
+    for k in ["post_net.linear2.weight", "post_net.linear2.bias"]:
+        sd[k] = torch.repeat_interleave(sd[k], 33, dim=0)
+    sep.load_state_dict(sd)
+    xs, aux = torch.rand(12, 40), [torch.rand(33) for _ in range(3)]
+    with torch.no_grad():
+        assert (vad(xs, aux).logit - sep(xs, aux).logit).abs().max().item() < 1e-6
+
+
+def test_dummy_reader_matches_oracle_generator():
+    from tssep_b200.data import DummyReader
+
+    ex = DummyReader(aux_size=513).get_example(3)
+    want = O.dummy_example(3, aux_size=513)
+    assert np.array_equal(ex["audio_data"]["observation"], want["observation"])
+    assert np.array_equal(ex["auxInput"], want["auxInput"])
+    assert np.array_equal(ex["audio_data"]["speaker_reverberation_early_ch0"], want["speaker_reverberation_early_ch0"])
+    assert ex["audio_data"]["observation"].shape == (1, 80000) and ex["auxInput"].shape == (8, 513)
+
+
+def test_frame_geometry_helpers():
+    from tssep_b200.feature_extractor import Log1pMaxNormAbsSTFT
+
+    fe = Log1pMaxNormAbsSTFT()
+    assert repr(fe) == ("Log1pMaxNormAbsSTFT(size=1024, shift=256, window_length=1024, pad=True, fading=True, "
+                        "output_size=513, window='blackman', statistics_axis='tf')")
+    assert [fe.num_frames(n) for n in (80000, 10000, 9600000)] == [316, 43, 37503]
+    s = np.arange(0, 4000, 13)
+    assert (fe.sample_index_to_frame_index(s) == O.sample_to_frame_index(s, 1024, 256)).all()
+
+
+def test_no_cpu_fallback():
+    """CPU tensors are rejected loudly; nothing silently falls back to PyTorch."""
+    from tssep_b200.feature_extractor import Log1pMaxNormAbsSTFT
+    from tssep_b200.net import MaskEstimator_v2
+    from tssep_b200.rnnp import RNNP_packed
+
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        Log1pMaxNormAbsSTFT().stft(torch.zeros(2000))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        RNNP_packed(8, 1, 4, 4, 0)(torch.zeros(5, 8))
+    me = MaskEstimator_v2.new({"idim": 16, "units": 4, "projs": 4})
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        me(torch.zeros(5, 16), [torch.zeros(100)] * 3)
+
+
+def test_product_never_imports_oracle():
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tssep_b200")
+    for dirpath, _, files in os.walk(root):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f
+
+
+def test_unsupported_options_raise():
+    from tssep_b200.feature_extractor import Log1pMaxNormAbsSTFT
+    from tssep_b200.rnnp import RNNP_packed
+
+    with pytest.raises(NotImplementedError):
+        RNNP_packed(8, 1, 4, 4, 0, typ="bgru")
+    with pytest.raises(NotImplementedError):
+        Log1pMaxNormAbsSTFT(statistics_axis="t")._feature_parts()

@@ -1,0 +1,47 @@
+"""The C-ABI library builds without a GPU, loads, and exports every symbol include/tssep_b200.h declares."""
+import ctypes
+import os
+import re
+
+HEADER = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "tssep_b200.h")
+
+
+def declared_symbols():
+    src = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    return sorted(set(re.findall(r"\b(tssep_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_declares_the_expected_entry_points():
+    syms = declared_symbols()
+    assert len(syms) >= 17 and "tssep_gemm" in syms and "tssep_blstm_recurrence" in syms
+
+
+def test_library_exports_every_declared_symbol(lib):
+    for name in declared_symbols():
+        assert hasattr(lib, name), name
+
+
+def test_binding_table_covers_header(lib):
+    from tssep_b200 import _lib
+
+    assert sorted(_lib.EXPORTED_SYMBOLS) == declared_symbols()
+
+
+def test_abi_version_and_error_channel(lib):
+    assert lib.tssep_abi_version() == 1
+    # argument validation happens on the host before any launch: a null pointer is reported through
+    # tssep_last_error without touching a device
+    rc = lib.tssep_cast_bf16(None, 4, 4, 4, None, 8, None)
+    assert rc != 0
+    assert b"tssep_cast_bf16" in lib.tssep_last_error()
+
+
+def test_gemm_descriptor_layout_matches_header():
+    """ctypes mirror of tssep_gemm_desc: field order and count as in the header."""
+    from tssep_b200._lib import GemmDesc
+
+    src = open(HEADER).read()
+    body = src[src.index("typedef struct tssep_gemm_desc {"):src.index("} tssep_gemm_desc;")]
+    names = re.findall(r"[\s\*]([A-Za-z_]+);", body)
+    assert names == [f[0] for f in GemmDesc._fields_]
+    assert ctypes.sizeof(GemmDesc) % 8 == 0
