@@ -120,6 +120,114 @@ __device__ __forceinline__ void epilogue_store(const GemmArgs& g, int z, int64_t
   }
 }
 
+// ---------------------------------------------------------------------------
+// Coalesced epilogue of the tensor-core kernel.  Each epilogue warp owns 32 tile rows (lane =
+// row in TMEM) and receives 32 consecutive columns per tcgen05.ld.  Writing those straight to
+// global memory gives 32 scattered 16-byte pieces per store instruction (~0.9 TB/s measured);
+// instead the warp transposes the 32x32 block through a private shared-memory tile so that
+// consecutive lanes hold consecutive columns and every store instruction writes whole 128-byte
+// lines.
+// ---------------------------------------------------------------------------
+constexpr int kStageLd = 36;  // words per staged row: 16-byte aligned rows, conflict-free STS.128 / LDS.128
+
+// Bias of the columns a lane owns in the write-out phase (issued one chunk ahead so the global
+// load latency never sits on the epilogue's critical path).
+struct ChunkBias {
+  float v[4];
+};
+__device__ __forceinline__ ChunkBias load_chunk_bias(const GemmArgs& g, int z, int n0, int lane) {
+  ChunkBias b;
+  b.v[0] = b.v[1] = b.v[2] = b.v[3] = 0.f;
+  if (g.bias == nullptr) return b;
+  const float* bias = g.bias + static_cast<int64_t>(z % g.b_mod) * g.bias_stride;
+  if (g.mode == EPI_HEAD) {
+    const int n = n0 + lane;
+    if (n < g.N) b.v[0] = __ldg(bias + n);
+  } else {
+    const int n = n0 + (lane & 7) * 4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (n + j < g.N) b.v[j] = __ldg(bias + n + j);
+  }
+  return b;
+}
+
+__device__ __forceinline__ void epilogue_coalesced(const GemmArgs& g, int z, int64_t m0, int n0, int limit,
+                                                   const uint32_t* v, const ChunkBias& cb, uint32_t stage, int lane) {
+  const int nvalid = min(limit, g.N - n0);
+  if (nvalid <= 0) return;
+  // 1. stage the lane's own row of raw accumulators (8 x STS.128)
+#pragma unroll
+  for (int i = 0; i < 32; i += 4)
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage + (lane * kStageLd + i) * 4), "r"(v[i]),
+                 "r"(v[i + 1]), "r"(v[i + 2]), "r"(v[i + 3])
+                 : "memory");
+  __syncwarp();
+  const int64_t rows_left = g.M - m0;  // rows of this warp that exist
+  if (g.mode == EPI_HEAD) {
+    // lane = column: block q, offset f, destination plane are fixed per lane for the whole chunk
+    const int n = n0 + lane;
+    const bool col_ok = lane < nvalid;
+    int q = 0, f = 0;
+    int64_t plane = 0;
+    if (col_ok) {
+      q = n / g.row_len;
+      f = n - q * g.row_len;
+      plane = g.plane_map[z * g.n_blocks + q];
+    }
+    float* lo = static_cast<float*>(g.out);
+    const int64_t base = (plane * g.M + m0) * g.row_len + f;
+    const int rmax = static_cast<int>(rows_left < 32 ? rows_left : 32);
+#pragma unroll 4
+    for (int r = 0; r < rmax; ++r) {
+      float val;
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(val) : "r"(stage + (r * kStageLd + lane) * 4));
+      val = fmaf(g.alpha, val, cb.v[0]);
+      if (col_ok) {
+        const int64_t idx = base + static_cast<int64_t>(r) * g.row_len;
+        if (lo) lo[idx] = val;
+        if (g.mask) g.mask[idx] = sigmoid_acc(val);
+      }
+    }
+  } else {
+    const int64_t zoff = static_cast<int64_t>(z / g.out_div) * g.out_stride_hi + static_cast<int64_t>(z % g.out_div) * g.out_stride;
+    const int sub = lane >> 3, c4 = (lane & 7) * 4;  // 4 rows per pass, 8 lanes x 4 columns per row
+#pragma unroll
+    for (int pass = 0; pass < 8; ++pass) {
+      const int r = pass * 4 + sub;
+      float x[4];
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                   : "=f"(x[0]), "=f"(x[1]), "=f"(x[2]), "=f"(x[3])
+                   : "r"(stage + (r * kStageLd + c4) * 4));
+#pragma unroll
+      for (int j = 0; j < 4; ++j) x[j] = apply_act(fmaf(g.alpha, x[j], cb.v[j]), g.act);
+      if (r < rows_left && c4 < nvalid) {
+        const int64_t off = zoff + (m0 + r) * g.ldo + n0 + c4;
+        if (g.mode == EPI_F32) {
+          float* o = static_cast<float*>(g.out) + off;
+          if (c4 + 4 <= nvalid && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+            *reinterpret_cast<float4*>(o) = make_float4(x[0], x[1], x[2], x[3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (c4 + j < nvalid) o[j] = x[j];
+          }
+        } else {
+          __nv_bfloat16* o = static_cast<__nv_bfloat16*>(g.out) + off;
+          if (c4 + 4 <= nvalid && (reinterpret_cast<uintptr_t>(o) & 7) == 0) {
+            *reinterpret_cast<uint2*>(o) = make_uint2(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (c4 + j < nvalid) o[j] = __float2bfloat16_rn(x[j]);
+          }
+        }
+      }
+    }
+  }
+  __syncwarp();  // the staging tile is reused by the next chunk
+}
+
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   // K-major, 128-byte swizzle: LBO (ignored) = 1, SBO = 1024 B, version 1, layout type 2
   return static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
@@ -137,6 +245,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t sBar = sB + kStages * b_bytes;  // 8-byte aligned (multiples of 1024 before it)
   const uint32_t full0 = sBar, empty0 = sBar + 8 * kStages, tfull0 = sBar + 16 * kStages,
                  tempty0 = tfull0 + 16, tptr = tempty0 + 16;
+  const uint32_t sStage = sBar + 128;  // 4 epilogue warps x 32 rows x kStageLd words
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -230,15 +339,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int z = static_cast<int>(tile / tiles_per_z);
       const int64_t rem = tile - z * tiles_per_z;
       const int mt = static_cast<int>(rem / g.n_tiles), nt = static_cast<int>(rem - static_cast<int64_t>(mt) * g.n_tiles);
-      const int64_t m = static_cast<int64_t>(mt) * BM + q * 32 + lane;
+      const int64_t m0 = static_cast<int64_t>(mt) * BM + q * 32;
       mbar_wait(tfull0 + 8 * as, aph);
       tc_fence_after();
       const uint32_t t0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kAccCols;
+      const uint32_t stage = sStage + static_cast<uint32_t>(warp - 2) * (32 * kStageLd * 4);
+      ChunkBias cb = load_chunk_bias(g, z, nt * g.bn, lane);
       for (int c0 = 0; c0 < g.bn; c0 += 32) {
         uint32_t v[32];
         tc_ld32(t0 + c0, v);
+        const ChunkBias cb_next = load_chunk_bias(g, z, nt * g.bn + c0 + 32, lane);  // prefetch for the next chunk
         tc_wait_ld();
-        if (m < g.M) epilogue_store(g, z, m, nt * g.bn + c0, min(32, g.bn - c0), reinterpret_cast<const float*>(v));
+        if (m0 < g.M) epilogue_coalesced(g, z, m0, nt * g.bn + c0, min(32, g.bn - c0), v, cb, stage, lane);
+        cb = cb_next;
       }
       tc_fence_before();
       __syncwarp();
@@ -355,7 +468,7 @@ static int launch_gemm(GemmArgs g, const uint16_t* A, int64_t lda, int64_t a_str
   int dev = 0, sms = 148;
   TSSEP_CUDA(cudaGetDevice(&dev));
   TSSEP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const size_t smem = 1024 + kStages * (BM * BK * 2 + static_cast<size_t>(g.bn) * BK * 2) + 256;
+  const size_t smem = 1024 + kStages * (BM * BK * 2 + static_cast<size_t>(g.bn) * BK * 2) + 128 + 4 * 32 * kStageLd * 4;
   TSSEP_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   const int grid = static_cast<int>(imin64(g.total_tiles, sms));
   gemm_tc_kernel<<<grid, kGemmThreads, smem, stream>>>(tmA, tmB, g);
