@@ -72,96 +72,111 @@ __global__ void head_expand_t_kernel(const float* __restrict__ small, int64_t Z,
 
 // ---------------------------------------------------------------------------
 // mask x X  ->  (stft_estimate)  ->  iSTFT overlap-add
-// One CTA produces `hops` output hops of all speakers of one item; the frames
-// it needs (hops + OV - 1) are inverse-transformed into shared memory and
-// overlap-added in gather form, so there are no atomics and every output sample
-// is written exactly once.  The mixture STFT tile is staged once per CTA and
-// reused for all speakers.
+// One CTA walks a contiguous range of output hops of ONE separated signal (item z, speaker k)
+// in rounds of 8 frames: every warp inverse-transforms one frame into a ring of
+// 8 + OV - 1 shared-memory slots, then the CTA overlap-adds the 8 hops that just became
+// complete in gather form (no atomics, every output sample written exactly once).  Only the
+// OV - 1 frames before the range are recomputed (a 2-3 % halo); the K CTAs that need the same
+// mixture rows run side by side, so X is served from L2.
 // ---------------------------------------------------------------------------
 constexpr int kEWarps = 8;
 constexpr int kEThreads = kEWarps * 32;
 
-__global__ void __launch_bounds__(kEThreads)
+__global__ void __launch_bounds__(kEThreads, 2)
 mask_istft_kernel(const float2* __restrict__ X, int64_t x_item_stride, const float* __restrict__ mask, int n_spk,
-                  int64_t T, int S, int log2m, int R, int wl, int trim, const float* __restrict__ synwin,
+                  int64_t T, int S, int R, int wl, int trim, const float* __restrict__ synwin,
                   const float2* __restrict__ twiddle, float2* __restrict__ est, float* __restrict__ time_out,
                   int64_t num_samples, int hops) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int M = S >> 1, F = M + 1, OV = wl / R;
-  const int nslots = hops + OV - 1;
-  float2* tw = reinterpret_cast<float2*>(smem_raw);       // M
-  float2* Xs = tw + M;                                     // nslots * F (only when mask != nullptr)
-  float* fbuf = reinterpret_cast<float*>(Xs + (mask ? nslots * F : 0));  // nslots * S
-  float* syn = fbuf + nslots * S;                          // wl
+  const int PL = padded_len(M);
+  const int NR = kEWarps + OV - 1;  // ring slots
+  float2* tw = reinterpret_cast<float2*>(smem_raw);               // M
+  float2* ring = tw + M;                                           // NR * PL : windowed time frames
+  float2* scratch = ring + NR * PL;                                // kEWarps * PL
+  float* syn = reinterpret_cast<float*>(scratch + kEWarps * PL);   // wl
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // speaker is the fastest-varying block index so that the K CTAs sharing mixture rows are co-resident
   const int64_t z = blockIdx.y;
-  const int64_t j0 = static_cast<int64_t>(blockIdx.x) * hops;
-  const int64_t tfirst = j0 - (OV - 1);
+  const int64_t sig = z * n_spk + (blockIdx.x % n_spk);
   const int64_t J = T + OV - 1;
+  const int64_t j_begin = static_cast<int64_t>(blockIdx.x / n_spk) * hops;
+  const int64_t j_end = imin64(J, j_begin + hops);
+  const int64_t t_lo = j_begin - (OV - 1);  // first frame that contributes to this range
   const float inv_m = 1.0f / static_cast<float>(M);
+  const bool odd_passes = fft_num_passes(M) & 1;
 
   for (int i = threadIdx.x; i < M; i += kEThreads) tw[i] = twiddle[i];
   for (int i = threadIdx.x; i < wl; i += kEThreads) syn[i] = synwin[i] * inv_m;
-  if (mask) {
-    for (int i = threadIdx.x; i < nslots * F; i += kEThreads) {
-      const int fl = i / F, f = i - fl * F;
-      const int64_t t = tfirst + fl;
-      Xs[i] = (t >= 0 && t < T) ? X[z * x_item_stride + t * F + f] : make_float2(0.f, 0.f);
-    }
-  }
   __syncthreads();
 
-  for (int k = 0; k < n_spk; ++k) {
-    const int64_t sig = z * n_spk + k;
-    for (int fl = warp; fl < nslots; fl += kEWarps) {
-      const int64_t t = tfirst + fl;
-      float* fr = fbuf + fl * S;
+  const float* sf = reinterpret_cast<const float*>(ring);
+  int64_t emitted = j_begin;
+  for (int64_t tb = t_lo; tb < j_end; tb += kEWarps) {
+    // ---- one frame per warp ------------------------------------------------------------------
+    const int64_t t = tb + warp;
+    if (t < j_end) {
+      float2* slot = ring + static_cast<int>((t - t_lo) % NR) * PL;
       if (t < 0 || t >= T) {
-        for (int i = lane; i < wl; i += 32) fr[i] = 0.f;
-        continue;
+        for (int i = lane; i < PL; i += 32) slot[i] = make_float2(0.f, 0.f);
+      } else {
+        // the FFT ping-pongs between two buffers; start so that the result lands in the slot
+        float2* scr = scratch + warp * PL;
+        float2* first = odd_passes ? scr : slot;
+        float2* other = odd_passes ? slot : scr;
+        const int64_t row = (sig * T + t) * F;
+        const float2* xrow = mask ? X + z * x_item_stride + t * F : X + row;
+        const bool own = est != nullptr && t >= j_begin;
+#pragma unroll 4
+        for (int kk = lane; kk < M; kk += 32) {
+          float2 yk = xrow[kk], ym = xrow[M - kk];
+          if (mask) {
+            const float mk = mask[row + kk], mm = mask[row + M - kk];
+            yk = make_float2(yk.x * mk, yk.y * mk);
+            ym = make_float2(ym.x * mm, ym.y * mm);
+          }
+          if (own) {
+            est[row + kk] = yk;
+            if (kk == 0) est[row + M] = ym;
+          }
+          if (kk == 0) {
+            yk.y = 0.f;  // c2r ignores the imaginary parts of DC and Nyquist
+            ym.y = 0.f;
+          }
+          first[padi(kk)] = irfft_pack(yk, ym, kk, tw);
+        }
+        __syncwarp();
+        float2* res = warp_fft<true>(first, other, M, tw, S, lane);  // == slot
+        for (int n = lane; n < M; n += 32) {
+          float2 c = res[padi(n)];
+          c.x *= (2 * n < wl) ? syn[2 * n] : 0.f;
+          c.y *= (2 * n + 1 < wl) ? syn[2 * n + 1] : 0.f;
+          res[padi(n)] = c;
+        }
       }
-      float2* zb = reinterpret_cast<float2*>(fr);
-      const int64_t row = (sig * T + t) * F;
-      const bool own = est != nullptr && t >= j0;
-      for (int kk = lane; kk < M; kk += 32) {
-        float2 yk, ym;
-        if (mask) {
-          const float mk = mask[row + kk], mm = mask[row + M - kk];
-          const float2 xk = Xs[fl * F + kk], xm = Xs[fl * F + M - kk];
-          yk = make_float2(xk.x * mk, xk.y * mk);
-          ym = make_float2(xm.x * mm, xm.y * mm);
-        } else {
-          yk = X[row + kk];
-          ym = X[row + M - kk];
-        }
-        if (own) {
-          est[row + kk] = yk;
-          if (kk == 0) est[row + M] = ym;
-        }
-        if (kk == 0) {
-          yk.y = 0.f;  // c2r ignores the imaginary parts of DC and Nyquist
-          ym.y = 0.f;
-        }
-        zb[bitrev(kk, log2m)] = irfft_pack(yk, ym, kk, tw);
-      }
-      __syncwarp();
-      warp_fft_inplace<true>(zb, log2m, tw, S, lane);
-      for (int i = lane; i < wl; i += 32) fr[i] *= syn[i];
     }
     __syncthreads();
-    if (time_out) {
-      for (int idx = threadIdx.x; idx < hops * R; idx += kEThreads) {
+    // ---- overlap-add the hops whose OV frames are all in the ring now ---------------------------
+    const int64_t ready = imin64(j_end, tb + kEWarps);  // frames < ready are done
+    if (time_out && ready > emitted) {
+      const int count = static_cast<int>(ready - emitted) * R;
+      for (int idx = threadIdx.x; idx < count; idx += kEThreads) {
         const int hj = idx / R, i = idx - hj * R;
-        const int64_t j = j0 + hj;
+        const int64_t j = emitted + hj;
         const int64_t n = j * R + i - trim;
-        if (j < J && n >= 0 && n < num_samples) {
+        if (n >= 0 && n < num_samples) {
           float acc = 0.f;
-          for (int o = 0; o < OV; ++o) acc += fbuf[(hj + OV - 1 - o) * S + o * R + i];
+          for (int o = 0; o < OV; ++o) {
+            const int e = o * R + i;
+            const int sl = static_cast<int>((j - o - t_lo) % NR);
+            acc += sf[2 * (sl * PL + padi(e >> 1)) + (e & 1)];
+          }
           time_out[sig * num_samples + n] = acc;
         }
       }
     }
+    if (ready > emitted) emitted = ready;
     __syncthreads();
   }
 }
@@ -219,21 +234,18 @@ int tssep_mask_istft(const float* X, int64_t x_item_stride, const float* mask, i
                 "tssep_mask_istft: need window_length <= size and window_length %% shift == 0");
   TSSEP_REQUIRE(Z >= 0 && Z < 65536 && n_spk >= 1 && T >= 0, "tssep_mask_istft: bad extent");
   if (Z == 0 || T == 0) return 0;
-  const int M = size / 2, F = M + 1, OV = window_length / shift;
-  int hops = 16;
-  auto smem_for = [&](int h) {
-    const size_t ns = h + OV - 1;
-    return sizeof(float2) * M + (mask ? sizeof(float2) * ns * F : 0) + sizeof(float) * ns * size +
-           sizeof(float) * window_length;
-  };
-  while (hops > 1 && smem_for(hops) > 200 * 1024) hops /= 2;
-  const size_t smem = smem_for(hops);
+  const int M = size / 2, OV = window_length / shift;
+  const size_t smem = sizeof(float2) * (M + (2 * kEWarps + OV - 1) * padded_len(M)) + sizeof(float) * window_length;
   TSSEP_REQUIRE(smem <= 227 * 1024, "tssep_mask_istft: frame geometry does not fit shared memory");
   TSSEP_CUDA(cudaFuncSetAttribute(mask_istft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   const int64_t J = T + OV - 1;
-  dim3 grid(static_cast<unsigned>((J + hops - 1) / hops), static_cast<unsigned>(Z));
+  const int64_t n_sig = Z * n_spk;
+  // ranges of 128 hops (a 2-3 % halo), shorter when that would leave SMs idle
+  int hops = 128;
+  while (hops > 8 && ((J + hops - 1) / hops) * n_sig < 4 * 148) hops /= 2;
+  dim3 grid(static_cast<unsigned>(((J + hops - 1) / hops) * n_spk), static_cast<unsigned>(Z));
   mask_istft_kernel<<<grid, kEThreads, smem, static_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const float2*>(X), x_item_stride, mask, n_spk, T, size, l2 - 1, shift, window_length,
+      reinterpret_cast<const float2*>(X), x_item_stride, mask, n_spk, T, size, shift, window_length,
       fading ? window_length - shift : 0, synwin, reinterpret_cast<const float2*>(twiddle),
       reinterpret_cast<float2*>(stft_estimate), time, num_samples, hops);
   return check_launch("tssep_mask_istft");

@@ -21,14 +21,15 @@ constexpr int kThreads = kWarps * 32;
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads)
 stft_kernel(const float* __restrict__ audio, int64_t N, const float* __restrict__ window,
-            const float2* __restrict__ twiddle, int S, int log2m, int R, int wl, int front_pad, int64_t T,
+            const float2* __restrict__ twiddle, int S, int R, int wl, int front_pad, int64_t T,
             float2* __restrict__ X, int frames_per_block) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int M = S >> 1;
-  float2* tw = reinterpret_cast<float2*>(smem_raw);           // M
-  float2* scratch = tw + M;                                    // kWarps * M
-  float* win = reinterpret_cast<float*>(scratch + kWarps * M); // wl
-  float* span = win + wl;                                      // (fpb-1)*R + wl
+  const int PL = padded_len(M);
+  float2* tw = reinterpret_cast<float2*>(smem_raw);                 // M
+  float2* scratch = tw + M;                                          // kWarps * 2 * PL
+  float* win = reinterpret_cast<float*>(scratch + kWarps * 2 * PL);  // wl
+  float* span = win + wl;                                            // (fpb-1)*R + wl
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t sig = blockIdx.y;
@@ -46,7 +47,8 @@ stft_kernel(const float* __restrict__ audio, int64_t N, const float* __restrict_
   }
   __syncthreads();
 
-  float2* z = scratch + warp * M;
+  float2* za = scratch + warp * 2 * PL;
+  float2* zb = za + PL;
   const int F = M + 1;
   for (int f = warp; f < nf; f += kWarps) {
     const float* fr = span + f * R;
@@ -54,10 +56,10 @@ stft_kernel(const float* __restrict__ audio, int64_t N, const float* __restrict_
       const int i0 = 2 * n, i1 = 2 * n + 1;
       const float v0 = i0 < wl ? fr[i0] * win[i0] : 0.f;
       const float v1 = i1 < wl ? fr[i1] * win[i1] : 0.f;
-      z[bitrev(n, log2m)] = make_float2(v0, v1);
+      za[padi(n)] = make_float2(v0, v1);
     }
     __syncwarp();
-    warp_fft_inplace<false>(z, log2m, tw, S, lane);
+    const float2* z = warp_fft<false>(za, zb, M, tw, S, lane);
     float2* out = X + (sig * T + t0 + f) * F;
     for (int k = lane; k <= M; k += 32) out[k] = rfft_unpack(z, k, M, tw);
     __syncwarp();
@@ -214,11 +216,12 @@ int tssep_stft(const float* audio, int64_t n_signals, int64_t num_samples, const
   if (n_signals == 0 || T == 0) return 0;
   const int fpb = 32;
   const int M = size / 2;
-  const size_t smem = sizeof(float2) * M * (1 + kWarps) + sizeof(float) * (window_length + (fpb - 1) * shift + window_length);
+  const size_t smem = sizeof(float2) * (M + kWarps * 2 * padded_len(M)) + sizeof(float) * (window_length + (fpb - 1) * shift + window_length);
+  TSSEP_REQUIRE(smem <= 227 * 1024, "tssep_stft: frame geometry does not fit shared memory");
   TSSEP_CUDA(cudaFuncSetAttribute(stft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   dim3 grid(static_cast<unsigned>((T + fpb - 1) / fpb), static_cast<unsigned>(n_signals));
   stft_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(
-      audio, num_samples, window, reinterpret_cast<const float2*>(twiddle), size, l2 - 1, shift, window_length,
+      audio, num_samples, window, reinterpret_cast<const float2*>(twiddle), size, shift, window_length,
       fading ? window_length - shift : 0, T, reinterpret_cast<float2*>(X), fpb);
   return check_launch("tssep_stft");
 }
