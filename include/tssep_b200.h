@@ -91,6 +91,13 @@ int tssep_fold_embedding(int mode, const float* W, int64_t ldw, const float* b, 
                          int64_t Z, int N, int F, int A, uint16_t* Wk, int64_t ld_wk, float* bias_k,
                          tssep_stream_t stream);
 
+/* Conditioned input rows for the tcgen05 recurrence path (net.py:862-896), rows ordered
+ * (group, t, b32) with z = group * 32 + b = item * K + speaker, groups = ceil(Z / 32):
+ *   mode 0 ('mul'): out[r, :F] = bf16(xs[item, t, :] * e[z, :]);  mode 1 ('cat'): out[r] = [xs[item, t, :] | e[z, :]].
+ * xs (items * T, ldx) bf16, e (Z, A) f32, out (groups * T * 32, ldo) bf16; rows with z >= Z are zero. */
+int tssep_condition_rows(int mode, const uint16_t* xs, int64_t ldx, const float* e, int64_t Z, int K,
+                         int64_t T, int F, int A, uint16_t* out, int64_t ldo, tssep_stream_t stream);
+
 /* Batched contraction on tcgen05/TMEM tensor cores:
  *   out[z] = act(alpha * A[z / a_div] . B[z % b_mod]^T + bias[z % b_mod])      z in [0, batch)
  * A (rows, K) bf16 row-major (lda), B (N, K) bf16 row-major (ldb); lda, ldb multiples
@@ -105,8 +112,14 @@ int tssep_fold_embedding(int mode, const float* W, int64_t ldw, const float* b, 
  *   logit[(p * M + m) * row_len + f] = v and mask[...] = sigmoid(v); either may be NULL.
  *   The caller folds the speaker rotation / trial mean into B and bias (K = trials*projs)
  *   and the un-permutation into plane_map.
+ * mode TSSEP_EPI_F32_BT (input of tssep_blstm_recurrence_tc): rows are ordered (group, t, b32), b = m % 32;
+ *   out[((m/32)*N + (n/32)*32)*32 + (b/4)*128 + (n%32)*4 + b%4]: per (group, t) and per block of 32 columns
+ *   a 4 KiB tile [b/4][column][b%4]  (batch == 1, M and N multiples of 32).
+ * mode TSSEP_EPI_BF16_ROWMAP (speaker-concat rearrange net.py:606-612 after the tcgen05 recurrence):
+ *   rows ordered (group, t, b32), z = group * 32 + b, item = z / rm_K, spk = z % rm_K; rows with
+ *   z >= rm_Z are dropped; out[(item * rm_T + t) * ldo + spk * rm_P + n] as bf16.
  * impl: 0 = tcgen05 (product path), 1 = plain SIMT kernel (debug / bisecting only). */
-enum { TSSEP_EPI_F32 = 0, TSSEP_EPI_BF16 = 1, TSSEP_EPI_HEAD = 2 };
+enum { TSSEP_EPI_F32 = 0, TSSEP_EPI_BF16 = 1, TSSEP_EPI_HEAD = 2, TSSEP_EPI_F32_BT = 3, TSSEP_EPI_BF16_ROWMAP = 4 };
 
 typedef struct tssep_gemm_desc {
   const uint16_t* A; int64_t lda; int64_t a_stride; int32_t a_div;
@@ -116,6 +129,7 @@ typedef struct tssep_gemm_desc {
   float alpha; int32_t act; int32_t mode;
   void* out; int64_t ldo; int64_t out_stride; int32_t out_div; int64_t out_stride_hi;
   float* mask; const int32_t* plane_map; int32_t n_blocks; int32_t row_len;
+  int64_t rm_T; int32_t rm_K; int32_t rm_Z; int32_t rm_P;
   int32_t impl;
 } tssep_gemm_desc;
 
@@ -141,6 +155,18 @@ int tssep_head_expand_t(const float* small, int64_t Z, int64_t T, int n_blocks, 
  * exp-based gates, 1 tanh.approx. */
 int tssep_blstm_recurrence(const float* G, const uint32_t* Wfrag, uint16_t* H, int64_t rows, int64_t T,
                            int Up, int cluster, int fast_math, tssep_stream_t stream);
+
+/* Throughput variant of the same recurrence for many batch rows: one cluster of ceil(Up/64) CTAs
+ * per (32 rows, direction), recurrent weights resident in shared memory as UMMA operands,
+ * tcgen05.mma (M=128, N=32, K=16) into TMEM, gates applied by 4 epilogue warps out of TMEM.
+ * G f32 in the tile layout written by tssep_gemm mode TSSEP_EPI_F32_BT with N = 8*Up columns ordered
+ * n = dir*4*Up + (unit/8)*32 + (unit%8)*4 + gate (the caller packs W_ih rows in that order),
+ * groups = ceil(rows / 32); H (groups, T, 32, 2*Up) bf16, i.e. rows ordered
+ * (group, t, b).  Wimg from tssep_pack_whh_tc (2 * C * 2 * C * 16 KiB, C = ceil(Up/64)); Up <= 512. */
+int tssep_blstm_recurrence_tc(const float* G, const uint16_t* Wimg, uint16_t* H, int64_t rows, int64_t T,
+                              int Up, int fast_math, tssep_stream_t stream);
+int tssep_pack_whh_tc(const float* whh_fwd, const float* whh_bwd, int U, int Up, uint16_t* Wimg,
+                      tssep_stream_t stream);
 
 /* weight_hh_l0 / weight_hh_l0_reverse (4U, U) f32 -> mma fragment order. */
 int tssep_pack_whh(const float* whh_fwd, const float* whh_bwd, int U, int Up, uint32_t* Wfrag,

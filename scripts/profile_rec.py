@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--clusters", type=int, nargs="+", default=[0])
     ap.add_argument("--fast", type=int, nargs="+", default=[0, 1])
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--kernel", default="regs", choices=["regs", "tc"])
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     U = a.units
@@ -26,27 +27,38 @@ def main():
     torch.manual_seed(0)
     w = (torch.rand((2, 4 * U, U), device=dev) - 0.5) * (2 / U ** 0.5)
     whh = ops.pack_whh(w[0], w[1], U, Up)
+    wimg = ops.pack_whh_tc(w[0].contiguous(), w[1].contiguous(), U, Up)
+
+    def run(G, rows, C, fast):
+        if a.kernel == "tc":
+            return ops.blstm_recurrence_tc(G, wimg, rows, a.frames, Up, fast_math=bool(fast))
+        return run(G, rows, C, fast)
+
     for rows in a.rows:
         G = torch.randn((rows, a.frames, 8 * Up), device=dev) * 0.3
         for C in a.clusters:
             for fast in a.fast:
                 for _ in range(2):
-                    ops.blstm_recurrence(G, whh, rows, a.frames, Up, cluster=C, fast_math=bool(fast))
+                    run(G, rows, C, fast)
                 torch.cuda.synchronize()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
                 for _ in range(a.reps):
-                    ops.blstm_recurrence(G, whh, rows, a.frames, Up, cluster=C, fast_math=bool(fast))
+                    run(G, rows, C, fast)
                 e1.record()
                 torch.cuda.synchronize()
                 us = e0.elapsed_time(e1) * 1e3 / a.reps / a.frames
-                prof = torch.zeros(6, dtype=torch.int32, device=dev)
+                prof = torch.zeros(8, dtype=torch.int32, device=dev)
                 os.environ["TSSEP_REC_PROF"] = str(prof.data_ptr())
-                ops.blstm_recurrence(G, whh, rows, a.frames, Up, cluster=C, fast_math=bool(fast))
+                run(G, rows, C, fast)
                 torch.cuda.synchronize()
                 del os.environ["TSSEP_REC_PROF"]
                 pc = prof.cpu().numpy().astype(float)
-                ph = " ".join(f"{n}={v / max(pc[5], 1):.0f}" for n, v in zip(["gwait", "hwait", "mma", "gates", "send"], pc[:5]))
+                if a.kernel == "tc":
+                    names = ["t0.wait", "t0.ld+act", "t0.cell", "t0.send", "t1.wait", "t1.ld+act", "t1.cell", "t1.send"]
+                    ph = " ".join(f"{n}={v / a.frames:.0f}" for n, v in zip(names, pc))
+                else:
+                    ph = " ".join(f"{n}={v / max(pc[5], 1):.0f}" for n, v in zip(["gwait", "hwait", "mma", "gates", "send"], pc[:5]))
                 print(f"U={U} rows={rows:4d} cluster={C} fast={fast}: {us:.3f} us/step | cycles/step {ph}", flush=True)
         del G
 

@@ -107,8 +107,11 @@ def test_reference_end_to_end_golden(cuda):
     dict(combination="mul", ts_vad=False, num_averaged_permutations=1, idim=513, nmask=2),
     dict(combination="mul", ts_vad=8, num_averaged_permutations=2, idim=513, explicit_vad=True),
 ])
-def test_mask_estimator_variants_batched(cuda, kw):
-    """MaskEstimator_v2 alone, batched (B, T, F) input, all option combinations the reference exposes."""
+@pytest.mark.parametrize("kernel", ["regs", "tc"])
+def test_mask_estimator_variants_batched(cuda, monkeypatch, kw, kernel):
+    """MaskEstimator_v2 alone, batched (B, T, F) input, all option combinations the reference exposes,
+    through both recurrence kernels (register-resident mma.sync / shared-memory tcgen05)."""
+    monkeypatch.setenv("TSSEP_LSTM_KERNEL", kernel)
     ref, me = make_pair(_me_kwargs(**kw))
     B, T, K = 2, 120, 8
     A = kw.get("aux_net_output_size", 513)
@@ -132,8 +135,10 @@ def test_mask_estimator_variants_batched(cuda, kw):
     assert (got.embedding.cpu() - want.embedding).abs().max().item() == 0.0
 
 
-def test_full_size_dims_short_meeting(cuda):
+@pytest.mark.parametrize("kernel", ["regs", "tc"])
+def test_full_size_dims_short_meeting(cuda, monkeypatch, kernel):
     """C3 dims (U=300, P=320, mul, ts_vad=8, R=2) on 20 s of audio; separate() with two meetings."""
+    monkeypatch.setenv("TSSEP_LSTM_KERNEL", kernel)
     ref, me = make_pair(_me_kwargs(units=300, projs=320))
     model = _product_model(me)
     tables = O.MFCCTables()

@@ -43,6 +43,29 @@ def test_rnnp_matches_torch(cuda, idim, units, hdim, shape):
     assert err < 1e-2, err
 
 
+@pytest.mark.parametrize("idim,units,hdim,shape", [
+    (64, 40, 42, (3, 100, 64)),      # one CTA, one k-atom, 3 of 32 rows used
+    (96, 64, 48, (40, 150, 96)),     # exactly 64 units, two row groups
+    (80, 128, 64, (33, 120, 80)),    # cluster of 2
+    (160, 300, 320, (64, 200, 160)), # full size: cluster of 5, partial last k-atom
+    (160, 300, 320, (5, 300, 160)),
+])
+def test_rnnp_tcgen05_recurrence_matches_torch(cuda, monkeypatch, idim, units, hdim, shape):
+    """The shared-memory / tcgen05 recurrence (csrc/lstm_tc.cu), forced for every row count."""
+    monkeypatch.setenv("TSSEP_LSTM_KERNEL", "tc")
+    ref, mine = _pair(idim, units, hdim)
+    x = torch.randn(shape, generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        want = ref(x)
+        got = mine(x.to(cuda)).cpu()
+    err = (got - want).abs().max().item()
+    assert err < 1e-2, err
+    monkeypatch.setenv("TSSEP_LSTM_KERNEL", "regs")
+    with torch.no_grad():
+        got2 = mine(x.to(cuda)).cpu()
+    assert (got2 - want).abs().max().item() < 1e-2
+
+
 def test_rnnp_stress_weights(cuda):
     """All weights x4 (saturating gates), as SURVEY.md §8d asks; looser bound, reported not hidden."""
     ref, mine = _pair(64, 40, 42)

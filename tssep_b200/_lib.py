@@ -29,11 +29,12 @@ class GemmDesc(C.Structure):
         ("alpha", c_f32), ("act", c_i32), ("mode", c_i32),
         ("out", c_vp), ("ldo", c_i64), ("out_stride", c_i64), ("out_div", c_i32), ("out_stride_hi", c_i64),
         ("mask", c_vp), ("plane_map", c_vp), ("n_blocks", c_i32), ("row_len", c_i32),
+        ("rm_T", c_i64), ("rm_K", c_i32), ("rm_Z", c_i32), ("rm_P", c_i32),
         ("impl", c_i32),
     ]
 
 
-EPI_F32, EPI_BF16, EPI_HEAD = 0, 1, 2
+EPI_F32, EPI_BF16, EPI_HEAD, EPI_F32_BT, EPI_BF16_ROWMAP = 0, 1, 2, 3, 4
 
 _SIGNATURES = {
     "tssep_abi_version": ([], C.c_int),
@@ -47,10 +48,13 @@ _SIGNATURES = {
     "tssep_instance_norm": ([c_vp, c_i64, c_i64, c_i32, c_vp, c_vp], C.c_int),
     "tssep_fold_embedding": ([c_i32, c_vp, c_i64, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_vp, c_i64, c_vp, c_vp],
                              C.c_int),
+    "tssep_condition_rows": ([c_i32, c_vp, c_i64, c_vp, c_i64, c_i32, c_i64, c_i32, c_i32, c_vp, c_i64, c_vp], C.c_int),
     "tssep_gemm": ([C.POINTER(GemmDesc), c_vp], C.c_int),
     "tssep_head_expand_t": ([c_vp, c_i64, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp], C.c_int),
     "tssep_blstm_recurrence": ([c_vp, c_vp, c_vp, c_i64, c_i64, c_i32, c_i32, c_i32, c_vp], C.c_int),
     "tssep_pack_whh": ([c_vp, c_vp, c_i32, c_i32, c_vp, c_vp], C.c_int),
+    "tssep_blstm_recurrence_tc": ([c_vp, c_vp, c_vp, c_i64, c_i64, c_i32, c_i32, c_vp], C.c_int),
+    "tssep_pack_whh_tc": ([c_vp, c_vp, c_i32, c_i32, c_vp, c_vp], C.c_int),
     "tssep_mask_istft": ([c_vp, c_i64, c_vp, c_i64, c_i32, c_i64, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp,
                           c_i64, c_vp], C.c_int),
     "tssep_activity": ([c_vp, c_i64, c_i64, c_i32, c_vp, c_vp], C.c_int),

@@ -46,6 +46,40 @@ __global__ void fold_cat_kernel(const float* __restrict__ W, int64_t ldw, const 
 }
 
 // ---------------------------------------------------------------------------
+// Conditioned input rows for the tcgen05 recurrence path: rows ordered (group, t, b32),
+// z = group * 32 + b = item * K + speaker.
+//   mul (net.py:871-874): row = xs[item, t, :] * e[z, :]
+//   cat (net.py:879-894): row = [xs[item, t, :] | e[z, :]]
+// ---------------------------------------------------------------------------
+__global__ void condition_rows_kernel(int mode, const __nv_bfloat16* __restrict__ xs, int64_t ldx,
+                                      const float* __restrict__ e, int64_t Z, int K, int64_t T, int F, int A,
+                                      __nv_bfloat16* __restrict__ out, int64_t ldo, int64_t n_rows) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int kdim = mode == 0 ? F : F + A;
+  for (int64_t r = blockIdx.x * static_cast<int64_t>(wpb) + (threadIdx.x >> 5); r < n_rows;
+       r += static_cast<int64_t>(gridDim.x) * wpb) {
+    const int64_t gt = r >> 5;
+    const int64_t grp = gt / T, t = gt - grp * T;
+    const int64_t z = grp * 32 + (r & 31);
+    __nv_bfloat16* o = out + r * ldo;
+    if (z >= Z) {
+      for (int c = lane; c < kdim; c += 32) o[c] = __float2bfloat16_rn(0.f);
+      continue;
+    }
+    const int64_t item = z / K;
+    const __nv_bfloat16* x = xs + (item * T + t) * ldx;
+    const float* ez = e + z * A;
+    if (mode == 0) {
+      for (int c = lane; c < F; c += 32) o[c] = __float2bfloat16_rn(__bfloat162float(x[c]) * ez[c]);
+    } else {
+      for (int c = lane; c < F; c += 32) o[c] = x[c];
+      for (int c = lane; c < A; c += 32) o[F + c] = __float2bfloat16_rn(ez[c]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
 // output_resolution 't': broadcast (Z, T, K) logits over frequency
 // ---------------------------------------------------------------------------
 __global__ void head_expand_t_kernel(const float* __restrict__ small, int64_t Z, int64_t T, int K, int F,
@@ -211,6 +245,21 @@ int tssep_fold_embedding(int mode, const float* W, int64_t ldw, const float* b, 
     fold_cat_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, s>>>(W, ldw, b, e, Z, N, F, A, bias_k);
   }
   return check_launch("tssep_fold_embedding");
+}
+
+int tssep_condition_rows(int mode, const uint16_t* xs, int64_t ldx, const float* e, int64_t Z, int K, int64_t T,
+                         int F, int A, uint16_t* out, int64_t ldo, tssep_stream_t stream) {
+  TSSEP_REQUIRE(xs && e && out, "tssep_condition_rows: null pointer");
+  TSSEP_REQUIRE(mode == 0 || mode == 1, "tssep_condition_rows: mode must be 0 (mul) or 1 (cat)");
+  TSSEP_REQUIRE(mode == 1 || A == F, "tssep_condition_rows(mul): needs A == F");
+  TSSEP_REQUIRE(K >= 1 && ldx >= F && ldo >= (mode == 0 ? F : F + A), "tssep_condition_rows: bad extent");
+  if (Z == 0 || T == 0) return 0;
+  const int64_t n_rows = ((Z + 31) / 32) * T * 32;
+  const int blocks = static_cast<int>(imin64((n_rows + 7) / 8, 148 * 32));
+  condition_rows_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      mode, reinterpret_cast<const __nv_bfloat16*>(xs), ldx, e, Z, K, T, F, A, reinterpret_cast<__nv_bfloat16*>(out), ldo,
+      n_rows);
+  return check_launch("tssep_condition_rows");
 }
 
 int tssep_head_expand_t(const float* small, int64_t Z, int64_t T, int n_spk, int F, const int32_t* perm,

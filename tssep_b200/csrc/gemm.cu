@@ -26,7 +26,7 @@ constexpr int kGemmThreads = 192;
 constexpr int kTmemCols = 512;
 constexpr int kAccCols = 256;
 
-enum EpiMode { EPI_F32 = 0, EPI_BF16 = 1, EPI_HEAD = 2 };
+enum EpiMode { EPI_F32 = 0, EPI_BF16 = 1, EPI_HEAD = 2, EPI_F32_BT = 3, EPI_BF16_ROWMAP = 4 };
 
 struct GemmArgs {
   int64_t M;
@@ -45,6 +45,9 @@ struct GemmArgs {
   float* mask;
   const int* plane_map;
   int n_blocks, row_len;
+  // row map of EPI_BF16_ROWMAP: input rows are ordered (group, t, b32); z = group*32 + b
+  int64_t rm_T;
+  int rm_K, rm_Z, rm_P;
   // tiling
   int bn, m_tiles, n_tiles, k_blocks;
   int64_t total_tiles;
@@ -99,6 +102,23 @@ __device__ __forceinline__ void epilogue_store(const GemmArgs& g, int z, int64_t
       for (int i = 0; i < 32; ++i)
         if (i < nvalid) o[i] = __float2bfloat16_rn(apply_act(g.alpha * acc[i] + (bias ? bias[i] : 0.f), g.act));
     }
+  } else if (g.mode == EPI_F32_BT) {
+    const int b = static_cast<int>(m & 31);
+    float* o = static_cast<float*>(g.out) + ((m >> 5) * g.N + n0) * 32 + (b >> 2) * 128 + (b & 3);
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (i < nvalid) o[i * 4] = apply_act(g.alpha * acc[i] + (bias ? bias[i] : 0.f), g.act);
+  } else if (g.mode == EPI_BF16_ROWMAP) {
+    const int64_t gt = m >> 5;
+    const int64_t grp = gt / g.rm_T, t = gt - grp * g.rm_T;
+    const int64_t zz = grp * 32 + (m & 31);
+    if (zz < g.rm_Z) {
+      const int64_t item = zz / g.rm_K, spk = zz - item * g.rm_K;
+      __nv_bfloat16* o = static_cast<__nv_bfloat16*>(g.out) + (item * g.rm_T + t) * g.ldo + spk * g.rm_P + n0;
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (i < nvalid) o[i] = __float2bfloat16_rn(apply_act(g.alpha * acc[i] + (bias ? bias[i] : 0.f), g.act));
+    }
   } else {  // EPI_HEAD
     int q = n0 / g.row_len;
     int f = n0 - q * g.row_len;
@@ -140,7 +160,7 @@ __device__ __forceinline__ ChunkBias load_chunk_bias(const GemmArgs& g, int z, i
   b.v[0] = b.v[1] = b.v[2] = b.v[3] = 0.f;
   if (g.bias == nullptr) return b;
   const float* bias = g.bias + static_cast<int64_t>(z % g.b_mod) * g.bias_stride;
-  if (g.mode == EPI_HEAD) {
+  if (g.mode == EPI_HEAD || g.mode == EPI_F32_BT) {
     const int n = n0 + lane;
     if (n < g.N) b.v[0] = __ldg(bias + n);
   } else {
@@ -201,8 +221,19 @@ __device__ __forceinline__ void epilogue_coalesced(const GemmArgs& g, int z, int
                    : "r"(stage + (r * kStageLd + c4) * 4));
 #pragma unroll
       for (int j = 0; j < 4; ++j) x[j] = apply_act(fmaf(g.alpha, x[j], cb.v[j]), g.act);
-      if (r < rows_left && c4 < nvalid) {
-        const int64_t off = zoff + (m0 + r) * g.ldo + n0 + c4;
+      bool row_ok = r < rows_left;
+      int64_t off = zoff + (m0 + r) * g.ldo + n0 + c4;
+      if (g.mode == EPI_BF16_ROWMAP) {
+        // rows are ordered (group, t, b): scatter to out[(item * T + t) * ldo + spk * P + n], z = item * K + spk
+        const int64_t row = m0 + r;
+        const int64_t gt = row >> 5;
+        const int64_t grp = gt / g.rm_T, t = gt - grp * g.rm_T;
+        const int64_t zz = grp * 32 + (row & 31);
+        row_ok = row_ok && zz < g.rm_Z;
+        const int64_t item = zz / g.rm_K, spk = zz - item * g.rm_K;
+        off = (item * g.rm_T + t) * g.ldo + spk * g.rm_P + n0 + c4;
+      }
+      if (row_ok && c4 < nvalid) {
         if (g.mode == EPI_F32) {
           float* o = static_cast<float*>(g.out) + off;
           if (c4 + 4 <= nvalid && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
@@ -226,6 +257,34 @@ __device__ __forceinline__ void epilogue_coalesced(const GemmArgs& g, int z, int
     }
   }
   __syncwarp();  // the staging tile is reused by the next chunk
+}
+
+// EPI_F32_BT: rows are ordered (group, t, b32) and the output is the layout the tcgen05 recurrence
+// streams: element (row m, column n) -> ((m/32)*N + (n/32)*32)*32 + (b/4)*128 + (n%32)*4 + b%4 with
+// b = m % 32, i.e. per (group, t) and per block of 32 columns a 4 KiB tile [b/4][column][b%4].  The
+// warp transposes its 32 x 32 block through shared memory and writes eight fully coalesced 512-byte
+// rows (lane = column).
+__device__ __forceinline__ void epilogue_bt(const GemmArgs& g, int64_t m0, int n0, const uint32_t* v, const ChunkBias& cb,
+                                            uint32_t stage, int lane) {
+  if (n0 >= g.N) return;
+#pragma unroll
+  for (int i = 0; i < 32; i += 4)
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage + (lane * kStageLd + i) * 4), "r"(v[i]),
+                 "r"(v[i + 1]), "r"(v[i + 2]), "r"(v[i + 3])
+                 : "memory");
+  __syncwarp();
+  float* o = static_cast<float*>(g.out) + ((m0 >> 5) * g.N + n0) * 32 + lane * 4;
+#pragma unroll
+  for (int bq = 0; bq < 8; ++bq) {
+    float x[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x[j]) : "r"(stage + ((bq * 4 + j) * kStageLd + lane) * 4));
+      x[j] = apply_act(fmaf(g.alpha, x[j], cb.v[0]), g.act);
+    }
+    *reinterpret_cast<float4*>(o + bq * 128) = make_float4(x[0], x[1], x[2], x[3]);
+  }
+  __syncwarp();
 }
 
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
@@ -350,7 +409,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc_ld32(t0 + c0, v);
         const ChunkBias cb_next = load_chunk_bias(g, z, nt * g.bn + c0 + 32, lane);  // prefetch for the next chunk
         tc_wait_ld();
-        if (m0 < g.M) epilogue_coalesced(g, z, m0, nt * g.bn + c0, min(32, g.bn - c0), v, cb, stage, lane);
+        if (m0 < g.M) {
+          if (g.mode == EPI_F32_BT) epilogue_bt(g, m0, nt * g.bn + c0, v, cb, stage, lane);
+          else epilogue_coalesced(g, z, m0, nt * g.bn + c0, min(32, g.bn - c0), v, cb, stage, lane);
+        }
         cb = cb_next;
       }
       tc_fence_before();
@@ -409,15 +471,15 @@ static int make_map_2d(CUtensorMap* map, const void* base, uint64_t inner, uint6
   return 0;
 }
 
-static int choose_bn(int N) {
+static int choose_bn(int N, int step = 16) {
   if (const char* e = getenv("TSSEP_GEMM_BN")) {
     const int v = atoi(e);
-    if (v >= 16 && v <= 256 && v % 16 == 0) return v;
+    if (v >= 16 && v <= 256 && v % step == 0) return v;
   }
-  if (N <= 256) return ((N + 15) / 16) * 16;
+  if (N <= 256) return ((N + step - 1) / step) * step;
   int best = 256;
   double best_score = 1e9;
-  for (int bn = 256; bn >= 128; bn -= 16) {
+  for (int bn = 256; bn >= 128; bn -= step) {
     const int tiles = (N + bn - 1) / bn;
     const double waste = static_cast<double>(tiles) * bn / N - 1.0;
     const double score = waste + 0.0002 * (256 - bn);
@@ -454,7 +516,7 @@ static int launch_gemm(GemmArgs g, const uint16_t* A, int64_t lda, int64_t a_str
                 (long long)ldb);
   TSSEP_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0,
                 "gemm: operands must be 16-byte aligned");
-  g.bn = choose_bn(g.N);
+  g.bn = choose_bn(g.N, g.mode == EPI_F32_BT ? 32 : 16);
   g.m_tiles = static_cast<int>((g.M + BM - 1) / BM);
   g.n_tiles = (g.N + g.bn - 1) / g.bn;
   g.k_blocks = (g.K + BK - 1) / BK;
@@ -483,8 +545,8 @@ extern "C" {
 
 int tssep_gemm(const tssep_gemm_desc* d, tssep_stream_t stream) {
   TSSEP_REQUIRE(d != nullptr, "tssep_gemm: null descriptor");
-  TSSEP_REQUIRE(d->mode == TSSEP_EPI_F32 || d->mode == TSSEP_EPI_BF16 || d->mode == TSSEP_EPI_HEAD,
-                "tssep_gemm: unknown epilogue mode %d", d->mode);
+  TSSEP_REQUIRE(d->mode >= TSSEP_EPI_F32 && d->mode <= TSSEP_EPI_BF16_ROWMAP, "tssep_gemm: unknown epilogue mode %d",
+                d->mode);
   TSSEP_REQUIRE(d->act == 0 || d->act == 1, "tssep_gemm: act must be 0 (none) or 1 (tanh)");
   GemmArgs g{};
   g.M = d->M;
@@ -507,11 +569,22 @@ int tssep_gemm(const tssep_gemm_desc* d, tssep_stream_t stream) {
   g.plane_map = d->plane_map;
   g.n_blocks = d->n_blocks;
   g.row_len = d->row_len;
+  g.rm_T = d->rm_T;
+  g.rm_K = d->rm_K;
+  g.rm_Z = d->rm_Z;
+  g.rm_P = d->rm_P;
   if (d->mode == TSSEP_EPI_HEAD) {
     TSSEP_REQUIRE(d->out || d->mask, "tssep_gemm(head): no output");
     TSSEP_REQUIRE(d->plane_map && d->n_blocks >= 1 && d->row_len >= 1 && d->N == d->n_blocks * d->row_len,
                   "tssep_gemm(head): need plane_map and N == n_blocks * row_len");
     TSSEP_REQUIRE(d->act == 0, "tssep_gemm(head): act must be 0");
+  } else if (d->mode == TSSEP_EPI_F32_BT) {
+    TSSEP_REQUIRE(d->out != nullptr && d->batch == 1 && d->M % 32 == 0 && d->N % 32 == 0 &&
+                      (reinterpret_cast<uintptr_t>(d->out) & 15) == 0,
+                  "tssep_gemm(f32_bt): needs a 16-byte aligned output, batch == 1, M %% 32 == 0 and N %% 32 == 0");
+  } else if (d->mode == TSSEP_EPI_BF16_ROWMAP) {
+    TSSEP_REQUIRE(d->out != nullptr && d->batch == 1 && d->M % 32 == 0 && d->rm_T >= 1 && d->rm_K >= 1 && d->rm_Z >= 1,
+                  "tssep_gemm(bf16_rowmap): needs an output, batch == 1, M %% 32 == 0 and a row map");
   } else {
     TSSEP_REQUIRE(d->out != nullptr, "tssep_gemm: null output");
     TSSEP_REQUIRE(d->ldo >= d->N, "tssep_gemm: ldo < N");

@@ -27,7 +27,7 @@ import torch
 
 from . import _lib, ops
 from .configurable import Configurable
-from .rnnp import RNNP_packed, param_key
+from .rnnp import RNNP_packed, param_key, use_tc_recurrence
 
 
 @dataclasses.dataclass
@@ -264,36 +264,76 @@ class MaskEstimator_v2(Configurable, torch.nn.Module):
         else:
             F = Din
 
-        # conditioning folded into birnn0's input projection (net.py:862-896)
         birnns = self._birnns()
         pk0 = birnns[0].layer_packs()[0]
         Up = pk0.Up
         e = aux_p.reshape(B * K, A).contiguous()
-        bias_k = torch.empty((B * K, 8 * Up), dtype=torch.float32, device=dev)
-        G = torch.empty((B * K * T, 8 * Up), dtype=torch.float32, device=dev)
         stream = _lib.stream_of(xs)
-        if self.combination == "mul":
-            assert A == F, ("combination='mul' needs aux_size == odim", A, F)
-            ldk = ops.round_up(F, 8)
-            Wk = torch.empty((B * K * 8 * Up, ldk), dtype=torch.bfloat16, device=dev)
-            _lib.call("tssep_fold_embedding", 0, pk0.w_ih_f32.data_ptr(), pk0.I, pk0.bias.data_ptr(), e.data_ptr(),
-                      B * K, 8 * Up, F, A, Wk.data_ptr(), ldk, bias_k.data_ptr(), stream)
-            ops.gemm(xb, ld, Wk, ldk, T, 8 * Up, F, G, mode=ops.EPI_F32, ldo=8 * Up, batch=B * K, a_stride=T * ld,
-                     a_div=K, b_stride=8 * Up * ldk, bias=bias_k, bias_stride=8 * Up, out_stride=T * 8 * Up)
-            del Wk
-        else:  # cat
-            assert pk0.I == F + A, (pk0.I, F, A)
-            _lib.call("tssep_fold_embedding", 1, pk0.w_ih_f32.data_ptr(), pk0.I, pk0.bias.data_ptr(), e.data_ptr(),
-                      B * K, 8 * Up, F, A, None, 0, bias_k.data_ptr(), stream)
-            ops.gemm(xb, ld, pk0.w_ih, pk0.ld_in, T, 8 * Up, F, G, mode=ops.EPI_F32, ldo=8 * Up, batch=B * K,
-                     a_stride=T * ld, a_div=K, b_stride=0, bias=bias_k, bias_stride=8 * Up, out_stride=T * 8 * Up)
-        del xb
-
         P = self.projs
         ldp = ops.round_up(P, 8)
+        mode = {"mul": 0, "cat": 1}[self.combination]
+        if self.combination == "mul":
+            assert A == F, ("combination='mul' needs aux_size == odim", A, F)
+        else:
+            assert pk0.I == F + A, (pk0.I, F, A)
+        start_l = 0
+        y, y_ld, G = None, None, None
+        if L >= 2 and use_tc_recurrence(B * K):
+            # ---- throughput path for the speaker-independent layers (all but the last) ---------------
+            # rows ordered (group, t, b32), z = group*32 + b = item*K + speaker: the conditioned rows are
+            # materialised once in bf16 (net.py:862-896), every input projection writes G with the batch
+            # row innermost, the recurrence runs on tcgen05 with the recurrent weights in shared memory.
+            Z = B * K
+            groups = (Z + 31) // 32
+            mrows = groups * T * 32
+            ld0 = ops.round_up(pk0.I, 8)
+            a0 = torch.empty((mrows, ld0), dtype=torch.bfloat16, device=dev)
+            _lib.call("tssep_condition_rows", mode, xb.data_ptr(), ld, e.data_ptr(), Z, K, T, F, A, a0.data_ptr(), ld0,
+                      stream)
+            y, y_ld = a0, ld0
+            for l in range(L - 1):
+                pk = birnns[l].layer_packs()[0]
+                G = pk.input_gemm_bt(y, y_ld, mrows)
+                H = pk.recurrence_tc(G, Z, T)
+                del G
+                if l < L - 2:
+                    y_ld = ldp
+                    y = torch.empty((mrows, y_ld), dtype=torch.bfloat16, device=dev)
+                    pk.projection(H, mrows, y, mode=ops.EPI_BF16, ldo=y_ld, act=1)
+                elif self.ts_vad is not False:
+                    # tanh(proj) straight into the speaker-concat layout (B, T, K*P)   net.py:606-612
+                    y_ld = ops.round_up(K * P, 8)
+                    y = torch.empty((B * T, y_ld), dtype=torch.bfloat16, device=dev)
+                    pk.projection(H, mrows, y, mode=ops.EPI_BF16_ROWMAP, ldo=y_ld, act=1, row_map=(T, K, Z, P))
+                else:
+                    y_ld = ldp
+                    y = torch.empty((Z * T, y_ld), dtype=torch.bfloat16, device=dev)
+                    pk.projection(H, mrows, y, mode=ops.EPI_BF16_ROWMAP, ldo=y_ld, act=1, row_map=(T, 1, Z, 0))
+                del H
+            start_l = L - 1
+        else:
+            # ---- latency path: conditioning folded into birnn0's input projection ----------------------
+            bias_k = torch.empty((B * K, 8 * Up), dtype=torch.float32, device=dev)
+            G = torch.empty((B * K * T, 8 * Up), dtype=torch.float32, device=dev)
+            if self.combination == "mul":
+                ldk = ops.round_up(F, 8)
+                Wk = torch.empty((B * K * 8 * Up, ldk), dtype=torch.bfloat16, device=dev)
+                _lib.call("tssep_fold_embedding", 0, pk0.w_ih_f32.data_ptr(), pk0.I, pk0.bias.data_ptr(),
+                          e.data_ptr(), B * K, 8 * Up, F, A, Wk.data_ptr(), ldk, bias_k.data_ptr(), stream)
+                ops.gemm(xb, ld, Wk, ldk, T, 8 * Up, F, G, mode=ops.EPI_F32, ldo=8 * Up, batch=B * K,
+                         a_stride=T * ld, a_div=K, b_stride=8 * Up * ldk, bias=bias_k, bias_stride=8 * Up,
+                         out_stride=T * 8 * Up)
+                del Wk
+            else:  # cat
+                _lib.call("tssep_fold_embedding", 1, pk0.w_ih_f32.data_ptr(), pk0.I, pk0.bias.data_ptr(),
+                          e.data_ptr(), B * K, 8 * Up, F, A, None, 0, bias_k.data_ptr(), stream)
+                ops.gemm(xb, ld, pk0.w_ih, pk0.ld_in, T, 8 * Up, F, G, mode=ops.EPI_F32, ldo=8 * Up, batch=B * K,
+                         a_stride=T * ld, a_div=K, b_stride=0, bias=bias_k, bias_stride=8 * Up,
+                         out_stride=T * 8 * Up)
+        del xb
+
         rows = B * K
-        y, y_ld = None, None
-        for l in range(L):
+        for l in range(start_l, L):
             pk = birnns[l].layer_packs()[0]
             last = l == L - 1
             tsv_last = last and self.ts_vad is not False

@@ -12,7 +12,7 @@ import os
 import torch
 
 from . import _lib
-from ._lib import EPI_BF16, EPI_F32, EPI_HEAD, GemmDesc
+from ._lib import EPI_BF16, EPI_BF16_ROWMAP, EPI_F32, EPI_F32_BT, EPI_HEAD, GemmDesc
 
 
 def round_up(x: int, m: int) -> int:
@@ -25,7 +25,7 @@ def _gemm_impl() -> int:
 
 def gemm(A, lda, B, ldb, M, N, K, out, *, mode, ldo=0, batch=1, a_stride=0, a_div=1, b_stride=0, b_mod=None,
          bias=None, bias_stride=0, alpha=1.0, act=0, out_stride=0, out_div=None, out_stride_hi=0, mask=None,
-         plane_map=None, n_blocks=0, row_len=0, impl=None):
+         plane_map=None, n_blocks=0, row_len=0, row_map=None, impl=None):
     """``tssep_gemm``: out[z] = act(alpha * A[z / a_div] . B[z % b_mod]^T + bias[z % b_mod])."""
     _lib.require_cuda(A, B, out, bias, mask, plane_map)
     d = GemmDesc()
@@ -37,6 +37,8 @@ def gemm(A, lda, B, ldb, M, N, K, out, *, mode, ldo=0, batch=1, a_stride=0, a_di
     d.out, d.ldo, d.out_stride, d.out_stride_hi = _lib.ptr(out), ldo, out_stride, out_stride_hi
     d.out_div = batch if out_div is None else out_div
     d.mask, d.plane_map, d.n_blocks, d.row_len = _lib.ptr(mask), _lib.ptr(plane_map), n_blocks, row_len
+    if row_map is not None:  # (T, K, Z, P) of EPI_BF16_ROWMAP
+        d.rm_T, d.rm_K, d.rm_Z, d.rm_P = row_map
     d.impl = _gemm_impl() if impl is None else impl
     _lib.call("tssep_gemm", C.byref(d), _lib.stream_of(A))
 
@@ -68,10 +70,33 @@ def blstm_recurrence(G: torch.Tensor, wfrag: torch.Tensor, rows: int, T: int, Up
     if cluster is None:
         cluster = int(os.environ.get("TSSEP_LSTM_CLUSTER", "0"))
     if fast_math is None:
-        fast_math = os.environ.get("TSSEP_LSTM_FAST_MATH", "0") == "1"
+        fast_math = os.environ.get("TSSEP_LSTM_FAST_MATH", "1") == "1"
     H = torch.empty((rows, T, 2 * Up), dtype=torch.bfloat16, device=G.device)
     _lib.call("tssep_blstm_recurrence", G.data_ptr(), wfrag.data_ptr(), H.data_ptr(), rows, T, Up, cluster,
               int(fast_math), _lib.stream_of(G))
+    return H
+
+
+def pack_whh_tc(w_fwd: torch.Tensor, w_bwd: torch.Tensor, U: int, Up: int) -> torch.Tensor:
+    """Shared-memory image of W_hh for the tcgen05 recurrence (pre-swizzled UMMA A operands)."""
+    _lib.require_cuda(w_fwd, w_bwd)
+    c = (Up + 63) // 64
+    out = torch.empty(2 * c * 2 * c * 8192, dtype=torch.bfloat16, device=w_fwd.device)
+    _lib.call("tssep_pack_whh_tc", w_fwd.contiguous().data_ptr(), w_bwd.contiguous().data_ptr(), U, Up,
+              out.data_ptr(), _lib.stream_of(w_fwd))
+    return out
+
+
+def blstm_recurrence_tc(G: torch.Tensor, wimg: torch.Tensor, rows: int, T: int, Up: int,
+                        fast_math: bool = None) -> torch.Tensor:
+    """tcgen05 variant: G in the EPI_F32_BT tile layout -> H (groups*T*32, 2*Up) bf16, rows (group, t, b)."""
+    _lib.require_cuda(G, wimg)
+    if fast_math is None:
+        fast_math = os.environ.get("TSSEP_LSTM_FAST_MATH", "1") == "1"
+    groups = (rows + 31) // 32
+    H = torch.empty((groups * T * 32, 2 * Up), dtype=torch.bfloat16, device=G.device)
+    _lib.call("tssep_blstm_recurrence_tc", G.data_ptr(), wimg.data_ptr(), H.data_ptr(), rows, T, Up, int(fast_math),
+              _lib.stream_of(G))
     return H
 
 
@@ -85,5 +110,5 @@ def instance_norm(x: torch.Tensor, unbiased=False) -> torch.Tensor:
     return out
 
 
-__all__ = ["gemm", "cast_bf16", "pack_whh", "blstm_recurrence", "instance_norm", "round_up", "EPI_F32", "EPI_BF16",
-           "EPI_HEAD"]
+__all__ = ["gemm", "cast_bf16", "pack_whh", "blstm_recurrence", "pack_whh_tc", "blstm_recurrence_tc", "instance_norm", "round_up", "EPI_F32", "EPI_BF16",
+           "EPI_HEAD", "EPI_F32_BT", "EPI_BF16_ROWMAP"]

@@ -13,9 +13,19 @@ on bf16 operands with fp32 accumulation and fp32 cell state.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _lib, ops
+
+TC_MIN_ROWS = 24  # batch rows from which the tcgen05 recurrence is used
+
+
+def use_tc_recurrence(rows: int) -> bool:
+    """TSSEP_LSTM_KERNEL=regs|tc|auto (default auto: tcgen05 kernel from TC_MIN_ROWS batch rows)."""
+    choice = os.environ.get("TSSEP_LSTM_KERNEL", "auto")
+    return choice == "tc" or (choice == "auto" and rows >= TC_MIN_ROWS)
 
 
 class LayerPack:
@@ -41,8 +51,11 @@ class LayerPack:
             self.bias = b.view(8 * Up).contiguous()
             self.ld_in = ops.round_up(I, 8)
             self.w_ih = ops.cast_bf16(self.w_ih_f32, self.ld_in)
-            self.whh = ops.pack_whh(lstm.weight_hh_l0.detach().float(), lstm.weight_hh_l0_reverse.detach().float(),
-                                    U, Up)
+            self._whh_f32 = (lstm.weight_hh_l0.detach().float().contiguous(),
+                             lstm.weight_hh_l0_reverse.detach().float().contiguous())
+            self.whh = ops.pack_whh(self._whh_f32[0], self._whh_f32[1], U, Up)
+            self.whh_tc = None  # built on first use by the tcgen05 recurrence
+            self.w_ih_tc = self.bias_tc = None
             wp = torch.zeros((self.hdim, 2 * Up), dtype=torch.float32, device=dev)
             wp[:, :U] = linear.weight.detach().float()[:, :U]
             wp[:, Up:Up + U] = linear.weight.detach().float()[:, U:]
@@ -58,14 +71,35 @@ class LayerPack:
         return G
 
     def recurrence(self, G: torch.Tensor, rows: int, T: int) -> torch.Tensor:
+        """Register-resident mma.sync kernel (csrc/lstm.cu): G (rows, T, 8Up) -> H (rows, T, 2Up)."""
         return ops.blstm_recurrence(G, self.whh, rows, T, self.Up)
 
+    # -- throughput path: rows ordered (group, t, b32), weights in shared memory, tcgen05 -------------
+    def input_gemm_bt(self, xb: torch.Tensor, ld: int, mrows: int, kdim: int = None) -> torch.Tensor:
+        """xb (groups*T*32, ld) bf16 -> G (groups, T, 8Up, 32) f32 (batch row innermost)."""
+        if self.w_ih_tc is None:
+            # column order of the tcgen05 recurrence: n = dir*4Up + (unit/8)*32 + (unit%8)*4 + gate
+            Up = self.Up
+            w = self.w_ih_f32.view(2, 4, Up // 8, 8, self.I).permute(0, 2, 3, 1, 4).reshape(8 * Up, self.I)
+            self.w_ih_tc = ops.cast_bf16(w.contiguous(), self.ld_in)
+            self.bias_tc = self.bias.view(2, 4, Up // 8, 8).permute(0, 2, 3, 1).reshape(8 * Up).contiguous()
+        G = torch.empty((mrows * 8 * self.Up,), dtype=torch.float32, device=xb.device)
+        ops.gemm(xb, ld, self.w_ih_tc, self.ld_in, mrows, 8 * self.Up, self.I if kdim is None else kdim, G,
+                 mode=ops.EPI_F32_BT, bias=self.bias_tc)
+        return G
+
+    def recurrence_tc(self, G: torch.Tensor, rows: int, T: int) -> torch.Tensor:
+        """Shared-memory / tcgen05 kernel (csrc/lstm_tc.cu): H (groups*T*32, 2Up), rows (group, t, b)."""
+        if self.whh_tc is None:
+            self.whh_tc = ops.pack_whh_tc(self._whh_f32[0], self._whh_f32[1], self.U, self.Up)
+        return ops.blstm_recurrence_tc(G, self.whh_tc, rows, T, self.Up)
+
     def projection(self, H: torch.Tensor, rows_t: int, out: torch.Tensor, *, mode: int, ldo: int, act: int,
-                   batch=1, a_stride=0, M=None, out_stride=0, out_div=None, out_stride_hi=0):
+                   batch=1, a_stride=0, M=None, out_stride=0, out_div=None, out_stride_hi=0, row_map=None):
         """H (rows*T, 2*Up) bf16 -> out (bias and optional tanh fused)."""
         ops.gemm(H, 2 * self.Up, self.w_proj, 2 * self.Up, rows_t if M is None else M, self.hdim, 2 * self.Up, out,
                  mode=mode, ldo=ldo, bias=self.b_proj, act=act, batch=batch, a_stride=a_stride, b_mod=1,
-                 out_stride=out_stride, out_div=out_div, out_stride_hi=out_stride_hi)
+                 out_stride=out_stride, out_div=out_div, out_stride_hi=out_stride_hi, row_map=row_map)
 
 
 def param_key(module: torch.nn.Module):
@@ -135,6 +169,8 @@ class RNNP_packed(torch.nn.Module):
             rows *= s
         x = xs_pack.reshape(rows * T, D).float()
         packs = self.layer_packs()
+        if use_tc_recurrence(rows):
+            return self._forward_tc(x, rows, T, D, packs).reshape(*shape[:-1], packs[-1].hdim)
         xb, ld = ops.cast_bf16(x), ops.round_up(D, 8)
         out = None
         for li, pk in enumerate(packs):
@@ -150,3 +186,29 @@ class RNNP_packed(torch.nn.Module):
                 pk.projection(H, rows * T, xb, mode=ops.EPI_BF16, ldo=ld, act=1)
             del H
         return out.reshape(*shape[:-1], packs[-1].hdim)
+
+    def _forward_tc(self, x, rows, T, D, packs):
+        """Same stack through the tcgen05 recurrence.  The kernels want rows ordered (group, t, b32);
+        this generic entry point re-orders with torch copies (MaskEstimator_v2 produces that order
+        directly and never takes this route)."""
+        groups = (rows + 31) // 32
+        mrows = groups * T * 32
+        xp = torch.zeros((groups * 32, T, D), dtype=torch.float32, device=x.device)
+        xp[:rows] = x.view(rows, T, D)
+        xb = ops.cast_bf16(xp.view(groups, 32, T, D).permute(0, 2, 1, 3).reshape(mrows, D))
+        ld = ops.round_up(D, 8)
+        out = None
+        for li, pk in enumerate(packs):
+            G = pk.input_gemm_bt(xb, ld, mrows)
+            H = pk.recurrence_tc(G, rows, T)
+            del G
+            if li == len(packs) - 1:
+                out = torch.empty((mrows, pk.hdim), dtype=torch.float32, device=x.device)
+                pk.projection(H, mrows, out, mode=ops.EPI_F32, ldo=pk.hdim, act=0)
+            else:
+                ld = ops.round_up(pk.hdim, 8)
+                xb = torch.empty((mrows, ld), dtype=torch.bfloat16, device=x.device)
+                pk.projection(H, mrows, xb, mode=ops.EPI_BF16, ldo=ld, act=1)
+            del H
+        out = out.view(groups, T, 32, -1).permute(0, 2, 1, 3).reshape(groups * 32, T, -1)[:rows]
+        return out.reshape(rows * T, -1)
