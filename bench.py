@@ -47,7 +47,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--meetings-per-gpu", type=int, default=int(os.environ.get("TSSEP_BENCH_MEETINGS", 8)))
+    ap.add_argument("--meetings-per-gpu", type=int, default=int(os.environ.get("TSSEP_BENCH_MEETINGS", 14)))
     ap.add_argument("--seconds", type=float, default=600.0, help="length of every synthetic meeting")
     ap.add_argument("--cpu-sample-seconds", type=float, default=60.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -296,6 +296,7 @@ def run_b200(args):
     # dominant kernel: the BLSTM recurrence (latency bound; expressed against the tensor peak as asked)
     rec = breakdown.get("tssep_blstm_recurrence", {"ms_per_step": 0.0, "launches_per_step": 1})
     rec_rows = M * (1 + 8 + 8 + 2)  # pre_net, birnn0, birnn1, birnn2 (R=2) batch rows
+    rec_cfg = "tanh.approx gates" if os.environ.get("TSSEP_LSTM_FAST_MATH", "1") == "1" else "exp-based gates"
     rec_flops = 2.0 * rec_rows * T * 2 * (4 * 300 * 300)
     rec_tflops = rec_flops / (rec["ms_per_step"] / 1e3) / 1e12 if rec["ms_per_step"] else 0.0
     gemm = breakdown.get("tssep_gemm", {"ms_per_step": 0.0})
@@ -308,6 +309,7 @@ def run_b200(args):
         "peak_source": peaks["source"] + " (sustained)",
         "note": "recurrence is bound by the latency of T dependent steps, not by the tensor pipe",
         "us_per_recurrent_step": rec["ms_per_step"] * 1e3 / (4 * T) if rec["ms_per_step"] else None,
+        "gate_math": rec_cfg,
         "share_of_step": rec["ms_per_step"] / (ms / args.steps),
         "top_kernel_by_time": top,
     }

@@ -32,7 +32,7 @@ def main():
     def run(G, rows, C, fast):
         if a.kernel == "tc":
             return ops.blstm_recurrence_tc(G, wimg, rows, a.frames, Up, fast_math=bool(fast))
-        return run(G, rows, C, fast)
+        return ops.blstm_recurrence(G, whh, rows, a.frames, Up, cluster=C, fast_math=bool(fast))
 
     for rows in a.rows:
         G = torch.randn((rows, a.frames, 8 * Up), device=dev) * 0.3

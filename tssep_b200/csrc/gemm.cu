@@ -21,8 +21,9 @@ namespace tssep {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int kStages = 4;
-constexpr int kGemmThreads = 192;
+constexpr int kMaxStages = 4;
+constexpr int kEpiWarps = 8;  // two sets of four: each set covers the 128 TMEM lanes, the sets split the column chunks
+constexpr int kGemmThreads = 64 + 32 * kEpiWarps;
 constexpr int kTmemCols = 512;
 constexpr int kAccCols = 256;
 
@@ -49,7 +50,7 @@ struct GemmArgs {
   int64_t rm_T;
   int rm_K, rm_Z, rm_P;
   // tiling
-  int bn, m_tiles, n_tiles, k_blocks;
+  int bn, m_tiles, n_tiles, k_blocks, stages;
   int64_t total_tiles;
   // simt only
   const __nv_bfloat16* A;
@@ -300,11 +301,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t a_bytes = BM * BK * 2;
   const uint32_t b_bytes = static_cast<uint32_t>(g.bn) * BK * 2;
   const uint32_t sA = base;
+  const int kStages = g.stages;
   const uint32_t sB = base + kStages * a_bytes;
   const uint32_t sBar = sB + kStages * b_bytes;  // 8-byte aligned (multiples of 1024 before it)
-  const uint32_t full0 = sBar, empty0 = sBar + 8 * kStages, tfull0 = sBar + 16 * kStages,
+  const uint32_t full0 = sBar, empty0 = sBar + 8 * kMaxStages, tfull0 = sBar + 16 * kMaxStages,
                  tempty0 = tfull0 + 16, tptr = tempty0 + 16;
-  const uint32_t sStage = sBar + 128;  // 4 epilogue warps x 32 rows x kStageLd words
+  const uint32_t sStage = sBar + 128;  // kEpiWarps x 32 rows x kStageLd words
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -320,7 +322,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       for (int s = 0; s < 2; ++s) {
         mbar_init(tfull0 + 8 * s, 1);
-        mbar_init(tempty0 + 8 * s, 4);
+        mbar_init(tempty0 + 8 * s, kEpiWarps);
       }
       mbar_fence_init();
     }
@@ -403,11 +405,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_after();
       const uint32_t t0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kAccCols;
       const uint32_t stage = sStage + static_cast<uint32_t>(warp - 2) * (32 * kStageLd * 4);
-      ChunkBias cb = load_chunk_bias(g, z, nt * g.bn, lane);
-      for (int c0 = 0; c0 < g.bn; c0 += 32) {
+      const int cset = (warp - 2) >> 2;  // column chunks are dealt alternately to the two warp sets
+      ChunkBias cb = load_chunk_bias(g, z, nt * g.bn + cset * 32, lane);
+      for (int c0 = cset * 32; c0 < g.bn; c0 += 64) {
         uint32_t v[32];
         tc_ld32(t0 + c0, v);
-        const ChunkBias cb_next = load_chunk_bias(g, z, nt * g.bn + c0 + 32, lane);  // prefetch for the next chunk
+        const ChunkBias cb_next = load_chunk_bias(g, z, nt * g.bn + c0 + 64, lane);  // prefetch for the next chunk
         tc_wait_ld();
         if (m0 < g.M) {
           if (g.mode == EPI_F32_BT) epilogue_bt(g, m0, nt * g.bn + c0, v, cb, stage, lane);
@@ -530,7 +533,11 @@ static int launch_gemm(GemmArgs g, const uint16_t* A, int64_t lda, int64_t a_str
   int dev = 0, sms = 148;
   TSSEP_CUDA(cudaGetDevice(&dev));
   TSSEP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const size_t smem = 1024 + kStages * (BM * BK * 2 + static_cast<size_t>(g.bn) * BK * 2) + 128 + 4 * 32 * kStageLd * 4;
+  const size_t stage_bytes = BM * BK * 2 + static_cast<size_t>(g.bn) * BK * 2;
+  const size_t fixed = 1024 + 128 + kEpiWarps * 32 * kStageLd * 4;
+  g.stages = static_cast<int>(imin64(kMaxStages, (227 * 1024 - fixed) / stage_bytes));
+  TSSEP_REQUIRE(g.stages >= 2, "gemm: tile does not fit shared memory");
+  const size_t smem = fixed + g.stages * stage_bytes;
   TSSEP_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   const int grid = static_cast<int>(imin64(g.total_tiles, sms));
   gemm_tc_kernel<<<grid, kGemmThreads, smem, stream>>>(tmA, tmB, g);

@@ -165,8 +165,6 @@ blstm_rec_kernel(const __grid_constant__ CUtensorMap gmap, const uint4* __restri
       const int t = dir ? T - 1 - s : s;
       int c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0;
       if (do_prof) c0 = clock();
-      // prefetch the next step's input projection into registers; its latency hides in the h wait
-      if (s + 1 < T) load_g(s + 1, g_nxt);
       if (do_prof) c1 = clock();
       const int rb = (s & 1) ^ 1;
       // The batch tiles are independent recurrences: while the new h of one tile travels through
@@ -202,6 +200,8 @@ blstm_rec_kernel(const __grid_constant__ CUtensorMap gmap, const uint4* __restri
             mma_bf16_16816(acc[kt & 3], a[kt], b0, b1);
           }
         }
+        // prefetch the next step's input projection into registers while the tensor pipe drains
+        if (b == 0 && s + 1 < T) load_g(s + 1, g_nxt);
         const float pA0 = (acc[0][0] + acc[1][0]) + (acc[2][0] + acc[3][0]) + g_cur[b][0];  // row r,   col n0
         const float pA1 = (acc[0][1] + acc[1][1]) + (acc[2][1] + acc[3][1]) + g_cur[b][1];  // row r,   col n0+1
         const float pB0 = (acc[0][2] + acc[1][2]) + (acc[2][2] + acc[3][2]) + g_cur[b][2];  // row r+8, col n0
