@@ -147,14 +147,15 @@ int tssep_head_expand_t(const float* small, int64_t Z, int64_t T, int n_blocks, 
 
 /* Persistent cluster kernel: recurrent weights register/SM resident, h exchanged
  * through distributed shared memory, both directions concurrently.
- * G    (rows, T, 2, 4, Up) f32  input projections + both biases, gate order i,f,g,o
+ * G    (rows, T, 2, 4, Up) f32 (g_dtype 0) or bf16 (g_dtype 1): input projections + both biases,
+ *      gate order i,f,g,o
  * Wfrag packed recurrent weights from tssep_pack_whh (2 * Up/4 * Up/16 * 128 u32)
  * H    (rows, T, 2*Up) bf16 out: [h_fwd(Up) | h_bwd(Up)]
  * Up = hidden units rounded up to a multiple of 16 (<= 320); padded units stay 0.
  * cluster: CTAs per cluster (1,2,4,8), 0 = choose.  fast_math: 0 accurate
  * exp-based gates, 1 tanh.approx. */
-int tssep_blstm_recurrence(const float* G, const uint32_t* Wfrag, uint16_t* H, int64_t rows, int64_t T,
-                           int Up, int cluster, int fast_math, tssep_stream_t stream);
+int tssep_blstm_recurrence(const void* G, int g_dtype, const uint32_t* Wfrag, uint16_t* H, int64_t rows,
+                           int64_t T, int Up, int cluster, int fast_math, tssep_stream_t stream);
 
 /* Throughput variant of the same recurrence for many batch rows: one cluster of ceil(Up/64) CTAs
  * per (32 rows, direction), recurrent weights resident in shared memory as UMMA operands,

@@ -51,7 +51,7 @@ _SIGNATURES = {
     "tssep_condition_rows": ([c_i32, c_vp, c_i64, c_vp, c_i64, c_i32, c_i64, c_i32, c_i32, c_vp, c_i64, c_vp], C.c_int),
     "tssep_gemm": ([C.POINTER(GemmDesc), c_vp], C.c_int),
     "tssep_head_expand_t": ([c_vp, c_i64, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp], C.c_int),
-    "tssep_blstm_recurrence": ([c_vp, c_vp, c_vp, c_i64, c_i64, c_i32, c_i32, c_i32, c_vp], C.c_int),
+    "tssep_blstm_recurrence": ([c_vp, c_i32, c_vp, c_vp, c_i64, c_i64, c_i32, c_i32, c_i32, c_vp], C.c_int),
     "tssep_pack_whh": ([c_vp, c_vp, c_i32, c_i32, c_vp, c_vp], C.c_int),
     "tssep_blstm_recurrence_tc": ([c_vp, c_vp, c_vp, c_i64, c_i64, c_i32, c_i32, c_vp], C.c_int),
     "tssep_pack_whh_tc": ([c_vp, c_vp, c_i32, c_i32, c_vp, c_vp], C.c_int),

@@ -52,14 +52,17 @@ constexpr int max_compute_warps(int kt) { return kt >= 13 ? 10 : kMaxWarpsComput
 template <int KT, int NB>
 __global__ void __launch_bounds__(32 * (max_compute_warps(KT) + 1), 1)
 blstm_rec_kernel(const __grid_constant__ CUtensorMap gmap, const uint4* __restrict__ Wfrag,
-                 __nv_bfloat16* __restrict__ H, int rows, int T, int NT, int fast, int* __restrict__ prof) {
+                 __nv_bfloat16* __restrict__ H, int rows, int T, int NT, int fast, int g_bf16,
+                 int* __restrict__ prof) {
   constexpr int Up = 16 * KT;
   constexpr int LDH = Up + 8;          // bf16 elements per h row (+8 keeps ldmatrix conflict free)
   constexpr int n_tiles = Up / 4;      // unit tiles per direction
   constexpr int BR = 8 * NB;           // batch rows per cluster
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const uint32_t sbase = smem_u32(smem_raw);
-  const uint32_t g_stage_bytes = static_cast<uint32_t>(4 * BR * 4 * NT) * 4;  // [gate][b][unit] f32
+  const int ld_u = 4 * ((NT + 1) & ~1);  // units per staged row (even tile count keeps bf16 rows 16-byte multiples)
+  const uint32_t g_elt = g_bf16 ? 2u : 4u;
+  const uint32_t g_stage_bytes = static_cast<uint32_t>(4 * BR * ld_u) * g_elt;  // [gate][b][unit] f32 or bf16
   const uint32_t s_gring = sbase;                                             // kGStages stages
   const uint32_t s_hbuf = s_gring + kGStages * g_stage_bytes;                 // [NB][2][8][LDH] bf16
   constexpr uint32_t h_buf_bytes = 8 * LDH * 2;
@@ -121,7 +124,6 @@ blstm_rec_kernel(const __grid_constant__ CUtensorMap gmap, const uint4* __restri
     // G offsets (floats) inside a ring stage: [gate][BR rows][unit]
     const int gA = upper ? 1 : 0, gB = upper ? 3 : 2;
     const int unit_local = warp * 4 + u;
-    const int ld_u = 4 * NT;
     const int offA = (gA * BR + n0) * ld_u + unit_local;
     const int offB = (gB * BR + n0) * ld_u + unit_local;
     // ldmatrix row address: matrix (lane>>3) covers k offset 8*(lane>>3), row (lane&7)
@@ -151,10 +153,17 @@ blstm_rec_kernel(const __grid_constant__ CUtensorMap gmap, const uint4* __restri
       const uint32_t gp = s_gring + gs * g_stage_bytes;
 #pragma unroll
       for (int b = 0; b < NB; ++b) {
-        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(g[b][0]) : "r"(gp + 4 * (offA + b * 8 * ld_u)));
-        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(g[b][1]) : "r"(gp + 4 * (offA + (b * 8 + 1) * ld_u)));
-        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(g[b][2]) : "r"(gp + 4 * (offB + b * 8 * ld_u)));
-        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(g[b][3]) : "r"(gp + 4 * (offB + (b * 8 + 1) * ld_u)));
+        const int o[4] = {offA + b * 8 * ld_u, offA + (b * 8 + 1) * ld_u, offB + b * 8 * ld_u, offB + (b * 8 + 1) * ld_u};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (g_bf16) {
+            unsigned short h;
+            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h) : "r"(gp + 2 * o[j]));
+            g[b][j] = __uint_as_float(static_cast<uint32_t>(h) << 16);
+          } else {
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(g[b][j]) : "r"(gp + 4 * o[j]));
+          }
+        }
       }
     };
     load_g(0, g_cur);
@@ -305,9 +314,9 @@ __global__ void pack_whh_kernel(const float* __restrict__ w_fwd, const float* __
 
 template <int KT, int NB>
 static int launch_rec(const CUtensorMap& gmap, const uint32_t* Wfrag, uint16_t* H, int64_t rows, int64_t T, int C,
-                      int NT, int fast, int* prof, cudaStream_t stream) {
+                      int NT, int fast, int g_bf16, int* prof, cudaStream_t stream) {
   constexpr int Up = 16 * KT;
-  const size_t smem = static_cast<size_t>(kGStages) * (4 * 8 * NB * 4 * NT) * 4 + NB * 2 * 8 * (Up + 8) * 2 + 16 * NB +
+  const size_t smem = static_cast<size_t>(kGStages) * (4 * 8 * NB * 4 * ((NT + 1) & ~1)) * 4 + NB * 2 * 8 * (Up + 8) * 2 + 16 * NB +
                       16 * kGStages + 128;
   TSSEP_CUDA(cudaFuncSetAttribute(blstm_rec_kernel<KT, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(smem)));
@@ -325,7 +334,7 @@ static int launch_rec(const CUtensorMap& gmap, const uint32_t* Wfrag, uint16_t* 
   cfg.numAttrs = 1;
   TSSEP_CUDA(cudaLaunchKernelEx(&cfg, blstm_rec_kernel<KT, NB>, gmap, reinterpret_cast<const uint4*>(Wfrag),
                                 reinterpret_cast<__nv_bfloat16*>(H), static_cast<int>(rows), static_cast<int>(T), NT,
-                                fast, prof));
+                                fast, g_bf16, prof));
   return check_launch("blstm_rec");
 }
 
@@ -344,9 +353,11 @@ int tssep_pack_whh(const float* whh_fwd, const float* whh_bwd, int U, int Up, ui
   return check_launch("tssep_pack_whh");
 }
 
-int tssep_blstm_recurrence(const float* G, const uint32_t* Wfrag, uint16_t* H, int64_t rows, int64_t T, int Up,
+int tssep_blstm_recurrence(const void* G, int g_dtype, const uint32_t* Wfrag, uint16_t* H, int64_t rows, int64_t T, int Up,
                            int cluster, int fast_math, tssep_stream_t stream) {
   TSSEP_REQUIRE(G && Wfrag && H, "tssep_blstm_recurrence: null pointer");
+  TSSEP_REQUIRE(g_dtype == 0 || g_dtype == 1, "tssep_blstm_recurrence: g_dtype must be 0 (f32) or 1 (bf16)");
+  const int g_bf16 = g_dtype;
   TSSEP_REQUIRE(Up >= 16 && Up % 16 == 0 && Up <= 320, "tssep_blstm_recurrence: Up must be a multiple of 16 in [16, 320], got %d", Up);
   TSSEP_REQUIRE(rows >= 0 && T >= 0 && T < (1ll << 31) && (rows + 7) / 8 <= 65535, "tssep_blstm_recurrence: bad extent");
   TSSEP_REQUIRE((reinterpret_cast<uintptr_t>(G) & 15) == 0 && (reinterpret_cast<uintptr_t>(H) & 7) == 0,
@@ -374,10 +385,12 @@ int tssep_blstm_recurrence(const float* G, const uint32_t* Wfrag, uint16_t* H, i
   CUtensorMap gmap;
   const cuuint64_t up = static_cast<cuuint64_t>(Up);
   cuuint64_t dims[5] = {up, static_cast<cuuint64_t>(rows), 4, 2, static_cast<cuuint64_t>(T)};
-  cuuint64_t strides[4] = {static_cast<cuuint64_t>(T) * 8 * up * 4, up * 4, 4 * up * 4, 8 * up * 4};
-  cuuint32_t box[5] = {static_cast<cuuint32_t>(4 * NT), static_cast<cuuint32_t>(8 * NB), 4, 1, 1};
+  const cuuint64_t esz = g_bf16 ? 2 : 4;
+  cuuint64_t strides[4] = {static_cast<cuuint64_t>(T) * 8 * up * esz, up * esz, 4 * up * esz, 8 * up * esz};
+  cuuint32_t box[5] = {static_cast<cuuint32_t>(4 * ((NT + 1) & ~1)), static_cast<cuuint32_t>(8 * NB), 4, 1, 1};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = enc(&gmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(G), dims, strides, box, estr,
+  CUresult r = enc(&gmap, g_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5,
+                   const_cast<void*>(G), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   TSSEP_REQUIRE(r == CUDA_SUCCESS, "tssep_blstm_recurrence: cuTensorMapEncodeTiled failed with code %d", static_cast<int>(r));
@@ -389,8 +402,8 @@ int tssep_blstm_recurrence(const float* G, const uint32_t* Wfrag, uint16_t* H, i
   switch (Up / 16) {
 #define TSSEP_CASE(kt)                                                                                  \
   case kt:                                                                                              \
-    return NB == 2 ? launch_rec<kt, 2>(gmap, Wfrag, H, rows, T, C, NT, fast_math & 1, prof, s)          \
-                   : launch_rec<kt, 1>(gmap, Wfrag, H, rows, T, C, NT, fast_math & 1, prof, s);
+    return NB == 2 ? launch_rec<kt, 2>(gmap, Wfrag, H, rows, T, C, NT, fast_math & 1, g_bf16, prof, s)          \
+                   : launch_rec<kt, 1>(gmap, Wfrag, H, rows, T, C, NT, fast_math & 1, g_bf16, prof, s);
     TSSEP_CASE(1) TSSEP_CASE(2) TSSEP_CASE(3) TSSEP_CASE(4) TSSEP_CASE(5) TSSEP_CASE(6) TSSEP_CASE(7) TSSEP_CASE(8)
     TSSEP_CASE(9) TSSEP_CASE(10) TSSEP_CASE(11) TSSEP_CASE(12) TSSEP_CASE(13) TSSEP_CASE(14) TSSEP_CASE(15)
     TSSEP_CASE(16) TSSEP_CASE(17) TSSEP_CASE(18) TSSEP_CASE(19) TSSEP_CASE(20)

@@ -314,20 +314,22 @@ class MaskEstimator_v2(Configurable, torch.nn.Module):
         else:
             # ---- latency path: conditioning folded into birnn0's input projection ----------------------
             bias_k = torch.empty((B * K, 8 * Up), dtype=torch.float32, device=dev)
-            G = torch.empty((B * K * T, 8 * Up), dtype=torch.float32, device=dev)
+            gd = ops.g_dtype()
+            gmode = ops.EPI_BF16 if gd == torch.bfloat16 else ops.EPI_F32
+            G = torch.empty((B * K * T, 8 * Up), dtype=gd, device=dev)
             if self.combination == "mul":
                 ldk = ops.round_up(F, 8)
                 Wk = torch.empty((B * K * 8 * Up, ldk), dtype=torch.bfloat16, device=dev)
                 _lib.call("tssep_fold_embedding", 0, pk0.w_ih_f32.data_ptr(), pk0.I, pk0.bias.data_ptr(),
                           e.data_ptr(), B * K, 8 * Up, F, A, Wk.data_ptr(), ldk, bias_k.data_ptr(), stream)
-                ops.gemm(xb, ld, Wk, ldk, T, 8 * Up, F, G, mode=ops.EPI_F32, ldo=8 * Up, batch=B * K,
+                ops.gemm(xb, ld, Wk, ldk, T, 8 * Up, F, G, mode=gmode, ldo=8 * Up, batch=B * K,
                          a_stride=T * ld, a_div=K, b_stride=8 * Up * ldk, bias=bias_k, bias_stride=8 * Up,
                          out_stride=T * 8 * Up)
                 del Wk
             else:  # cat
                 _lib.call("tssep_fold_embedding", 1, pk0.w_ih_f32.data_ptr(), pk0.I, pk0.bias.data_ptr(),
                           e.data_ptr(), B * K, 8 * Up, F, A, None, 0, bias_k.data_ptr(), stream)
-                ops.gemm(xb, ld, pk0.w_ih, pk0.ld_in, T, 8 * Up, F, G, mode=ops.EPI_F32, ldo=8 * Up, batch=B * K,
+                ops.gemm(xb, ld, pk0.w_ih, pk0.ld_in, T, 8 * Up, F, G, mode=gmode, ldo=8 * Up, batch=B * K,
                          a_stride=T * ld, a_div=K, b_stride=0, bias=bias_k, bias_stride=8 * Up,
                          out_stride=T * 8 * Up)
         del xb
@@ -341,8 +343,10 @@ class MaskEstimator_v2(Configurable, torch.nn.Module):
                 if tsv_last:
                     rot = self._rotated_input_weights(pk, K, R)
                     rows = B * R
-                    G = torch.empty((rows * T, 8 * pk.Up), dtype=torch.float32, device=dev)
-                    ops.gemm(y, y_ld, rot["w"], rot["ld"], T, 8 * pk.Up, K * P, G, mode=ops.EPI_F32, ldo=8 * pk.Up,
+                    gd = ops.g_dtype()
+                    G = torch.empty((rows * T, 8 * pk.Up), dtype=gd, device=dev)
+                    ops.gemm(y, y_ld, rot["w"], rot["ld"], T, 8 * pk.Up, K * P, G,
+                             mode=ops.EPI_BF16 if gd == torch.bfloat16 else ops.EPI_F32, ldo=8 * pk.Up,
                              batch=rows, a_stride=T * y_ld, a_div=R, b_stride=8 * pk.Up * rot["ld"], b_mod=R,
                              bias=pk.bias, bias_stride=0, out_stride=T * 8 * pk.Up)
                 else:

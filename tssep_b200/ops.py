@@ -19,6 +19,12 @@ def round_up(x: int, m: int) -> int:
     return (x + m - 1) // m * m
 
 
+def g_dtype() -> torch.dtype:
+    """Storage type of the input projections G between the GEMM and the recurrence
+    (TSSEP_G_DTYPE=f32|bf16).  bf16 halves the traffic of the output-bound projection GEMMs."""
+    return torch.bfloat16 if os.environ.get("TSSEP_G_DTYPE", "f32") == "bf16" else torch.float32
+
+
 def _gemm_impl() -> int:
     return 1 if os.environ.get("TSSEP_GEMM_IMPL", "tcgen05") == "simt" else 0
 
@@ -65,14 +71,15 @@ def pack_whh(w_fwd: torch.Tensor, w_bwd: torch.Tensor, U: int, Up: int) -> torch
 
 def blstm_recurrence(G: torch.Tensor, wfrag: torch.Tensor, rows: int, T: int, Up: int, cluster: int = None,
                      fast_math: bool = None) -> torch.Tensor:
-    """G (rows, T, 2, 4, Up) f32 -> H (rows, T, 2*Up) bf16."""
+    """G (rows, T, 2, 4, Up) f32 or bf16 -> H (rows, T, 2*Up) bf16."""
     _lib.require_cuda(G, wfrag)
     if cluster is None:
         cluster = int(os.environ.get("TSSEP_LSTM_CLUSTER", "0"))
     if fast_math is None:
         fast_math = os.environ.get("TSSEP_LSTM_FAST_MATH", "1") == "1"
     H = torch.empty((rows, T, 2 * Up), dtype=torch.bfloat16, device=G.device)
-    _lib.call("tssep_blstm_recurrence", G.data_ptr(), wfrag.data_ptr(), H.data_ptr(), rows, T, Up, cluster,
+    _lib.call("tssep_blstm_recurrence", G.data_ptr(), int(G.dtype == torch.bfloat16), wfrag.data_ptr(), H.data_ptr(),
+              rows, T, Up, cluster,
               int(fast_math), _lib.stream_of(G))
     return H
 

@@ -68,9 +68,10 @@ class LayerPack:
     # -- the three stages ------------------------------------------------------
     def input_gemm(self, xb: torch.Tensor, ld: int, rows_t: int) -> torch.Tensor:
         """xb (rows*T, ld) bf16 -> G (rows*T, 8*Up) f32."""
-        G = torch.empty((rows_t, 8 * self.Up), dtype=torch.float32, device=xb.device)
-        ops.gemm(xb, ld, self.w_ih, self.ld_in, rows_t, 8 * self.Up, self.I, G, mode=ops.EPI_F32, ldo=8 * self.Up,
-                 bias=self.bias)
+        gd = ops.g_dtype()
+        G = torch.empty((rows_t, 8 * self.Up), dtype=gd, device=xb.device)
+        ops.gemm(xb, ld, self.w_ih, self.ld_in, rows_t, 8 * self.Up, self.I, G,
+                 mode=ops.EPI_BF16 if gd == torch.bfloat16 else ops.EPI_F32, ldo=8 * self.Up, bias=self.bias)
         return G
 
     def recurrence(self, G: torch.Tensor, rows: int, T: int) -> torch.Tensor:
