@@ -213,45 +213,94 @@ __device__ __forceinline__ void epilogue_coalesced(const GemmArgs& g, int z, int
   } else {
     const int64_t zoff = static_cast<int64_t>(z / g.out_div) * g.out_stride_hi + static_cast<int64_t>(z % g.out_div) * g.out_stride;
     const int sub = lane >> 3, c4 = (lane & 7) * 4;  // 4 rows per pass, 8 lanes x 4 columns per row
+    const uint32_t lds0 = stage + (sub * kStageLd + c4) * 4;
+    // fast path: a full 32 x 32 block with vector-aligned rows -> per pass one LDS.128, four FMAs, one vector store
+    const bool full = nvalid == 32 && rows_left >= 32 && g.mode != EPI_BF16_ROWMAP;
+    if (full && g.mode == EPI_F32 && ((reinterpret_cast<uintptr_t>(g.out) | static_cast<uintptr_t>(zoff * 4) |
+                                       static_cast<uintptr_t>(g.ldo * 4)) & 15) == 0) {
+      float* o = static_cast<float*>(g.out) + zoff + (m0 + sub) * g.ldo + n0 + c4;
+      const int64_t step = 4 * g.ldo;
 #pragma unroll
-    for (int pass = 0; pass < 8; ++pass) {
-      const int r = pass * 4 + sub;
-      float x[4];
-      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                   : "=f"(x[0]), "=f"(x[1]), "=f"(x[2]), "=f"(x[3])
-                   : "r"(stage + (r * kStageLd + c4) * 4));
-#pragma unroll
-      for (int j = 0; j < 4; ++j) x[j] = apply_act(fmaf(g.alpha, x[j], cb.v[j]), g.act);
-      bool row_ok = r < rows_left;
-      int64_t off = zoff + (m0 + r) * g.ldo + n0 + c4;
-      if (g.mode == EPI_BF16_ROWMAP) {
-        // rows are ordered (group, t, b): scatter to out[(item * T + t) * ldo + spk * P + n], z = item * K + spk
-        const int64_t row = m0 + r;
-        const int64_t gt = row >> 5;
-        const int64_t grp = gt / g.rm_T, t = gt - grp * g.rm_T;
-        const int64_t zz = grp * 32 + (row & 31);
-        row_ok = row_ok && zz < g.rm_Z;
-        const int64_t item = zz / g.rm_K, spk = zz - item * g.rm_K;
-        off = (item * g.rm_T + t) * g.ldo + spk * g.rm_P + n0 + c4;
+      for (int pass = 0; pass < 8; ++pass) {
+        float4 x;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w)
+                     : "r"(lds0 + pass * 4 * kStageLd * 4));
+        x.x = fmaf(g.alpha, x.x, cb.v[0]);
+        x.y = fmaf(g.alpha, x.y, cb.v[1]);
+        x.z = fmaf(g.alpha, x.z, cb.v[2]);
+        x.w = fmaf(g.alpha, x.w, cb.v[3]);
+        if (g.act == 1) {
+          x.x = tanh_acc(x.x);
+          x.y = tanh_acc(x.y);
+          x.z = tanh_acc(x.z);
+          x.w = tanh_acc(x.w);
+        }
+        *reinterpret_cast<float4*>(o + pass * step) = x;
       }
-      if (row_ok && c4 < nvalid) {
-        if (g.mode == EPI_F32) {
-          float* o = static_cast<float*>(g.out) + off;
-          if (c4 + 4 <= nvalid && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
-            *reinterpret_cast<float4*>(o) = make_float4(x[0], x[1], x[2], x[3]);
-          } else {
+    } else if (full && g.mode == EPI_BF16 && ((reinterpret_cast<uintptr_t>(g.out) | static_cast<uintptr_t>(zoff * 2) |
+                                               static_cast<uintptr_t>(g.ldo * 2)) & 7) == 0) {
+      __nv_bfloat16* o = static_cast<__nv_bfloat16*>(g.out) + zoff + (m0 + sub) * g.ldo + n0 + c4;
+      const int64_t step = 4 * g.ldo;
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (c4 + j < nvalid) o[j] = x[j];
-          }
-        } else {
-          __nv_bfloat16* o = static_cast<__nv_bfloat16*>(g.out) + off;
-          if (c4 + 4 <= nvalid && (reinterpret_cast<uintptr_t>(o) & 7) == 0) {
-            *reinterpret_cast<uint2*>(o) = make_uint2(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]));
-          } else {
+      for (int pass = 0; pass < 8; ++pass) {
+        float4 x;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w)
+                     : "r"(lds0 + pass * 4 * kStageLd * 4));
+        x.x = fmaf(g.alpha, x.x, cb.v[0]);
+        x.y = fmaf(g.alpha, x.y, cb.v[1]);
+        x.z = fmaf(g.alpha, x.z, cb.v[2]);
+        x.w = fmaf(g.alpha, x.w, cb.v[3]);
+        if (g.act == 1) {
+          x.x = tanh_acc(x.x);
+          x.y = tanh_acc(x.y);
+          x.z = tanh_acc(x.z);
+          x.w = tanh_acc(x.w);
+        }
+        *reinterpret_cast<uint2*>(o + pass * step) = make_uint2(pack_bf16x2(x.x, x.y), pack_bf16x2(x.z, x.w));
+      }
+    } else {
+#pragma unroll 1
+      for (int pass = 0; pass < 8; ++pass) {
+        const int r = pass * 4 + sub;
+        float x[4];
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(x[0]), "=f"(x[1]), "=f"(x[2]), "=f"(x[3])
+                     : "r"(stage + (r * kStageLd + c4) * 4));
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (c4 + j < nvalid) o[j] = __float2bfloat16_rn(x[j]);
+        for (int j = 0; j < 4; ++j) x[j] = apply_act(fmaf(g.alpha, x[j], cb.v[j]), g.act);
+        bool row_ok = r < rows_left;
+        int64_t off = zoff + (m0 + r) * g.ldo + n0 + c4;
+        if (g.mode == EPI_BF16_ROWMAP) {
+          // rows are ordered (group, t, b): scatter to out[(item * T + t) * ldo + spk * P + n], z = item * K + spk
+          const int64_t row = m0 + r;
+          const int64_t gt = row >> 5;
+          const int64_t grp = gt / g.rm_T, t = gt - grp * g.rm_T;
+          const int64_t zz = grp * 32 + (row & 31);
+          row_ok = row_ok && zz < g.rm_Z;
+          const int64_t item = zz / g.rm_K, spk = zz - item * g.rm_K;
+          off = (item * g.rm_T + t) * g.ldo + spk * g.rm_P + n0 + c4;
+        }
+        if (row_ok && c4 < nvalid) {
+          if (g.mode == EPI_F32) {
+            float* o = static_cast<float*>(g.out) + off;
+            if (c4 + 4 <= nvalid && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+              *reinterpret_cast<float4*>(o) = make_float4(x[0], x[1], x[2], x[3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (c4 + j < nvalid) o[j] = x[j];
+            }
+          } else {
+            __nv_bfloat16* o = static_cast<__nv_bfloat16*>(g.out) + off;
+            if (c4 + 4 <= nvalid && (reinterpret_cast<uintptr_t>(o) & 7) == 0) {
+              *reinterpret_cast<uint2*>(o) = make_uint2(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (c4 + j < nvalid) o[j] = __float2bfloat16_rn(x[j]);
+            }
           }
         }
       }
