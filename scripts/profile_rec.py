@@ -32,7 +32,10 @@ def main():
     def run(G, rows, C, fast):
         if a.kernel == "tc":
             return ops.blstm_recurrence_tc(G, wimg, rows, a.frames, Up, fast_math=bool(fast))
-        return ops.blstm_recurrence(G, whh, rows, a.frames, Up, cluster=C, fast_math=bool(fast))
+        H = torch.empty((rows, a.frames, 2 * Up), dtype=torch.bfloat16, device=G.device)
+        _lib.call("tssep_blstm_recurrence", G.data_ptr(), 0, whh.data_ptr(), H.data_ptr(), rows, a.frames, Up, C, int(fast),
+                  _lib.stream_of(G))
+        return H
 
     for rows in a.rows:
         G = torch.randn((rows, a.frames, 8 * Up), device=dev) * 0.3

@@ -219,7 +219,7 @@ blstm_rec_kernel(const __grid_constant__ CUtensorMap gmap, const uint4* __restri
 
         // lower half-warp holds (i, g), upper half-warp holds (f, o) of unit u, columns n0, n0+1
         float sA0, sA1, sB0, sB1;
-        if (fast) {
+        if (fast & 1) {
           sA0 = fmaf(0.5f, tanh_fast(0.5f * pA0), 0.5f);
           sA1 = fmaf(0.5f, tanh_fast(0.5f * pA1), 0.5f);
           sB0 = upper ? fmaf(0.5f, tanh_fast(0.5f * pB0), 0.5f) : tanh_fast(pB0);
@@ -242,7 +242,7 @@ blstm_rec_kernel(const __grid_constant__ CUtensorMap gmap, const uint4* __restri
         const float inew = upper ? x1 : ig0;
         const float ogate = upper ? sB1 : x2;
         c_state[b] = fmaf(fgate, c_state[b], inew);
-        const float hval = ogate * (fast ? tanh_fast(c_state[b]) : tanh_acc(c_state[b]));
+        const float hval = ogate * ((fast & 1) ? tanh_fast(c_state[b]) : tanh_acc(c_state[b]));
 
         // transpose: lane (nn, dg) gathers units 0..3 of batch column nn
         const float v0 = __shfl_sync(0xffffffffu, hval, src_base + 0);
@@ -402,8 +402,8 @@ int tssep_blstm_recurrence(const void* G, int g_dtype, const uint32_t* Wfrag, ui
   switch (Up / 16) {
 #define TSSEP_CASE(kt)                                                                                  \
   case kt:                                                                                              \
-    return NB == 2 ? launch_rec<kt, 2>(gmap, Wfrag, H, rows, T, C, NT, fast_math & 1, g_bf16, prof, s)          \
-                   : launch_rec<kt, 1>(gmap, Wfrag, H, rows, T, C, NT, fast_math & 1, g_bf16, prof, s);
+    return NB == 2 ? launch_rec<kt, 2>(gmap, Wfrag, H, rows, T, C, NT, fast_math, g_bf16, prof, s)          \
+                   : launch_rec<kt, 1>(gmap, Wfrag, H, rows, T, C, NT, fast_math, g_bf16, prof, s);
     TSSEP_CASE(1) TSSEP_CASE(2) TSSEP_CASE(3) TSSEP_CASE(4) TSSEP_CASE(5) TSSEP_CASE(6) TSSEP_CASE(7) TSSEP_CASE(8)
     TSSEP_CASE(9) TSSEP_CASE(10) TSSEP_CASE(11) TSSEP_CASE(12) TSSEP_CASE(13) TSSEP_CASE(14) TSSEP_CASE(15)
     TSSEP_CASE(16) TSSEP_CASE(17) TSSEP_CASE(18) TSSEP_CASE(19) TSSEP_CASE(20)
