@@ -371,9 +371,17 @@ int tssep_blstm_recurrence(const void* G, int g_dtype, const uint32_t* Wfrag, ui
   }
   TSSEP_REQUIRE(C == 1 || C == 2 || C == 4 || C == 8, "tssep_blstm_recurrence: cluster must be 0, 1, 2, 4 or 8");
   const int NT = (tiles + C - 1) / C;
-  // two batch tiles per cluster (interleaved, so one tile's DSMEM hop hides behind the other's math)
-  // as soon as there is more than one tile of rows; TSSEP_LSTM_NB overrides
-  int NB = rows > 8 ? 2 : 1;
+  // One batch tile (8 rows) per cluster has the lowest step latency (1.2 us vs 1.7 us measured at U=300) but
+  // only ~15 clusters of 8 CTAs are co-resident on 148 SMs; when the tiles of both directions do not fit in
+  // one wave, two tiles are interleaved per cluster (one tile's DSMEM hop hides behind the other's math).
+  int max_clusters = 148 / C;
+  {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess)
+      max_clusters = sms / C;
+    if (C == 8) max_clusters -= 3;  // GPC boundaries: 15 clusters of 8 were measured co-resident on B200
+  }
+  int NB = 2 * ((rows + 7) / 8) <= max_clusters ? 1 : 2;
   if (const char* e = getenv("TSSEP_LSTM_NB")) NB = atoi(e) == 2 ? 2 : 1;
   TSSEP_REQUIRE(NT <= max_compute_warps(Up / 16), "tssep_blstm_recurrence: %d unit tiles per CTA exceed %d (raise cluster)",
                 NT, max_compute_warps(Up / 16));
