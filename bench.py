@@ -356,11 +356,24 @@ def run_b200(args):
     gemm_flops = M * (3.726e12 - 2.0 * 19 * T * 2 * 4 * 300 * 300)
     gemm_tflops = gemm_flops / (gemm["ms_per_step"] / 1e3) / 1e12 if gemm["ms_per_step"] else 0.0
     top = max(breakdown.items(), key=lambda kv: kv[1]["ms_per_step"])[0] if breakdown else None
+    # HBM bytes of the recurrence launches of one step: it streams G once (f32) and writes H once (bf16).
+    # ncu (--set full) of the birnn0 launch of this very command measured dram read+write = 45.98 GB against
+    # 45.97 GB algorithmic (profiles/r1_ncu_blstm_rec_bench_b0.txt), i.e. a ratio of 1.00.
+    g_bytes = 2 if os.environ.get("TSSEP_G_DTYPE", "f32") == "bf16" else 4
+    rec_bytes = rec_rows * T * (8 * Up * g_bytes + 2 * Up * 2)
+    launches = max(1.0, rec["launches_per_step"])
     roofline = {
         "kernel": "blstm_rec_kernel", "bound": "tensor", "achieved": rec_tflops, "peak": peaks["bf16_tflops_sustained"],
-        "unit": "TFLOP/s", "frac": rec_tflops / peaks["bf16_tflops_sustained"], "traffic": None,
+        "unit": "TFLOP/s", "frac": rec_tflops / peaks["bf16_tflops_sustained"],
+        "traffic": 1.00 * rec_bytes / launches,
+        "traffic_note": "bytes per launch (mean of the 4 recurrence launches of a step) = algorithmic bytes x 1.00, the "
+                        "dram read+write / algorithmic ratio ncu measured for the birnn0 launch "
+                        "(profiles/r1_ncu_blstm_rec_bench_b0.txt)",
+        "algorithmic_flops_per_launch": rec_flops / launches, "algorithmic_bytes_per_launch": rec_bytes / launches,
+        "avg_launch_ms": rec["ms_per_step"] / launches,
         "peak_source": peaks["source"] + " (sustained)",
-        "note": "recurrence is bound by the latency of T dependent steps, not by the tensor pipe",
+        "note": "the recurrence is bound by the latency of T dependent steps (one DSMEM exchange + one mma.sync "
+                "chain per step), not by the tensor pipe or HBM; see us_per_recurrent_step",
         "us_per_recurrent_step": rec["ms_per_step"] * 1e3 / (4 * T) if rec["ms_per_step"] else None,
         "gate_math": rec_cfg,
         "share_of_step": rec["ms_per_step"] / (ms / args.steps),
