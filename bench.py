@@ -47,7 +47,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--meetings-per-gpu", type=int, default=int(os.environ.get("TSSEP_BENCH_MEETINGS", 14)))
+    ap.add_argument("--meetings-per-gpu", type=int, default=int(os.environ.get("TSSEP_BENCH_MEETINGS", 28)))
     ap.add_argument("--seconds", type=float, default=600.0, help="length of every synthetic meeting")
     ap.add_argument("--streams", type=int, default=int(os.environ.get("TSSEP_BENCH_STREAMS", 1)),
                     help="meeting groups processed concurrently on separate CUDA streams")
@@ -58,13 +58,35 @@ def parse_args():
 
 
 # ----------------------------------------------------------------------------------------------
-def synth_meeting(seed: int, num_samples: int, aux_size=513):
-    """tssep/data.py:75-139 generator at arbitrary length (product-side restatement)."""
+def synth_meeting(seed: int, num_samples: int, aux_size=513, device=None):
+    """tssep/data.py:75-139 generator at arbitrary length (product-side restatement).  With ``device`` the
+    24 float64 sinusoids are evaluated on the GPU (same formula and RNG draws; the CPU version needs ~4 s per
+    10-min meeting), everything else follows tssep_b200.data.DummyReader.get_example."""
     from tssep_b200.data import DummyReader
 
-    ex = DummyReader(sample_rate=SAMPLE_RATE, aux_size=aux_size).get_example(seed, num_samples=num_samples,
-                                                                           with_targets=False)
-    return ex["audio_data"]["observation"][0].astype(np.float32), ex["auxInput"]
+    reader = DummyReader(sample_rate=SAMPLE_RATE, aux_size=aux_size)
+    if device is None:
+        ex = reader.get_example(seed, num_samples=num_samples, with_targets=False)
+        return ex["audio_data"]["observation"][0].astype(np.float32), ex["auxInput"]
+    K = reader.num_speakers
+    rng = np.random.RandomState(seed)
+    frequency = rng.randint(100, 7000, size=(3, K))
+    vad = torch.as_tensor(reader._get_vad(num_samples, K), device=device)
+    time_ax = torch.arange(num_samples, device=device, dtype=torch.float64) / SAMPLE_RATE
+    obs = torch.zeros(num_samples, dtype=torch.float32, device=device)
+    for k in range(K):
+        acc = torch.sin(2 * np.pi * float(frequency[0, k]) * time_ax)
+        acc += torch.sin(2 * np.pi * float(frequency[1, k]) * time_ax)
+        acc += torch.sin(2 * np.pi * float(frequency[2, k]) * time_ax)
+        obs += acc.to(torch.float32) * vad[k]
+    noise = rng.rand(1, num_samples).astype(np.float32)
+    obs = obs.cpu().numpy() + noise[0]
+    aux = np.zeros((K, aux_size), dtype=np.float32)
+    for spk, fs in enumerate(frequency.T):
+        for f in fs:
+            f = (f * aux_size) // 7001
+            aux[spk, f:f + 2] = 1
+    return obs, aux
 
 
 class ClockSampler:
@@ -212,7 +234,16 @@ def run_b200(args):
     M = args.meetings_per_gpu
     n = int(args.seconds * SAMPLE_RATE)
     model = build_product_model(dev)
-    meetings = [synth_meeting(rank * M + i, n) for i in range(M)]
+    # memory guard: the step keeps every output of M meetings resident (about 4.5 GB per 10-min meeting incl.
+    # intermediates); shrink M instead of failing on a smaller / busier device
+    free_b, _ = torch.cuda.mem_get_info(dev)
+    per_meeting = 5.2e9 * (args.seconds / 600.0)
+    M = max(1, min(M, int(0.9 * free_b / per_meeting)))
+    if world > 1:
+        mt = torch.tensor([M], device=dev)
+        torch.distributed.all_reduce(mt, op=torch.distributed.ReduceOp.MIN)
+        M = int(mt.item())
+    meetings = [synth_meeting(rank * M + i, n, device=dev) for i in range(M)]
     obs_host = torch.tensor(np.stack([m[0] for m in meetings])).pin_memory()
     aux_host = torch.tensor(np.stack([m[1] for m in meetings])).pin_memory()
     obs_dev, aux_dev = obs_host.to(dev), aux_host.to(dev)
@@ -293,7 +324,10 @@ def run_b200(args):
     copy_stream = torch.cuda.Stream(device=dev)   # device -> host
     in_stream = torch.cuda.Stream(device=dev)     # host -> device (separate, or it would queue behind the D2H)
     main_stream = torch.cuda.current_stream(dev)
-    time_hosts = [time_host, torch.empty_like(time_host).pin_memory()]
+    try:
+        time_hosts = [time_host, torch.empty_like(time_host).pin_memory()]
+    except RuntimeError:  # not enough pinnable host memory for double buffering
+        time_hosts = [time_host, time_host]
 
     def e2e_step(i):
         ev_in, ev_done = torch.cuda.Event(), torch.cuda.Event()
@@ -359,7 +393,7 @@ def run_b200(args):
     # HBM bytes of the recurrence launches of one step: it streams G once (f32) and writes H once (bf16).
     # ncu (--set full) of the birnn0 launch of this very command measured dram read+write = 45.98 GB against
     # 45.97 GB algorithmic (profiles/r1_ncu_blstm_rec_bench_b0.txt), i.e. a ratio of 1.00.
-    g_bytes = 2 if os.environ.get("TSSEP_G_DTYPE", "f32") == "bf16" else 4
+    g_bytes = 4 if os.environ.get("TSSEP_G_DTYPE", "bf16") == "f32" else 2
     rec_bytes = rec_rows * T * (8 * Up * g_bytes + 2 * Up * 2)
     launches = max(1.0, rec["launches_per_step"])
     roofline = {

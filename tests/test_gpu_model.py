@@ -135,10 +135,12 @@ def test_mask_estimator_variants_batched(cuda, monkeypatch, kw, kernel):
     assert (got.embedding.cpu() - want.embedding).abs().max().item() == 0.0
 
 
-@pytest.mark.parametrize("kernel", ["regs", "tc"])
-def test_full_size_dims_short_meeting(cuda, monkeypatch, kernel):
-    """C3 dims (U=300, P=320, mul, ts_vad=8, R=2) on 20 s of audio; separate() with two meetings."""
+@pytest.mark.parametrize("kernel,g_dtype", [("regs", "bf16"), ("regs", "f32"), ("tc", "bf16")])
+def test_full_size_dims_short_meeting(cuda, monkeypatch, kernel, g_dtype):
+    """C3 dims (U=300, P=320, mul, ts_vad=8, R=2) on 20 s of audio; separate() with two meetings; both
+    recurrence kernels and both storage types of the input projections."""
     monkeypatch.setenv("TSSEP_LSTM_KERNEL", kernel)
+    monkeypatch.setenv("TSSEP_G_DTYPE", g_dtype)
     ref, me = make_pair(_me_kwargs(units=300, projs=320))
     model = _product_model(me)
     tables = O.MFCCTables()
