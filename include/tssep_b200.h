@@ -112,14 +112,15 @@ int tssep_condition_rows(int mode, const uint16_t* xs, int64_t ldx, const float*
  *   logit[(p * M + m) * row_len + f] = v and mask[...] = sigmoid(v); either may be NULL.
  *   The caller folds the speaker rotation / trial mean into B and bias (K = trials*projs)
  *   and the un-permutation into plane_map.
- * mode TSSEP_EPI_F32_BT (input of tssep_blstm_recurrence_tc): rows are ordered (group, t, b32), b = m % 32;
+ * mode TSSEP_EPI_F32_BT / TSSEP_EPI_BF16_BT (input of tssep_blstm_recurrence_tc, f32 or bf16 elements): rows are ordered (group, t, b32), b = m % 32;
  *   out[((m/32)*N + (n/32)*32)*32 + (b/4)*128 + (n%32)*4 + b%4]: per (group, t) and per block of 32 columns
  *   a 4 KiB tile [b/4][column][b%4]  (batch == 1, M and N multiples of 32).
  * mode TSSEP_EPI_BF16_ROWMAP (speaker-concat rearrange net.py:606-612 after the tcgen05 recurrence):
  *   rows ordered (group, t, b32), z = group * 32 + b, item = z / rm_K, spk = z % rm_K; rows with
  *   z >= rm_Z are dropped; out[(item * rm_T + t) * ldo + spk * rm_P + n] as bf16.
  * impl: 0 = tcgen05 (product path), 1 = plain SIMT kernel (debug / bisecting only). */
-enum { TSSEP_EPI_F32 = 0, TSSEP_EPI_BF16 = 1, TSSEP_EPI_HEAD = 2, TSSEP_EPI_F32_BT = 3, TSSEP_EPI_BF16_ROWMAP = 4 };
+enum { TSSEP_EPI_F32 = 0, TSSEP_EPI_BF16 = 1, TSSEP_EPI_HEAD = 2, TSSEP_EPI_F32_BT = 3, TSSEP_EPI_BF16_ROWMAP = 4,
+       TSSEP_EPI_BF16_BT = 5 };
 
 typedef struct tssep_gemm_desc {
   const uint16_t* A; int64_t lda; int64_t a_stride; int32_t a_div;
@@ -160,12 +161,13 @@ int tssep_blstm_recurrence(const void* G, int g_dtype, const uint32_t* Wfrag, ui
 /* Throughput variant of the same recurrence for many batch rows: one cluster of ceil(Up/64) CTAs
  * per (32 rows, direction), recurrent weights resident in shared memory as UMMA operands,
  * tcgen05.mma (M=128, N=32, K=16) into TMEM, gates applied by 4 epilogue warps out of TMEM.
- * G f32 in the tile layout written by tssep_gemm mode TSSEP_EPI_F32_BT with N = 8*Up columns ordered
+ * G f32 (g_dtype 0) or bf16 (g_dtype 1) in the tile layout written by tssep_gemm mode TSSEP_EPI_F32_BT /
+ * TSSEP_EPI_BF16_BT with N = 8*Up columns ordered
  * n = dir*4*Up + (unit/8)*32 + (unit%8)*4 + gate (the caller packs W_ih rows in that order),
  * groups = ceil(rows / 32); H (groups, T, 32, 2*Up) bf16, i.e. rows ordered
  * (group, t, b).  Wimg from tssep_pack_whh_tc (2 * C * 2 * C * 16 KiB, C = ceil(Up/64)); Up <= 512. */
-int tssep_blstm_recurrence_tc(const float* G, const uint16_t* Wimg, uint16_t* H, int64_t rows, int64_t T,
-                              int Up, int fast_math, tssep_stream_t stream);
+int tssep_blstm_recurrence_tc(const void* G, int g_dtype, const uint16_t* Wimg, uint16_t* H, int64_t rows,
+                              int64_t T, int Up, int fast_math, tssep_stream_t stream);
 int tssep_pack_whh_tc(const float* whh_fwd, const float* whh_bwd, int U, int Up, uint16_t* Wimg,
                       tssep_stream_t stream);
 

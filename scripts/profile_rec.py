@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--fast", type=int, nargs="+", default=[0, 1])
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--kernel", default="regs", choices=["regs", "tc"])
+    ap.add_argument("--g-bf16", type=int, default=0)
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     U = a.units
@@ -33,12 +34,14 @@ def main():
         if a.kernel == "tc":
             return ops.blstm_recurrence_tc(G, wimg, rows, a.frames, Up, fast_math=bool(fast))
         H = torch.empty((rows, a.frames, 2 * Up), dtype=torch.bfloat16, device=G.device)
-        _lib.call("tssep_blstm_recurrence", G.data_ptr(), 0, whh.data_ptr(), H.data_ptr(), rows, a.frames, Up, C, int(fast),
+        _lib.call("tssep_blstm_recurrence", G.data_ptr(), a.g_bf16, whh.data_ptr(), H.data_ptr(), rows, a.frames, Up, C, int(fast),
                   _lib.stream_of(G))
         return H
 
     for rows in a.rows:
-        G = torch.randn((rows, a.frames, 8 * Up), device=dev) * 0.3
+        G = torch.randn((((rows + 31) // 32) * 32, a.frames, 8 * Up), device=dev) * 0.3
+        if a.g_bf16:
+            G = G.to(torch.bfloat16)
         for C in a.clusters:
             for fast in a.fast:
                 for _ in range(2):

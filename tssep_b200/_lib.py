@@ -34,7 +34,7 @@ class GemmDesc(C.Structure):
     ]
 
 
-EPI_F32, EPI_BF16, EPI_HEAD, EPI_F32_BT, EPI_BF16_ROWMAP = 0, 1, 2, 3, 4
+EPI_F32, EPI_BF16, EPI_HEAD, EPI_F32_BT, EPI_BF16_ROWMAP, EPI_BF16_BT = 0, 1, 2, 3, 4, 5
 
 _SIGNATURES = {
     "tssep_abi_version": ([], C.c_int),
@@ -53,7 +53,7 @@ _SIGNATURES = {
     "tssep_head_expand_t": ([c_vp, c_i64, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp], C.c_int),
     "tssep_blstm_recurrence": ([c_vp, c_i32, c_vp, c_vp, c_i64, c_i64, c_i32, c_i32, c_i32, c_vp], C.c_int),
     "tssep_pack_whh": ([c_vp, c_vp, c_i32, c_i32, c_vp, c_vp], C.c_int),
-    "tssep_blstm_recurrence_tc": ([c_vp, c_vp, c_vp, c_i64, c_i64, c_i32, c_i32, c_vp], C.c_int),
+    "tssep_blstm_recurrence_tc": ([c_vp, c_i32, c_vp, c_vp, c_i64, c_i64, c_i32, c_i32, c_vp], C.c_int),
     "tssep_pack_whh_tc": ([c_vp, c_vp, c_i32, c_i32, c_vp, c_vp], C.c_int),
     "tssep_mask_istft": ([c_vp, c_i64, c_vp, c_i64, c_i32, c_i64, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp,
                           c_i64, c_vp], C.c_int),

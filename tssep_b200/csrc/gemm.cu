@@ -27,7 +27,7 @@ constexpr int kGemmThreads = 64 + 32 * kEpiWarps;
 constexpr int kTmemCols = 512;
 constexpr int kAccCols = 256;
 
-enum EpiMode { EPI_F32 = 0, EPI_BF16 = 1, EPI_HEAD = 2, EPI_F32_BT = 3, EPI_BF16_ROWMAP = 4 };
+enum EpiMode { EPI_F32 = 0, EPI_BF16 = 1, EPI_HEAD = 2, EPI_F32_BT = 3, EPI_BF16_ROWMAP = 4, EPI_BF16_BT = 5 };
 
 struct GemmArgs {
   int64_t M;
@@ -103,12 +103,17 @@ __device__ __forceinline__ void epilogue_store(const GemmArgs& g, int z, int64_t
       for (int i = 0; i < 32; ++i)
         if (i < nvalid) o[i] = __float2bfloat16_rn(apply_act(g.alpha * acc[i] + (bias ? bias[i] : 0.f), g.act));
     }
-  } else if (g.mode == EPI_F32_BT) {
+  } else if (g.mode == EPI_F32_BT || g.mode == EPI_BF16_BT) {
     const int b = static_cast<int>(m & 31);
-    float* o = static_cast<float*>(g.out) + ((m >> 5) * g.N + n0) * 32 + (b >> 2) * 128 + (b & 3);
+    const int64_t o0 = ((m >> 5) * g.N + n0) * 32 + (b >> 2) * 128 + (b & 3);
 #pragma unroll
-    for (int i = 0; i < 32; ++i)
-      if (i < nvalid) o[i * 4] = apply_act(g.alpha * acc[i] + (bias ? bias[i] : 0.f), g.act);
+    for (int i = 0; i < 32; ++i) {
+      if (i < nvalid) {
+        const float v = apply_act(g.alpha * acc[i] + (bias ? bias[i] : 0.f), g.act);
+        if (g.mode == EPI_F32_BT) static_cast<float*>(g.out)[o0 + i * 4] = v;
+        else static_cast<__nv_bfloat16*>(g.out)[o0 + i * 4] = __float2bfloat16_rn(v);
+      }
+    }
   } else if (g.mode == EPI_BF16_ROWMAP) {
     const int64_t gt = m >> 5;
     const int64_t grp = gt / g.rm_T, t = gt - grp * g.rm_T;
@@ -161,7 +166,7 @@ __device__ __forceinline__ ChunkBias load_chunk_bias(const GemmArgs& g, int z, i
   b.v[0] = b.v[1] = b.v[2] = b.v[3] = 0.f;
   if (g.bias == nullptr) return b;
   const float* bias = g.bias + static_cast<int64_t>(z % g.b_mod) * g.bias_stride;
-  if (g.mode == EPI_HEAD || g.mode == EPI_F32_BT) {
+  if (g.mode == EPI_HEAD || g.mode == EPI_F32_BT || g.mode == EPI_BF16_BT) {
     const int n = n0 + lane;
     if (n < g.N) b.v[0] = __ldg(bias + n);
   } else {
@@ -323,7 +328,7 @@ __device__ __forceinline__ void epilogue_bt(const GemmArgs& g, int64_t m0, int n
                  "r"(v[i + 1]), "r"(v[i + 2]), "r"(v[i + 3])
                  : "memory");
   __syncwarp();
-  float* o = static_cast<float*>(g.out) + ((m0 >> 5) * g.N + n0) * 32 + lane * 4;
+  const int64_t o0 = ((m0 >> 5) * g.N + n0) * 32 + lane * 4;
 #pragma unroll
   for (int bq = 0; bq < 8; ++bq) {
     float x[4];
@@ -332,7 +337,11 @@ __device__ __forceinline__ void epilogue_bt(const GemmArgs& g, int64_t m0, int n
       asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x[j]) : "r"(stage + ((bq * 4 + j) * kStageLd + lane) * 4));
       x[j] = apply_act(fmaf(g.alpha, x[j], cb.v[0]), g.act);
     }
-    *reinterpret_cast<float4*>(o + bq * 128) = make_float4(x[0], x[1], x[2], x[3]);
+    if (g.mode == EPI_F32_BT)
+      *reinterpret_cast<float4*>(static_cast<float*>(g.out) + o0 + bq * 128) = make_float4(x[0], x[1], x[2], x[3]);
+    else
+      *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(g.out) + o0 + bq * 128) =
+          make_uint2(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]));
   }
   __syncwarp();
 }
@@ -462,7 +471,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const ChunkBias cb_next = load_chunk_bias(g, z, nt * g.bn + c0 + 64, lane);  // prefetch for the next chunk
         tc_wait_ld();
         if (m0 < g.M) {
-          if (g.mode == EPI_F32_BT) epilogue_bt(g, m0, nt * g.bn + c0, v, cb, stage, lane);
+          if (g.mode == EPI_F32_BT || g.mode == EPI_BF16_BT) epilogue_bt(g, m0, nt * g.bn + c0, v, cb, stage, lane);
           else epilogue_coalesced(g, z, m0, nt * g.bn + c0, min(32, g.bn - c0), v, cb, stage, lane);
         }
         cb = cb_next;
@@ -568,7 +577,7 @@ static int launch_gemm(GemmArgs g, const uint16_t* A, int64_t lda, int64_t a_str
                 (long long)ldb);
   TSSEP_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0,
                 "gemm: operands must be 16-byte aligned");
-  g.bn = choose_bn(g.N, g.mode == EPI_F32_BT ? 32 : 16);
+  g.bn = choose_bn(g.N, (g.mode == EPI_F32_BT || g.mode == EPI_BF16_BT) ? 32 : 16);
   g.m_tiles = static_cast<int>((g.M + BM - 1) / BM);
   g.n_tiles = (g.N + g.bn - 1) / g.bn;
   g.k_blocks = (g.K + BK - 1) / BK;
@@ -601,7 +610,7 @@ extern "C" {
 
 int tssep_gemm(const tssep_gemm_desc* d, tssep_stream_t stream) {
   TSSEP_REQUIRE(d != nullptr, "tssep_gemm: null descriptor");
-  TSSEP_REQUIRE(d->mode >= TSSEP_EPI_F32 && d->mode <= TSSEP_EPI_BF16_ROWMAP, "tssep_gemm: unknown epilogue mode %d",
+  TSSEP_REQUIRE(d->mode >= TSSEP_EPI_F32 && d->mode <= TSSEP_EPI_BF16_BT, "tssep_gemm: unknown epilogue mode %d",
                 d->mode);
   TSSEP_REQUIRE(d->act == 0 || d->act == 1, "tssep_gemm: act must be 0 (none) or 1 (tanh)");
   GemmArgs g{};
@@ -634,7 +643,7 @@ int tssep_gemm(const tssep_gemm_desc* d, tssep_stream_t stream) {
     TSSEP_REQUIRE(d->plane_map && d->n_blocks >= 1 && d->row_len >= 1 && d->N == d->n_blocks * d->row_len,
                   "tssep_gemm(head): need plane_map and N == n_blocks * row_len");
     TSSEP_REQUIRE(d->act == 0, "tssep_gemm(head): act must be 0");
-  } else if (d->mode == TSSEP_EPI_F32_BT) {
+  } else if (d->mode == TSSEP_EPI_F32_BT || d->mode == TSSEP_EPI_BF16_BT) {
     TSSEP_REQUIRE(d->out != nullptr && d->batch == 1 && d->M % 32 == 0 && d->N % 32 == 0 &&
                       (reinterpret_cast<uintptr_t>(d->out) & 15) == 0,
                   "tssep_gemm(f32_bt): needs a 16-byte aligned output, batch == 1, M %% 32 == 0 and N %% 32 == 0");

@@ -31,10 +31,10 @@ constexpr int kAtomA = 128 * 128; // bytes of one 128-row x 64-k swizzle atom
 constexpr int kAtomB = kTcN * 128;
 
 struct RecTcArgs {
-  const float* G;        // tiles [group][t][dir][unit octet][b/4][4*(unit%8)+gate][b%4] (GEMM mode EPI_F32_BT)
+  const void* G;         // tiles [group][t][dir][unit octet][b/4][4*(unit%8)+gate][b%4], f32 or bf16 (GEMM BT modes)
   const uint4* Wimg;     // [dir][cta][tile][atom] pre-swizzled 16 KB blocks
   __nv_bfloat16* H;      // (groups, T, 32, 2*Up): rows ordered (group, t, b)
-  int rows, T, Up, NA, fast;
+  int rows, T, Up, NA, fast, g_bf16;
   int* prof;  // optional: per-phase cycle counters of one epilogue warp (debugging aid)
 };
 
@@ -157,27 +157,33 @@ __global__ void __launch_bounds__(kTcThreads, 1) blstm_rec_tc_kernel(const RecTc
     const bool unit_ok = unit < Up;
     // G tile of this warp's unit octet: [b/4][lane][b%4] -> instruction i reads 512 contiguous bytes
     const int octet = static_cast<int>(crank) * 8 + tl * 4 + q;
-    const float4* gbase = reinterpret_cast<const float4*>(a.G) +
-                          (((static_cast<int64_t>(bg) * T) * 2 + dir) * (static_cast<int64_t>(Up) / 8) + octet) * 256 + lane;
-    const int64_t g_tstride = 2 * (static_cast<int64_t>(Up) / 8) * 256;  // float4 per time step
+    const int64_t g_tile = (((static_cast<int64_t>(bg) * T) * 2 + dir) * (static_cast<int64_t>(Up) / 8) + octet);
+    const int64_t g_tstride = 2 * (static_cast<int64_t>(Up) / 8);  // tiles per time step
+    const float4* gbase32 = reinterpret_cast<const float4*>(a.G) + g_tile * 256 + lane;  // 1024 floats per tile
+    const uint2* gbase16 = reinterpret_cast<const uint2*>(a.G) + g_tile * 256 + lane;    // 1024 bf16 per tile
     __nv_bfloat16* hbase = a.H + ((static_cast<int64_t>(bg) * T) * kTcN + lane) * (2 * static_cast<int64_t>(Up)) + dir * Up + unit0;
     const int64_t h_tstride = static_cast<int64_t>(kTcN) * 2 * Up;
 
     float cst[8];
-    float4 gcur[8];
+    uint4 gcur[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) cst[i] = 0.f;
-    auto load_g = [&](int s, float4* g) {
+    // raw loads only: the values are converted where they are consumed (one step later), otherwise the
+    // in-order issue would stall on every load
+    auto load_g = [&](int s, uint4* g) {
       const int t = dir ? T - 1 - s : s;
-      const float4* p = gbase + static_cast<int64_t>(t) * g_tstride;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        if (unit_ok) {
-          asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
-                       : "=f"(g[i].x), "=f"(g[i].y), "=f"(g[i].z), "=f"(g[i].w)
-                       : "l"(p + i * 32));
+        if (!unit_ok) {
+          g[i] = make_uint4(0u, 0u, 0u, 0u);
+        } else if (a.g_bf16) {
+          asm volatile("ld.global.nc.L1::no_allocate.v2.b32 {%0, %1}, [%2];"
+                       : "=r"(g[i].x), "=r"(g[i].y)
+                       : "l"(gbase16 + static_cast<int64_t>(t) * g_tstride * 256 + i * 32));
         } else {
-          g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          asm volatile("ld.global.nc.L1::no_allocate.v4.b32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(g[i].x), "=r"(g[i].y), "=r"(g[i].z), "=r"(g[i].w)
+                       : "l"(gbase32 + static_cast<int64_t>(t) * g_tstride * 256 + i * 32));
         }
       }
     };
@@ -204,7 +210,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) blstm_rec_tc_kernel(const RecTc
       float act[kTcN];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const float gv[4] = {gcur[i].x, gcur[i].y, gcur[i].z, gcur[i].w};
+        float gv[4];
+        if (a.g_bf16) {
+          gv[0] = __uint_as_float(gcur[i].x << 16);
+          gv[1] = __uint_as_float(gcur[i].x & 0xffff0000u);
+          gv[2] = __uint_as_float(gcur[i].y << 16);
+          gv[3] = __uint_as_float(gcur[i].y & 0xffff0000u);
+        } else {
+          gv[0] = __uint_as_float(gcur[i].x);
+          gv[1] = __uint_as_float(gcur[i].y);
+          gv[2] = __uint_as_float(gcur[i].z);
+          gv[3] = __uint_as_float(gcur[i].w);
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float x = (__uint_as_float(v[4 * i + j]) + gv[j]) * sc;
@@ -341,9 +358,10 @@ int tssep_pack_whh_tc(const float* whh_fwd, const float* whh_bwd, int U, int Up,
   return check_launch("tssep_pack_whh_tc");
 }
 
-int tssep_blstm_recurrence_tc(const float* G, const uint16_t* Wimg, uint16_t* H, int64_t rows, int64_t T, int Up,
-                              int fast_math, tssep_stream_t stream) {
+int tssep_blstm_recurrence_tc(const void* G, int g_dtype, const uint16_t* Wimg, uint16_t* H, int64_t rows, int64_t T,
+                              int Up, int fast_math, tssep_stream_t stream) {
   TSSEP_REQUIRE(G && Wimg && H, "tssep_blstm_recurrence_tc: null pointer");
+  TSSEP_REQUIRE(g_dtype == 0 || g_dtype == 1, "tssep_blstm_recurrence_tc: g_dtype must be 0 (f32) or 1 (bf16)");
   TSSEP_REQUIRE(Up >= 16 && Up % 16 == 0 && Up <= 512, "tssep_blstm_recurrence_tc: Up must be a multiple of 16 in [16, 512]");
   TSSEP_REQUIRE(rows >= 0 && T >= 0 && T < (1ll << 31) && (rows + kTcN - 1) / kTcN <= 65535,
                 "tssep_blstm_recurrence_tc: bad extent");
@@ -361,6 +379,7 @@ int tssep_blstm_recurrence_tc(const float* G, const uint16_t* Wimg, uint16_t* H,
   a.Up = Up;
   a.NA = NA;
   a.fast = fast_math & 1;
+  a.g_bf16 = g_dtype;
   a.prof = nullptr;
   if (const char* e = getenv("TSSEP_REC_PROF")) a.prof = reinterpret_cast<int*>(strtoull(e, nullptr, 0));
   const size_t smem = 1024 + 2ull * NA * kAtomA + 2ull * NA * kAtomB + 8 * 512 + 128;

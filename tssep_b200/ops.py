@@ -12,7 +12,7 @@ import os
 import torch
 
 from . import _lib
-from ._lib import EPI_BF16, EPI_BF16_ROWMAP, EPI_F32, EPI_F32_BT, EPI_HEAD, GemmDesc
+from ._lib import EPI_BF16, EPI_BF16_BT, EPI_BF16_ROWMAP, EPI_F32, EPI_F32_BT, EPI_HEAD, GemmDesc
 
 
 def round_up(x: int, m: int) -> int:
@@ -104,7 +104,8 @@ def blstm_recurrence_tc(G: torch.Tensor, wimg: torch.Tensor, rows: int, T: int, 
         fast_math = os.environ.get("TSSEP_LSTM_FAST_MATH", "1") == "1"
     groups = (rows + 31) // 32
     H = torch.empty((groups * T * 32, 2 * Up), dtype=torch.bfloat16, device=G.device)
-    _lib.call("tssep_blstm_recurrence_tc", G.data_ptr(), wimg.data_ptr(), H.data_ptr(), rows, T, Up, int(fast_math),
+    _lib.call("tssep_blstm_recurrence_tc", G.data_ptr(), int(G.dtype == torch.bfloat16), wimg.data_ptr(), H.data_ptr(),
+              rows, T, Up, int(fast_math),
               _lib.stream_of(G))
     return H
 
@@ -120,4 +121,4 @@ def instance_norm(x: torch.Tensor, unbiased=False) -> torch.Tensor:
 
 
 __all__ = ["gemm", "cast_bf16", "pack_whh", "blstm_recurrence", "pack_whh_tc", "blstm_recurrence_tc", "instance_norm", "round_up", "EPI_F32", "EPI_BF16",
-           "EPI_HEAD", "EPI_F32_BT", "EPI_BF16_ROWMAP"]
+           "EPI_HEAD", "EPI_F32_BT", "EPI_BF16_ROWMAP", "EPI_BF16_BT"]

@@ -20,9 +20,9 @@ import torch
 from . import _lib, ops
 
 # Batch rows from which the tcgen05 recurrence is used.  Measured on B200 (U=300): the register-resident
-# kernel needs 1.55 us per step for up to 15 concurrent clusters of 16 rows (240 rows per wave), the
-# tcgen05 kernel 3.2 us per step for up to 28 clusters of 32 rows, so it only wins beyond one wave.
-TC_MIN_ROWS = 241
+# kernel interleaves up to 4 batch tiles per cluster and covers 480 rows in one wave at 3.4 us per step; the
+# tcgen05 kernel needs 3.2-3.5 us per step for up to 28 clusters of 32 rows (896 rows), so it wins beyond that.
+TC_MIN_ROWS = 481
 
 
 def use_tc_recurrence(rows: int) -> bool:
@@ -87,9 +87,10 @@ class LayerPack:
             w = self.w_ih_f32.view(2, 4, Up // 8, 8, self.I).permute(0, 2, 3, 1, 4).reshape(8 * Up, self.I)
             self.w_ih_tc = ops.cast_bf16(w.contiguous(), self.ld_in)
             self.bias_tc = self.bias.view(2, 4, Up // 8, 8).permute(0, 2, 3, 1).reshape(8 * Up).contiguous()
-        G = torch.empty((mrows * 8 * self.Up,), dtype=torch.float32, device=xb.device)
+        gd = ops.g_dtype()
+        G = torch.empty((mrows * 8 * self.Up,), dtype=gd, device=xb.device)
         ops.gemm(xb, ld, self.w_ih_tc, self.ld_in, mrows, 8 * self.Up, self.I if kdim is None else kdim, G,
-                 mode=ops.EPI_F32_BT, bias=self.bias_tc)
+                 mode=ops.EPI_BF16_BT if gd == torch.bfloat16 else ops.EPI_F32_BT, bias=self.bias_tc)
         return G
 
     def recurrence_tc(self, G: torch.Tensor, rows: int, T: int) -> torch.Tensor:
