@@ -47,7 +47,8 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--meetings-per-gpu", type=int, default=int(os.environ.get("TSSEP_BENCH_MEETINGS", 28)))
+    ap.add_argument("--meetings-per-gpu", type=int, default=int(os.environ.get("TSSEP_BENCH_MEETINGS", 0)),
+                    help="0 = as many as fit in memory (at most 28), trimmed to one wave of recurrence clusters")
     ap.add_argument("--seconds", type=float, default=600.0, help="length of every synthetic meeting")
     ap.add_argument("--streams", type=int, default=int(os.environ.get("TSSEP_BENCH_STREAMS", 1)),
                     help="meeting groups processed concurrently on separate CUDA streams")
@@ -238,7 +239,15 @@ def run_b200(args):
     # intermediates); shrink M instead of failing on a smaller / busier device
     free_b, _ = torch.cuda.mem_get_info(dev)
     per_meeting = 5.2e9 * (args.seconds / 600.0)
-    M = max(1, min(M, int(0.9 * free_b / per_meeting)))
+    m_mem = max(1, min(M if M > 0 else 28, int(0.9 * free_b / per_meeting)))
+    if M <= 0:
+        # The K=8 speaker rows of every meeting advance together in the tensor-memory recurrence; a batch
+        # that fits in one wave of 16-row clusters steps in 1.4 us, one row more costs a second wave.
+        from tssep_b200 import ops as _ops
+        cap = _ops.recurrence_ts_capacity(304, 16) // 8
+        M = cap if 0.7 * m_mem <= cap <= m_mem else m_mem
+    else:
+        M = m_mem
     if world > 1:
         mt = torch.tensor([M], device=dev)
         torch.distributed.all_reduce(mt, op=torch.distributed.ReduceOp.MIN)
@@ -381,7 +390,9 @@ def run_b200(args):
     T = model.fe.num_frames(n)
     Up = 304
     # dominant kernel: the BLSTM recurrence (latency bound; expressed against the tensor peak as asked)
-    rec = breakdown.get("tssep_blstm_recurrence", {"ms_per_step": 0.0, "launches_per_step": 1})
+    rec_parts = {k: v for k, v in breakdown.items() if k.startswith("tssep_blstm_recurrence")}
+    rec = {"ms_per_step": sum(v["ms_per_step"] for v in rec_parts.values()),
+           "launches_per_step": sum(v["launches_per_step"] for v in rec_parts.values()) or 1}
     rec_rows = M * (1 + 8 + 8 + 2)  # pre_net, birnn0, birnn1, birnn2 (R=2) batch rows
     rec_cfg = "tanh.approx gates" if os.environ.get("TSSEP_LSTM_FAST_MATH", "1") == "1" else "exp-based gates"
     rec_flops = 2.0 * rec_rows * T * 2 * (4 * 300 * 300)
@@ -395,19 +406,20 @@ def run_b200(args):
     # 45.97 GB algorithmic (profiles/r1_ncu_blstm_rec_bench_b0.txt), i.e. a ratio of 1.00.
     g_bytes = 4 if os.environ.get("TSSEP_G_DTYPE", "bf16") == "f32" else 2
     rec_bytes = rec_rows * T * (8 * Up * g_bytes + 2 * Up * 2)
-    launches = max(1.0, rec["launches_per_step"])
+    rec_launches = max(1.0, rec["launches_per_step"])
     roofline = {
-        "kernel": "blstm_rec_kernel", "bound": "tensor", "achieved": rec_tflops, "peak": peaks["bf16_tflops_sustained"],
+        "kernel": "blstm_rec_ts_kernel + blstm_rec_kernel", "bound": "tensor", "achieved": rec_tflops, "peak": peaks["bf16_tflops_sustained"],
         "unit": "TFLOP/s", "frac": rec_tflops / peaks["bf16_tflops_sustained"],
-        "traffic": 1.00 * rec_bytes / launches,
+        "traffic": 1.00 * rec_bytes / rec_launches,
         "traffic_note": "bytes per launch (mean of the 4 recurrence launches of a step) = algorithmic bytes x 1.00, the "
                         "dram read+write / algorithmic ratio ncu measured for the birnn0 launch "
                         "(profiles/r1_ncu_blstm_rec_bench_b0.txt)",
-        "algorithmic_flops_per_launch": rec_flops / launches, "algorithmic_bytes_per_launch": rec_bytes / launches,
-        "avg_launch_ms": rec["ms_per_step"] / launches,
+        "algorithmic_flops_per_launch": rec_flops / rec_launches, "algorithmic_bytes_per_launch": rec_bytes / rec_launches,
+        "avg_launch_ms": rec["ms_per_step"] / rec_launches,
         "peak_source": peaks["source"] + " (sustained)",
-        "note": "the recurrence is bound by the latency of T dependent steps (one DSMEM exchange + one mma.sync "
-                "chain per step), not by the tensor pipe or HBM; see us_per_recurrent_step",
+        "note": "the recurrence is bound by the latency of T dependent steps (one DSMEM exchange + one tcgen05 / "
+                "mma.sync chain + the gate math per step), not by the tensor pipe or HBM; see us_per_recurrent_step",
+        "launches": {k: v for k, v in rec_parts.items()},
         "us_per_recurrent_step": rec["ms_per_step"] * 1e3 / (4 * T) if rec["ms_per_step"] else None,
         "gate_math": rec_cfg,
         "share_of_step": rec["ms_per_step"] / (ms / args.steps),

@@ -171,6 +171,21 @@ int tssep_blstm_recurrence_tc(const void* G, int g_dtype, const uint16_t* Wimg, 
 int tssep_pack_whh_tc(const float* whh_fwd, const float* whh_bwd, int U, int Up, uint16_t* Wimg,
                       tssep_stream_t stream);
 
+/* Same recurrence, same G / H layouts as tssep_blstm_recurrence_tc, with the recurrent weights
+ * resident in TENSOR MEMORY (A operand of tcgen05.mma read from TMEM, B = h_{t-1} from shared
+ * memory): one cluster of ceil(Up/64) CTAs per (rows_per_cluster batch rows, direction),
+ * rows_per_cluster = 16 or 32 (0 = choose: 16 while both directions fit in one wave of clusters).
+ * G streamed with cp.async.bulk through an mbarrier ring.  Only the first
+ * ceil(rows / rows_per_cluster) * rows_per_cluster rows of H are written.
+ * Wimg from tssep_pack_whh_ts: 2 * C * 2 * (Up/16) * 128 * 8 words, C = ceil(Up/64); Up <= 448. */
+int tssep_blstm_recurrence_ts(const void* G, int g_dtype, const uint32_t* Wimg, uint16_t* H, int64_t rows,
+                              int64_t T, int Up, int rows_per_cluster, int fast_math, tssep_stream_t stream);
+/* Batch rows that fit in ONE wave of co-resident clusters (both directions running) on the current
+ * device at the given rows_per_cluster (16 or 32); < 0 on error. */
+int tssep_blstm_recurrence_ts_capacity(int Up, int rows_per_cluster, int g_dtype);
+int tssep_pack_whh_ts(const float* whh_fwd, const float* whh_bwd, int U, int Up, uint32_t* Wimg,
+                      tssep_stream_t stream);
+
 /* weight_hh_l0 / weight_hh_l0_reverse (4U, U) f32 -> mma fragment order. */
 int tssep_pack_whh(const float* whh_fwd, const float* whh_bwd, int U, int Up, uint32_t* Wfrag,
                    tssep_stream_t stream);

@@ -19,7 +19,7 @@ def main():
     ap.add_argument("--clusters", type=int, nargs="+", default=[0])
     ap.add_argument("--fast", type=int, nargs="+", default=[0, 1])
     ap.add_argument("--reps", type=int, default=3)
-    ap.add_argument("--kernel", default="regs", choices=["regs", "tc"])
+    ap.add_argument("--kernel", default="regs", choices=["regs", "tc", "ts"])
     ap.add_argument("--g-bf16", type=int, default=0)
     a = ap.parse_args()
     dev = torch.device("cuda:0")
@@ -29,8 +29,11 @@ def main():
     w = (torch.rand((2, 4 * U, U), device=dev) - 0.5) * (2 / U ** 0.5)
     whh = ops.pack_whh(w[0], w[1], U, Up)
     wimg = ops.pack_whh_tc(w[0].contiguous(), w[1].contiguous(), U, Up)
+    wts = ops.pack_whh_ts(w[0].contiguous(), w[1].contiguous(), U, Up)
 
     def run(G, rows, C, fast):
+        if a.kernel == "ts":
+            return ops.blstm_recurrence_ts(G, wts, rows, a.frames, Up, fast_math=bool(fast), rows_per_cluster=C)
         if a.kernel == "tc":
             return ops.blstm_recurrence_tc(G, wimg, rows, a.frames, Up, fast_math=bool(fast))
         H = torch.empty((rows, a.frames, 2 * Up), dtype=torch.bfloat16, device=G.device)
@@ -60,7 +63,10 @@ def main():
                 torch.cuda.synchronize()
                 del os.environ["TSSEP_REC_PROF"]
                 pc = prof.cpu().numpy().astype(float)
-                if a.kernel == "tc":
+                if a.kernel == "ts":
+                    names = ["t0.g", "t0.wait", "t0.math", "t0.send", "t1.g", "t1.wait", "t1.math", "t1.send"]
+                    ph = " ".join(f"{n}={v / a.frames:.0f}" for n, v in zip(names, pc))
+                elif a.kernel == "tc":
                     names = ["t0.wait", "t0.ld+act", "t0.cell", "t0.send", "t1.wait", "t1.ld+act", "t1.cell", "t1.send"]
                     ph = " ".join(f"{n}={v / a.frames:.0f}" for n, v in zip(names, pc))
                 else:

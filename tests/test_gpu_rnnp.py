@@ -66,6 +66,28 @@ def test_rnnp_tcgen05_recurrence_matches_torch(cuda, monkeypatch, idim, units, h
     assert (got2 - want).abs().max().item() < 1e-2
 
 
+@pytest.mark.parametrize("rows_per_cluster", ["16", "32"])
+@pytest.mark.parametrize("idim,units,hdim,shape", [
+    (64, 40, 42, (3, 100, 64)),      # one CTA, 3 of 16 rows used
+    (96, 64, 48, (40, 150, 96)),     # exactly 64 units, two row groups, second one partly computed
+    (80, 128, 64, (33, 120, 80)),    # cluster of 2
+    (160, 300, 320, (64, 200, 160)), # full size: cluster of 5, partial last k-atom
+    (160, 300, 320, (5, 300, 160)),
+    (72, 10, 12, (17, 60, 72)),      # one k-step, Up = 16
+])
+def test_rnnp_tmem_recurrence_matches_torch(cuda, monkeypatch, rows_per_cluster, idim, units, hdim, shape):
+    """The tensor-memory recurrence (csrc/lstm_ts.cu), forced for every row count, both cluster widths."""
+    monkeypatch.setenv("TSSEP_LSTM_KERNEL", "ts")
+    monkeypatch.setenv("TSSEP_TS_ROWS", rows_per_cluster)
+    ref, mine = _pair(idim, units, hdim)
+    x = torch.randn(shape, generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        want = ref(x)
+        got = mine(x.to(cuda)).cpu()
+    err = (got - want).abs().max().item()
+    assert err < 1e-2, err
+
+
 def test_rnnp_stress_weights(cuda):
     """All weights x4 (saturating gates), as SURVEY.md §8d asks; looser bound, reported not hidden."""
     ref, mine = _pair(64, 40, 42)

@@ -396,60 +396,62 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int64_t tiles_per_z = static_cast<int64_t>(g.m_tiles) * g.n_tiles;
 
+  // Producer and MMA warps run their loops with all 32 lanes converged and guard only the issue block
+  // with elect.sync: inside a divergent `if (lane == 0)` ptxas wraps every UTMALDG / UTCHMMA / UTCBAR in
+  // an ELECT + BRA.U.ANY waterfall (~70 cycles per MMA, measured on the recurrence kernel).
   if (warp == 0) {
-    if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
-      for (int64_t tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
-        const int z = static_cast<int>(tile / tiles_per_z);
-        const int64_t rem = tile - z * tiles_per_z;
-        const int mt = static_cast<int>(rem / g.n_tiles), nt = static_cast<int>(rem - static_cast<int64_t>(mt) * g.n_tiles);
-        const int a_row = static_cast<int>((z / g.a_div) * g.a_row_stride + static_cast<int64_t>(mt) * BM);
-        const int b_row = static_cast<int>((z % g.b_mod) * g.b_row_stride + static_cast<int64_t>(nt) * g.bn);
-        for (int kb = 0; kb < g.k_blocks; ++kb) {
-          mbar_wait(empty0 + 8 * s, ph ^ 1);
+    int s = 0;
+    uint32_t ph = 0;
+    for (int64_t tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+      const int z = static_cast<int>(tile / tiles_per_z);
+      const int64_t rem = tile - z * tiles_per_z;
+      const int mt = static_cast<int>(rem / g.n_tiles), nt = static_cast<int>(rem - static_cast<int64_t>(mt) * g.n_tiles);
+      const int a_row = static_cast<int>((z / g.a_div) * g.a_row_stride + static_cast<int64_t>(mt) * BM);
+      const int b_row = static_cast<int>((z % g.b_mod) * g.b_row_stride + static_cast<int64_t>(nt) * g.bn);
+      for (int kb = 0; kb < g.k_blocks; ++kb) {
+        mbar_wait(empty0 + 8 * s, ph ^ 1);
+        if (elect_one()) {
           mbar_arrive_expect_tx(full0 + 8 * s, a_bytes + b_bytes);
           tma_load_2d(sA + s * a_bytes, &tmA, full0 + 8 * s, kb * BK, a_row);
           tma_load_2d(sB + s * b_bytes, &tmB, full0 + 8 * s, kb * BK, b_row);
-          if (++s == kStages) {
-            s = 0;
-            ph ^= 1;
-          }
+        }
+        __syncwarp();
+        if (++s == kStages) {
+          s = 0;
+          ph ^= 1;
         }
       }
     }
-    __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(g.bn >> 3) << 17) |
-                             (static_cast<uint32_t>(BM >> 4) << 24);
-      int s = 0;
-      uint32_t ph = 0;
-      uint32_t it = 0;
-      for (int64_t tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++it) {
-        const uint32_t as = it & 1, aph = (it >> 1) & 1;
-        mbar_wait(tempty0 + 8 * as, aph ^ 1);
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(g.bn >> 3) << 17) |
+                           (static_cast<uint32_t>(BM >> 4) << 24);
+    const uint64_t adesc0 = make_smem_desc(sA), bdesc0 = make_smem_desc(sB);
+    const uint32_t a_step = a_bytes >> 4, b_step = b_bytes >> 4;  // encoded distance of two pipeline stages
+    int s = 0;
+    uint32_t ph = 0;
+    uint32_t it = 0;
+    for (int64_t tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++it) {
+      const uint32_t as = it & 1, aph = (it >> 1) & 1;
+      mbar_wait(tempty0 + 8 * as, aph ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * kAccCols;
+      for (int kb = 0; kb < g.k_blocks; ++kb) {
+        mbar_wait(full0 + 8 * s, ph);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * kAccCols;
-        for (int kb = 0; kb < g.k_blocks; ++kb) {
-          mbar_wait(full0 + 8 * s, ph);
-          tc_fence_after();
-          const uint32_t a0 = sA + s * a_bytes, b0 = sB + s * b_bytes;
+        if (elect_one()) {
+          const uint64_t ad = adesc0 + static_cast<uint64_t>(s * a_step), bd = bdesc0 + static_cast<uint64_t>(s * b_step);
 #pragma unroll
-          for (int k4 = 0; k4 < BK / 16; ++k4) {
-            tc_mma_bf16(d_tmem, make_smem_desc(a0 + k4 * 32), make_smem_desc(b0 + k4 * 32), idesc,
-                        (kb | k4) != 0 ? 1u : 0u);
-          }
+          for (int k4 = 0; k4 < BK / 16; ++k4) tc_mma_bf16(d_tmem, ad + 2 * k4, bd + 2 * k4, idesc, (kb | k4) != 0 ? 1u : 0u);
           tc_commit(empty0 + 8 * s);
-          if (++s == kStages) {
-            s = 0;
-            ph ^= 1;
-          }
+          if (kb == g.k_blocks - 1) tc_commit(tfull0 + 8 * as);
         }
-        tc_commit(tfull0 + 8 * as);
+        __syncwarp();
+        if (++s == kStages) {
+          s = 0;
+          ph ^= 1;
+        }
       }
     }
-    __syncwarp();
   } else {
     const int q = warp & 3;  // TMEM lane quarter this warp may touch
     uint32_t it = 0;

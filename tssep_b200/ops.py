@@ -110,6 +110,41 @@ def blstm_recurrence_tc(G: torch.Tensor, wimg: torch.Tensor, rows: int, T: int, 
     return H
 
 
+def pack_whh_ts(w_fwd: torch.Tensor, w_bwd: torch.Tensor, U: int, Up: int) -> torch.Tensor:
+    """Tensor-memory image of W_hh for the TMEM-resident recurrence (bf16 pairs per 32-bit column)."""
+    _lib.require_cuda(w_fwd, w_bwd)
+    c = (Up + 63) // 64
+    out = torch.empty(2 * c * 2 * (Up // 16) * 128 * 8, dtype=torch.int32, device=w_fwd.device)
+    _lib.call("tssep_pack_whh_ts", w_fwd.contiguous().data_ptr(), w_bwd.contiguous().data_ptr(), U, Up,
+              out.data_ptr(), _lib.stream_of(w_fwd))
+    return out
+
+
+def blstm_recurrence_ts(G: torch.Tensor, wimg: torch.Tensor, rows: int, T: int, Up: int,
+                        fast_math: bool = None, rows_per_cluster: int = 0) -> torch.Tensor:
+    """TMEM-resident variant: G in the BT tile layout -> H (groups*T*32, 2*Up) bf16, rows (group, t, b).
+    Padding rows the kernel does not compute are zero."""
+    _lib.require_cuda(G, wimg)
+    if fast_math is None:
+        fast_math = os.environ.get("TSSEP_LSTM_FAST_MATH", "1") == "1"
+    groups = (rows + 31) // 32
+    H = torch.empty((groups * T * 32, 2 * Up), dtype=torch.bfloat16, device=G.device)
+    done = ((rows + 15) // 16) * 16  # the kernel computes whole 16-row blocks at least
+    if done < groups * 32:
+        H.view(groups, T, 32, 2 * Up)[-1, :, done - (groups - 1) * 32:].zero_()
+    _lib.call("tssep_blstm_recurrence_ts", G.data_ptr(), int(G.dtype == torch.bfloat16), wimg.data_ptr(), H.data_ptr(),
+              rows, T, Up, rows_per_cluster, int(fast_math), _lib.stream_of(G))
+    return H
+
+
+def recurrence_ts_capacity(Up: int, rows_per_cluster: int = 16, g_bf16: bool = True) -> int:
+    """Batch rows one launch of the tensor-memory recurrence advances in a single wave of clusters."""
+    n = _lib.load().tssep_blstm_recurrence_ts_capacity(Up, rows_per_cluster, int(g_bf16))
+    if n < 0:
+        _lib.check(n, "tssep_blstm_recurrence_ts_capacity")
+    return n
+
+
 def instance_norm(x: torch.Tensor, unbiased=False) -> torch.Tensor:
     _lib.require_cuda(x)
     x = x.contiguous().float()
@@ -120,5 +155,5 @@ def instance_norm(x: torch.Tensor, unbiased=False) -> torch.Tensor:
     return out
 
 
-__all__ = ["gemm", "cast_bf16", "pack_whh", "blstm_recurrence", "pack_whh_tc", "blstm_recurrence_tc", "instance_norm", "round_up", "EPI_F32", "EPI_BF16",
+__all__ = ["gemm", "cast_bf16", "pack_whh", "blstm_recurrence", "pack_whh_tc", "blstm_recurrence_tc", "pack_whh_ts", "blstm_recurrence_ts", "recurrence_ts_capacity", "instance_norm", "round_up", "EPI_F32", "EPI_BF16",
            "EPI_HEAD", "EPI_F32_BT", "EPI_BF16_ROWMAP", "EPI_BF16_BT"]

@@ -19,16 +19,24 @@ import torch
 
 from . import _lib, ops
 
-# Batch rows from which the tcgen05 recurrence is used.  Measured on B200 (U=300): the register-resident
-# kernel interleaves up to 4 batch tiles per cluster and covers 480 rows in one wave at 3.4 us per step; the
-# tcgen05 kernel needs 3.2-3.5 us per step for up to 28 clusters of 32 rows (896 rows), so it wins beyond that.
-TC_MIN_ROWS = 481
+# Recurrence kernels (all compute the same operator):
+#   regs  csrc/lstm.cu     W_hh in registers, mma.sync, rows in the plain (row, t) layout
+#   ts    csrc/lstm_ts.cu  W_hh in tensor memory, tcgen05.mma with A from TMEM, rows ordered (group, t, b32)
+#   tc    csrc/lstm_tc.cu  W_hh in shared memory, tcgen05.mma (kept for A/B measurements)
+# TSSEP_LSTM_KERNEL=regs|ts|tc|auto; auto takes the tensor-memory kernel from TS_MIN_ROWS batch rows on.
+TS_MIN_ROWS = int(os.environ.get("TSSEP_TS_MIN_ROWS", "17"))
+
+
+def rec_kernel(rows: int) -> str:
+    choice = os.environ.get("TSSEP_LSTM_KERNEL", "auto")
+    if choice == "auto":
+        return "ts" if rows >= TS_MIN_ROWS else "regs"
+    return choice
 
 
 def use_tc_recurrence(rows: int) -> bool:
-    """TSSEP_LSTM_KERNEL=regs|tc|auto (default auto: tcgen05 kernel from TC_MIN_ROWS batch rows)."""
-    choice = os.environ.get("TSSEP_LSTM_KERNEL", "auto")
-    return choice == "tc" or (choice == "auto" and rows >= TC_MIN_ROWS)
+    """True when the recurrence runs on a tcgen05 kernel, i.e. on rows ordered (group, t, b32)."""
+    return rec_kernel(rows) in ("ts", "tc")
 
 
 class LayerPack:
@@ -57,7 +65,7 @@ class LayerPack:
             self._whh_f32 = (lstm.weight_hh_l0.detach().float().contiguous(),
                              lstm.weight_hh_l0_reverse.detach().float().contiguous())
             self.whh = ops.pack_whh(self._whh_f32[0], self._whh_f32[1], U, Up)
-            self.whh_tc = None  # built on first use by the tcgen05 recurrence
+            self.whh_tc = self.whh_ts = None  # built on first use by the tcgen05 recurrences
             self.w_ih_tc = self.bias_tc = None
             wp = torch.zeros((self.hdim, 2 * Up), dtype=torch.float32, device=dev)
             wp[:, :U] = linear.weight.detach().float()[:, :U]
@@ -94,10 +102,14 @@ class LayerPack:
         return G
 
     def recurrence_tc(self, G: torch.Tensor, rows: int, T: int) -> torch.Tensor:
-        """Shared-memory / tcgen05 kernel (csrc/lstm_tc.cu): H (groups*T*32, 2Up), rows (group, t, b)."""
-        if self.whh_tc is None:
-            self.whh_tc = ops.pack_whh_tc(self._whh_f32[0], self._whh_f32[1], self.U, self.Up)
-        return ops.blstm_recurrence_tc(G, self.whh_tc, rows, T, self.Up)
+        """tcgen05 kernels (csrc/lstm_ts.cu, csrc/lstm_tc.cu): H (groups*T*32, 2Up), rows (group, t, b)."""
+        if rec_kernel(rows) == "tc":
+            if self.whh_tc is None:
+                self.whh_tc = ops.pack_whh_tc(self._whh_f32[0], self._whh_f32[1], self.U, self.Up)
+            return ops.blstm_recurrence_tc(G, self.whh_tc, rows, T, self.Up)
+        if self.whh_ts is None:
+            self.whh_ts = ops.pack_whh_ts(self._whh_f32[0], self._whh_f32[1], self.U, self.Up)
+        return ops.blstm_recurrence_ts(G, self.whh_ts, rows, T, self.Up)
 
     def projection(self, H: torch.Tensor, rows_t: int, out: torch.Tensor, *, mode: int, ldo: int, act: int,
                    batch=1, a_stride=0, M=None, out_stride=0, out_div=None, out_stride_hi=0, row_map=None):
