@@ -207,13 +207,20 @@ def build_product_model(device):
 
 
 def kernel_breakdown(timeline, steps):
-    agg = {}
-    for name, s, e in timeline:
+    """Per entry point, and per (entry point, detail) for the calls that carry one (the GEMM shapes)."""
+    agg, fine = {}, {}
+    for name, s, e, detail in timeline:
         ms = s.elapsed_time(e)
         a = agg.setdefault(name, [0.0, 0])
         a[0] += ms
         a[1] += 1
-    return {k: {"ms_per_step": v[0] / steps, "launches_per_step": v[1] / steps} for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])}
+        if detail is not None:
+            f = fine.setdefault(f"{name}[{detail}]", [0.0, 0])
+            f[0] += ms
+            f[1] += 1
+    out = {k: {"ms_per_step": v[0] / steps, "launches_per_step": v[1] / steps} for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])}
+    detail = {k: {"ms_per_step": v[0] / steps, "launches_per_step": v[1] / steps} for k, v in sorted(fine.items(), key=lambda kv: -kv[1][0])}
+    return out, detail
 
 
 def run_b200(args):
@@ -319,7 +326,7 @@ def run_b200(args):
     _lib.set_timeline(None)
     launches = _lib.launch_count - l0
     ms = ev0.elapsed_time(ev1)
-    breakdown = kernel_breakdown(timeline, args.steps)
+    breakdown, breakdown_detail = kernel_breakdown(timeline, args.steps)
 
     # ---- end-to-end: pinned host buffers in, separated audio + segments back on the host ----
     k = 8
@@ -465,7 +472,7 @@ def run_b200(args):
         "gpu_launches": launches,
         "roofline": roofline, "roofline_gemm": roofline_gemm, "hbm_kernels": hbm,
         "cpu_baseline": cpu,
-        "kernels": breakdown,
+        "kernels": breakdown, "gemm_shapes": breakdown_detail,
     }
     print(json.dumps(line))
     if args.profile_json:

@@ -127,7 +127,8 @@ def set_timeline(timeline):
     _timeline = timeline
 
 
-def call(name: str, *args):
+def call(name: str, *args, detail: str = None):
+    """Calls one C-ABI entry point; ``detail`` only refines the timeline entry (e.g. the GEMM shape)."""
     global launch_count
     fn = getattr(load(), name)
     launch_count += 1
@@ -138,4 +139,4 @@ def call(name: str, *args):
     start.record()
     check(fn(*args), name)
     end.record()
-    _timeline.append((name, start, end))
+    _timeline.append((name, start, end, detail))

@@ -153,159 +153,170 @@ __device__ __forceinline__ void epilogue_store(const GemmArgs& g, int z, int64_t
 // instead the warp transposes the 32x32 block through a private shared-memory tile so that
 // consecutive lanes hold consecutive columns and every store instruction writes whole 128-byte
 // lines.
+//
+// The kernel is instantiated per (epilogue mode, activation): with both as run-time values the
+// inner loops carried 57 branches and per-chunk integer divisions, the eight epilogue warps were
+// busy 88 % of the time and the tensor pipe only 25 % (ncu, profiles/r1_ncu_gemm_b1_inbt.txt).
+// Everything that depends only on the tile is computed once per tile (EpiTile).
 // ---------------------------------------------------------------------------
 constexpr int kStageLd = 36;  // words per staged row: 16-byte aligned rows, conflict-free STS.128 / LDS.128
 
-// Bias of the columns a lane owns in the write-out phase (issued one chunk ahead so the global
-// load latency never sits on the epilogue's critical path).
+template <int ACT>
+__device__ __forceinline__ float act_t(float v) {
+  return ACT == 1 ? tanh_acc(v) : v;
+}
+
+// What a lane needs for the columns it writes in the next chunk; loaded one chunk ahead so that the
+// global-load latency never sits on the epilogue's critical path.
 struct ChunkBias {
   float v[4];
+  int plane;  // EPI_HEAD: destination plane of the lane's column
 };
-__device__ __forceinline__ ChunkBias load_chunk_bias(const GemmArgs& g, int z, int n0, int lane) {
+
+template <int MODE>
+__device__ __forceinline__ ChunkBias load_chunk_bias(const GemmArgs& g, const float* bias, const int* plane_row, int n0,
+                                                     int lane) {
   ChunkBias b;
   b.v[0] = b.v[1] = b.v[2] = b.v[3] = 0.f;
-  if (g.bias == nullptr) return b;
-  const float* bias = g.bias + static_cast<int64_t>(z % g.b_mod) * g.bias_stride;
-  if (g.mode == EPI_HEAD || g.mode == EPI_F32_BT || g.mode == EPI_BF16_BT) {
+  b.plane = 0;
+  if (MODE == EPI_HEAD || MODE == EPI_F32_BT || MODE == EPI_BF16_BT) {
     const int n = n0 + lane;
-    if (n < g.N) b.v[0] = __ldg(bias + n);
-  } else {
+    if (n < g.N) {
+      if (bias) b.v[0] = __ldg(bias + n);
+      if (MODE == EPI_HEAD) b.plane = __ldg(plane_row + n / g.row_len);
+    }
+  } else if (bias) {
     const int n = n0 + (lane & 7) * 4;
+    if (n + 3 < g.N) {
+      if ((reinterpret_cast<uintptr_t>(bias + n) & 15) == 0) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(bias + n));
+        b.v[0] = t.x, b.v[1] = t.y, b.v[2] = t.z, b.v[3] = t.w;
+      } else {
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-      if (n + j < g.N) b.v[j] = __ldg(bias + n + j);
+        for (int j = 0; j < 4; ++j) b.v[j] = __ldg(bias + n + j);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (n + j < g.N) b.v[j] = __ldg(bias + n + j);
+    }
   }
   return b;
 }
 
-__device__ __forceinline__ void epilogue_coalesced(const GemmArgs& g, int z, int64_t m0, int n0, int limit,
-                                                   const uint32_t* v, const ChunkBias& cb, uint32_t stage, int lane) {
-  const int nvalid = min(limit, g.N - n0);
-  if (nvalid <= 0) return;
-  // 1. stage the lane's own row of raw accumulators (8 x STS.128)
+// Per (tile, warp) invariants of the epilogue.
+struct EpiTile {
+  int64_t rows_left;   // rows of this warp's 32-row block that exist
+  int64_t base;        // element offset of (row m0 + sub, column c4) [row modes] / of the tile [BT] in the output
+  int64_t row_off[8];  // EPI_BF16_ROWMAP: element offset of row pass*4 + sub
+  uint32_t row_ok;     // EPI_BF16_ROWMAP: bit pass set when that row is written
+  bool fast;           // vector-aligned full block: one LDS.128 + one vector store per pass
+};
+
+template <int MODE>
+__device__ __forceinline__ EpiTile make_epi_tile(const GemmArgs& g, int z, int64_t m0, int lane) {
+  EpiTile t;
+  t.rows_left = g.M - m0;
+  t.row_ok = 0;
+  t.base = 0;
+  t.fast = false;
+  const int sub = lane >> 3, c4 = (lane & 7) * 4;
+  if (MODE == EPI_F32 || MODE == EPI_BF16) {
+    const int64_t zoff = static_cast<int64_t>(z / g.out_div) * g.out_stride_hi + static_cast<int64_t>(z % g.out_div) * g.out_stride;
+    t.base = zoff + (m0 + sub) * g.ldo + c4;
+    const int esz = MODE == EPI_F32 ? 4 : 2;
+    const uintptr_t amask = MODE == EPI_F32 ? 15 : 7;
+    t.fast = t.rows_left >= 32 && ((reinterpret_cast<uintptr_t>(g.out) | static_cast<uintptr_t>(zoff * esz) |
+                                    static_cast<uintptr_t>(g.ldo * esz)) & amask) == 0;
+  } else if (MODE == EPI_BF16_ROWMAP) {
+    // rows are ordered (group, t, b32) and m0 is a multiple of 32: group and t are the same for the whole block
+    const int64_t gt = m0 >> 5;
+    const int64_t grp = gt / g.rm_T, tt = gt - grp * g.rm_T;
+#pragma unroll
+    for (int pass = 0; pass < 8; ++pass) {
+      const int r = pass * 4 + sub;
+      const int zz = static_cast<int>(grp) * 32 + r;  // < 2^31: the launcher bounds the row count
+      const int item = zz / g.rm_K, spk = zz - item * g.rm_K;
+      t.row_off[pass] = (static_cast<int64_t>(item) * g.rm_T + tt) * g.ldo + static_cast<int64_t>(spk) * g.rm_P + c4;
+      if (zz < g.rm_Z && r < t.rows_left) t.row_ok |= 1u << pass;
+    }
+    t.fast = ((reinterpret_cast<uintptr_t>(g.out) | static_cast<uintptr_t>(g.ldo * 2) | static_cast<uintptr_t>(g.rm_P * 2)) & 7) == 0;
+  } else if (MODE == EPI_F32_BT || MODE == EPI_BF16_BT) {
+    t.base = (m0 >> 5) * static_cast<int64_t>(g.N) * 32 + lane * 4;
+  }
+  return t;
+}
+
+__device__ __forceinline__ void stage_rows(uint32_t stage, int lane, const uint32_t* v) {
 #pragma unroll
   for (int i = 0; i < 32; i += 4)
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage + (lane * kStageLd + i) * 4), "r"(v[i]),
                  "r"(v[i + 1]), "r"(v[i + 2]), "r"(v[i + 3])
                  : "memory");
   __syncwarp();
-  const int64_t rows_left = g.M - m0;  // rows of this warp that exist
-  if (g.mode == EPI_HEAD) {
-    // lane = column: block q, offset f, destination plane are fixed per lane for the whole chunk
-    const int n = n0 + lane;
-    const bool col_ok = lane < nvalid;
-    int q = 0, f = 0;
-    int64_t plane = 0;
-    if (col_ok) {
-      q = n / g.row_len;
-      f = n - q * g.row_len;
-      plane = g.plane_map[z * g.n_blocks + q];
-    }
-    float* lo = static_cast<float*>(g.out);
-    const int64_t base = (plane * g.M + m0) * g.row_len + f;
-    const int rmax = static_cast<int>(rows_left < 32 ? rows_left : 32);
-#pragma unroll 4
-    for (int r = 0; r < rmax; ++r) {
-      float val;
-      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(val) : "r"(stage + (r * kStageLd + lane) * 4));
-      val = fmaf(g.alpha, val, cb.v[0]);
-      if (col_ok) {
-        const int64_t idx = base + static_cast<int64_t>(r) * g.row_len;
-        if (lo) lo[idx] = val;
-        if (g.mask) g.mask[idx] = sigmoid_acc(val);
+}
+
+// EPI_F32 / EPI_BF16 / EPI_BF16_ROWMAP: per pass 4 rows x (8 lanes x 4 columns)
+template <int MODE, int ACT>
+__device__ __forceinline__ void epilogue_rows(const GemmArgs& g, const EpiTile& t, int n0, int limit, const uint32_t* v,
+                                              const ChunkBias& cb, uint32_t stage, int lane) {
+  const int nvalid = min(limit, g.N - n0);
+  if (nvalid <= 0) return;
+  stage_rows(stage, lane, v);
+  const int sub = lane >> 3, c4 = (lane & 7) * 4;
+  const uint32_t lds0 = stage + (sub * kStageLd + c4) * 4;
+  if (t.fast && nvalid == 32) {
+    const int64_t step = 4 * g.ldo;
+#pragma unroll
+    for (int pass = 0; pass < 8; ++pass) {
+      float4 x;
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                   : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w)
+                   : "r"(lds0 + pass * 4 * kStageLd * 4));
+      x.x = act_t<ACT>(fmaf(g.alpha, x.x, cb.v[0]));
+      x.y = act_t<ACT>(fmaf(g.alpha, x.y, cb.v[1]));
+      x.z = act_t<ACT>(fmaf(g.alpha, x.z, cb.v[2]));
+      x.w = act_t<ACT>(fmaf(g.alpha, x.w, cb.v[3]));
+      if (MODE == EPI_F32) {
+        *reinterpret_cast<float4*>(static_cast<float*>(g.out) + t.base + pass * step + n0) = x;
+      } else if (MODE == EPI_BF16) {
+        *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(g.out) + t.base + pass * step + n0) =
+            make_uint2(pack_bf16x2(x.x, x.y), pack_bf16x2(x.z, x.w));
+      } else if ((t.row_ok >> pass) & 1u) {
+        *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(g.out) + t.row_off[pass] + n0) =
+            make_uint2(pack_bf16x2(x.x, x.y), pack_bf16x2(x.z, x.w));
       }
     }
   } else {
-    const int64_t zoff = static_cast<int64_t>(z / g.out_div) * g.out_stride_hi + static_cast<int64_t>(z % g.out_div) * g.out_stride;
-    const int sub = lane >> 3, c4 = (lane & 7) * 4;  // 4 rows per pass, 8 lanes x 4 columns per row
-    const uint32_t lds0 = stage + (sub * kStageLd + c4) * 4;
-    // fast path: a full 32 x 32 block with vector-aligned rows -> per pass one LDS.128, four FMAs, one vector store
-    const bool full = nvalid == 32 && rows_left >= 32 && g.mode != EPI_BF16_ROWMAP;
-    if (full && g.mode == EPI_F32 && ((reinterpret_cast<uintptr_t>(g.out) | static_cast<uintptr_t>(zoff * 4) |
-                                       static_cast<uintptr_t>(g.ldo * 4)) & 15) == 0) {
-      float* o = static_cast<float*>(g.out) + zoff + (m0 + sub) * g.ldo + n0 + c4;
-      const int64_t step = 4 * g.ldo;
 #pragma unroll
-      for (int pass = 0; pass < 8; ++pass) {
-        float4 x;
-        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                     : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w)
-                     : "r"(lds0 + pass * 4 * kStageLd * 4));
-        x.x = fmaf(g.alpha, x.x, cb.v[0]);
-        x.y = fmaf(g.alpha, x.y, cb.v[1]);
-        x.z = fmaf(g.alpha, x.z, cb.v[2]);
-        x.w = fmaf(g.alpha, x.w, cb.v[3]);
-        if (g.act == 1) {
-          x.x = tanh_acc(x.x);
-          x.y = tanh_acc(x.y);
-          x.z = tanh_acc(x.z);
-          x.w = tanh_acc(x.w);
-        }
-        *reinterpret_cast<float4*>(o + pass * step) = x;
-      }
-    } else if (full && g.mode == EPI_BF16 && ((reinterpret_cast<uintptr_t>(g.out) | static_cast<uintptr_t>(zoff * 2) |
-                                               static_cast<uintptr_t>(g.ldo * 2)) & 7) == 0) {
-      __nv_bfloat16* o = static_cast<__nv_bfloat16*>(g.out) + zoff + (m0 + sub) * g.ldo + n0 + c4;
-      const int64_t step = 4 * g.ldo;
+    for (int pass = 0; pass < 8; ++pass) {
+      const int r = pass * 4 + sub;
+      float x[4];
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                   : "=f"(x[0]), "=f"(x[1]), "=f"(x[2]), "=f"(x[3])
+                   : "r"(stage + (r * kStageLd + c4) * 4));
 #pragma unroll
-      for (int pass = 0; pass < 8; ++pass) {
-        float4 x;
-        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                     : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w)
-                     : "r"(lds0 + pass * 4 * kStageLd * 4));
-        x.x = fmaf(g.alpha, x.x, cb.v[0]);
-        x.y = fmaf(g.alpha, x.y, cb.v[1]);
-        x.z = fmaf(g.alpha, x.z, cb.v[2]);
-        x.w = fmaf(g.alpha, x.w, cb.v[3]);
-        if (g.act == 1) {
-          x.x = tanh_acc(x.x);
-          x.y = tanh_acc(x.y);
-          x.z = tanh_acc(x.z);
-          x.w = tanh_acc(x.w);
-        }
-        *reinterpret_cast<uint2*>(o + pass * step) = make_uint2(pack_bf16x2(x.x, x.y), pack_bf16x2(x.z, x.w));
-      }
-    } else {
-#pragma unroll 1
-      for (int pass = 0; pass < 8; ++pass) {
-        const int r = pass * 4 + sub;
-        float x[4];
-        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                     : "=f"(x[0]), "=f"(x[1]), "=f"(x[2]), "=f"(x[3])
-                     : "r"(stage + (r * kStageLd + c4) * 4));
-#pragma unroll
-        for (int j = 0; j < 4; ++j) x[j] = apply_act(fmaf(g.alpha, x[j], cb.v[j]), g.act);
-        bool row_ok = r < rows_left;
-        int64_t off = zoff + (m0 + r) * g.ldo + n0 + c4;
-        if (g.mode == EPI_BF16_ROWMAP) {
-          // rows are ordered (group, t, b): scatter to out[(item * T + t) * ldo + spk * P + n], z = item * K + spk
-          const int64_t row = m0 + r;
-          const int64_t gt = row >> 5;
-          const int64_t grp = gt / g.rm_T, t = gt - grp * g.rm_T;
-          const int64_t zz = grp * 32 + (row & 31);
-          row_ok = row_ok && zz < g.rm_Z;
-          const int64_t item = zz / g.rm_K, spk = zz - item * g.rm_K;
-          off = (item * g.rm_T + t) * g.ldo + spk * g.rm_P + n0 + c4;
-        }
-        if (row_ok && c4 < nvalid) {
-          if (g.mode == EPI_F32) {
-            float* o = static_cast<float*>(g.out) + off;
-            if (c4 + 4 <= nvalid && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
-              *reinterpret_cast<float4*>(o) = make_float4(x[0], x[1], x[2], x[3]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                if (c4 + j < nvalid) o[j] = x[j];
-            }
+      for (int j = 0; j < 4; ++j) x[j] = act_t<ACT>(fmaf(g.alpha, x[j], cb.v[j]));
+      const bool row_ok = MODE == EPI_BF16_ROWMAP ? ((t.row_ok >> pass) & 1u) != 0 : r < t.rows_left;
+      const int64_t off = (MODE == EPI_BF16_ROWMAP ? t.row_off[pass] : t.base + pass * 4 * g.ldo) + n0;
+      if (row_ok && c4 < nvalid) {
+        if (MODE == EPI_F32) {
+          float* o = static_cast<float*>(g.out) + off;
+          if (c4 + 4 <= nvalid && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+            *reinterpret_cast<float4*>(o) = make_float4(x[0], x[1], x[2], x[3]);
           } else {
-            __nv_bfloat16* o = static_cast<__nv_bfloat16*>(g.out) + off;
-            if (c4 + 4 <= nvalid && (reinterpret_cast<uintptr_t>(o) & 7) == 0) {
-              *reinterpret_cast<uint2*>(o) = make_uint2(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]));
-            } else {
 #pragma unroll
-              for (int j = 0; j < 4; ++j)
-                if (c4 + j < nvalid) o[j] = __float2bfloat16_rn(x[j]);
-            }
+            for (int j = 0; j < 4; ++j)
+              if (c4 + j < nvalid) o[j] = x[j];
+          }
+        } else {
+          __nv_bfloat16* o = static_cast<__nv_bfloat16*>(g.out) + off;
+          if (c4 + 4 <= nvalid && (reinterpret_cast<uintptr_t>(o) & 7) == 0) {
+            *reinterpret_cast<uint2*>(o) = make_uint2(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (c4 + j < nvalid) o[j] = __float2bfloat16_rn(x[j]);
           }
         }
       }
@@ -314,30 +325,66 @@ __device__ __forceinline__ void epilogue_coalesced(const GemmArgs& g, int z, int
   __syncwarp();  // the staging tile is reused by the next chunk
 }
 
-// EPI_F32_BT: rows are ordered (group, t, b32) and the output is the layout the tcgen05 recurrence
-// streams: element (row m, column n) -> ((m/32)*N + (n/32)*32)*32 + (b/4)*128 + (n%32)*4 + b%4 with
-// b = m % 32, i.e. per (group, t) and per block of 32 columns a 4 KiB tile [b/4][column][b%4].  The
-// warp transposes its 32 x 32 block through shared memory and writes eight fully coalesced 512-byte
-// rows (lane = column).
-__device__ __forceinline__ void epilogue_bt(const GemmArgs& g, int64_t m0, int n0, const uint32_t* v, const ChunkBias& cb,
-                                            uint32_t stage, int lane) {
-  if (n0 >= g.N) return;
-#pragma unroll
-  for (int i = 0; i < 32; i += 4)
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage + (lane * kStageLd + i) * 4), "r"(v[i]),
-                 "r"(v[i + 1]), "r"(v[i + 2]), "r"(v[i + 3])
-                 : "memory");
+// EPI_HEAD: lane = column; block q, offset f and the destination plane are fixed per lane for the chunk
+__device__ __forceinline__ void epilogue_head(const GemmArgs& g, const EpiTile& t, int64_t m0, int n0, int limit,
+                                              const uint32_t* v, const ChunkBias& cb, uint32_t stage, int lane) {
+  const int nvalid = min(limit, g.N - n0);
+  if (nvalid <= 0) return;
+  stage_rows(stage, lane, v);
+  const int n = n0 + lane;
+  const bool col_ok = lane < nvalid;
+  const int q = n / g.row_len, f = n - q * g.row_len;
+  float* lo = static_cast<float*>(g.out);
+  float* mk = g.mask;
+  const int64_t base = col_ok ? (static_cast<int64_t>(cb.plane) * g.M + m0) * g.row_len + f : 0;
+  const int rmax = static_cast<int>(t.rows_left < 32 ? t.rows_left : 32);
+  const uint32_t lds0 = stage + lane * 4;
+  if (rmax == 32 && col_ok) {
+#pragma unroll 8
+    for (int r = 0; r < 32; ++r) {
+      float val;
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(val) : "r"(lds0 + r * kStageLd * 4));
+      val = fmaf(g.alpha, val, cb.v[0]);
+      const int64_t idx = base + static_cast<int64_t>(r) * g.row_len;
+      if (lo) lo[idx] = val;
+      if (mk) mk[idx] = sigmoid_acc(val);
+    }
+  } else {
+#pragma unroll 1
+    for (int r = 0; r < rmax; ++r) {
+      float val;
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(val) : "r"(lds0 + r * kStageLd * 4));
+      val = fmaf(g.alpha, val, cb.v[0]);
+      if (col_ok) {
+        const int64_t idx = base + static_cast<int64_t>(r) * g.row_len;
+        if (lo) lo[idx] = val;
+        if (mk) mk[idx] = sigmoid_acc(val);
+      }
+    }
+  }
   __syncwarp();
-  const int64_t o0 = ((m0 >> 5) * g.N + n0) * 32 + lane * 4;
+}
+
+// EPI_F32_BT / EPI_BF16_BT: rows are ordered (group, t, b32) and the output is the layout the tcgen05
+// recurrences stream: element (row m, column n) -> ((m/32)*N + (n/32)*32)*32 + (b/4)*128 + (n%32)*4 + b%4
+// with b = m % 32, i.e. per (group, t) and per block of 32 columns a tile [b/4][column][b%4].  The warp
+// transposes its 32 x 32 block through shared memory and writes eight fully coalesced rows (lane = column).
+template <int MODE, int ACT>
+__device__ __forceinline__ void epilogue_bt(const GemmArgs& g, const EpiTile& t, int n0, const uint32_t* v,
+                                            const ChunkBias& cb, uint32_t stage, int lane) {
+  if (n0 >= g.N) return;
+  stage_rows(stage, lane, v);
+  const int64_t o0 = t.base + static_cast<int64_t>(n0) * 32;
+  const uint32_t lds0 = stage + lane * 4;
 #pragma unroll
   for (int bq = 0; bq < 8; ++bq) {
     float x[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x[j]) : "r"(stage + ((bq * 4 + j) * kStageLd + lane) * 4));
-      x[j] = apply_act(fmaf(g.alpha, x[j], cb.v[0]), g.act);
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x[j]) : "r"(lds0 + (bq * 4 + j) * kStageLd * 4));
+      x[j] = act_t<ACT>(fmaf(g.alpha, x[j], cb.v[0]));
     }
-    if (g.mode == EPI_F32_BT)
+    if (MODE == EPI_F32_BT)
       *reinterpret_cast<float4*>(static_cast<float*>(g.out) + o0 + bq * 128) = make_float4(x[0], x[1], x[2], x[3]);
     else
       *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(g.out) + o0 + bq * 128) =
@@ -351,6 +398,7 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   return static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
 
+template <int MODE, int ACT>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -454,6 +502,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     const int q = warp & 3;  // TMEM lane quarter this warp may touch
+    const uint32_t stage = sStage + static_cast<uint32_t>(warp - 2) * (32 * kStageLd * 4);
+    const int cset = (warp - 2) >> 2;  // column chunks are dealt alternately to the two warp sets
     uint32_t it = 0;
     for (int64_t tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++it) {
       const uint32_t as = it & 1, aph = (it >> 1) & 1;
@@ -461,20 +511,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int64_t rem = tile - z * tiles_per_z;
       const int mt = static_cast<int>(rem / g.n_tiles), nt = static_cast<int>(rem - static_cast<int64_t>(mt) * g.n_tiles);
       const int64_t m0 = static_cast<int64_t>(mt) * BM + q * 32;
+      const int nbase = nt * g.bn;
+      const float* bias = g.bias ? g.bias + static_cast<int64_t>(z % g.b_mod) * g.bias_stride : nullptr;
+      const int* plane_row = MODE == EPI_HEAD ? g.plane_map + static_cast<int64_t>(z) * g.n_blocks : nullptr;
+      const EpiTile et = make_epi_tile<MODE>(g, z, m0, lane);
+      ChunkBias cb = load_chunk_bias<MODE>(g, bias, plane_row, nbase + cset * 32, lane);
       mbar_wait(tfull0 + 8 * as, aph);
       tc_fence_after();
       const uint32_t t0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kAccCols;
-      const uint32_t stage = sStage + static_cast<uint32_t>(warp - 2) * (32 * kStageLd * 4);
-      const int cset = (warp - 2) >> 2;  // column chunks are dealt alternately to the two warp sets
-      ChunkBias cb = load_chunk_bias(g, z, nt * g.bn + cset * 32, lane);
       for (int c0 = cset * 32; c0 < g.bn; c0 += 64) {
         uint32_t v[32];
         tc_ld32(t0 + c0, v);
-        const ChunkBias cb_next = load_chunk_bias(g, z, nt * g.bn + c0 + 64, lane);  // prefetch for the next chunk
+        const ChunkBias cb_next = load_chunk_bias<MODE>(g, bias, plane_row, nbase + c0 + 64, lane);  // for the next chunk
         tc_wait_ld();
         if (m0 < g.M) {
-          if (g.mode == EPI_F32_BT || g.mode == EPI_BF16_BT) epilogue_bt(g, m0, nt * g.bn + c0, v, cb, stage, lane);
-          else epilogue_coalesced(g, z, m0, nt * g.bn + c0, min(32, g.bn - c0), v, cb, stage, lane);
+          if (MODE == EPI_F32_BT || MODE == EPI_BF16_BT) epilogue_bt<MODE, ACT>(g, et, nbase + c0, v, cb, stage, lane);
+          else if (MODE == EPI_HEAD) epilogue_head(g, et, m0, nbase + c0, min(32, g.bn - c0), v, cb, stage, lane);
+          else epilogue_rows<MODE, ACT>(g, et, nbase + c0, min(32, g.bn - c0), v, cb, stage, lane);
         }
         cb = cb_next;
       }
@@ -598,10 +651,28 @@ static int launch_gemm(GemmArgs g, const uint16_t* A, int64_t lda, int64_t a_str
   g.stages = static_cast<int>(imin64(kMaxStages, (227 * 1024 - fixed) / stage_bytes));
   TSSEP_REQUIRE(g.stages >= 2, "gemm: tile does not fit shared memory");
   const size_t smem = fixed + g.stages * stage_bytes;
-  TSSEP_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   const int grid = static_cast<int>(imin64(g.total_tiles, sms));
-  gemm_tc_kernel<<<grid, kGemmThreads, smem, stream>>>(tmA, tmB, g);
-  return check_launch("gemm_tc");
+#define TSSEP_GEMM_CASE(MODE_, ACT_)                                                                                     \
+  if (g.mode == MODE_ && g.act == ACT_) {                                                                                \
+    TSSEP_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<MODE_, ACT_>, cudaFuncAttributeMaxDynamicSharedMemorySize,           \
+                                    static_cast<int>(smem)));                                                           \
+    gemm_tc_kernel<MODE_, ACT_><<<grid, kGemmThreads, smem, stream>>>(tmA, tmB, g);                                      \
+    return check_launch("gemm_tc");                                                                                      \
+  }
+  TSSEP_GEMM_CASE(EPI_F32, 0)
+  TSSEP_GEMM_CASE(EPI_F32, 1)
+  TSSEP_GEMM_CASE(EPI_BF16, 0)
+  TSSEP_GEMM_CASE(EPI_BF16, 1)
+  TSSEP_GEMM_CASE(EPI_HEAD, 0)
+  TSSEP_GEMM_CASE(EPI_F32_BT, 0)
+  TSSEP_GEMM_CASE(EPI_F32_BT, 1)
+  TSSEP_GEMM_CASE(EPI_BF16_BT, 0)
+  TSSEP_GEMM_CASE(EPI_BF16_BT, 1)
+  TSSEP_GEMM_CASE(EPI_BF16_ROWMAP, 0)
+  TSSEP_GEMM_CASE(EPI_BF16_ROWMAP, 1)
+#undef TSSEP_GEMM_CASE
+  set_error("gemm: no tensor-core instantiation for mode %d act %d", g.mode, g.act);
+  return -1;
 }
 
 }  // namespace tssep

@@ -14,7 +14,8 @@
 //                        with cp.async.bulk through an mbarrier ring, several steps ahead;
 //   warp 1 (one thread)  waits for h_{t-1} (NR x Up bf16, written by every CTA of the cluster
 //                        through DSMEM), issues the MMAs of both tiles and commits each tile;
-//   warps 2-9            (lane = gate row) tcgen05.ld the pre-activations, add G, apply the gates,
+//   warps 2..            (lane = gate row; 8 * NR/NC of them, each owning NC batch columns of one row
+//                        tile and TMEM lane quarter) tcgen05.ld the pre-activations, add G, apply the gates,
 //                        transpose 4x4 blocks inside lane quads, update c_t (registers) and h_t,
 //                        regroup 8 units into 16-byte chunks and push them to every CTA's next B
 //                        operand with st.async (complete_tx on the destination mbarrier) and to H.
@@ -25,7 +26,6 @@
 
 namespace tssep {
 
-constexpr int kTsThreads = 320;
 constexpr int kTsMaxStages = 8;
 
 struct RecTsArgs {
@@ -71,21 +71,27 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t* v) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tc_ld8(uint32_t taddr, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar)
                : "memory");
 }
 
-// NR batch rows per cluster; J independent accumulators per row tile: consecutive k-steps go to different
-// accumulators (summed by the epilogue) so that the small MMAs do not serialise on one accumulator's
-// read-modify-write latency.
-template <int NR, int J>
-__global__ void __launch_bounds__(kTsThreads, 1) blstm_rec_ts_kernel(const RecTsArgs a) {
+// NR batch rows per cluster, NC of them per epilogue warp (8 * NR/NC epilogue warps).
+template <int NR, int NC>
+__global__ void __launch_bounds__(64 + 256 * (NR / NC), 1) blstm_rec_ts_kernel(const RecTsArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr uint32_t kAtomB = NR * 128;  // one 64-k atom of the B operand: NR rows x 128 bytes, 128-byte swizzle
-  constexpr int NQ = NR / 4;             // batch-row quads
+  constexpr int EW = NR / NC;            // epilogue warps per (row tile, TMEM lane quarter)
+  constexpr int NQ = NC / 4;             // batch-row quads per epilogue warp
   constexpr int SUBS = 32 / NR;          // clusters per 32-row group
+  constexpr int kThreads = 64 + 256 * EW;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int NA = a.NA, KS = a.KS, GS = a.stages;
   const uint32_t esz = a.g_bf16 ? 2u : 4u;
@@ -93,7 +99,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) blstm_rec_ts_kernel(const RecTs
   const uint32_t g_stage = 8u * oct_bytes;
   const uint32_t sB = base;                         // [2 buffers][NA] x kAtomB
   const uint32_t sG = sB + 2u * NA * kAtomB;        // [GS] x g_stage
-  const uint32_t sT = sG + GS * g_stage;            // [8 warps] x NR x 16 B
+  const uint32_t sT = sG + GS * g_stage;            // [8 * EW warps] x NC x 16 B
   const uint32_t sBar = sT + 8u * NR * 16u;
   const uint32_t hfull0 = sBar, accfull0 = sBar + 16, gfull0 = sBar + 32, gempty0 = gfull0 + 8 * kTsMaxStages,
                  tptr = gempty0 + 8 * kTsMaxStages;
@@ -109,7 +115,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) blstm_rec_ts_kernel(const RecTs
   oct_valid = oct_valid < 0 ? 0 : (oct_valid > 8 ? 8 : oct_valid);
 
   // ---- one-time setup ---------------------------------------------------------------------------
-  for (uint32_t i = threadIdx.x; i < 2u * NA * kAtomB / 16; i += kTsThreads)
+  for (uint32_t i = threadIdx.x; i < 2u * NA * kAtomB / 16; i += kThreads)
     asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(sB + 16 * i), "r"(0u) : "memory");
   if (warp == 1) {
     if (lane == 0) {
@@ -119,7 +125,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) blstm_rec_ts_kernel(const RecTs
       mbar_init(accfull0 + 8, 1);
       for (int i = 0; i < GS; ++i) {
         mbar_init(gfull0 + 8 * i, 1);
-        mbar_init(gempty0 + 8 * i, 8);
+        mbar_init(gempty0 + 8 * i, 8 * EW);
       }
       mbar_fence_init();
       mbar_arrive_expect_tx(hfull0, tx_bytes);
@@ -138,7 +144,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) blstm_rec_ts_kernel(const RecTs
   const uint32_t a_tile_cols = (static_cast<uint32_t>(Up) / 2 + 31u) & ~31u;  // columns per A tile (32-aligned)
   const uint32_t acc_col = 2u * a_tile_cols;                                   // accumulators behind the A tiles
 
-  if (warp >= 2) {
+  if (warp >= 2 && warp < 10) {
     // W_hh -> TMEM: lane = gate row of the tile, 8 columns (16 k values) per store
     const int tl = (warp - 2) >> 2, q = warp & 3;
     const uint4* src = a.Wimg + ((static_cast<size_t>(dir) * C + crank) * 2 + tl) * static_cast<size_t>(KS) * 256 +
@@ -193,27 +199,27 @@ __global__ void __launch_bounds__(kTsThreads, 1) blstm_rec_ts_kernel(const RecTs
       if (s > 0) {
         mbar_wait(hfull0 + 8 * rb, ((s - 1) >> 1) & 1);
         if (lane == 0) mbar_arrive_expect_tx(hfull0 + 8 * rb, tx_bytes);  // re-arm for the data of step s+1
-        ts_fence_proxy_async();  // h arrived through st.async (generic proxy); the MMA reads via the async proxy
+        // h arrived through st.async (generic proxy); the MMA reads it through the async proxy
+        ts_fence_proxy_async();
       }
       tc_fence_after();
       if (elect_one()) {
         const uint64_t bd = bdesc0 + static_cast<uint64_t>(rb ? buf_step : 0u);
 #pragma unroll
         for (int tile = 0; tile < 2; ++tile) {
-          const uint32_t d = d0 + tile * (J * NR);
+          const uint32_t d = d0 + tile * NR;
           uint32_t at = tmem_base + static_cast<uint32_t>(tile) * a_tile_cols;
           uint64_t bk = bd;
           for (int atom = 0; atom < full_atoms; ++atom) {
 #pragma unroll
             for (int k4 = 0; k4 < 4; ++k4)
-              tc_mma_bf16_ts(d + (k4 % J) * NR, at + k4 * 8, bk + 2 * k4, idesc, (atom > 0 || k4 >= J) ? 1u : 0u);
+              tc_mma_bf16_ts(d, at + k4 * 8, bk + 2 * k4, idesc, (atom > 0 || k4 > 0) ? 1u : 0u);
             at += 32;
             bk += kAtomB >> 4;
           }
 #pragma unroll
           for (int k4 = 0; k4 < 3; ++k4)
-            if (k4 < rem)
-              tc_mma_bf16_ts(d + (k4 % J) * NR, at + k4 * 8, bk + 2 * k4, idesc, (full_atoms > 0 || k4 >= J) ? 1u : 0u);
+            if (k4 < rem) tc_mma_bf16_ts(d, at + k4 * 8, bk + 2 * k4, idesc, (full_atoms > 0 || k4 > 0) ? 1u : 0u);
           tc_commit(accfull0 + 8 * tile);
         }
       }
@@ -221,27 +227,29 @@ __global__ void __launch_bounds__(kTsThreads, 1) blstm_rec_ts_kernel(const RecTs
     }
   } else {
     // ---- epilogue: gates, cell update, h exchange --------------------------------------------------
-    const int tl = (warp - 2) >> 2;  // row tile handled by this warp
-    const int q = warp & 3;          // TMEM lane quarter
+    const int tl = ((warp - 2) >> 2) & 1;  // row tile handled by this warp
+    const int q = warp & 3;                // TMEM lane quarter
+    const int half = (warp - 2) >> 3;      // which NC columns (batch rows) of the tile
     const int gate = lane & 3;       // i, f, g, o
     const int ul = lane >> 2;        // unit within the warp's octet
     const bool is_g = gate == 2;
     const float sc = a.fast ? (is_g ? 1.0f : 0.5f) : (is_g ? 2.0f : 1.0f);
     const float ka = a.fast ? (is_g ? 1.0f : 0.5f) : (is_g ? 2.0f : 1.0f);
     const float kb = a.fast ? (is_g ? 0.0f : 0.5f) : (is_g ? -1.0f : 0.0f);
-    const uint32_t myT = sT + static_cast<uint32_t>(warp - 2) * (NR * 16);
+    const uint32_t myT = sT + static_cast<uint32_t>(warp - 2) * (NC * 16);
     const int oc = tl * 4 + q;  // unit octet inside the CTA = 16-byte chunk of the CTA's k-atom
     const int unit0 = static_cast<int>(crank) * 64 + oc * 8;
     const bool oct_ok = unit0 < Up;
-    // sender role: lane ships batch row r to CTAs d0, d0 + 32/NR, ...
-    const int r = lane % NR, d0 = lane / NR;
+    // sender role: lane ships batch row r to CTAs d0, d0 + 32/NC, ...
+    constexpr int DG = 32 / NC;
+    const int rl = lane % NC, r = half * NC + rl, d0 = lane / NC;
     const uint32_t chunk_off = crank * kAtomB + static_cast<uint32_t>(r >> 3) * 1024 + static_cast<uint32_t>(r & 7) * 128 +
                                ((static_cast<uint32_t>(oc) ^ static_cast<uint32_t>(r & 7)) << 4);
-    constexpr int ND = (8 + SUBS - 1) / SUBS;
+    constexpr int ND = (8 + DG - 1) / DG;
     uint32_t r_b[ND], r_bar[ND];
 #pragma unroll
     for (int j = 0; j < ND; ++j) {
-      const uint32_t d = static_cast<uint32_t>(d0 + j * SUBS);
+      const uint32_t d = static_cast<uint32_t>(d0 + j * DG);
       r_b[j] = d < C ? mapa(sB, d) + chunk_off : 0;
       r_bar[j] = d < C ? mapa(hfull0, d) : 0;
     }
@@ -249,9 +257,8 @@ __global__ void __launch_bounds__(kTsThreads, 1) blstm_rec_ts_kernel(const RecTs
                            dir * Up + unit0;
     const int64_t h_tstride = 32ll * 2 * Up;
     const bool h_store = oct_ok && d0 == 0;
-    const uint32_t g_lane = static_cast<uint32_t>(oc) * oct_bytes + static_cast<uint32_t>(lane) * 4u * esz;
-    const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc_col + tl * (J * NR);
-    const int jn = KS < J ? KS : J;  // accumulators that receive at least one k-step
+    const uint32_t g_lane = static_cast<uint32_t>(oc) * oct_bytes + static_cast<uint32_t>(half * NQ * 32 + lane) * 4u * esz;
+    const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc_col + tl * NR + half * NC;
 
     float cst[NQ];
 #pragma unroll
@@ -266,7 +273,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) blstm_rec_ts_kernel(const RecTs
       int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
       if (do_prof) c0 = clock();
       // input projection of this step: shared-memory ring -> registers, slot handed back at once
-      float gv[NR];
+      float gv[NC];
       mbar_wait(gfull0 + 8 * slot, (s / GS) & 1);
       {
         const uint32_t gp = sG + slot * g_stage + g_lane;
@@ -295,26 +302,18 @@ __global__ void __launch_bounds__(kTsThreads, 1) blstm_rec_ts_kernel(const RecTs
       mbar_wait(accfull0 + 8 * tl, s & 1);
       if (do_prof) c2 = clock();
       tc_fence_after();
-      uint32_t v[J][NR];
-#pragma unroll
-      for (int j = 0; j < J; ++j) {
-        if (j < jn) {
-          if constexpr (NR == 32) tc_ld32(t_acc + j * NR, v[j]);
-          else tc_ld16(t_acc + j * NR, v[j]);
-        }
-      }
+      uint32_t v[NC];
+      if constexpr (NC == 32) tc_ld32(t_acc, v);
+      else if constexpr (NC == 16) tc_ld16(t_acc, v);
+      else tc_ld8(t_acc, v);
       tc_wait_ld();
       tc_fence_before();
 
-      // gate non-linearity of this lane's row for all NR batch rows
-      float act[NR];
+      // gate non-linearity of this lane's row for the warp's NC batch rows
+      float act[NC];
 #pragma unroll
-      for (int i = 0; i < NR; ++i) {
-        float pre = gv[i];
-#pragma unroll
-        for (int j = 0; j < J; ++j)
-          if (j < jn) pre += __uint_as_float(v[j][i]);
-        const float x = pre * sc;
+      for (int i = 0; i < NC; ++i) {
+        const float x = (__uint_as_float(v[i]) + gv[i]) * sc;
         const float y = a.fast ? tanh_fast(x) : sigmoid_acc(x);
         act[i] = fmaf(y, ka, kb);
       }
@@ -363,13 +362,13 @@ __global__ void __launch_bounds__(kTsThreads, 1) blstm_rec_ts_kernel(const RecTs
       uint4 chunk;
       asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
                    : "=r"(chunk.x), "=r"(chunk.y), "=r"(chunk.z), "=r"(chunk.w)
-                   : "r"(myT + static_cast<uint32_t>(r) * 16));
+                   : "r"(myT + static_cast<uint32_t>(rl) * 16));
       __syncwarp();
       if (s + 1 < T) {
         const uint32_t boff = static_cast<uint32_t>(wb) * NA * kAtomB;
 #pragma unroll
         for (int j = 0; j < ND; ++j)
-          if (static_cast<uint32_t>(d0 + j * SUBS) < C) ts_st_async_v4(r_b[j] + boff, chunk, r_bar[j] + 8 * wb);
+          if (static_cast<uint32_t>(d0 + j * DG) < C) ts_st_async_v4(r_b[j] + boff, chunk, r_bar[j] + 8 * wb);
       }
       if (h_store) *reinterpret_cast<uint4*>(hbase + static_cast<int64_t>(t) * h_tstride) = chunk;
       if (do_prof) {
@@ -420,14 +419,14 @@ __global__ void pack_whh_ts_kernel(const float* __restrict__ w_fwd, const float*
   }
 }
 
-template <int NR, int J>
+template <int NR, int NC>
 static int max_clusters_ts(int C, size_t smem) {
-  if (cudaFuncSetAttribute(blstm_rec_ts_kernel<NR, J>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) !=
+  if (cudaFuncSetAttribute(blstm_rec_ts_kernel<NR, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) !=
       cudaSuccess)
     return 0;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(C, 64, 2);
-  cfg.blockDim = dim3(kTsThreads);
+  cfg.blockDim = dim3(64 + 256 * (NR / NC));
   cfg.dynamicSmemBytes = smem;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -437,7 +436,7 @@ static int max_clusters_ts(int C, size_t smem) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   int n = 0;
-  if (cudaOccupancyMaxActiveClusters(&n, blstm_rec_ts_kernel<NR, J>, &cfg) != cudaSuccess) {
+  if (cudaOccupancyMaxActiveClusters(&n, blstm_rec_ts_kernel<NR, NC>, &cfg) != cudaSuccess) {
     cudaGetLastError();
     return 0;
   }
@@ -462,12 +461,12 @@ static size_t ts_smem(int C, int NR, int g_dtype, int* stages_out) {
   return smem < 120 * 1024 ? 120 * 1024 : smem;
 }
 
-template <int NR, int J>
+template <int NR, int NC>
 static int launch_ts(const RecTsArgs& a, int C, int nsub, size_t smem, cudaStream_t stream) {
-  TSSEP_CUDA(cudaFuncSetAttribute(blstm_rec_ts_kernel<NR, J>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  TSSEP_CUDA(cudaFuncSetAttribute(blstm_rec_ts_kernel<NR, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(C, static_cast<unsigned>(nsub), 2);
-  cfg.blockDim = dim3(kTsThreads);
+  cfg.blockDim = dim3(64 + 256 * (NR / NC));
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -477,7 +476,7 @@ static int launch_ts(const RecTsArgs& a, int C, int nsub, size_t smem, cudaStrea
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  TSSEP_CUDA(cudaLaunchKernelEx(&cfg, blstm_rec_ts_kernel<NR, J>, a));
+  TSSEP_CUDA(cudaLaunchKernelEx(&cfg, blstm_rec_ts_kernel<NR, NC>, a));
   return check_launch("blstm_rec_ts");
 }
 
@@ -503,8 +502,8 @@ int tssep_blstm_recurrence_ts_capacity(int Up, int rows_per_cluster, int g_dtype
                 "tssep_blstm_recurrence_ts_capacity: rows_per_cluster must be 16 or 32");
   const int C = (Up + 63) / 64;
   int st = 0;
-  const int m = rows_per_cluster == 16 ? max_clusters_ts<16, 1>(C, ts_smem(C, 16, g_dtype, &st))
-                                       : max_clusters_ts<32, 1>(C, ts_smem(C, 32, g_dtype, &st));
+  const int m = rows_per_cluster == 16 ? max_clusters_ts<16, 8>(C, ts_smem(C, 16, g_dtype, &st))
+                                       : max_clusters_ts<32, 16>(C, ts_smem(C, 32, g_dtype, &st));
   return (m / 2) * rows_per_cluster;
 }
 
@@ -530,8 +529,8 @@ int tssep_blstm_recurrence_ts(const void* G, int g_dtype, const uint32_t* Wimg, 
     // 16 rows per cluster has the shortest step (1.3-1.4 us at U=300 vs 2.25 us for 32 rows); a launch that
     // does not fit in one wave of co-resident clusters runs its waves back to back
     int st = 0;
-    const int m16 = max_clusters_ts<16, 1>(C, ts_smem(C, 16, g_dtype, &st));
-    const int m32 = max_clusters_ts<32, 1>(C, ts_smem(C, 32, g_dtype, &st));
+    const int m16 = max_clusters_ts<16, 8>(C, ts_smem(C, 16, g_dtype, &st));
+    const int m32 = max_clusters_ts<32, 16>(C, ts_smem(C, 32, g_dtype, &st));
     const int64_t n16 = 2 * ((rows + 15) / 16), n32 = 2 * ((rows + 31) / 32);
     const double t16 = m16 > 0 ? 1.0 * static_cast<double>((n16 + m16 - 1) / m16) : 1e9;
     const double t32 = m32 > 0 ? 1.6 * static_cast<double>((n32 + m32 - 1) / m32) : 2e9;
@@ -558,17 +557,15 @@ int tssep_blstm_recurrence_ts(const void* G, int g_dtype, const uint32_t* Wimg, 
   TSSEP_REQUIRE(stages >= 2, "tssep_blstm_recurrence_ts: G ring does not fit shared memory");
   a.stages = stages;
   const int nsub = static_cast<int>((rows + NR - 1) / NR);
-  // independent accumulators per row tile (TMEM columns: 2 A tiles + 2 * J * NR <= 512); measured: one is best
-  int J = 1;
-  if (const char* e = getenv("TSSEP_TS_NACC")) {
+  // batch columns per epilogue warp (TSSEP_TS_COLS): 16 epilogue warps by default, 8 on request
+  int NC = NR / 2;
+  if (const char* e = getenv("TSSEP_TS_COLS")) {
     const int v = atoi(e);
-    if (v == 1 || v == 2 || (v == 4 && NR == 16) || (v == 3 && NR == 32)) J = v;
+    if (v == NR || v == NR / 2) NC = v;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (NR == 16) return J == 1 ? launch_ts<16, 1>(a, C, nsub, smem, st) : J == 2 ? launch_ts<16, 2>(a, C, nsub, smem, st)
-                                                                                : launch_ts<16, 4>(a, C, nsub, smem, st);
-  return J == 1 ? launch_ts<32, 1>(a, C, nsub, smem, st) : J == 2 ? launch_ts<32, 2>(a, C, nsub, smem, st)
-                                                                  : launch_ts<32, 3>(a, C, nsub, smem, st);
+  if (NR == 16) return NC == 16 ? launch_ts<16, 16>(a, C, nsub, smem, st) : launch_ts<16, 8>(a, C, nsub, smem, st);
+  return NC == 32 ? launch_ts<32, 32>(a, C, nsub, smem, st) : launch_ts<32, 16>(a, C, nsub, smem, st);
 }
 
 }  // extern "C"

@@ -227,7 +227,16 @@ class MaskEstimator_v2(Configurable, torch.nn.Module):
         else:
             raise RuntimeError(xs.shape)
         _lib.require_cuda(aux_t)
-        perm_t = torch.as_tensor(np.stack(perms), device=dev, dtype=torch.long)
+        # Both index tables go to the device NOW, through pinned memory: a pageable copy issued later would
+        # block the host until every kernel queued before it has run and serialise concurrent streams.
+        perm_np = np.stack(perms)  # (B, K)
+        nmask = self.nmask
+        if self.ts_vad is not False:
+            planes = (np.arange(B)[:, None, None] * K + perm_np[:, :, None]) * nmask + np.arange(nmask)[None, None, :]
+        else:
+            planes = ((np.arange(B)[:, None] * K + perm_np)[:, :, None]) * nmask + np.arange(nmask)[None, None, :]
+        perm_t = torch.from_numpy(perm_np.astype(np.int64)).pin_memory().to(dev, non_blocking=True)
+        plane_map = torch.from_numpy(planes.reshape(-1).astype(np.int32)).pin_memory().to(dev, non_blocking=True)
         aux_p = torch.gather(aux_t.float(), 1, perm_t[:, :, None].expand(B, K, aux_t.shape[-1]))  # slot order
         if batched and self.aux_normalizer is not None:
             aux_p = self.aux_normalizer(aux_p)
@@ -377,14 +386,10 @@ class MaskEstimator_v2(Configurable, torch.nn.Module):
         tf = self.output_resolution == "tf"
         row_len = fh if tf else 1
         hp = self._head_pack(K, R, row_len)
-        perm_np = np.stack(perms)  # (B, K)
         if self.ts_vad is not False:
             items, nb = B, K * nmask
-            planes = (np.arange(B)[:, None, None] * K + perm_np[:, :, None]) * nmask + np.arange(nmask)[None, None, :]
         else:
             items, nb = B * K, nmask
-            planes = ((np.arange(B)[:, None] * K + perm_np)[:, :, None]) * nmask + np.arange(nmask)[None, None, :]
-        plane_map = torch.as_tensor(planes.reshape(-1).astype(np.int32), device=dev)
         shape = (B, K, nmask, T, fh if tf else odim)
         logit = torch.empty(shape, dtype=torch.float32, device=dev)
         mask = torch.empty(shape, dtype=torch.float32, device=dev)

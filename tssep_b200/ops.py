@@ -48,7 +48,7 @@ def gemm(A, lda, B, ldb, M, N, K, out, *, mode, ldo=0, batch=1, a_stride=0, a_di
     if row_map is not None:  # (T, K, Z, P) of EPI_BF16_ROWMAP
         d.rm_T, d.rm_K, d.rm_Z, d.rm_P = row_map
     d.impl = _gemm_impl() if impl is None else impl
-    _lib.call("tssep_gemm", C.byref(d), _lib.stream_of(A))
+    _lib.call("tssep_gemm", C.byref(d), _lib.stream_of(A), detail=f"M={M} N={N} K={K} batch={batch} mode={mode}")
 
 
 def cast_bf16(src: torch.Tensor, ld_dst: int = None) -> torch.Tensor:
