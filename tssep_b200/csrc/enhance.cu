@@ -9,6 +9,8 @@
 #include "common.cuh"
 #include "fft.cuh"
 
+#include <cstdlib>
+
 namespace tssep {
 
 // ---------------------------------------------------------------------------
@@ -215,6 +217,191 @@ mask_istft_kernel(const float2* __restrict__ X, int64_t x_item_stride, const flo
   }
 }
 
+// ---------------------------------------------------------------------------
+// Fast path for the frame geometry of every shipped config (size 1024, shift 256, window 1024).
+//
+// The 512-point inverse FFT behind the real iFFT is factored 16 x 32 with BOTH factors in registers:
+//   pass A  lane k2 holds Z[32 k1 + k2], k1 < 16 (coalesced loads of X and the mask), runs a
+//           16-point DFT, multiplies by w512^(k2 n1) and drops Y[n1][k2] into a padded
+//           shared-memory tile: the only shared-memory round trip of the transform;
+//   pass B  lane l of a half-warp picks up Y[l][0..31], runs a 32-point DFT and owns
+//           z[l + 16 n2], n2 < 32, i.e. samples 2 (l + 16 n2) + {0, 1} of the frame.
+// With that ownership the four 256-sample quarters of a frame are the register groups n2 / 8, so
+// the overlap-add of consecutive frames is a shift of register groups: the accumulator lives in
+// registers, every output sample is written once (128-byte rows per half-warp), no ring, no
+// atomics.  A warp transforms the SAME frame of two speakers (lanes 0-15 / 16-31 in pass B) and
+// loads the mixture row once for both; the warps of a CTA cover up to 8 speakers of one meeting so
+// that the mixture row is served from L1/L2.  Each warp walks a range of `hops` hops and recomputes
+// only the 3 frames before it.
+// ---------------------------------------------------------------------------
+constexpr int kFastWarps = 4;   // speaker pairs per CTA
+constexpr int kXLd = 33;        // padded row (float2) of the exchange tile: conflict-free both ways
+
+// exp(+2 pi i k / 32)
+__device__ __forceinline__ float2 w32(int k) {
+  const float c[32] = {1.000000000e+00f, 9.807852804e-01f, 9.238795325e-01f, 8.314696123e-01f, 7.071067812e-01f, 5.555702330e-01f, 3.826834324e-01f, 1.950903220e-01f, 6.123233996e-17f, -1.950903220e-01f, -3.826834324e-01f, -5.555702330e-01f, -7.071067812e-01f, -8.314696123e-01f, -9.238795325e-01f, -9.807852804e-01f, -1.000000000e+00f, -9.807852804e-01f, -9.238795325e-01f, -8.314696123e-01f, -7.071067812e-01f, -5.555702330e-01f, -3.826834324e-01f, -1.950903220e-01f, -1.836970199e-16f, 1.950903220e-01f, 3.826834324e-01f, 5.555702330e-01f, 7.071067812e-01f, 8.314696123e-01f, 9.238795325e-01f, 9.807852804e-01f};
+  const float sn[32] = {0.000000000e+00f, 1.950903220e-01f, 3.826834324e-01f, 5.555702330e-01f, 7.071067812e-01f, 8.314696123e-01f, 9.238795325e-01f, 9.807852804e-01f, 1.000000000e+00f, 9.807852804e-01f, 9.238795325e-01f, 8.314696123e-01f, 7.071067812e-01f, 5.555702330e-01f, 3.826834324e-01f, 1.950903220e-01f, 1.224646799e-16f, -1.950903220e-01f, -3.826834324e-01f, -5.555702330e-01f, -7.071067812e-01f, -8.314696123e-01f, -9.238795325e-01f, -9.807852804e-01f, -1.000000000e+00f, -9.807852804e-01f, -9.238795325e-01f, -8.314696123e-01f, -7.071067812e-01f, -5.555702330e-01f, -3.826834324e-01f, -1.950903220e-01f};
+  return make_float2(c[k], sn[k]);
+}
+
+// in-place inverse DFT (unnormalised, exp(+i...)) of N register values, natural order in and out
+template <int N>
+__device__ __forceinline__ void idft_reg(float2 (&v)[N]) {
+  if constexpr (N == 2) {
+    const float2 a = v[0], b = v[1];
+    v[0] = cadd(a, b);
+    v[1] = csub(a, b);
+  } else {
+    float2 e[N / 2], o[N / 2];
+#pragma unroll
+    for (int i = 0; i < N / 2; ++i) {
+      e[i] = v[2 * i];
+      o[i] = v[2 * i + 1];
+    }
+    idft_reg<N / 2>(e);
+    idft_reg<N / 2>(o);
+#pragma unroll
+    for (int k = 0; k < N / 2; ++k) {
+      float2 t;
+      if (k == 0) t = o[0];
+      else if (k == N / 4) t = make_float2(-o[k].y, o[k].x);  // * (+i)
+      else t = cmul(o[k], w32(k * (32 / N)));
+      v[k] = cadd(e[k], t);
+      v[k + N / 2] = csub(e[k], t);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(32 * kFastWarps, 3)
+mask_istft_1024_kernel(const float2* __restrict__ X, int64_t x_item_stride, const float* __restrict__ mask, int n_spk,
+                       int groups, int64_t T, int trim, const float* __restrict__ synwin, const float2* __restrict__ twiddle,
+                       float2* __restrict__ est, float* __restrict__ time_out, int64_t num_samples, int hops) {
+  constexpr int M = 512, F = 513, R = 256;
+  __shared__ float2 tw[M];                              // exp(-2 pi i k / 1024)
+  __shared__ float2 twA[16 * 32];                       // exp(+2 pi i k2 n1 / 512) at [n1 * 32 + k2]
+  __shared__ float2 syn2[M];                            // synthesis window pairs / 512
+  __shared__ float2 xch[kFastWarps][2][16 * kXLd];      // Y[n1][k2] of the warp's two frames
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < M; i += blockDim.x) {
+    tw[i] = twiddle[i];
+    syn2[i] = make_float2(synwin[2 * i] * (1.0f / M), synwin[2 * i + 1] * (1.0f / M));
+    const int n1 = i >> 5, k2 = i & 31;
+    const int idx = 2 * k2 * n1;  // < 1024
+    float2 w = twiddle[idx & (M - 1)];
+    if (idx >= M) w = make_float2(-w.x, -w.y);
+    twA[i] = make_float2(w.x, -w.y);  // conj: exp(+...)
+  }
+  __syncthreads();
+
+  const int64_t z = blockIdx.y / groups;
+  const int spk0 = (blockIdx.y % groups) * (2 * kFastWarps) + 2 * warp;
+  if (spk0 >= n_spk) return;
+  const bool has_b = spk0 + 1 < n_spk;
+  const int64_t sig_a = z * n_spk + spk0, sig_b = sig_a + (has_b ? 1 : 0);
+  const int64_t J = T + 3;
+  const int64_t j_begin = static_cast<int64_t>(blockIdx.x) * hops;
+  const int64_t j_end = imin64(J, j_begin + hops);
+  const int half = lane >> 4, l = lane & 15;
+  const int64_t sig_mine = half ? sig_b : sig_a;
+  const bool store_mine = time_out != nullptr && (half == 0 || has_b);
+  float2* xa = xch[warp][0];
+  float2* xb = xch[warp][1];
+  const float2* mine = half ? xb : xa;
+
+  float2 acc[3][8];
+#pragma unroll
+  for (int g = 0; g < 3; ++g)
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[g][q] = make_float2(0.f, 0.f);
+
+  for (int64_t t = j_begin - 3; t < j_end; ++t) {
+    float2 u[32];
+    if (t >= 0 && t < T) {
+      // ---- pass A: both speakers, element k = 32 k1 + lane ------------------------------------------
+      float2 va[16], vb[16];
+      const int64_t row_a = (sig_a * T + t) * F, row_b = (sig_b * T + t) * F;
+      const float2* xrow_a = mask ? X + z * x_item_stride + t * F : X + row_a;
+      const float2* xrow_b = mask ? xrow_a : X + row_b;
+      const bool own = est != nullptr && t >= j_begin;
+#pragma unroll
+      for (int k1 = 0; k1 < 16; ++k1) {
+        const int kk = 32 * k1 + lane;
+        float2 yk = xrow_a[kk], ym = xrow_a[M - kk];
+        float2 yk2 = yk, ym2 = ym;
+        if (mask) {
+          const float mk = mask[row_a + kk], mm = mask[row_a + M - kk];
+          const float mk2 = mask[row_b + kk], mm2 = mask[row_b + M - kk];
+          yk = make_float2(yk.x * mk, yk.y * mk);
+          ym = make_float2(ym.x * mm, ym.y * mm);
+          yk2 = make_float2(yk2.x * mk2, yk2.y * mk2);
+          ym2 = make_float2(ym2.x * mm2, ym2.y * mm2);
+        } else if (has_b) {
+          yk2 = xrow_b[kk];
+          ym2 = xrow_b[M - kk];
+        }
+        if (own) {
+          est[row_a + kk] = yk;
+          if (has_b) est[row_b + kk] = yk2;
+          if (kk == 0) {
+            est[row_a + M] = ym;
+            if (has_b) est[row_b + M] = ym2;
+          }
+        }
+        if (kk == 0) {  // c2r ignores the imaginary parts of DC and Nyquist
+          yk.y = ym.y = 0.f;
+          yk2.y = ym2.y = 0.f;
+        }
+        const float2 w = tw[kk];
+        va[k1] = irfft_pack_w(yk, ym, w);
+        vb[k1] = irfft_pack_w(yk2, ym2, w);
+      }
+      idft_reg<16>(va);
+      idft_reg<16>(vb);
+#pragma unroll
+      for (int n1 = 0; n1 < 16; ++n1) {
+        const float2 w = twA[n1 * 32 + lane];
+        xa[n1 * kXLd + lane] = n1 ? cmul(va[n1], w) : va[0];
+        xb[n1 * kXLd + lane] = n1 ? cmul(vb[n1], w) : vb[0];
+      }
+      __syncwarp();
+      // ---- pass B: 32-point DFT of row l, then the synthesis window -----------------------------------
+#pragma unroll
+      for (int k2 = 0; k2 < 32; ++k2) u[k2] = mine[l * kXLd + k2];
+      __syncwarp();
+      idft_reg<32>(u);
+#pragma unroll
+      for (int n2 = 0; n2 < 32; ++n2) {
+        const float2 w = syn2[l + 16 * n2];
+        u[n2] = make_float2(u[n2].x * w.x, u[n2].y * w.y);
+      }
+    } else {
+#pragma unroll
+      for (int n2 = 0; n2 < 32; ++n2) u[n2] = make_float2(0.f, 0.f);
+    }
+    // ---- overlap-add in registers: hop t is complete once frame t's first quarter is added -------------
+    const bool emit = store_mine && t >= j_begin;
+    float* orow = time_out + sig_mine * num_samples;
+    const int64_t n0 = t * R + 2 * l - trim;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float2 o = cadd(acc[0][q], u[q]);
+      const int64_t n = n0 + 32 * q;
+      if (emit) {
+        if (n >= 0 && n + 1 < num_samples && ((reinterpret_cast<uintptr_t>(orow + n) & 7) == 0)) {
+          *reinterpret_cast<float2*>(orow + n) = o;
+        } else {
+          if (n >= 0 && n < num_samples) orow[n] = o.x;
+          if (n + 1 >= 0 && n + 1 < num_samples) orow[n + 1] = o.y;
+        }
+      }
+      acc[0][q] = cadd(acc[1][q], u[8 + q]);
+      acc[1][q] = cadd(acc[2][q], u[16 + q]);
+      acc[2][q] = u[24 + q];
+    }
+  }
+}
+
 static int ilog2_exact(int v) {
   int l = 0;
   while ((1 << l) < v) ++l;
@@ -283,6 +470,17 @@ int tssep_mask_istft(const float* X, int64_t x_item_stride, const float* mask, i
                 "tssep_mask_istft: need window_length <= size and window_length %% shift == 0");
   TSSEP_REQUIRE(Z >= 0 && Z < 65536 && n_spk >= 1 && T >= 0, "tssep_mask_istft: bad extent");
   if (Z == 0 || T == 0) return 0;
+  if (size == 1024 && shift == 256 && window_length == 1024 && getenv("TSSEP_ISTFT_GENERIC") == nullptr) {
+    const int64_t J = T + 3;
+    int hops = 128;
+    const int groups = (n_spk + 2 * kFastWarps - 1) / (2 * kFastWarps);
+    while (hops > 16 && ((J + hops - 1) / hops) * Z * groups < 3 * 148) hops /= 2;
+    dim3 grid(static_cast<unsigned>((J + hops - 1) / hops), static_cast<unsigned>(Z * groups));
+    mask_istft_1024_kernel<<<grid, 32 * kFastWarps, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const float2*>(X), x_item_stride, mask, n_spk, groups, T, fading ? window_length - shift : 0, synwin,
+        reinterpret_cast<const float2*>(twiddle), reinterpret_cast<float2*>(stft_estimate), time, num_samples, hops);
+    return check_launch("tssep_mask_istft");
+  }
   const int M = size / 2, OV = window_length / shift;
   const size_t smem = sizeof(float2) * (M + (2 * kEWarps + OV - 1) * padded_len(M)) + sizeof(float) * window_length;
   TSSEP_REQUIRE(smem <= 227 * 1024, "tssep_mask_istft: frame geometry does not fit shared memory");

@@ -151,4 +151,14 @@ __device__ __forceinline__ float2 irfft_pack(float2 xk, float2 xm, int k, const 
   return make_float2(ex - oy, ey + ox);  // E + i*O
 }
 
+// Same with the table value w = exp(-2 pi i k / S) passed in.
+__device__ __forceinline__ float2 irfft_pack_w(float2 xk, float2 xm, float2 w) {
+  xm.y = -xm.y;
+  const float ex = 0.5f * (xk.x + xm.x), ey = 0.5f * (xk.y + xm.y);
+  const float dx = 0.5f * (xk.x - xm.x), dy = 0.5f * (xk.y - xm.y);
+  w.y = -w.y;  // conj
+  const float ox = dx * w.x - dy * w.y, oy = dx * w.y + dy * w.x;
+  return make_float2(ex - oy, ey + ox);  // E + i*O
+}
+
 }  // namespace tssep
