@@ -21,8 +21,12 @@ import sys
 import threading
 import time
 
-import numpy as np
-import torch
+# GB-sized buffers of different shapes come and go every step: without expandable segments the caching
+# allocator strands tens of GB in blocks the next request cannot use (must be set before CUDA initialises).
+os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "expandable_segments:True")
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
@@ -50,8 +54,9 @@ def parse_args():
     ap.add_argument("--meetings-per-gpu", type=int, default=int(os.environ.get("TSSEP_BENCH_MEETINGS", 0)),
                     help="0 = as many as fit in memory (at most 28), trimmed to one wave of recurrence clusters")
     ap.add_argument("--seconds", type=float, default=600.0, help="length of every synthetic meeting")
-    ap.add_argument("--streams", type=int, default=int(os.environ.get("TSSEP_BENCH_STREAMS", 1)),
-                    help="meeting groups processed concurrently on separate CUDA streams")
+    ap.add_argument("--waves", type=int, default=int(os.environ.get("TSSEP_BENCH_WAVES", 2)),
+                    help="with --meetings-per-gpu 0: waves of recurrence-capacity meetings per step (the row-light "
+                         "pre_net / speaker-concat recurrences are shared by all waves of a step)")
     ap.add_argument("--cpu-sample-seconds", type=float, default=60.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-json", default=None, help="also write the per-kernel breakdown to this file")
@@ -246,15 +251,21 @@ def run_b200(args):
     # intermediates); shrink M instead of failing on a smaller / busier device
     free_b, _ = torch.cuda.mem_get_info(dev)
     per_meeting = 5.2e9 * (args.seconds / 600.0)
-    m_mem = max(1, min(M if M > 0 else 28, int(0.9 * free_b / per_meeting)))
+    from tssep_b200 import ops as _ops
+    # The K=8 speaker rows of every meeting advance together in the tensor-memory recurrence; one wave of
+    # 16-row clusters steps in 1.4 us whatever its fill, one row more costs a second wave.
+    wave = max(1, _ops.recurrence_ts_capacity(304, 16) // 8)
+    light = 1.0e9 * (args.seconds / 600.0)  # per meeting outside the current wave: STFT, features, time_estimate, concat rows
     if M <= 0:
-        # The K=8 speaker rows of every meeting advance together in the tensor-memory recurrence; a batch
-        # that fits in one wave of 16-row clusters steps in 1.4 us, one row more costs a second wave.
-        from tssep_b200 import ops as _ops
-        cap = _ops.recurrence_ts_capacity(304, 16) // 8
-        M = cap if 0.7 * m_mem <= cap <= m_mem else m_mem
+        M = wave * max(1, args.waves)
+        while M > wave and wave * per_meeting + (M - wave) * light > 0.9 * free_b:
+            M -= wave
+        if M == wave:
+            M = max(1, min(wave, int(0.9 * free_b / per_meeting)))
     else:
-        M = m_mem
+        M = max(1, min(M, int((0.9 * free_b - min(M, wave) * per_meeting) / light) + min(M, wave)))
+    wave = min(wave, M)
+    out_wave = (wave + 1) // 2 if M > wave else wave  # output stages in half waves when several waves share a step
     if world > 1:
         mt = torch.tensor([M], device=dev)
         torch.distributed.all_reduce(mt, op=torch.distributed.ReduceOp.MIN)
@@ -266,36 +277,26 @@ def run_b200(args):
     diar = dict(threshold=0.5, median_width=11, max_segments=256)
     global_ids = list(range(rank * M, rank * M + M))
 
-    S = max(1, min(args.streams, M))
-    bounds = [round(i * M / S) for i in range(S + 1)]
-    streams = [torch.cuda.Stream(device=dev) for _ in range(S)] if S > 1 else [None]
-
     class StepOut:
         pass
 
-    def step(obs, aux):
-        """One pass over the rank's meetings.  With --streams S the meetings are split into S groups whose
-        kernel chains run on separate CUDA streams, so one group's GEMM / iSTFT phases fill the SMs the
-        other groups' latency-bound recurrences leave idle.  Speaker permutations are drawn on the host in
-        meeting order, exactly as in the sequential case."""
+    def step(obs, aux, on_wave=None, time_out=None):
+        """One pass over the rank's meetings, ``wave`` meetings at a time (Model.separate_waves).  The big
+        per-wave outputs (mask, logit, stft_estimate) are fully written to HBM and released when the next wave
+        starts; time_estimate and the segment tables of all waves stay.  Speaker permutations are drawn on the
+        host in meeting order."""
         np.random.seed(0)
-        outs = []
-        cur = torch.cuda.current_stream(dev)
-        for gi in range(S):
-            lo, hi = bounds[gi], bounds[gi + 1]
-            if S == 1:
-                outs.append(model.separate(obs[lo:hi], aux[lo:hi], diarize=diar))
-            else:
-                streams[gi].wait_stream(cur)
-                with torch.cuda.stream(streams[gi]):
-                    outs.append(model.separate(obs[lo:hi], aux[lo:hi], diarize=diar))
-        if S > 1:
-            for st in streams:
-                cur.wait_stream(st)
         out = StepOut()
-        out.groups = outs
-        out.segments = torch.cat([o.segments.segments for o in outs]) if S > 1 else outs[0].segments.segments
-        out.counts = torch.cat([o.segments.counts for o in outs]) if S > 1 else outs[0].segments.counts
+        out.groups, segs, cnts = [], [], []
+        for lo, hi, o in model.separate_waves(obs, aux, wave=wave, out_wave=out_wave, diarize=diar, time_out=time_out):
+            out.groups.append((lo, hi, o.time_estimate))
+            segs.append(o.segments.segments)
+            cnts.append(o.segments.counts)
+            if on_wave is not None:
+                on_wave(lo, hi, o.time_estimate)
+            del o
+        out.segments = torch.cat(segs) if len(segs) > 1 else segs[0]
+        out.counts = torch.cat(cnts) if len(cnts) > 1 else cnts[0]
         if world > 1:
             tdist.gather_segments(global_ids, out.segments, out.counts, world * M)
         return out
@@ -345,30 +346,85 @@ def run_b200(args):
     except RuntimeError:  # not enough pinnable host memory for double buffering
         time_hosts = [time_host, time_host]
 
+    dbg = os.environ.get("TSSEP_BENCH_E2E_DEBUG") == "1"
+    dbg_rows = []
+
+    # Persistent device buffers of the serving loop (two of each, used alternately): the inputs land in them by
+    # H2D copy, the separated audio is written into them by the enhancement kernel and read back by D2H copy.
+    # Nothing the copy streams touch goes through the caching allocator, so its footprint stays what the
+    # device-resident loop needs.
+    torch.cuda.empty_cache()
+    obs_bufs = [torch.empty_like(obs_dev) for _ in range(2)]
+    aux_bufs = [torch.empty_like(aux_dev) for _ in range(2)]
+    time_bufs = [torch.empty((M, k, n), dtype=torch.float32, device=dev) for _ in range(2)]
+    copied = [None, None]   # event: the D2H copies out of time_bufs[j] are done
+    in_free = [None, None]  # event: the step that read obs_bufs[j] / aux_bufs[j] is done
+
     def e2e_step(i):
-        ev_in, ev_done = torch.cuda.Event(), torch.cuda.Event()
+        h0 = time.perf_counter()
+        j = i % 2
+        m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c_ev = []
+        ev_in = torch.cuda.Event()
         with torch.cuda.stream(in_stream):
-            o = obs_host.to(dev, non_blocking=True)
-            a = aux_host.to(dev, non_blocking=True)
+            if in_free[j] is not None:
+                in_stream.wait_event(in_free[j])
+            obs_bufs[j].copy_(obs_host, non_blocking=True)
+            aux_bufs[j].copy_(aux_host, non_blocking=True)
             ev_in.record(in_stream)
         main_stream.wait_event(ev_in)
-        o.record_stream(main_stream)
-        a.record_stream(main_stream)
-        out = step(o, a)
+        if copied[j] is not None:
+            main_stream.wait_event(copied[j])  # step i-2 has left time_bufs[j]
+        th = time_hosts[j]
+        if dbg:
+            m0.record(main_stream)
+
+        def ship(lo, hi, time_estimate):  # D2H of a wave's separated audio as soon as it exists
+            ev = torch.cuda.Event()
+            ev.record(main_stream)
+            copy_stream.wait_event(ev)
+            with torch.cuda.stream(copy_stream):
+                if dbg:
+                    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    c0.record(copy_stream)
+                th[lo:hi].copy_(time_estimate, non_blocking=True)
+                if dbg:
+                    c1.record(copy_stream)
+                    c_ev.append((c0, c1))
+
+        out = step(obs_bufs[j], aux_bufs[j], on_wave=ship, time_out=time_bufs[j])
+        if dbg:
+            m1.record(main_stream)
+            dbg_rows.append((i, h0, time.perf_counter(), m0, m1, c_ev))
+        ev_done = torch.cuda.Event()
         ev_done.record(main_stream)
+        in_free[j] = ev_done  # the inputs of step i+2 may overwrite obs_bufs[j] only after this step
         copy_stream.wait_event(ev_done)
         with torch.cuda.stream(copy_stream):
-            th = time_hosts[i % 2]
-            for gi, og in enumerate(out.groups):
-                og.time_estimate.record_stream(copy_stream)
-                th[bounds[gi]:bounds[gi + 1]].copy_(og.time_estimate, non_blocking=True)
             out.segments.record_stream(copy_stream)
             out.counts.record_stream(copy_stream)
             seg_host.copy_(out.segments, non_blocking=True)
             cnt_host.copy_(out.counts, non_blocking=True)
+            copied[j] = torch.cuda.Event()
+            copied[j].record(copy_stream)
 
-    e2e_step(0)
+    # plain D2H bandwidth of this box (what bounds the end-to-end number: 512 KB of separated audio per audio-second)
+    probe = torch.empty((wave, k, n), dtype=torch.float32, device=dev)
+    torch.cuda.synchronize()
+    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pe0.record()
+    time_host[:wave].copy_(probe, non_blocking=True)
+    pe1.record()
+    torch.cuda.synchronize()
+    d2h_gbs = probe.numel() * 4 / (pe0.elapsed_time(pe1) / 1e3) / 1e9
+    del probe
+
+    # the end-to-end loop has its own buffers (host-to-device inputs, copies in flight): warm it up until the
+    # allocator has reached its steady state, or the first timed step pays for the growth
+    for i in range(max(2, min(args.warmup, 3))):
+        e2e_step(i)
     copy_stream.synchronize()
+    dbg_rows.clear()
     barrier()
     ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ee0.record(main_stream)
@@ -380,6 +436,15 @@ def run_b200(args):
     ee1.record(main_stream)
     barrier()
     e2e_ms = ee0.elapsed_time(ee1)
+    if dbg and rank == 0:
+        st = torch.cuda.memory_stats(dev)
+        print(f"[e2e debug] alloc_retries={st.get('num_alloc_retries')} peak_alloc={st.get('allocated_bytes.all.peak', 0) / 1e9:.1f} GB "
+              f"peak_reserved={st.get('reserved_bytes.all.peak', 0) / 1e9:.1f} GB", file=sys.stderr)
+        t00 = dbg_rows[0][1]
+        for i, h0, h1, m0, m1, c_ev in dbg_rows:
+            cs = " ".join(f"[{ee0.elapsed_time(c0):.0f}-{ee0.elapsed_time(c1):.0f}]" for c0, c1 in c_ev)
+            print(f"[e2e debug] step {i}: host enqueue {1e3 * (h0 - t00):.0f}-{1e3 * (h1 - t00):.0f} ms | main "
+                  f"{ee0.elapsed_time(m0):.0f}-{ee0.elapsed_time(m1):.0f} ms | copies {cs}", file=sys.stderr)
 
     if world > 1:
         t = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
@@ -461,14 +526,17 @@ def run_b200(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16 operands, f32 accumulate/state/FFT", "data": "synthetic",
         "config": {"workload": f"{M} LibriCSS-shaped synthetic {args.seconds:.0f}-s 16 kHz meetings per GPU per step, "
                                "8 speakers, TS-SEP (U=300, P=320, mul, ts_vad=8, 2 averaged permutations), "
-                               "random-init weights; all ForwardOutput fields + time_estimate + segments materialised",
-                   "meetings_per_gpu": M, "meeting_seconds": args.seconds, "frames": T, "concurrent_streams": S,
+                               "random-init weights; every ForwardOutput field + time_estimate + segments written to HBM "
+                               f"(mask / logit / stft_estimate buffers are reused from one output wave of {out_wave} meetings to the next)",
+                   "meetings_per_gpu": M, "meetings_per_wave": wave, "meetings_per_output_wave": out_wave, "meeting_seconds": args.seconds, "frames": T,
                    "l2": "inputs and intermediates (GBs per step) far exceed the 126 MB L2; no explicit flush",
                    "parallelism": f"dp{world} over meetings"},
         "clocks": clocks.summary(),
         "e2e": {"value": e2e_value, "unit": "audio-s/s", "ms_per_step": e2e_ms / args.steps,
                 "h2d_bytes_per_step": int(obs_host.numel() * 4 + aux_host.numel() * 4),
-                "d2h_bytes_per_step": int(time_host.numel() * 4 + seg_host.numel() * 4 + cnt_host.numel() * 4)},
+                "d2h_bytes_per_step": int(time_host.numel() * 4 + seg_host.numel() * 4 + cnt_host.numel() * 4),
+                "d2h_GBps_measured": d2h_gbs,
+                "note": "bounded by the device-to-host copy of the separated audio (8 speakers x f32 = 512 KB per audio-second)"},
         "gpu_launches": launches,
         "roofline": roofline, "roofline_gemm": roofline_gemm, "hbm_kernels": hbm,
         "cpu_baseline": cpu,

@@ -135,7 +135,7 @@ def test_mask_estimator_variants_batched(cuda, monkeypatch, kw, kernel):
     assert (got.embedding.cpu() - want.embedding).abs().max().item() == 0.0
 
 
-@pytest.mark.parametrize("kernel,g_dtype", [("regs", "bf16"), ("regs", "f32"), ("tc", "bf16")])
+@pytest.mark.parametrize("kernel,g_dtype", [("regs", "bf16"), ("regs", "f32"), ("tc", "bf16"), ("ts", "bf16"), ("ts", "f32")])
 def test_full_size_dims_short_meeting(cuda, monkeypatch, kernel, g_dtype):
     """C3 dims (U=300, P=320, mul, ts_vad=8, R=2) on 20 s of audio; separate() with two meetings; both
     recurrence kernels and both storage types of the input projections."""
@@ -160,6 +160,34 @@ def test_full_size_dims_short_meeting(cuda, monkeypatch, kernel, g_dtype):
         d_sdr = abs(sdr_db(got.time_estimate[i].cpu().numpy(), tgt) - sdr_db(wants[i].time_estimate.numpy(), tgt))
         assert d_sdr <= 0.05, d_sdr
         assert (got.stft_estimate[i].cpu() - wants[i].stft_estimate).abs().max().item() < 5e-2
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(ts_vad=False, num_averaged_permutations=1, combination="cat",
+                                              aux_net_output_size=100)])
+def test_separate_waves_equals_one_batch(cuda, monkeypatch, kw):
+    """Model.separate_waves shares the row-light layers across waves and runs the rest per wave; every output
+    must be identical to the one-batch result (the rows of a recurrence launch are independent)."""
+    monkeypatch.setenv("TSSEP_LSTM_KERNEL", "ts")
+    _, me = make_pair(_me_kwargs(**kw))
+    model = _product_model(me)
+    n = 16000 * 3
+    exs = [_ex(s, kw.get("aux_net_output_size", 513), n) for s in range(5)]
+    obs = torch.tensor(np.stack([e["observation"][0] for e in exs])).to(cuda)
+    aux = torch.tensor(np.stack([e["auxInput"] for e in exs])).to(cuda)
+    diar = dict(threshold=0.5, median_width=5)
+    np.random.seed(7)
+    want = model.separate(obs, aux, diarize=diar)
+    np.random.seed(7)
+    seen = []
+    for lo, hi, got in model.separate_waves(obs, aux, wave=3, out_wave=2, diarize=diar):
+        seen.append((lo, hi))
+        assert torch.equal(got.mask, want.mask[lo:hi])
+        assert torch.equal(got.logit, want.logit[lo:hi])
+        assert torch.equal(torch.view_as_real(got.stft_estimate), torch.view_as_real(want.stft_estimate[lo:hi]))
+        assert torch.equal(got.time_estimate, want.time_estimate[lo:hi])
+        assert torch.equal(got.segments.segments, want.segments.segments[lo:hi])
+        assert torch.equal(got.segments.counts, want.segments.counts[lo:hi])
+    assert seen == [(0, 2), (2, 4), (4, 5)]
 
 
 def test_state_dict_round_trip_and_cache_invalidation(cuda):

@@ -27,9 +27,12 @@ class Masking(ABC):
         return self.apply(masks, ex["Observation"], ex["reference_channel"], fe=model.fe)[0]
 
     @staticmethod
-    def apply(masks, Observation, reference_channel, fe, want_estimate=True, want_time=False, num_samples=None):
+    def apply(masks, Observation, reference_channel, fe, want_estimate=True, want_time=False, num_samples=None,
+              time_out=None):
         """masks (K,1,T,F) or (B,K,1,T,F) f32; Observation ([B,] C, T, F) complex64 (or without the channel
-        axis when ``reference_channel`` is None).  Returns (stft_estimate | None, time_estimate | None)."""
+        axis when ``reference_channel`` is None).  Returns (stft_estimate | None, time_estimate | None).
+        ``time_out``: optional preallocated contiguous float32 device tensor ([B,] K, n) for time_estimate (a
+        serving loop that ships the audio to the host keeps its own buffers instead of churning the allocator)."""
         batched = {4: False, 5: True}[masks.dim()]
         if isinstance(Observation, np.ndarray):
             Observation = torch.as_tensor(Observation, device=masks.device)
@@ -54,7 +57,13 @@ class Masking(ABC):
         if want_time:
             total = (T - 1) * fe.shift + fe.window_length - (2 * (fe.window_length - fe.shift) if fe.fading else 0)
             n = total if num_samples is None else min(int(num_samples), total)
-            time = torch.empty((*lead, n), dtype=torch.float32, device=m.device)
+            if time_out is not None:
+                if (tuple(time_out.shape) != (*lead, n) or time_out.dtype != torch.float32 or not time_out.is_contiguous()
+                        or time_out.device != m.device):
+                    raise ValueError(f"time_out must be a contiguous float32 tensor of shape {(*lead, n)} on {m.device}")
+                time = time_out
+            else:
+                time = torch.empty((*lead, n), dtype=torch.float32, device=m.device)
         tab = fe._device_tables(m.device)
         _lib.call("tssep_mask_istft", obs.data_ptr(), T * F, m.data_ptr(), Z, K, T, fe.size, fe.shift,
                   fe.window_length, int(bool(fe.fading)), tab["synwin"].data_ptr(), tab["twiddle"].data_ptr(),

@@ -127,18 +127,45 @@ class Model(Configurable, torch.nn.Module):
         statistics, one ``np.random.permutation`` draw per meeting, in order).
         ``diarize`` = dict(threshold=, median_width=, max_segments=) adds ``.segments``.
         """
+        (_, _, out), = self.separate_waves(observation, aux, wave=None, want_estimate=want_estimate, want_time=want_time,
+                                           diarize=diarize)
+        return out
+
+    @torch.no_grad()
+    def separate_waves(self, observation: torch.Tensor, aux: torch.Tensor, *, wave: Optional[int] = None,
+                       out_wave: Optional[int] = None, want_estimate=True, want_time=True,
+                       diarize: Optional[dict] = None, time_out: Optional[torch.Tensor] = None):
+        """``separate`` for more meetings than one wave of the recurrence kernels holds: a generator of
+        ``(lo, hi, ForwardOutput)`` for meetings [lo, hi), ``wave`` meetings at a time.
+
+        Front end, pre_net and the speaker-concat layer run once for all M meetings (their recurrences
+        cost the same T dependent steps for 1 or 100 rows), the K-rows-per-meeting layers and every
+        output stage run per wave (``MaskEstimator_v2.forward_waves``).  A consumer that drops a wave's
+        big outputs (mask, logit, stft_estimate: 2.5 GB per 10-min meeting) before asking for the next
+        one lets them share memory; ``out_wave`` (default ``wave``) is the number of meetings per yielded
+        output.  ``time_out`` (M, K, N) float32: optional caller-owned buffer the separated signals are written
+        to (each yielded ``time_estimate`` is then a view of it).  Results do not depend on ``wave`` / ``out_wave``.
+        """
         _lib.require_cuda(observation, aux)
         if observation.dim() == 2:
             observation = observation[:, None, :]
+        n = observation.shape[-1]
         ex = {"observation": observation, "reference_channel": 0}
         feats = self._features(ex, couple=False)
-        me_out = self.mask_estimator(feats["f32"], [a for a in aux], _features_bf16=(feats["bf16"], feats["ld"]))
-        est, time = Masking.apply(me_out.mask, ex["Observation"], 0, self.fe, want_estimate=want_estimate,
-                                  want_time=want_time, num_samples=observation.shape[-1])
-        out = ForwardOutput(mask=me_out.mask, logit=me_out.logit, embedding=me_out.embedding, stft_estimate=est,
-                            time_estimate=time, vad_mask=me_out.vad_mask, vad_logit=me_out.vad_logit)
-        if diarize is not None:
-            from .postprocess import diarize as run_diarize
+        Obs = ex["Observation"]
+        waves = self.mask_estimator.forward_waves(feats["f32"], [a for a in aux], wave=wave, out_wave=out_wave,
+                                                  _features_bf16=(feats["bf16"], feats["ld"]))
+        del feats
+        for lo, hi, me_out in waves:
+            est, time = Masking.apply(me_out.mask, Obs[lo:hi], 0, self.fe, want_estimate=want_estimate,
+                                      want_time=want_time, num_samples=n,
+                                      time_out=None if time_out is None else time_out[lo:hi])
+            out = ForwardOutput(mask=me_out.mask, logit=me_out.logit, embedding=me_out.embedding, stft_estimate=est,
+                                time_estimate=time, vad_mask=me_out.vad_mask, vad_logit=me_out.vad_logit)
+            if diarize is not None:
+                from .postprocess import diarize as run_diarize
 
-            out.segments = run_diarize(me_out.mask, self.fe, num_samples=observation.shape[-1], **diarize)
-        return out
+                out.segments = run_diarize(me_out.mask, self.fe, num_samples=n, **diarize)
+            del me_out, est, time
+            yield lo, hi, out
+            del out

@@ -88,6 +88,28 @@ class _SequentialDict:
         raise RuntimeError(key)
 
 
+class _PinnedRing:
+    """A few persistent pinned staging buffers for small host -> device uploads that must not block the host."""
+
+    def __init__(self, depth: int = 4):
+        self.bufs, self.events, self.i = [None] * depth, [None] * depth, 0
+
+    def upload(self, arr: np.ndarray, device) -> torch.Tensor:
+        i, self.i = self.i, (self.i + 1) % len(self.bufs)
+        n = int(arr.size)
+        if self.bufs[i] is None or self.bufs[i].numel() < n:
+            self.bufs[i] = torch.empty(max(n, 4096), dtype=torch.int32).pin_memory()  # first uses only
+            self.events[i] = None
+        if self.events[i] is not None:
+            self.events[i].synchronize()  # the copy issued `depth` uploads ago; long done
+        self.bufs[i][:n].copy_(torch.from_numpy(arr))
+        out = self.bufs[i][:n].to(device, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(device))
+        self.events[i] = ev
+        return out
+
+
 class MaskEstimator_v2(Configurable, torch.nn.Module):
     @classmethod
     def finalize_dogmatic_config(cls, config):
@@ -159,6 +181,7 @@ class MaskEstimator_v2(Configurable, torch.nn.Module):
         self.final_activation = torch.nn.Sigmoid()
         self._head_cache = None
         self._rot_cache = None
+        self._staging = _PinnedRing()
 
     def extra_repr(self) -> str:
         return f"combination={self.combination!r},"
@@ -212,6 +235,23 @@ class MaskEstimator_v2(Configurable, torch.nn.Module):
         ``_features_bf16=(tensor, ld)`` lets ``Model.forward`` hand over the bf16 feature rows the
         feature kernel already produced.
         """
+        (_, _, out), = self.forward_waves(xs, aux, wave=None, _features_bf16=_features_bf16)
+        return out
+
+    def forward_waves(self, xs, aux=None, wave=None, _features_bf16=None, out_wave=None):
+        """Same computation as ``forward`` for a batch of B items, produced in waves of ``wave`` items:
+        a generator of ``(lo, hi, Output)`` for items [lo, hi).
+
+        The recurrences cost T dependent steps whatever their batch; a step advances up to
+        ``ops.recurrence_ts_capacity`` rows (26 eight-speaker items on a B200) at the same latency.  The
+        row-light layers (pre_net: 1 row per item, the speaker-concat layer: R rows per item) therefore
+        run ONCE for all B items, the row-heavy speaker-independent layers (K rows per item) run per
+        wave, and the head writes each wave's logit / mask when the consumer asks for it, so the big
+        outputs of one wave can be dropped before the next is produced.  ``out_wave`` (default ``wave``)
+        is the number of items per yielded ``Output``: smaller output waves bound the memory of the
+        GB-sized logit / mask tensors without touching the recurrence batching.  Results are independent
+        of ``wave`` and ``out_wave``; speaker permutations are drawn for all items up front, in order.
+        """
         _lib.require_cuda(xs)
         dev = xs.device
         if xs.dim() == 2:
@@ -227,16 +267,19 @@ class MaskEstimator_v2(Configurable, torch.nn.Module):
         else:
             raise RuntimeError(xs.shape)
         _lib.require_cuda(aux_t)
-        # Both index tables go to the device NOW, through pinned memory: a pageable copy issued later would
-        # block the host until every kernel queued before it has run and serialise concurrent streams.
+        # Both index tables go to the device NOW, in one asynchronous copy from a persistent pinned buffer: a
+        # pageable copy makes torch synchronise the stream (the host could not enqueue the next batch while
+        # this one runs), and a fresh pin_memory() may stall in cudaHostAlloc.
         perm_np = np.stack(perms)  # (B, K)
         nmask = self.nmask
         if self.ts_vad is not False:
             planes = (np.arange(B)[:, None, None] * K + perm_np[:, :, None]) * nmask + np.arange(nmask)[None, None, :]
         else:
             planes = ((np.arange(B)[:, None] * K + perm_np)[:, :, None]) * nmask + np.arange(nmask)[None, None, :]
-        perm_t = torch.from_numpy(perm_np.astype(np.int64)).pin_memory().to(dev, non_blocking=True)
-        plane_map = torch.from_numpy(planes.reshape(-1).astype(np.int32)).pin_memory().to(dev, non_blocking=True)
+        packed = np.concatenate([perm_np.reshape(-1), planes.reshape(-1)]).astype(np.int32)
+        packed_t = self._staging.upload(packed, dev)
+        perm_t = packed_t[:B * K].view(B, K).long()
+        plane_map = packed_t[B * K:]
         aux_p = torch.gather(aux_t.float(), 1, perm_t[:, :, None].expand(B, K, aux_t.shape[-1]))  # slot order
         if batched and self.aux_normalizer is not None:
             aux_p = self.aux_normalizer(aux_p)
@@ -259,6 +302,8 @@ class MaskEstimator_v2(Configurable, torch.nn.Module):
             xb = ops.cast_bf16(xs.reshape(B * T, Din).float())
             ld = ops.round_up(Din, 8)
 
+        del xs, _features_bf16  # only the bf16 rows are used from here on
+
         # pre_net on the mixture (net.py:860)
         if isinstance(self.pre_net, RNNP_packed):
             for pk in self.pre_net.layer_packs():
@@ -277,7 +322,7 @@ class MaskEstimator_v2(Configurable, torch.nn.Module):
         pk0 = birnns[0].layer_packs()[0]
         Up = pk0.Up
         e = aux_p.reshape(B * K, A).contiguous()
-        stream = _lib.stream_of(xs)
+        stream = _lib.stream_of(xb)
         P = self.projs
         ldp = ops.round_up(P, 8)
         mode = {"mul": 0, "cat": 1}[self.combination]
@@ -287,38 +332,47 @@ class MaskEstimator_v2(Configurable, torch.nn.Module):
             assert pk0.I == F + A, (pk0.I, F, A)
         start_l = 0
         y, y_ld, G = None, None, None
-        if L >= 2 and use_tc_recurrence(B * K):
+        wave = B if wave is None else max(1, min(int(wave), B))
+        if L >= 2 and use_tc_recurrence(wave * K):
             # ---- throughput path for the speaker-independent layers (all but the last) ---------------
             # rows ordered (group, t, b32), z = group*32 + b = item*K + speaker: the conditioned rows are
             # materialised once in bf16 (net.py:862-896), every input projection writes G with the batch
-            # row innermost, the recurrence runs on tcgen05 with the recurrent weights in shared memory.
-            Z = B * K
-            groups = (Z + 31) // 32
-            mrows = groups * T * 32
+            # row innermost, the recurrence runs on tcgen05 with the recurrent weights in tensor memory.
+            # One pass per wave of items; all waves write into the same output of the last of these layers.
+            if self.ts_vad is not False:
+                y_ld = ops.round_up(K * P, 8)   # speaker-concat layout (B, T, K*P)   net.py:606-612
+                y = torch.empty((B * T, y_ld), dtype=torch.bfloat16, device=dev)
+            else:
+                y_ld = ldp
+                y = torch.empty((B * K * T, y_ld), dtype=torch.bfloat16, device=dev)
             ld0 = ops.round_up(pk0.I, 8)
-            a0 = torch.empty((mrows, ld0), dtype=torch.bfloat16, device=dev)
-            _lib.call("tssep_condition_rows", mode, xb.data_ptr(), ld, e.data_ptr(), Z, K, T, F, A, a0.data_ptr(), ld0,
-                      stream)
-            y, y_ld = a0, ld0
-            for l in range(L - 1):
-                pk = birnns[l].layer_packs()[0]
-                G = pk.input_gemm_bt(y, y_ld, mrows)
-                H = pk.recurrence_tc(G, Z, T)
-                del G
-                if l < L - 2:
-                    y_ld = ldp
-                    y = torch.empty((mrows, y_ld), dtype=torch.bfloat16, device=dev)
-                    pk.projection(H, mrows, y, mode=ops.EPI_BF16, ldo=y_ld, act=1)
-                elif self.ts_vad is not False:
-                    # tanh(proj) straight into the speaker-concat layout (B, T, K*P)   net.py:606-612
-                    y_ld = ops.round_up(K * P, 8)
-                    y = torch.empty((B * T, y_ld), dtype=torch.bfloat16, device=dev)
-                    pk.projection(H, mrows, y, mode=ops.EPI_BF16_ROWMAP, ldo=y_ld, act=1, row_map=(T, K, Z, P))
-                else:
-                    y_ld = ldp
-                    y = torch.empty((Z * T, y_ld), dtype=torch.bfloat16, device=dev)
-                    pk.projection(H, mrows, y, mode=ops.EPI_BF16_ROWMAP, ldo=y_ld, act=1, row_map=(T, 1, Z, 0))
-                del H
+            for lo in range(0, B, wave):
+                hi = min(B, lo + wave)
+                Z = (hi - lo) * K
+                groups = (Z + 31) // 32
+                mrows = groups * T * 32
+                a0 = torch.empty((mrows, ld0), dtype=torch.bfloat16, device=dev)
+                _lib.call("tssep_condition_rows", mode, xb[lo * T:].data_ptr(), ld, e[lo * K:].data_ptr(), Z, K, T, F, A,
+                          a0.data_ptr(), ld0, stream)
+                yw, yw_ld = a0, ld0
+                del a0
+                for l in range(L - 1):
+                    pk = birnns[l].layer_packs()[0]
+                    G = pk.input_gemm_bt(yw, yw_ld, mrows)
+                    H = pk.recurrence_tc(G, Z, T)
+                    del G
+                    if l < L - 2:
+                        yw_ld = ldp
+                        yw = torch.empty((mrows, yw_ld), dtype=torch.bfloat16, device=dev)
+                        pk.projection(H, mrows, yw, mode=ops.EPI_BF16, ldo=yw_ld, act=1)
+                    elif self.ts_vad is not False:
+                        pk.projection(H, mrows, y[lo * T:], mode=ops.EPI_BF16_ROWMAP, ldo=y_ld, act=1,
+                                      row_map=(T, K, Z, P))
+                    else:
+                        pk.projection(H, mrows, y[lo * K * T:], mode=ops.EPI_BF16_ROWMAP, ldo=y_ld, act=1,
+                                      row_map=(T, 1, Z, 0))
+                    del H
+                del yw
             start_l = L - 1
         else:
             # ---- latency path: conditioning folded into birnn0's input projection ----------------------
@@ -380,35 +434,46 @@ class MaskEstimator_v2(Configurable, torch.nn.Module):
                 pk.projection(H, rows * T, y, mode=ops.EPI_BF16, ldo=y_ld, act=0 if last else 1)
             del H
 
-        # head: Linear + rearrange + trial mean + un-permute + sigmoid (net.py:629-668, :928-986)
+        # head: Linear + rearrange + trial mean + un-permute + sigmoid (net.py:629-668, :928-986), per wave
         nmask, odim = self.nmask, self.odim
         fh = odim + int(self.explicit_vad)
         tf = self.output_resolution == "tf"
         row_len = fh if tf else 1
         hp = self._head_pack(K, R, row_len)
-        if self.ts_vad is not False:
-            items, nb = B, K * nmask
-        else:
-            items, nb = B * K, nmask
-        shape = (B, K, nmask, T, fh if tf else odim)
-        logit = torch.empty(shape, dtype=torch.float32, device=dev)
-        mask = torch.empty(shape, dtype=torch.float32, device=dev)
-        if tf:
-            ops.gemm(y, y_ld, hp["w"], hp["ld"], T, hp["n"], hp["kdim"], logit, mode=ops.EPI_HEAD, batch=items,
-                     a_stride=T * y_ld, b_stride=0, b_mod=1, bias=hp["b"], alpha=1.0 / R, mask=mask,
-                     plane_map=plane_map, n_blocks=nb, row_len=row_len)
-        else:
-            small = torch.empty((items * T, nb), dtype=torch.float32, device=dev)
-            ops.gemm(y, y_ld, hp["w"], hp["ld"], items * T, hp["n"], hp["kdim"], small, mode=ops.EPI_F32, ldo=nb,
-                     b_mod=1, bias=hp["b"], alpha=1.0 / R)
-            _lib.call("tssep_head_expand_t", small.data_ptr(), items, T, nb, odim, plane_map.data_ptr(),
-                      logit.data_ptr(), mask.data_ptr(), stream)
-        del y
-        embedding = aux_p.unsqueeze(-2)
-        if not batched:
-            logit, mask, embedding = logit[0], mask[0], embedding[0]
-        if self.explicit_vad:
-            vad_mask = mask[..., 0]
-            return Output(mask=mask[..., 1:] * vad_mask[..., None], logit=None, vad_mask=vad_mask,
-                          vad_logit=logit[..., 0], embedding=embedding)
-        return Output(mask=mask, logit=logit, embedding=embedding)
+        per_item, nb = (1, K * nmask) if self.ts_vad is not False else (K, nmask)  # GEMM batch entries / planes per item
+        embedding_all = aux_p.unsqueeze(-2)
+        out_wave = wave if out_wave is None else max(1, min(int(out_wave), B))
+        for lo in range(0, B, out_wave):
+            hi = min(B, lo + out_wave)
+            Bw = hi - lo
+            items = Bw * per_item
+            y_w = y[lo * per_item * T:]
+            pm = plane_map if Bw == B else plane_map[lo * K * nmask:hi * K * nmask] - lo * K * nmask
+            shape = (Bw, K, nmask, T, fh if tf else odim)
+            logit = torch.empty(shape, dtype=torch.float32, device=dev)
+            mask = torch.empty(shape, dtype=torch.float32, device=dev)
+            if tf:
+                ops.gemm(y_w, y_ld, hp["w"], hp["ld"], T, hp["n"], hp["kdim"], logit, mode=ops.EPI_HEAD, batch=items,
+                         a_stride=T * y_ld, b_stride=0, b_mod=1, bias=hp["b"], alpha=1.0 / R, mask=mask,
+                         plane_map=pm, n_blocks=nb, row_len=row_len)
+            else:
+                small = torch.empty((items * T, nb), dtype=torch.float32, device=dev)
+                ops.gemm(y_w, y_ld, hp["w"], hp["ld"], items * T, hp["n"], hp["kdim"], small, mode=ops.EPI_F32, ldo=nb,
+                         b_mod=1, bias=hp["b"], alpha=1.0 / R)
+                _lib.call("tssep_head_expand_t", small.data_ptr(), items, T, nb, odim, pm.data_ptr(),
+                          logit.data_ptr(), mask.data_ptr(), stream)
+                del small
+            embedding = embedding_all[lo:hi]
+            if hi == B:
+                del y, y_w
+            if not batched:
+                logit, mask, embedding = logit[0], mask[0], embedding[0]
+            if self.explicit_vad:
+                vad_mask = mask[..., 0]
+                out = Output(mask=mask[..., 1:] * vad_mask[..., None], logit=None, vad_mask=vad_mask,
+                             vad_logit=logit[..., 0], embedding=embedding)
+            else:
+                out = Output(mask=mask, logit=logit, embedding=embedding)
+            del logit, mask
+            yield lo, hi, out
+            del out
