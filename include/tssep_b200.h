@@ -177,9 +177,13 @@ int tssep_pack_whh_tc(const float* whh_fwd, const float* whh_bwd, int U, int Up,
  * rows_per_cluster = 16 or 32 (0 = choose: 16 while both directions fit in one wave of clusters).
  * G streamed with cp.async.bulk through an mbarrier ring.  Only the first
  * ceil(rows / rows_per_cluster) * rows_per_cluster rows of H are written.
+ * layout TSSEP_REC_LAYOUT_ROWS: G (rows, T, 2, 4, Up) bf16 and H (rows, T, 2*Up), exactly the layouts of
+ * tssep_blstm_recurrence (G streamed with one 5-D TMA box per step).
  * Wimg from tssep_pack_whh_ts: 2 * C * 2 * (Up/16) * 128 * 8 words, C = ceil(Up/64); Up <= 448. */
+enum { TSSEP_REC_LAYOUT_BT = 0, TSSEP_REC_LAYOUT_ROWS = 1 };
 int tssep_blstm_recurrence_ts(const void* G, int g_dtype, const uint32_t* Wimg, uint16_t* H, int64_t rows,
-                              int64_t T, int Up, int rows_per_cluster, int fast_math, tssep_stream_t stream);
+                              int64_t T, int Up, int layout, int rows_per_cluster, int fast_math,
+                              tssep_stream_t stream);
 /* Batch rows that fit in ONE wave of co-resident clusters (both directions running) on the current
  * device at the given rows_per_cluster (16 or 32); < 0 on error. */
 int tssep_blstm_recurrence_ts_capacity(int Up, int rows_per_cluster, int g_dtype);

@@ -19,7 +19,7 @@ def main():
     ap.add_argument("--clusters", type=int, nargs="+", default=[0])
     ap.add_argument("--fast", type=int, nargs="+", default=[0, 1])
     ap.add_argument("--reps", type=int, default=3)
-    ap.add_argument("--kernel", default="regs", choices=["regs", "tc", "ts"])
+    ap.add_argument("--kernel", default="regs", choices=["regs", "tc", "ts", "ts_rows"])
     ap.add_argument("--g-bf16", type=int, default=0)
     a = ap.parse_args()
     dev = torch.device("cuda:0")
@@ -32,6 +32,8 @@ def main():
     wts = ops.pack_whh_ts(w[0].contiguous(), w[1].contiguous(), U, Up)
 
     def run(G, rows, C, fast):
+        if a.kernel == "ts_rows":
+            return ops.blstm_recurrence_ts(G, wts, rows, a.frames, Up, fast_math=bool(fast), rows_per_cluster=C, layout="rows")
         if a.kernel == "ts":
             return ops.blstm_recurrence_ts(G, wts, rows, a.frames, Up, fast_math=bool(fast), rows_per_cluster=C)
         if a.kernel == "tc":
@@ -63,7 +65,7 @@ def main():
                 torch.cuda.synchronize()
                 del os.environ["TSSEP_REC_PROF"]
                 pc = prof.cpu().numpy().astype(float)
-                if a.kernel == "ts":
+                if a.kernel in ("ts", "ts_rows"):
                     names = ["t0.g", "t0.wait", "t0.math", "t0.send", "t1.g", "t1.wait", "t1.math", "t1.send"]
                     ph = " ".join(f"{n}={v / a.frames:.0f}" for n, v in zip(names, pc))
                 elif a.kernel == "tc":

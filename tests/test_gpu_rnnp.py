@@ -66,6 +66,7 @@ def test_rnnp_tcgen05_recurrence_matches_torch(cuda, monkeypatch, idim, units, h
     assert (got2 - want).abs().max().item() < 1e-2
 
 
+@pytest.mark.parametrize("layout", ["bt", "rows"])
 @pytest.mark.parametrize("rows_per_cluster", ["16", "32"])
 @pytest.mark.parametrize("idim,units,hdim,shape", [
     (64, 40, 42, (3, 100, 64)),      # one CTA, 3 of 16 rows used
@@ -75,10 +76,12 @@ def test_rnnp_tcgen05_recurrence_matches_torch(cuda, monkeypatch, idim, units, h
     (160, 300, 320, (5, 300, 160)),
     (72, 10, 12, (17, 60, 72)),      # one k-step, Up = 16
 ])
-def test_rnnp_tmem_recurrence_matches_torch(cuda, monkeypatch, rows_per_cluster, idim, units, hdim, shape):
-    """The tensor-memory recurrence (csrc/lstm_ts.cu), forced for every row count, both cluster widths."""
+def test_rnnp_tmem_recurrence_matches_torch(cuda, monkeypatch, layout, rows_per_cluster, idim, units, hdim, shape):
+    """The tensor-memory recurrence (csrc/lstm_ts.cu), forced for every row count, both cluster widths, both
+    G / H layouts (GEMM "BT" tiles with rows ordered (group, t, b32); plain rows streamed by TMA)."""
     monkeypatch.setenv("TSSEP_LSTM_KERNEL", "ts")
     monkeypatch.setenv("TSSEP_TS_ROWS", rows_per_cluster)
+    monkeypatch.setenv("TSSEP_TS_LAYOUT", layout)
     ref, mine = _pair(idim, units, hdim)
     x = torch.randn(shape, generator=torch.Generator().manual_seed(1))
     with torch.no_grad():

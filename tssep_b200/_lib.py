@@ -55,7 +55,7 @@ _SIGNATURES = {
     "tssep_pack_whh": ([c_vp, c_vp, c_i32, c_i32, c_vp, c_vp], C.c_int),
     "tssep_blstm_recurrence_tc": ([c_vp, c_i32, c_vp, c_vp, c_i64, c_i64, c_i32, c_i32, c_vp], C.c_int),
     "tssep_pack_whh_tc": ([c_vp, c_vp, c_i32, c_i32, c_vp, c_vp], C.c_int),
-    "tssep_blstm_recurrence_ts": ([c_vp, c_i32, c_vp, c_vp, c_i64, c_i64, c_i32, c_i32, c_i32, c_vp], C.c_int),
+    "tssep_blstm_recurrence_ts": ([c_vp, c_i32, c_vp, c_vp, c_i64, c_i64, c_i32, c_i32, c_i32, c_i32, c_vp], C.c_int),
     "tssep_blstm_recurrence_ts_capacity": ([c_i32, c_i32, c_i32], C.c_int),
     "tssep_pack_whh_ts": ([c_vp, c_vp, c_i32, c_i32, c_vp, c_vp], C.c_int),
     "tssep_mask_istft": ([c_vp, c_i64, c_vp, c_i64, c_i32, c_i64, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp,

@@ -29,9 +29,9 @@ namespace tssep {
 constexpr int kTsMaxStages = 8;
 
 struct RecTsArgs {
-  const uint8_t* G;   // tiles [group][t][dir][unit octet][b/4][4*(unit%8)+gate][b%4], f32 or bf16
+  const uint8_t* G;   // BT: tiles [group][t][dir][unit octet][b/4][4*(unit%8)+gate][b%4], f32 or bf16 (PLAIN: via gmap)
   const uint4* Wimg;  // [dir][cta][tile][kstep][row 128][8 words]
-  __nv_bfloat16* H;   // (groups, T, 32, 2*Up): rows ordered (group, t, b)
+  __nv_bfloat16* H;   // BT: (groups, T, 32, 2*Up), rows ordered (group, t, b); PLAIN: (rows, T, 2*Up)
   int rows, T, Up, NA, KS, fast, g_bf16, stages, hack_m, hack_n;
   int* prof;
 };
@@ -83,9 +83,15 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                : "memory");
 }
 
-// NR batch rows per cluster, NC of them per epilogue warp (8 * NR/NC epilogue warps).
-template <int NR, int NC>
-__global__ void __launch_bounds__(64 + 256 * (NR / NC), 1) blstm_rec_ts_kernel(const RecTsArgs a) {
+// NR batch rows per cluster, NC of them per epilogue warp (8 * NR/NC epilogue warps); FAST: tanh.approx gates;
+// GBF16: G stored as bf16.  Everything the per-step loops branch on is a template parameter: the epilogue is
+// close to issue bound (ncu: 44 % of all issue slots over the whole step, profiles/r1_ncu_rec_ts.txt).
+// PLAIN: G (rows, T, 2, 4, Up) bf16 and H (rows, T, 2*Up), the layouts of the register kernel (csrc/lstm.cu): one
+// 5-D TMA box (64 units, 4 gates, NR rows) per step, 128-byte swizzled so that lane (unit, gate) reads without
+// bank conflicts.  Otherwise the "BT" tile layout of the GEMM (rows ordered (group, t, b32)).
+template <int NR, int NC, bool FAST, bool GBF16, bool PLAIN>
+__global__ void __launch_bounds__(64 + 256 * (NR / NC), 1)
+blstm_rec_ts_kernel(const RecTsArgs a, const __grid_constant__ CUtensorMap gmap) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr uint32_t kAtomB = NR * 128;  // one 64-k atom of the B operand: NR rows x 128 bytes, 128-byte swizzle
   constexpr int EW = NR / NC;            // epilogue warps per (row tile, TMEM lane quarter)
@@ -94,7 +100,7 @@ __global__ void __launch_bounds__(64 + 256 * (NR / NC), 1) blstm_rec_ts_kernel(c
   constexpr int kThreads = 64 + 256 * EW;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int NA = a.NA, KS = a.KS, GS = a.stages;
-  const uint32_t esz = a.g_bf16 ? 2u : 4u;
+  constexpr uint32_t esz = GBF16 ? 2u : 4u;
   const uint32_t oct_bytes = NR * 32u * esz;  // one unit octet of one step: [b/4][lane][b%4]
   const uint32_t g_stage = 8u * oct_bytes;
   const uint32_t sB = base;                         // [2 buffers][NA] x kAtomB
@@ -108,6 +114,7 @@ __global__ void __launch_bounds__(64 + 256 * (NR / NC), 1) blstm_rec_ts_kernel(c
   const uint32_t crank = cluster_ctarank();
   const uint32_t C = cluster_nctarank();
   const int grp = blockIdx.y / SUBS, sub = blockIdx.y % SUBS, dir = blockIdx.z;
+  const int row0 = blockIdx.y * NR;  // PLAIN: first batch row of this cluster
   const int T = a.T, Up = a.Up;
   const uint32_t tx_bytes = static_cast<uint32_t>(NR) * 128u * C;  // every CTA ships 64 units x NR rows
   const int n_oct = Up / 8;
@@ -163,19 +170,40 @@ __global__ void __launch_bounds__(64 + 256 * (NR / NC), 1) blstm_rec_ts_kernel(c
 
   if (warp == 0) {
     // ---- G producer ---------------------------------------------------------------------------------
-    if (lane == 0 && oct_valid > 0) {
+    if (PLAIN) {
+      if (lane == 0 && oct_valid > 0) {
+        tma_prefetch_desc(&gmap);
+        int slot = 0;
+        uint32_t gph = 0;
+        for (int s = 0; s < T; ++s) {
+          const int t = dir ? T - 1 - s : s;
+          mbar_wait(gempty0 + 8 * slot, gph ^ 1);
+          mbar_arrive_expect_tx(gfull0 + 8 * slot, g_stage);
+          tma_load_5d(sG + slot * g_stage, &gmap, gfull0 + 8 * slot, static_cast<int>(crank) * 64, 0, row0, dir, t);
+          if (++slot == GS) {
+            slot = 0;
+            gph ^= 1;
+          }
+        }
+      }
+    } else if (lane == 0 && oct_valid > 0) {
       const int64_t tile_bytes = 1024ll * esz;  // one (group, t, dir, octet) tile: 32 rows x 32 columns
       const int64_t t_stride = 2ll * n_oct * tile_bytes;
       const uint8_t* g0 = a.G + ((static_cast<int64_t>(grp) * T * 2 + dir) * n_oct + crank * 8) * tile_bytes +
                           static_cast<int64_t>(sub) * oct_bytes;
+      int slot = 0;
+      uint32_t gph = 0;
       for (int s = 0; s < T; ++s) {
-        const int slot = s % GS;
         const int t = dir ? T - 1 - s : s;
-        mbar_wait(gempty0 + 8 * slot, ((s / GS) & 1) ^ 1);
+        mbar_wait(gempty0 + 8 * slot, gph ^ 1);
         mbar_arrive_expect_tx(gfull0 + 8 * slot, static_cast<uint32_t>(oct_valid) * oct_bytes);
         const uint8_t* src = g0 + static_cast<int64_t>(t) * t_stride;
         const uint32_t dst = sG + slot * g_stage;
         for (int o = 0; o < oct_valid; ++o) bulk_g2s(dst + o * oct_bytes, src + o * tile_bytes, oct_bytes, gfull0 + 8 * slot);
+        if (++slot == GS) {
+          slot = 0;
+          gph ^= 1;
+        }
       }
     }
     __syncwarp();
@@ -233,9 +261,9 @@ __global__ void __launch_bounds__(64 + 256 * (NR / NC), 1) blstm_rec_ts_kernel(c
     const int gate = lane & 3;       // i, f, g, o
     const int ul = lane >> 2;        // unit within the warp's octet
     const bool is_g = gate == 2;
-    const float sc = a.fast ? (is_g ? 1.0f : 0.5f) : (is_g ? 2.0f : 1.0f);
-    const float ka = a.fast ? (is_g ? 1.0f : 0.5f) : (is_g ? 2.0f : 1.0f);
-    const float kb = a.fast ? (is_g ? 0.0f : 0.5f) : (is_g ? -1.0f : 0.0f);
+    const float sc = FAST ? (is_g ? 1.0f : 0.5f) : (is_g ? 2.0f : 1.0f);
+    const float ka = FAST ? (is_g ? 1.0f : 0.5f) : (is_g ? 2.0f : 1.0f);
+    const float kb = FAST ? (is_g ? 0.0f : 0.5f) : (is_g ? -1.0f : 0.0f);
     const uint32_t myT = sT + static_cast<uint32_t>(warp - 2) * (NC * 16);
     const int oc = tl * 4 + q;  // unit octet inside the CTA = 16-byte chunk of the CTA's k-atom
     const int unit0 = static_cast<int>(crank) * 64 + oc * 8;
@@ -253,10 +281,15 @@ __global__ void __launch_bounds__(64 + 256 * (NR / NC), 1) blstm_rec_ts_kernel(c
       r_b[j] = d < C ? mapa(sB, d) + chunk_off : 0;
       r_bar[j] = d < C ? mapa(hfull0, d) : 0;
     }
-    __nv_bfloat16* hbase = a.H + ((static_cast<int64_t>(grp) * T) * 32 + sub * NR + r) * (2 * static_cast<int64_t>(Up)) +
-                           dir * Up + unit0;
-    const int64_t h_tstride = 32ll * 2 * Up;
-    const bool h_store = oct_ok && d0 == 0;
+    __nv_bfloat16* hbase =
+        PLAIN ? a.H + (static_cast<int64_t>(row0 + r) * T) * (2 * static_cast<int64_t>(Up)) + dir * Up + unit0
+              : a.H + ((static_cast<int64_t>(grp) * T) * 32 + sub * NR + r) * (2 * static_cast<int64_t>(Up)) + dir * Up + unit0;
+    const int64_t h_tstride = PLAIN ? 2ll * Up : 32ll * 2 * Up;
+    __nv_bfloat16* hptr = hbase + (dir ? static_cast<int64_t>(T - 1) * h_tstride : 0);  // frame of step 0
+    const int64_t h_step = dir ? -h_tstride : h_tstride;
+    int slot = 0;
+    uint32_t gph = 0;
+    const bool h_store = oct_ok && d0 == 0 && (!PLAIN || row0 + r < a.rows);
     const uint32_t g_lane = static_cast<uint32_t>(oc) * oct_bytes + static_cast<uint32_t>(half * NQ * 32 + lane) * 4u * esz;
     const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc_col + tl * NR + half * NC;
 
@@ -267,21 +300,32 @@ __global__ void __launch_bounds__(64 + 256 * (NR / NC), 1) blstm_rec_ts_kernel(c
     const bool do_prof = a.prof != nullptr && blockIdx.y == 0 && blockIdx.z == 0 && crank == 0 && (warp == 4 || warp == 8);
     int pc[4] = {0, 0, 0, 0};
     for (int s = 0; s < T; ++s) {
-      const int t = dir ? T - 1 - s : s;
       const int wb = s & 1;
-      const int slot = s % GS;
       int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
       if (do_prof) c0 = clock();
       // input projection of this step: shared-memory ring -> registers, slot handed back at once
       float gv[NC];
-      mbar_wait(gfull0 + 8 * slot, (s / GS) & 1);
+      mbar_wait(gfull0 + 8 * slot, gph);
       {
         const uint32_t gp = sG + slot * g_stage + g_lane;
+        if constexpr (PLAIN) {
+          // stage = [row][gate][64 units] bf16, 128-byte lines, 16-byte chunks XOR-swizzled with (line & 7)
+#pragma unroll
+          for (int i = 0; i < NC; ++i) {
+            const uint32_t line = static_cast<uint32_t>((half * NC + i) * 4 + gate);
+            unsigned short hv = 0;
+            if (oct_ok)
+              asm volatile("ld.shared.u16 %0, [%1];"
+                           : "=h"(hv)
+                           : "r"(sG + slot * g_stage + line * 128u + ((static_cast<uint32_t>(oc) ^ (line & 7u)) << 4) + ul * 2u));
+            gv[i] = __uint_as_float(static_cast<uint32_t>(hv) << 16);
+          }
+        } else {
 #pragma unroll
         for (int i = 0; i < NQ; ++i) {
           if (!oct_ok) {
             gv[4 * i] = gv[4 * i + 1] = gv[4 * i + 2] = gv[4 * i + 3] = 0.f;
-          } else if (a.g_bf16) {
+          } else if (GBF16) {
             uint32_t x, y;
             asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(x), "=r"(y) : "r"(gp + i * 256));
             gv[4 * i + 0] = __uint_as_float(x << 16);
@@ -294,9 +338,14 @@ __global__ void __launch_bounds__(64 + 256 * (NR / NC), 1) blstm_rec_ts_kernel(c
                          : "r"(gp + i * 512));
           }
         }
+        }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(gempty0 + 8 * slot);
+      if (++slot == GS) {
+        slot = 0;
+        gph ^= 1;
+      }
       if (do_prof) c1 = clock();
 
       mbar_wait(accfull0 + 8 * tl, s & 1);
@@ -314,7 +363,7 @@ __global__ void __launch_bounds__(64 + 256 * (NR / NC), 1) blstm_rec_ts_kernel(c
 #pragma unroll
       for (int i = 0; i < NC; ++i) {
         const float x = (__uint_as_float(v[i]) + gv[i]) * sc;
-        const float y = a.fast ? tanh_fast(x) : sigmoid_acc(x);
+        const float y = FAST ? tanh_fast(x) : sigmoid_acc(x);
         act[i] = fmaf(y, ka, kb);
       }
       // 4x4 transposes inside lane quads: afterwards act[4i + g] = gate g of batch row 4i + (lane & 3)
@@ -350,7 +399,7 @@ __global__ void __launch_bounds__(64 + 256 * (NR / NC), 1) blstm_rec_ts_kernel(c
         const float ig = act[4 * i + 0], fg = act[4 * i + 1], gg = act[4 * i + 2], og = act[4 * i + 3];
         const float c = fmaf(fg, cst[i], ig * gg);
         cst[i] = c;
-        const float h = og * (a.fast ? tanh_fast(c) : tanh_acc(c));
+        const float h = og * (FAST ? tanh_fast(c) : tanh_acc(c));
         const int b = 4 * i + gate;
         const __nv_bfloat16 hb = __float2bfloat16_rn(h);
         asm volatile("st.shared.u16 [%0], %1;" ::"r"(myT + static_cast<uint32_t>(b * 8 + ul) * 2),
@@ -366,11 +415,14 @@ __global__ void __launch_bounds__(64 + 256 * (NR / NC), 1) blstm_rec_ts_kernel(c
       __syncwarp();
       if (s + 1 < T) {
         const uint32_t boff = static_cast<uint32_t>(wb) * NA * kAtomB;
+        // st.async: the bytes complete the destination's mbarrier themselves.  (Measured alternatives, all slower:
+        // plain st.shared::cluster + one release-arrive per warp, one cp.async.bulk per peer, per-atom barriers.)
 #pragma unroll
         for (int j = 0; j < ND; ++j)
           if (static_cast<uint32_t>(d0 + j * DG) < C) ts_st_async_v4(r_b[j] + boff, chunk, r_bar[j] + 8 * wb);
       }
-      if (h_store) *reinterpret_cast<uint4*>(hbase + static_cast<int64_t>(t) * h_tstride) = chunk;
+      if (h_store) *reinterpret_cast<uint4*>(hptr) = chunk;
+      hptr += h_step;
       if (do_prof) {
         const int c4 = clock();
         pc[0] += c1 - c0;  // G ring wait + loads
@@ -419,9 +471,9 @@ __global__ void pack_whh_ts_kernel(const float* __restrict__ w_fwd, const float*
   }
 }
 
-template <int NR, int NC>
+template <int NR, int NC, bool FAST, bool GBF16, bool PLAIN>
 static int max_clusters_ts(int C, size_t smem) {
-  if (cudaFuncSetAttribute(blstm_rec_ts_kernel<NR, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) !=
+  if (cudaFuncSetAttribute(blstm_rec_ts_kernel<NR, NC, FAST, GBF16, PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) !=
       cudaSuccess)
     return 0;
   cudaLaunchConfig_t cfg{};
@@ -436,7 +488,7 @@ static int max_clusters_ts(int C, size_t smem) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   int n = 0;
-  if (cudaOccupancyMaxActiveClusters(&n, blstm_rec_ts_kernel<NR, NC>, &cfg) != cudaSuccess) {
+  if (cudaOccupancyMaxActiveClusters(&n, blstm_rec_ts_kernel<NR, NC, FAST, GBF16, PLAIN>, &cfg) != cudaSuccess) {
     cudaGetLastError();
     return 0;
   }
@@ -461,9 +513,9 @@ static size_t ts_smem(int C, int NR, int g_dtype, int* stages_out) {
   return smem < 120 * 1024 ? 120 * 1024 : smem;
 }
 
-template <int NR, int NC>
-static int launch_ts(const RecTsArgs& a, int C, int nsub, size_t smem, cudaStream_t stream) {
-  TSSEP_CUDA(cudaFuncSetAttribute(blstm_rec_ts_kernel<NR, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+template <int NR, int NC, bool FAST, bool GBF16, bool PLAIN>
+static int launch_ts(const RecTsArgs& a, const CUtensorMap& gmap, int C, int nsub, size_t smem, cudaStream_t stream) {
+  TSSEP_CUDA(cudaFuncSetAttribute(blstm_rec_ts_kernel<NR, NC, FAST, GBF16, PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(C, static_cast<unsigned>(nsub), 2);
   cfg.blockDim = dim3(64 + 256 * (NR / NC));
@@ -476,7 +528,7 @@ static int launch_ts(const RecTsArgs& a, int C, int nsub, size_t smem, cudaStrea
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  TSSEP_CUDA(cudaLaunchKernelEx(&cfg, blstm_rec_ts_kernel<NR, NC>, a));
+  TSSEP_CUDA(cudaLaunchKernelEx(&cfg, blstm_rec_ts_kernel<NR, NC, FAST, GBF16, PLAIN>, a, gmap));
   return check_launch("blstm_rec_ts");
 }
 
@@ -502,14 +554,16 @@ int tssep_blstm_recurrence_ts_capacity(int Up, int rows_per_cluster, int g_dtype
                 "tssep_blstm_recurrence_ts_capacity: rows_per_cluster must be 16 or 32");
   const int C = (Up + 63) / 64;
   int st = 0;
-  const int m = rows_per_cluster == 16 ? max_clusters_ts<16, 8>(C, ts_smem(C, 16, g_dtype, &st))
-                                       : max_clusters_ts<32, 16>(C, ts_smem(C, 32, g_dtype, &st));
+  const int m = rows_per_cluster == 16 ? max_clusters_ts<16, 16, true, true, false>(C, ts_smem(C, 16, g_dtype, &st))
+                                       : max_clusters_ts<32, 16, true, true, false>(C, ts_smem(C, 32, g_dtype, &st));
   return (m / 2) * rows_per_cluster;
 }
 
 int tssep_blstm_recurrence_ts(const void* G, int g_dtype, const uint32_t* Wimg, uint16_t* H, int64_t rows, int64_t T,
-                              int Up, int rows_per_cluster, int fast_math, tssep_stream_t stream) {
+                              int Up, int layout, int rows_per_cluster, int fast_math, tssep_stream_t stream) {
   TSSEP_REQUIRE(G && Wimg && H, "tssep_blstm_recurrence_ts: null pointer");
+  TSSEP_REQUIRE(layout == TSSEP_REC_LAYOUT_BT || layout == TSSEP_REC_LAYOUT_ROWS, "tssep_blstm_recurrence_ts: unknown layout %d", layout);
+  TSSEP_REQUIRE(layout == TSSEP_REC_LAYOUT_BT || g_dtype == 1, "tssep_blstm_recurrence_ts: the row layout needs bf16 G");
   TSSEP_REQUIRE(g_dtype == 0 || g_dtype == 1, "tssep_blstm_recurrence_ts: g_dtype must be 0 (f32) or 1 (bf16)");
   TSSEP_REQUIRE(Up >= 16 && Up % 16 == 0 && Up <= 448, "tssep_blstm_recurrence_ts: Up must be a multiple of 16 in [16, 448]");
   TSSEP_REQUIRE(rows >= 0 && T >= 0 && T < (1ll << 31) && (rows + 15) / 16 <= 65535, "tssep_blstm_recurrence_ts: bad extent");
@@ -529,8 +583,8 @@ int tssep_blstm_recurrence_ts(const void* G, int g_dtype, const uint32_t* Wimg, 
     // 16 rows per cluster has the shortest step (1.3-1.4 us at U=300 vs 2.25 us for 32 rows); a launch that
     // does not fit in one wave of co-resident clusters runs its waves back to back
     int st = 0;
-    const int m16 = max_clusters_ts<16, 8>(C, ts_smem(C, 16, g_dtype, &st));
-    const int m32 = max_clusters_ts<32, 16>(C, ts_smem(C, 32, g_dtype, &st));
+    const int m16 = max_clusters_ts<16, 16, true, true, false>(C, ts_smem(C, 16, g_dtype, &st));
+    const int m32 = max_clusters_ts<32, 16, true, true, false>(C, ts_smem(C, 32, g_dtype, &st));
     const int64_t n16 = 2 * ((rows + 15) / 16), n32 = 2 * ((rows + 31) / 32);
     const double t16 = m16 > 0 ? 1.0 * static_cast<double>((n16 + m16 - 1) / m16) : 1e9;
     const double t32 = m32 > 0 ? 1.6 * static_cast<double>((n32 + m32 - 1) / m32) : 2e9;
@@ -557,15 +611,45 @@ int tssep_blstm_recurrence_ts(const void* G, int g_dtype, const uint32_t* Wimg, 
   TSSEP_REQUIRE(stages >= 2, "tssep_blstm_recurrence_ts: G ring does not fit shared memory");
   a.stages = stages;
   const int nsub = static_cast<int>((rows + NR - 1) / NR);
-  // batch columns per epilogue warp (TSSEP_TS_COLS): 16 epilogue warps by default, 8 on request
-  int NC = NR / 2;
+  // batch columns per epilogue warp (TSSEP_TS_COLS): 16 measured best for both cluster widths
+  int NC = 16;
   if (const char* e = getenv("TSSEP_TS_COLS")) {
     const int v = atoi(e);
     if (v == NR || v == NR / 2) NC = v;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (NR == 16) return NC == 16 ? launch_ts<16, 16>(a, C, nsub, smem, st) : launch_ts<16, 8>(a, C, nsub, smem, st);
-  return NC == 32 ? launch_ts<32, 32>(a, C, nsub, smem, st) : launch_ts<32, 16>(a, C, nsub, smem, st);
+  CUtensorMap gmap{};
+  if (layout == TSSEP_REC_LAYOUT_ROWS) {
+    // G (rows, T, 2, 4, Up) bf16 viewed as (unit, gate, row, dir, t); box = 64 units x 4 gates x NR rows
+    EncodeTiledFn enc = get_encode_tiled();
+    TSSEP_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+    const cuuint64_t up = static_cast<cuuint64_t>(Up);
+    cuuint64_t dims[5] = {up, 4, static_cast<cuuint64_t>(rows), 2, static_cast<cuuint64_t>(T)};
+    cuuint64_t strides[4] = {up * 2, static_cast<cuuint64_t>(T) * 8 * up * 2, 4 * up * 2, 8 * up * 2};
+    cuuint32_t box[5] = {64, 4, static_cast<cuuint32_t>(NR), 1, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(&gmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(G), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    TSSEP_REQUIRE(r == CUDA_SUCCESS, "tssep_blstm_recurrence_ts: cuTensorMapEncodeTiled failed with code %d", static_cast<int>(r));
+  }
+#define TSSEP_TS_CASE(NR_, NC_)                                                                                   \
+  if (NR == NR_ && NC == NC_) {                                                                                   \
+    if (layout == TSSEP_REC_LAYOUT_ROWS)                                                                          \
+      return a.fast ? launch_ts<NR_, NC_, true, true, true>(a, gmap, C, nsub, smem, st)                           \
+                    : launch_ts<NR_, NC_, false, true, true>(a, gmap, C, nsub, smem, st);                         \
+    if (a.fast) return g_dtype ? launch_ts<NR_, NC_, true, true, false>(a, gmap, C, nsub, smem, st)               \
+                               : launch_ts<NR_, NC_, true, false, false>(a, gmap, C, nsub, smem, st);             \
+    return g_dtype ? launch_ts<NR_, NC_, false, true, false>(a, gmap, C, nsub, smem, st)                          \
+                   : launch_ts<NR_, NC_, false, false, false>(a, gmap, C, nsub, smem, st);                        \
+  }
+  TSSEP_TS_CASE(16, 8)
+  TSSEP_TS_CASE(16, 16)
+  TSSEP_TS_CASE(32, 16)
+  TSSEP_TS_CASE(32, 32)
+#undef TSSEP_TS_CASE
+  set_error("tssep_blstm_recurrence_ts: no instantiation for %d rows per cluster, %d columns per warp", NR, NC);
+  return -1;
 }
 
 }  // extern "C"

@@ -121,19 +121,23 @@ def pack_whh_ts(w_fwd: torch.Tensor, w_bwd: torch.Tensor, U: int, Up: int) -> to
 
 
 def blstm_recurrence_ts(G: torch.Tensor, wimg: torch.Tensor, rows: int, T: int, Up: int,
-                        fast_math: bool = None, rows_per_cluster: int = 0) -> torch.Tensor:
-    """TMEM-resident variant: G in the BT tile layout -> H (groups*T*32, 2*Up) bf16, rows (group, t, b).
-    Padding rows the kernel does not compute are zero."""
+                        fast_math: bool = None, rows_per_cluster: int = 0, layout: str = "bt") -> torch.Tensor:
+    """Tensor-memory recurrence.  layout "bt": G in the BT tile layout -> H (groups*T*32, 2*Up) bf16, rows
+    (group, t, b), padding rows the kernel does not compute are zero.  layout "rows": G (rows, T, 8*Up) bf16
+    -> H (rows, T, 2*Up), the layouts of ``blstm_recurrence``."""
     _lib.require_cuda(G, wimg)
     if fast_math is None:
         fast_math = os.environ.get("TSSEP_LSTM_FAST_MATH", "1") == "1"
-    groups = (rows + 31) // 32
-    H = torch.empty((groups * T * 32, 2 * Up), dtype=torch.bfloat16, device=G.device)
-    done = ((rows + 15) // 16) * 16  # the kernel computes whole 16-row blocks at least
-    if done < groups * 32:
-        H.view(groups, T, 32, 2 * Up)[-1, :, done - (groups - 1) * 32:].zero_()
+    if layout == "rows":
+        H = torch.empty((rows, T, 2 * Up), dtype=torch.bfloat16, device=G.device)
+    else:
+        groups = (rows + 31) // 32
+        H = torch.empty((groups * T * 32, 2 * Up), dtype=torch.bfloat16, device=G.device)
+        done = ((rows + 15) // 16) * 16  # the kernel computes whole 16-row blocks at least
+        if done < groups * 32:
+            H.view(groups, T, 32, 2 * Up)[-1, :, done - (groups - 1) * 32:].zero_()
     _lib.call("tssep_blstm_recurrence_ts", G.data_ptr(), int(G.dtype == torch.bfloat16), wimg.data_ptr(), H.data_ptr(),
-              rows, T, Up, rows_per_cluster, int(fast_math), _lib.stream_of(G))
+              rows, T, Up, {"bt": 0, "rows": 1}[layout], rows_per_cluster, int(fast_math), _lib.stream_of(G))
     return H
 
 

@@ -83,7 +83,12 @@ class LayerPack:
         return G
 
     def recurrence(self, G: torch.Tensor, rows: int, T: int) -> torch.Tensor:
-        """Register-resident mma.sync kernel (csrc/lstm.cu): G (rows, T, 8Up) -> H (rows, T, 2Up)."""
+        """G (rows, T, 8Up) -> H (rows, T, 2Up): the tensor-memory kernel (csrc/lstm_ts.cu, row layout) from
+        TS_MIN_ROWS rows on when G is bf16, else the register-resident mma.sync kernel (csrc/lstm.cu)."""
+        if rec_kernel(rows) == "ts" and G.dtype == torch.bfloat16:
+            if self.whh_ts is None:
+                self.whh_ts = ops.pack_whh_ts(self._whh_f32[0], self._whh_f32[1], self.U, self.Up)
+            return ops.blstm_recurrence_ts(G, self.whh_ts, rows, T, self.Up, layout="rows")
         return ops.blstm_recurrence(G, self.whh, rows, T, self.Up)
 
     # -- throughput path: rows ordered (group, t, b32), weights in shared memory, tcgen05 -------------
@@ -186,7 +191,10 @@ class RNNP_packed(torch.nn.Module):
             rows *= s
         x = xs_pack.reshape(rows * T, D).float()
         packs = self.layer_packs()
-        if use_tc_recurrence(rows):
+        # TSSEP_TS_LAYOUT=bt routes this generic entry point through the (group, t, b32) row order the mask
+        # estimator uses for its speaker-independent layers; by default the tensor-memory kernel reads and
+        # writes plain (row, t) layouts here and no re-ordering copies are needed.
+        if rec_kernel(rows) == "tc" or (rec_kernel(rows) == "ts" and os.environ.get("TSSEP_TS_LAYOUT", "rows") == "bt"):
             return self._forward_tc(x, rows, T, D, packs).reshape(*shape[:-1], packs[-1].hdim)
         xb, ld = ops.cast_bf16(x), ops.round_up(D, 8)
         out = None
