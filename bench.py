@@ -473,26 +473,28 @@ def run_b200(args):
     gemm_flops = M * (3.726e12 - 2.0 * 19 * T * 2 * 4 * 300 * 300)
     gemm_tflops = gemm_flops / (gemm["ms_per_step"] / 1e3) / 1e12 if gemm["ms_per_step"] else 0.0
     top = max(breakdown.items(), key=lambda kv: kv[1]["ms_per_step"])[0] if breakdown else None
-    # HBM bytes of the recurrence launches of one step: it streams G once (f32) and writes H once (bf16).
-    # ncu (--set full) of the birnn0 launch of this very command measured dram read+write = 45.98 GB against
-    # 45.97 GB algorithmic (profiles/r1_ncu_blstm_rec_bench_b0.txt), i.e. a ratio of 1.00.
+    # HBM bytes of the recurrence launches of one step: G is streamed once, H written once.  ncu (--set full) of the
+    # 208-row launch measured dram read + write = 7.58 GB against 7.59 GB algorithmic (profiles/r1_ncu_rec_ts.txt).
     g_bytes = 4 if os.environ.get("TSSEP_G_DTYPE", "bf16") == "f32" else 2
     rec_bytes = rec_rows * T * (8 * Up * g_bytes + 2 * Up * 2)
     rec_launches = max(1.0, rec["launches_per_step"])
+    rec_gbs = rec_bytes / (rec["ms_per_step"] / 1e3) / 1e9 if rec["ms_per_step"] else 0.0
     roofline = {
-        "kernel": "blstm_rec_ts_kernel + blstm_rec_kernel", "bound": "tensor", "achieved": rec_tflops, "peak": peaks["bf16_tflops_sustained"],
+        "kernel": "blstm_rec_ts_kernel", "bound": "tensor", "achieved": rec_tflops, "peak": peaks["bf16_tflops_sustained"],
         "unit": "TFLOP/s", "frac": rec_tflops / peaks["bf16_tflops_sustained"],
         "traffic": 1.00 * rec_bytes / rec_launches,
-        "traffic_note": "bytes per launch (mean of the 4 recurrence launches of a step) = algorithmic bytes x 1.00, the "
-                        "dram read+write / algorithmic ratio ncu measured for the birnn0 launch "
-                        "(profiles/r1_ncu_blstm_rec_bench_b0.txt)",
+        "traffic_note": "bytes per launch (mean over the recurrence launches of a step) = algorithmic bytes x 1.00, the "
+                        "dram read+write / algorithmic ratio ncu measured (profiles/r1_ncu_rec_ts.txt)",
         "algorithmic_flops_per_launch": rec_flops / rec_launches, "algorithmic_bytes_per_launch": rec_bytes / rec_launches,
         "avg_launch_ms": rec["ms_per_step"] / rec_launches,
         "peak_source": peaks["source"] + " (sustained)",
-        "note": "the recurrence is bound by the latency of T dependent steps (one DSMEM exchange + one tcgen05 / "
-                "mma.sync chain + the gate math per step), not by the tensor pipe or HBM; see us_per_recurrent_step",
+        "note": "the recurrence is bound by the latency of T dependent steps (per step: DSMEM exchange of h with st.async, "
+                "2 x Up/16 tcgen05.mma with W_hh resident in tensor memory, gate math), not by the tensor pipe or HBM; "
+                "see us_per_recurrent_step",
+        "hbm_GBps": rec_gbs, "hbm_frac": rec_gbs / peaks["hbm_gbs"],
+        "us_per_recurrent_step": rec["ms_per_step"] * 1e3 / (rec_launches * T) if rec["ms_per_step"] else None,
+        "dependent_steps_per_step": rec_launches * T,
         "launches": {k: v for k, v in rec_parts.items()},
-        "us_per_recurrent_step": rec["ms_per_step"] * 1e3 / (4 * T) if rec["ms_per_step"] else None,
         "gate_math": rec_cfg,
         "share_of_step": rec["ms_per_step"] / (ms / args.steps),
         "top_kernel_by_time": top,
