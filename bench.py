@@ -54,7 +54,11 @@ def parse_args():
     ap.add_argument("--meetings-per-gpu", type=int, default=int(os.environ.get("TSSEP_BENCH_MEETINGS", 0)),
                     help="0 = as many as fit in memory (at most 28), trimmed to one wave of recurrence clusters")
     ap.add_argument("--seconds", type=float, default=600.0, help="length of every synthetic meeting")
-    ap.add_argument("--waves", type=int, default=int(os.environ.get("TSSEP_BENCH_WAVES", 2)),
+    ap.add_argument("--wave-meetings", type=int, default=int(os.environ.get("TSSEP_BENCH_WAVE", 0)),
+                    help="meetings per recurrence wave (0 = what fits in one wave of 32-row clusters)")
+    ap.add_argument("--out-wave-meetings", type=int, default=int(os.environ.get("TSSEP_BENCH_OUT_WAVE", 13)),
+                    help="meetings per output wave (head -> mask x STFT -> iSTFT -> diarization)")
+    ap.add_argument("--waves", type=int, default=int(os.environ.get("TSSEP_BENCH_WAVES", 1)),
                     help="with --meetings-per-gpu 0: waves of recurrence-capacity meetings per step (the row-light "
                          "pre_net / speaker-concat recurrences are shared by all waves of a step)")
     ap.add_argument("--cpu-sample-seconds", type=float, default=60.0)
@@ -252,20 +256,30 @@ def run_b200(args):
     free_b, _ = torch.cuda.mem_get_info(dev)
     per_meeting = 5.2e9 * (args.seconds / 600.0)
     from tssep_b200 import ops as _ops
-    # The K=8 speaker rows of every meeting advance together in the tensor-memory recurrence; one wave of
-    # 16-row clusters steps in 1.4 us whatever its fill, one row more costs a second wave.
-    wave = max(1, _ops.recurrence_ts_capacity(304, 16) // 8)
-    light = 1.0e9 * (args.seconds / 600.0)  # per meeting outside the current wave: STFT, features, time_estimate, concat rows
+    # The K=8 speaker rows of every meeting advance together in the tensor-memory recurrence.  One wave of 32-row
+    # clusters (52 meetings) steps in 2.5 us, one wave of 16-row clusters (26 meetings) in 1.3 us; a row more costs
+    # a second wave.  The row-light layers (pre_net, speaker-concat layer) always run once per step.
+    wave = args.wave_meetings if args.wave_meetings > 0 else max(1, _ops.recurrence_ts_capacity(304, 32) // 8)
+    # memory model per 10-min meeting, calibrated on torch.cuda.memory_stats (116 GB peak for 52 meetings in one wave
+    # plus the serving loop's buffers): 0.7 GB that lives for the whole step (audio, STFT, pre_net rows, the
+    # separated audio of the step and the serving loop's input / output buffers), 2.05 GB while its wave is in the
+    # K-rows-per-meeting layers (bf16 G + H + layer input), 2.5 GB while its output wave exists (logit, mask,
+    # stft_estimate)
+    scale = args.seconds / 600.0
+    light, heavy, outs = 0.7e9 * scale, 2.05e9 * scale, 2.5e9 * scale
+    out_w = max(1, args.out_wave_meetings)
+
+    def fits(m, w):
+        return m * light + max(min(m, w) * heavy, min(m, out_w) * outs) <= 0.92 * free_b
+
     if M <= 0:
         M = wave * max(1, args.waves)
-        while M > wave and wave * per_meeting + (M - wave) * light > 0.9 * free_b:
-            M -= wave
-        if M == wave:
-            M = max(1, min(wave, int(0.9 * free_b / per_meeting)))
-    else:
-        M = max(1, min(M, int((0.9 * free_b - min(M, wave) * per_meeting) / light) + min(M, wave)))
+    if not fits(M, wave) and args.wave_meetings <= 0:
+        wave = max(1, _ops.recurrence_ts_capacity(304, 16) // 8)  # waves of 16-row clusters need half the G buffer
+    while M > 1 and not fits(M, wave) and os.environ.get("TSSEP_BENCH_NO_MEM_GUARD") != "1":
+        M -= 1
     wave = min(wave, M)
-    out_wave = (wave + 1) // 2 if M > wave else wave  # output stages in half waves when several waves share a step
+    out_wave = min(M, max(1, args.out_wave_meetings))  # the GB-sized logit / mask / stft_estimate live per output wave
     if world > 1:
         mt = torch.tensor([M], device=dev)
         torch.distributed.all_reduce(mt, op=torch.distributed.ReduceOp.MIN)
@@ -356,8 +370,8 @@ def run_b200(args):
     torch.cuda.empty_cache()
     obs_bufs = [torch.empty_like(obs_dev) for _ in range(2)]
     aux_bufs = [torch.empty_like(aux_dev) for _ in range(2)]
-    time_bufs = [torch.empty((M, k, n), dtype=torch.float32, device=dev) for _ in range(2)]
-    copied = [None, None]   # event: the D2H copies out of time_bufs[j] are done
+    time_buf = torch.empty((M, k, n), dtype=torch.float32, device=dev)  # one: it is written only at the end of a step
+    copied = [None]         # event: the D2H copies of the previous step out of time_buf are done
     in_free = [None, None]  # event: the step that read obs_bufs[j] / aux_bufs[j] is done
 
     def e2e_step(i):
@@ -373,9 +387,12 @@ def run_b200(args):
             aux_bufs[j].copy_(aux_host, non_blocking=True)
             ev_in.record(in_stream)
         main_stream.wait_event(ev_in)
-        if copied[j] is not None:
-            main_stream.wait_event(copied[j])  # step i-2 has left time_bufs[j]
         th = time_hosts[j]
+
+        def time_out():  # called right before the first output wave of this step is written
+            if copied[0] is not None:
+                main_stream.wait_event(copied[0])  # the previous step's audio has left time_buf
+            return time_buf
         if dbg:
             m0.record(main_stream)
 
@@ -392,7 +409,7 @@ def run_b200(args):
                     c1.record(copy_stream)
                     c_ev.append((c0, c1))
 
-        out = step(obs_bufs[j], aux_bufs[j], on_wave=ship, time_out=time_bufs[j])
+        out = step(obs_bufs[j], aux_bufs[j], on_wave=ship, time_out=time_out)
         if dbg:
             m1.record(main_stream)
             dbg_rows.append((i, h0, time.perf_counter(), m0, m1, c_ev))
@@ -405,8 +422,8 @@ def run_b200(args):
             out.counts.record_stream(copy_stream)
             seg_host.copy_(out.segments, non_blocking=True)
             cnt_host.copy_(out.counts, non_blocking=True)
-            copied[j] = torch.cuda.Event()
-            copied[j].record(copy_stream)
+            copied[0] = torch.cuda.Event()
+            copied[0].record(copy_stream)
 
     # plain D2H bandwidth of this box (what bounds the end-to-end number: 512 KB of separated audio per audio-second)
     probe = torch.empty((wave, k, n), dtype=torch.float32, device=dev)

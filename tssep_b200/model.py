@@ -144,7 +144,9 @@ class Model(Configurable, torch.nn.Module):
         big outputs (mask, logit, stft_estimate: 2.5 GB per 10-min meeting) before asking for the next
         one lets them share memory; ``out_wave`` (default ``wave``) is the number of meetings per yielded
         output.  ``time_out`` (M, K, N) float32: optional caller-owned buffer the separated signals are written
-        to (each yielded ``time_estimate`` is then a view of it).  Results do not depend on ``wave`` / ``out_wave``.
+        to (each yielded ``time_estimate`` is then a view of it); a callable is invoked right before the first
+        output wave is written and must return the buffer (a serving loop waits there for the previous batch's
+        device-to-host copy).  Results do not depend on ``wave`` / ``out_wave``.
         """
         _lib.require_cuda(observation, aux)
         if observation.dim() == 2:
@@ -157,6 +159,8 @@ class Model(Configurable, torch.nn.Module):
                                                   _features_bf16=(feats["bf16"], feats["ld"]))
         del feats
         for lo, hi, me_out in waves:
+            if callable(time_out):  # resolved when the first output wave is about to be written
+                time_out = time_out()
             est, time = Masking.apply(me_out.mask, Obs[lo:hi], 0, self.fe, want_estimate=want_estimate,
                                       want_time=want_time, num_samples=n,
                                       time_out=None if time_out is None else time_out[lo:hi])

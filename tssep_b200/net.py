@@ -359,6 +359,7 @@ class MaskEstimator_v2(Configurable, torch.nn.Module):
                 for l in range(L - 1):
                     pk = birnns[l].layer_packs()[0]
                     G = pk.input_gemm_bt(yw, yw_ld, mrows)
+                    del yw  # the layer input is dead once its projection exists (G is the largest buffer of the path)
                     H = pk.recurrence_tc(G, Z, T)
                     del G
                     if l < L - 2:
@@ -372,7 +373,7 @@ class MaskEstimator_v2(Configurable, torch.nn.Module):
                         pk.projection(H, mrows, y[lo * K * T:], mode=ops.EPI_BF16_ROWMAP, ldo=y_ld, act=1,
                                       row_map=(T, 1, Z, 0))
                     del H
-                del yw
+                yw = None
             start_l = L - 1
         else:
             # ---- latency path: conditioning folded into birnn0's input projection ----------------------
