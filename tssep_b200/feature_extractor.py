@@ -194,7 +194,7 @@ def _compute_features(fe: STFT, X: torch.Tensor, want_f32=True, want_bf16=False,
               _lib.ptr(meldb), stream)
     out = {}
     f32 = torch.empty((*lead, t, din), dtype=torch.float32, device=dev) if want_f32 else None
-    ld = _round_up(din, 8)
+    ld = _round_up(din, 64) if din >= 64 else _round_up(din, 8)  # ops.operand_ld
     bf16 = torch.empty((n_items * t, ld), dtype=torch.bfloat16, device=dev) if want_bf16 else None
     xv = torch.view_as_real(X).reshape(n_items, t, f, 2)
     for start, count in groups:

@@ -210,7 +210,7 @@ class MaskEstimator_v2(Configurable, torch.nn.Module):
                     b2 = torch.stack([bv[(q - r) % K] for r in range(R)], 0).mean(0).reshape(-1)
                 else:
                     W2, b2 = W, b
-                pack = {"w": ops.cast_bf16(W2.contiguous()), "ld": ops.round_up(W2.shape[1], 8),
+                pack = {"w": ops.cast_bf16(W2.contiguous()), "ld": ops.operand_ld(W2.shape[1]),
                         "b": b2.contiguous(), "kdim": W2.shape[1], "n": W2.shape[0]}
             self._head_cache = (key, pack)
         return self._head_cache[1]
@@ -224,7 +224,7 @@ class MaskEstimator_v2(Configurable, torch.nn.Module):
                 Wv = pk.w_ih_f32.view(8 * pk.Up, K, P)
                 q = torch.arange(K, device=Wv.device)
                 Wr = torch.stack([Wv[:, (q - r) % K] for r in range(R)], 0).reshape(R * 8 * pk.Up, K * P)
-                ld = ops.round_up(K * P, 8)
+                ld = ops.operand_ld(K * P)
                 self._rot_cache = (key, {"w": ops.cast_bf16(Wr.contiguous(), ld), "ld": ld})
         return self._rot_cache[1]
 
@@ -300,7 +300,7 @@ class MaskEstimator_v2(Configurable, torch.nn.Module):
             xb, ld = _features_bf16
         else:
             xb = ops.cast_bf16(xs.reshape(B * T, Din).float())
-            ld = ops.round_up(Din, 8)
+            ld = ops.operand_ld(Din)
 
         del xs, _features_bf16  # only the bf16 rows are used from here on
 
@@ -310,7 +310,7 @@ class MaskEstimator_v2(Configurable, torch.nn.Module):
                 G = pk.input_gemm(xb, ld, B * T)
                 H = pk.recurrence(G, B, T)
                 del G
-                ld = ops.round_up(pk.hdim, 8)
+                ld = ops.operand_ld(pk.hdim)
                 xb = torch.empty((B * T, ld), dtype=torch.bfloat16, device=dev)
                 pk.projection(H, B * T, xb, mode=ops.EPI_BF16, ldo=ld, act=0)
                 del H
@@ -324,7 +324,7 @@ class MaskEstimator_v2(Configurable, torch.nn.Module):
         e = aux_p.reshape(B * K, A).contiguous()
         stream = _lib.stream_of(xb)
         P = self.projs
-        ldp = ops.round_up(P, 8)
+        ldp = ops.operand_ld(P)
         mode = {"mul": 0, "cat": 1}[self.combination]
         if self.combination == "mul":
             assert A == F, ("combination='mul' needs aux_size == odim", A, F)
@@ -340,12 +340,12 @@ class MaskEstimator_v2(Configurable, torch.nn.Module):
             # row innermost, the recurrence runs on tcgen05 with the recurrent weights in tensor memory.
             # One pass per wave of items; all waves write into the same output of the last of these layers.
             if self.ts_vad is not False:
-                y_ld = ops.round_up(K * P, 8)   # speaker-concat layout (B, T, K*P)   net.py:606-612
+                y_ld = ops.operand_ld(K * P)   # speaker-concat layout (B, T, K*P)   net.py:606-612
                 y = torch.empty((B * T, y_ld), dtype=torch.bfloat16, device=dev)
             else:
                 y_ld = ldp
                 y = torch.empty((B * K * T, y_ld), dtype=torch.bfloat16, device=dev)
-            ld0 = ops.round_up(pk0.I, 8)
+            ld0 = ops.operand_ld(pk0.I)
             for lo in range(0, B, wave):
                 hi = min(B, lo + wave)
                 Z = (hi - lo) * K
@@ -382,7 +382,7 @@ class MaskEstimator_v2(Configurable, torch.nn.Module):
             gmode = ops.EPI_BF16 if gd == torch.bfloat16 else ops.EPI_F32
             G = torch.empty((B * K * T, 8 * Up), dtype=gd, device=dev)
             if self.combination == "mul":
-                ldk = ops.round_up(F, 8)
+                ldk = ops.operand_ld(F)
                 Wk = torch.empty((B * K * 8 * Up, ldk), dtype=torch.bfloat16, device=dev)
                 _lib.call("tssep_fold_embedding", 0, pk0.w_ih_f32.data_ptr(), pk0.I, pk0.bias.data_ptr(),
                           e.data_ptr(), B * K, 8 * Up, F, A, Wk.data_ptr(), ldk, bias_k.data_ptr(), stream)
@@ -419,13 +419,13 @@ class MaskEstimator_v2(Configurable, torch.nn.Module):
             del G
             if not last and l == L - 2 and self.ts_vad is not False:
                 # write tanh(proj) straight into the speaker-concat layout (B, T, K*P)   net.py:606-612
-                y_ld = ops.round_up(K * P, 8)
+                y_ld = ops.operand_ld(K * P)
                 y = torch.empty((B * T, y_ld), dtype=torch.bfloat16, device=dev)
                 pk.projection(H, 0, y, mode=ops.EPI_BF16, ldo=y_ld, act=1, batch=rows, a_stride=T * 2 * pk.Up, M=T,
                               out_stride=P, out_div=K, out_stride_hi=T * y_ld)
             elif tsv_last:
                 # trial-concat layout (B, T, R*P) feeding the averaged head
-                y_ld = ops.round_up(R * P, 8)
+                y_ld = ops.operand_ld(R * P)
                 y = torch.empty((B * T, y_ld), dtype=torch.bfloat16, device=dev)
                 pk.projection(H, 0, y, mode=ops.EPI_BF16, ldo=y_ld, act=0, batch=rows, a_stride=T * 2 * pk.Up, M=T,
                               out_stride=P, out_div=R, out_stride_hi=T * y_ld)

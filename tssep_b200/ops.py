@@ -27,6 +27,13 @@ def g_dtype() -> torch.dtype:
     return torch.float32 if os.environ.get("TSSEP_G_DTYPE", "bf16") == "f32" else torch.bfloat16
 
 
+def operand_ld(cols: int) -> int:
+    """Leading dimension (elements) of a bf16 GEMM operand with ``cols`` columns: rows of 128 bytes or more start
+    on 128-byte boundaries, so that a 64-column TMA box row never straddles an extra L2 line (K = 513 rows of
+    1040 bytes cost 13 % more L2 -> SM traffic than rows of 1152 bytes; measured on the birnn0 input projection)."""
+    return round_up(cols, 64) if cols >= 64 else round_up(cols, 8)
+
+
 def _gemm_impl() -> int:
     return 1 if os.environ.get("TSSEP_GEMM_IMPL", "tcgen05") == "simt" else 0
 
@@ -56,7 +63,7 @@ def cast_bf16(src: torch.Tensor, ld_dst: int = None) -> torch.Tensor:
     _lib.require_cuda(src)
     src = src.contiguous()
     rows, cols = src.shape
-    ld_dst = round_up(cols, 8) if ld_dst is None else ld_dst
+    ld_dst = operand_ld(cols) if ld_dst is None else ld_dst
     dst = torch.empty((rows, ld_dst), dtype=torch.bfloat16, device=src.device)
     _lib.call("tssep_cast_bf16", src.data_ptr(), rows, cols, cols, dst.data_ptr(), ld_dst, _lib.stream_of(src))
     return dst
@@ -159,5 +166,5 @@ def instance_norm(x: torch.Tensor, unbiased=False) -> torch.Tensor:
     return out
 
 
-__all__ = ["gemm", "cast_bf16", "pack_whh", "blstm_recurrence", "pack_whh_tc", "blstm_recurrence_tc", "pack_whh_ts", "blstm_recurrence_ts", "recurrence_ts_capacity", "instance_norm", "round_up", "EPI_F32", "EPI_BF16",
+__all__ = ["gemm", "cast_bf16", "operand_ld", "pack_whh", "blstm_recurrence", "pack_whh_tc", "blstm_recurrence_tc", "pack_whh_ts", "blstm_recurrence_ts", "recurrence_ts_capacity", "instance_norm", "round_up", "EPI_F32", "EPI_BF16",
            "EPI_HEAD", "EPI_F32_BT", "EPI_BF16_ROWMAP", "EPI_BF16_BT"]

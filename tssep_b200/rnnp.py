@@ -60,7 +60,7 @@ class LayerPack:
             b[0, :, :U] = (lstm.bias_ih_l0 + lstm.bias_hh_l0).detach().float().view(4, U)
             b[1, :, :U] = (lstm.bias_ih_l0_reverse + lstm.bias_hh_l0_reverse).detach().float().view(4, U)
             self.bias = b.view(8 * Up).contiguous()
-            self.ld_in = ops.round_up(I, 8)
+            self.ld_in = ops.operand_ld(I)
             self.w_ih = ops.cast_bf16(self.w_ih_f32, self.ld_in)
             self._whh_f32 = (lstm.weight_hh_l0.detach().float().contiguous(),
                              lstm.weight_hh_l0_reverse.detach().float().contiguous())
@@ -196,7 +196,7 @@ class RNNP_packed(torch.nn.Module):
         # writes plain (row, t) layouts here and no re-ordering copies are needed.
         if rec_kernel(rows) == "tc" or (rec_kernel(rows) == "ts" and os.environ.get("TSSEP_TS_LAYOUT", "rows") == "bt"):
             return self._forward_tc(x, rows, T, D, packs).reshape(*shape[:-1], packs[-1].hdim)
-        xb, ld = ops.cast_bf16(x), ops.round_up(D, 8)
+        xb, ld = ops.cast_bf16(x), ops.operand_ld(D)
         out = None
         for li, pk in enumerate(packs):
             G = pk.input_gemm(xb, ld, rows * T)
@@ -206,7 +206,7 @@ class RNNP_packed(torch.nn.Module):
                 out = torch.empty((rows * T, pk.hdim), dtype=torch.float32, device=x.device)
                 pk.projection(H, rows * T, out, mode=ops.EPI_F32, ldo=pk.hdim, act=0)
             else:
-                ld = ops.round_up(pk.hdim, 8)
+                ld = ops.operand_ld(pk.hdim)
                 xb = torch.empty((rows * T, ld), dtype=torch.bfloat16, device=x.device)
                 pk.projection(H, rows * T, xb, mode=ops.EPI_BF16, ldo=ld, act=1)
             del H
@@ -221,7 +221,7 @@ class RNNP_packed(torch.nn.Module):
         xp = torch.zeros((groups * 32, T, D), dtype=torch.float32, device=x.device)
         xp[:rows] = x.view(rows, T, D)
         xb = ops.cast_bf16(xp.view(groups, 32, T, D).permute(0, 2, 1, 3).reshape(mrows, D))
-        ld = ops.round_up(D, 8)
+        ld = ops.operand_ld(D)
         out = None
         for li, pk in enumerate(packs):
             G = pk.input_gemm_bt(xb, ld, mrows)
@@ -231,7 +231,7 @@ class RNNP_packed(torch.nn.Module):
                 out = torch.empty((mrows, pk.hdim), dtype=torch.float32, device=x.device)
                 pk.projection(H, mrows, out, mode=ops.EPI_F32, ldo=pk.hdim, act=0)
             else:
-                ld = ops.round_up(pk.hdim, 8)
+                ld = ops.operand_ld(pk.hdim)
                 xb = torch.empty((mrows, ld), dtype=torch.bfloat16, device=x.device)
                 pk.projection(H, mrows, xb, mode=ops.EPI_BF16, ldo=ld, act=1)
             del H
