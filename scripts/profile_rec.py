@@ -44,9 +44,8 @@ def main():
         return H
 
     for rows in a.rows:
-        G = torch.randn((((rows + 31) // 32) * 32, a.frames, 8 * Up), device=dev) * 0.3
-        if a.g_bf16:
-            G = G.to(torch.bfloat16)
+        G = torch.empty((((rows + 31) // 32) * 32, a.frames, 8 * Up), device=dev,
+                        dtype=torch.bfloat16 if a.g_bf16 else torch.float32).normal_(0.0, 0.3)
         for C in a.clusters:
             for fast in a.fast:
                 for _ in range(2):

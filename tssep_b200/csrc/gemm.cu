@@ -334,20 +334,28 @@ __device__ __forceinline__ void epilogue_head(const GemmArgs& g, const EpiTile& 
   const int n = n0 + lane;
   const bool col_ok = lane < nvalid;
   const int q = n / g.row_len, f = n - q * g.row_len;
-  float* lo = static_cast<float*>(g.out);
-  float* mk = g.mask;
   const int64_t base = col_ok ? (static_cast<int64_t>(cb.plane) * g.M + m0) * g.row_len + f : 0;
   const int rmax = static_cast<int>(t.rows_left < 32 ? t.rows_left : 32);
   const uint32_t lds0 = stage + lane * 4;
-  if (rmax == 32 && col_ok) {
-#pragma unroll 8
+  float* lo = static_cast<float*>(g.out);
+  float* mk = g.mask;
+  if (rmax == 32 && lo != nullptr && mk != nullptr) {
+    // all 32 rows of the lane's column at once: 32 independent loads, then the stores walk two running pointers
+    float val[32];
+#pragma unroll
+    for (int r = 0; r < 32; ++r) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(val[r]) : "r"(lds0 + r * kStageLd * 4));
+    float* plo = lo + base;
+    float* pmk = mk + base;
+    const int64_t step = g.row_len;
+#pragma unroll
     for (int r = 0; r < 32; ++r) {
-      float val;
-      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(val) : "r"(lds0 + r * kStageLd * 4));
-      val = fmaf(g.alpha, val, cb.v[0]);
-      const int64_t idx = base + static_cast<int64_t>(r) * g.row_len;
-      if (lo) lo[idx] = val;
-      if (mk) mk[idx] = sigmoid_acc(val);
+      const float x = fmaf(g.alpha, val[r], cb.v[0]);
+      if (col_ok) {
+        *plo = x;
+        *pmk = sigmoid_acc(x);
+      }
+      plo += step;
+      pmk += step;
     }
   } else {
 #pragma unroll 1
@@ -651,7 +659,14 @@ static int launch_gemm(GemmArgs g, const uint16_t* A, int64_t lda, int64_t a_str
   g.stages = static_cast<int>(imin64(kMaxStages, (227 * 1024 - fixed) / stage_bytes));
   TSSEP_REQUIRE(g.stages >= 2, "gemm: tile does not fit shared memory");
   const size_t smem = fixed + g.stages * stage_bytes;
-  const int grid = static_cast<int>(imin64(g.total_tiles, sms));
+  int grid = static_cast<int>(imin64(g.total_tiles, sms));
+  // TSSEP_GEMM_MAX_CTAS: run the persistent kernel on fewer SMs.  Under the board power cap a large GEMM is power
+  // limited, and the clocks it leaves behind decide the speed of the latency-bound recurrence that follows
+  // (profiles/r1_power_cap_probe.txt).
+  if (const char* e = getenv("TSSEP_GEMM_MAX_CTAS")) {
+    const int v = atoi(e);
+    if (v >= 1 && v < grid) grid = v;
+  }
 #define TSSEP_GEMM_CASE(MODE_, ACT_)                                                                                     \
   if (g.mode == MODE_ && g.act == ACT_) {                                                                                \
     TSSEP_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<MODE_, ACT_>, cudaFuncAttributeMaxDynamicSharedMemorySize,           \

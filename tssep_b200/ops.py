@@ -144,7 +144,8 @@ def blstm_recurrence_ts(G: torch.Tensor, wimg: torch.Tensor, rows: int, T: int, 
         if done < groups * 32:
             H.view(groups, T, 32, 2 * Up)[-1, :, done - (groups - 1) * 32:].zero_()
     _lib.call("tssep_blstm_recurrence_ts", G.data_ptr(), int(G.dtype == torch.bfloat16), wimg.data_ptr(), H.data_ptr(),
-              rows, T, Up, {"bt": 0, "rows": 1}[layout], rows_per_cluster, int(fast_math), _lib.stream_of(G))
+              rows, T, Up, {"bt": 0, "rows": 1}[layout], rows_per_cluster, int(fast_math), _lib.stream_of(G),
+              detail=f"rows={rows} T={T} layout={layout}")
     return H
 
 
