@@ -276,7 +276,9 @@ def run_b200(args):
     if M <= 0:
         M = wave * max(1, args.waves)
     if not fits(M, wave) and args.wave_meetings <= 0:
-        wave = max(1, _ops.recurrence_ts_capacity(304, 16) // 8)  # waves of 16-row clusters need half the G buffer
+        # waves of 16-row clusters need half the G buffer; only the tile layout runs the K-row layers per wave
+        wave = max(1, _ops.recurrence_ts_capacity(304, 16) // 8)
+        os.environ["TSSEP_NET_LAYOUT"] = "bt"
     while M > 1 and not fits(M, wave) and os.environ.get("TSSEP_BENCH_NO_MEM_GUARD") != "1":
         M -= 1
     wave = min(wave, M)

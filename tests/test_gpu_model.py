@@ -107,10 +107,11 @@ def test_reference_end_to_end_golden(cuda):
     dict(combination="mul", ts_vad=False, num_averaged_permutations=1, idim=513, nmask=2),
     dict(combination="mul", ts_vad=8, num_averaged_permutations=2, idim=513, explicit_vad=True),
 ])
-@pytest.mark.parametrize("kernel", ["regs", "tc"])
-def test_mask_estimator_variants_batched(cuda, monkeypatch, kw, kernel):
+@pytest.mark.parametrize("kernel,layout", [("regs", "rows"), ("tc", "bt"), ("ts", "bt"), ("ts", "rows")])
+def test_mask_estimator_variants_batched(cuda, monkeypatch, kw, kernel, layout):
     """MaskEstimator_v2 alone, batched (B, T, F) input, all option combinations the reference exposes,
     through both recurrence kernels (register-resident mma.sync / shared-memory tcgen05)."""
+    monkeypatch.setenv("TSSEP_NET_LAYOUT", layout)
     monkeypatch.setenv("TSSEP_LSTM_KERNEL", kernel)
     ref, me = make_pair(_me_kwargs(**kw))
     B, T, K = 2, 120, 8
@@ -135,12 +136,14 @@ def test_mask_estimator_variants_batched(cuda, monkeypatch, kw, kernel):
     assert (got.embedding.cpu() - want.embedding).abs().max().item() == 0.0
 
 
-@pytest.mark.parametrize("kernel,g_dtype", [("regs", "bf16"), ("regs", "f32"), ("tc", "bf16"), ("ts", "bf16"), ("ts", "f32")])
-def test_full_size_dims_short_meeting(cuda, monkeypatch, kernel, g_dtype):
-    """C3 dims (U=300, P=320, mul, ts_vad=8, R=2) on 20 s of audio; separate() with two meetings; both
-    recurrence kernels and both storage types of the input projections."""
+@pytest.mark.parametrize("kernel,g_dtype,layout", [("regs", "bf16", "rows"), ("regs", "f32", "rows"), ("tc", "bf16", "bt"),
+                                                   ("ts", "bf16", "bt"), ("ts", "f32", "bt"), ("ts", "bf16", "rows")])
+def test_full_size_dims_short_meeting(cuda, monkeypatch, kernel, g_dtype, layout):
+    """C3 dims (U=300, P=320, mul, ts_vad=8, R=2) on 20 s of audio; separate() with two meetings; every
+    recurrence kernel, both storage types of the input projections, both row orders of the mask estimator."""
     monkeypatch.setenv("TSSEP_LSTM_KERNEL", kernel)
     monkeypatch.setenv("TSSEP_G_DTYPE", g_dtype)
+    monkeypatch.setenv("TSSEP_NET_LAYOUT", layout)
     ref, me = make_pair(_me_kwargs(units=300, projs=320))
     model = _product_model(me)
     tables = O.MFCCTables()
@@ -162,12 +165,14 @@ def test_full_size_dims_short_meeting(cuda, monkeypatch, kernel, g_dtype):
         assert (got.stft_estimate[i].cpu() - wants[i].stft_estimate).abs().max().item() < 5e-2
 
 
+@pytest.mark.parametrize("layout", ["rows", "bt"])
 @pytest.mark.parametrize("kw", [dict(), dict(ts_vad=False, num_averaged_permutations=1, combination="cat",
                                               aux_net_output_size=100)])
-def test_separate_waves_equals_one_batch(cuda, monkeypatch, kw):
+def test_separate_waves_equals_one_batch(cuda, monkeypatch, kw, layout):
     """Model.separate_waves shares the row-light layers across waves and runs the rest per wave; every output
     must be identical to the one-batch result (the rows of a recurrence launch are independent)."""
     monkeypatch.setenv("TSSEP_LSTM_KERNEL", "ts")
+    monkeypatch.setenv("TSSEP_NET_LAYOUT", layout)
     _, me = make_pair(_me_kwargs(**kw))
     model = _product_model(me)
     n = 16000 * 3

@@ -167,3 +167,29 @@ def test_unsupported_options_raise():
         RNNP_packed(8, 1, 4, 4, 0, typ="bgru")
     with pytest.raises(NotImplementedError):
         Log1pMaxNormAbsSTFT(statistics_axis="t")._feature_parts()
+
+
+def test_operand_leading_dimension_is_128_byte_aligned_for_long_rows():
+    """ops.operand_ld: bf16 GEMM operand rows of 128 bytes or more start on 128-byte boundaries (64 elements),
+    short rows only need the 16-byte TMA alignment (8 elements)."""
+    from tssep_b200 import ops
+
+    assert ops.operand_ld(513) == 576 and ops.operand_ld(553) == 576 and ops.operand_ld(320) == 320
+    assert ops.operand_ld(2560) == 2560 and ops.operand_ld(640) == 640 and ops.operand_ld(64) == 64
+    assert ops.operand_ld(33) == 40 and ops.operand_ld(12) == 16 and ops.operand_ld(3) == 8
+    for cols in range(1, 700):
+        ld = ops.operand_ld(cols)
+        assert ld >= cols and ld % 8 == 0 and (cols < 64 or ld % 64 == 0) and ld - cols < 64
+
+
+def test_recurrence_kernel_selection(monkeypatch):
+    """TSSEP_LSTM_KERNEL / TS_MIN_ROWS: the tensor-memory kernel from 17 batch rows on, the register kernel below."""
+    from tssep_b200 import rnnp
+
+    monkeypatch.delenv("TSSEP_LSTM_KERNEL", raising=False)
+    assert rnnp.rec_kernel(1) == "regs" and rnnp.rec_kernel(16) == "regs"
+    assert rnnp.rec_kernel(17) == "ts" and rnnp.rec_kernel(416) == "ts"
+    monkeypatch.setenv("TSSEP_LSTM_KERNEL", "tc")
+    assert rnnp.rec_kernel(1) == "tc" and rnnp.use_tc_recurrence(1)
+    monkeypatch.setenv("TSSEP_LSTM_KERNEL", "regs")
+    assert rnnp.rec_kernel(1000) == "regs" and not rnnp.use_tc_recurrence(1000)

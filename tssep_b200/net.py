@@ -19,6 +19,8 @@ materialises the reference's intermediate tensors:
 """
 from __future__ import annotations
 
+import os
+
 import collections
 import dataclasses
 
@@ -243,10 +245,9 @@ class MaskEstimator_v2(Configurable, torch.nn.Module):
         a generator of ``(lo, hi, Output)`` for items [lo, hi).
 
         The recurrences cost T dependent steps whatever their batch; a step advances up to
-        ``ops.recurrence_ts_capacity`` rows (26 eight-speaker items on a B200) at the same latency.  The
-        row-light layers (pre_net: 1 row per item, the speaker-concat layer: R rows per item) therefore
-        run ONCE for all B items, the row-heavy speaker-independent layers (K rows per item) run per
-        wave, and the head writes each wave's logit / mask when the consumer asks for it, so the big
+        ``ops.recurrence_ts_capacity`` rows at the same latency.  All recurrent layers therefore run ONCE
+        for all B items (with ``TSSEP_NET_LAYOUT=bt`` the K-rows-per-item layers run per ``wave`` items, which
+        bounds their G buffer), and the head writes each wave's logit / mask when the consumer asks for it, so the big
         outputs of one wave can be dropped before the next is produced.  ``out_wave`` (default ``wave``)
         is the number of items per yielded ``Output``: smaller output waves bound the memory of the
         GB-sized logit / mask tensors without touching the recurrence batching.  Results are independent
@@ -333,7 +334,11 @@ class MaskEstimator_v2(Configurable, torch.nn.Module):
         start_l = 0
         y, y_ld, G = None, None, None
         wave = B if wave is None else max(1, min(int(wave), B))
-        if L >= 2 and use_tc_recurrence(wave * K):
+        # Default: the fold-embedding path below for every batch size (plain (row, t) layouts all the way, the
+        # conditioning folded into birnn0's input weights, nothing materialised).  TSSEP_NET_LAYOUT=bt selects the
+        # (group, t, b32) tile layout from 17 rows on: conditioned rows materialised, one pass per wave of items
+        # (measured 5.7 % slower per step; kept for A/B runs and for devices where only a wave's G buffer fits).
+        if L >= 2 and use_tc_recurrence(wave * K) and os.environ.get("TSSEP_NET_LAYOUT", "rows") == "bt":
             # ---- throughput path for the speaker-independent layers (all but the last) ---------------
             # rows ordered (group, t, b32), z = group*32 + b = item*K + speaker: the conditioned rows are
             # materialised once in bf16 (net.py:862-896), every input projection writes G with the batch
