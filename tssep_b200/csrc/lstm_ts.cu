@@ -32,7 +32,7 @@ struct RecTsArgs {
   const uint8_t* G;   // BT: tiles [group][t][dir][unit octet][b/4][4*(unit%8)+gate][b%4], f32 or bf16 (PLAIN: via gmap)
   const uint4* Wimg;  // [dir][cta][tile][kstep][row 128][8 words]
   __nv_bfloat16* H;   // BT: (groups, T, 32, 2*Up), rows ordered (group, t, b); PLAIN: (rows, T, 2*Up)
-  int rows, T, Up, NA, KS, fast, g_bf16, stages, hack_m, hack_n;
+  int rows, T, Up, NA, KS, fast, g_bf16, stages;
   int* prof;
 };
 
@@ -213,11 +213,8 @@ blstm_rec_ts_kernel(const RecTsArgs a, const __grid_constant__ CUtensorMap gmap)
     // divergent `if (lane == 0)` ptxas wraps every UTCHMMA in an ELECT / BRA.U.ANY waterfall and
     // rebuilds the descriptor through a long uniform-datapath chain (~70 cycles per MMA, measured).
     // Descriptors advance by adding a constant to the encoded start address (16-byte units).
-    uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(NR >> 3) << 17) |
-                     (static_cast<uint32_t>(128 >> 4) << 24);
-    if (a.hack_m || a.hack_n)  // timing experiments only (results are garbage)
-      idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>((a.hack_n ? a.hack_n : NR) >> 3) << 17) |
-              (static_cast<uint32_t>((a.hack_m ? a.hack_m : 128) >> 4) << 24);
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(NR >> 3) << 17) |
+                           (static_cast<uint32_t>(128 >> 4) << 24);
     const uint64_t bdesc0 = ts_desc_sw128(sB);
     const uint32_t buf_step = static_cast<uint32_t>(NA) * (kAtomB >> 4);  // encoded distance of the two h buffers
     const uint32_t d0 = tmem_base + acc_col;
@@ -602,9 +599,6 @@ int tssep_blstm_recurrence_ts(const void* G, int g_dtype, const uint32_t* Wimg, 
   a.fast = fast_math & 1;
   a.g_bf16 = g_dtype;
   a.prof = nullptr;
-  a.hack_m = a.hack_n = 0;
-  if (const char* e = getenv("TSSEP_TS_HACK_M")) a.hack_m = atoi(e);
-  if (const char* e = getenv("TSSEP_TS_HACK_N")) a.hack_n = atoi(e);
   if (const char* e = getenv("TSSEP_REC_PROF")) a.prof = reinterpret_cast<int*>(strtoull(e, nullptr, 0));
   int stages = 0;
   const size_t smem = ts_smem(C, NR, g_dtype, &stages);
