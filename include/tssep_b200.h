@@ -202,7 +202,10 @@ int tssep_pack_whh(const float* whh_fwd, const float* whh_bwd, int U, int Up, ui
 /* If mask != NULL:  Y[z,k] = X[z] * mask[z,k]  (X (Z,T,F) cfloat with item stride,
  * mask (Z,K,T,F) f32) else Y = X viewed as (Z*K, T, F) cfloat.
  * stft_estimate (Z,K,T,F) cfloat and time (Z,K,num_samples) f32 are optional outputs.
- * synwin (window_length) f32 synthesis window, twiddle as in tssep_stft. */
+ * synwin (window_length) f32 synthesis window, twiddle as in tssep_stft.
+ * size 1024 / shift 256 / window_length 1024 (every shipped config) takes a specialised kernel: 16 x 32
+ * register FFT, two speakers per warp, overlap-add accumulator in registers; other geometries a generic
+ * shared-memory kernel (TSSEP_ISTFT_GENERIC=1 forces it). */
 int tssep_mask_istft(const float* X, int64_t x_item_stride, const float* mask, int64_t Z, int n_spk,
                      int64_t T, int size, int shift, int window_length, int fading,
                      const float* synwin, const float* twiddle, float* stft_estimate, float* time,

@@ -1,5 +1,9 @@
-// BLSTM recurrence, throughput variant: recurrent weights resident in SHARED MEMORY, the
+// BLSTM recurrence, first throughput variant: recurrent weights resident in SHARED MEMORY, the
 // per-step contraction on tcgen05 tensor cores with TMEM accumulators.
+//
+// SUPERSEDED by csrc/lstm_ts.cu (weights in tensor memory, convergent MMA issue: 1.3 us/step instead of 3.4 for
+// 208 rows); kept selectable (TSSEP_LSTM_KERNEL=tc) as the A/B baseline the profiles refer to.  Its issuer still
+// sits in a divergent lane-0 branch, which costs ~70 cycles per MMA (see lstm_ts.cu).
 //
 // Same operator as csrc/lstm.cu (torch.nn.LSTM time loop, tssep/train/rnnp.py:87-95, :143-159)
 // for many batch rows at once.  One cluster of C = ceil(Up/64) CTAs per (32 batch rows,

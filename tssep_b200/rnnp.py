@@ -6,7 +6,8 @@ Same constructor arguments, module list (so ``repr`` and ``state_dict`` keys
 parameters; ``forward`` runs
 
     x . W_ih^T (+ b_ih + b_hh)      tcgen05 GEMM, both directions at once
-    time recurrence                 persistent cluster kernel (csrc/lstm.cu)
+    time recurrence                 persistent cluster kernel: W_hh resident in tensor memory (csrc/lstm_ts.cu)
+                                    from 17 batch rows on, in registers (csrc/lstm.cu) below
     [h_fwd | h_bwd] . W_proj^T + b  tcgen05 GEMM with fused bias (+ tanh)
 
 on bf16 operands with fp32 accumulation and fp32 cell state.
