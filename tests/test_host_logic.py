@@ -193,3 +193,25 @@ def test_recurrence_kernel_selection(monkeypatch):
     assert rnnp.rec_kernel(1) == "tc" and rnnp.use_tc_recurrence(1)
     monkeypatch.setenv("TSSEP_LSTM_KERNEL", "regs")
     assert rnnp.rec_kernel(1000) == "regs" and not rnnp.use_tc_recurrence(1000)
+
+
+def test_mask_estimator_can_be_deep_copied_and_pickled():
+    """The kernel-side caches of the module (packed weights, pinned staging ring) are derived state: copies and
+    pickles of the module carry the parameters only."""
+    import copy
+    import io
+
+    import torch
+
+    from tssep_b200.net import MaskEstimator_v2
+
+    me = MaskEstimator_v2.new(dict(idim=80, odim=33, units=4, projs=6, combination="cat", aux_net_output_size=10,
+                                   ts_vad=False, num_averaged_permutations=1))
+    me2 = copy.deepcopy(me)
+    assert me2._staging is not me._staging
+    assert all(torch.equal(a, b) for a, b in zip(me.state_dict().values(), me2.state_dict().values()))
+    buf = io.BytesIO()
+    torch.save(me, buf)
+    buf.seek(0)
+    me3 = torch.load(buf, weights_only=False)
+    assert list(me3.state_dict().keys()) == list(me.state_dict().keys())

@@ -96,6 +96,16 @@ class _PinnedRing:
     def __init__(self, depth: int = 4):
         self.bufs, self.events, self.i = [None] * depth, [None] * depth, 0
 
+    # a derived cache: copies and pickles of the owning module start with an empty ring
+    def __deepcopy__(self, memo):
+        return _PinnedRing(len(self.bufs))
+
+    def __getstate__(self):
+        return {"depth": len(self.bufs)}
+
+    def __setstate__(self, state):
+        self.__init__(state["depth"])
+
     def upload(self, arr: np.ndarray, device) -> torch.Tensor:
         i, self.i = self.i, (self.i + 1) % len(self.bufs)
         n = int(arr.size)
