@@ -549,11 +549,12 @@ def run_b200(args):
     line = {
         "metric": "audio_seconds_per_second", "value": value, "unit": "audio-s/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "bf16 operands, f32 accumulate/state/FFT", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": f"{M} LibriCSS-shaped synthetic {args.seconds:.0f}-s 16 kHz meetings per GPU per step, "
                                "8 speakers, TS-SEP (U=300, P=320, mul, ts_vad=8, 2 averaged permutations), "
                                "random-init weights; every ForwardOutput field + time_estimate + segments written to HBM "
                                f"(mask / logit / stft_estimate buffers are reused from one output wave of {out_wave} meetings to the next)",
+                   "precision": "bf16 GEMM / recurrence operands, f32 accumulation, f32 cell state, f32 STFT / iSTFT",
                    "meetings_per_gpu": M, "meetings_per_wave": wave, "meetings_per_output_wave": out_wave, "meeting_seconds": args.seconds, "frames": T,
                    "l2": "inputs and intermediates (GBs per step) far exceed the 126 MB L2; no explicit flush",
                    "parallelism": f"dp{world} over meetings"},
