@@ -254,10 +254,8 @@ def run_b200(args):
     M = args.meetings_per_gpu
     n = int(args.seconds * SAMPLE_RATE)
     model = build_product_model(dev)
-    # memory guard: the step keeps every output of M meetings resident (about 4.5 GB per 10-min meeting incl.
-    # intermediates); shrink M instead of failing on a smaller / busier device
+    # memory guard (model below): shrink the batch instead of failing on a smaller / busier device
     free_b, _ = torch.cuda.mem_get_info(dev)
-    per_meeting = 5.2e9 * (args.seconds / 600.0)
     from tssep_b200 import ops as _ops
     # The K=8 speaker rows of every meeting advance together in the tensor-memory recurrence.  One wave of 32-row
     # clusters (52 meetings) steps in 2.5 us, one wave of 16-row clusters (26 meetings) in 1.3 us; a row more costs
