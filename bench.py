@@ -162,11 +162,11 @@ def oracle_setup(units, projs):
     return O, net, O.MFCCTables()
 
 
-def time_oracle(sample_seconds: float, reps: int, warmup: int = 1):
+def time_oracle(sample_seconds: float, reps: int, warmup: int = 1, threads: int = None):
     """The reference's CPU arithmetic (oracle restatement: torch.nn.LSTM/Linear, torchaudio, torch.fft)
-    on all host cores, on a bounded sample of the workload (the path is linear in the audio length)."""
+    on all host cores (or ``threads``), on a bounded sample of the workload (the path is linear in the audio length)."""
     O, net, tables = oracle_setup(MODEL_KW["units"], MODEL_KW["projs"])
-    cores = os.cpu_count() or 1
+    cores = threads or os.cpu_count() or 1
     torch.set_num_threads(cores)
     n = int(sample_seconds * SAMPLE_RATE)
     obs, aux = synth_meeting(0, n)
@@ -543,6 +543,12 @@ def run_b200(args):
         cpu = {"value": v, "unit": "audio-s/s", "cores": cores, "kind": "port",
                "sample": f"oracle (reference CPU arithmetic) on a {args.cpu_sample_seconds:.0f}-s slice of meeting 0, "
                          f"median of 2 after 1 warm-up, torch threads={cores}; cost is linear in audio length"}
+        # the reference's documented setting (README.md:51-56, CI): one thread; a shorter slice keeps the run bounded
+        s1 = max(5.0, args.cpu_sample_seconds / 2.0)
+        v1, _, _ = time_oracle(s1, reps=2, warmup=1, threads=1)
+        cpu["single_thread"] = {"value": v1, "unit": "audio-s/s", "cores": 1,
+                                "sample": f"same, {s1:.0f}-s slice, median of 2 after 1 warm-up, torch threads=1"}
+        torch.set_num_threads(os.cpu_count() or 1)
 
     line = {
         "metric": "audio_seconds_per_second", "value": value, "unit": "audio-s/s", "n_gpus": world,
