@@ -14,6 +14,10 @@
  *   - return 0 on success, negative on error; message via tssep_last_error()
  *     (thread-local, valid until the next failing call on the same thread);
  *   - no exceptions cross this boundary, there is no CPU fallback;
+ *   - no hidden inputs: the library reads no environment variables (tuning knobs exist only in a debug
+ *     build, -DTSSEP_DEBUG_KNOBS) and keeps no mutable global state besides the thread-local error message;
+ *   - kernels launch on the CURRENT CUDA device: the caller makes the device that owns `stream` and the
+ *     pointers current (tssep_b200/_lib.py does so for every call);
  *   - "bf16" pointers are raw uint16 bfloat16 bit patterns; cfloat = float[2].
  */
 #ifndef TSSEP_B200_H_
@@ -26,6 +30,10 @@ extern "C" {
 #endif
 
 typedef void* tssep_stream_t; /* cudaStream_t */
+
+/* Bumped whenever a signature or struct layout below changes; tssep_b200/_lib.py refuses a library that
+ * reports another value. */
+#define TSSEP_ABI_VERSION 2
 
 const char* tssep_last_error(void);
 int tssep_abi_version(void);
@@ -73,9 +81,12 @@ int tssep_feature_write(const float* X, int64_t n_items, int64_t x_item_stride, 
 int tssep_cast_bf16(const float* src, int64_t rows, int64_t cols, int64_t ld_src, uint16_t* dst,
                     int64_t ld_dst, tssep_stream_t stream);
 
-/* InstanceNorm over the last axis (tssep/train/net.py:250-285), rows of `cols`. */
-int tssep_instance_norm(const float* src, int64_t rows, int64_t cols, int unbiased, float* dst,
-                        tssep_stream_t stream);
+/* InstanceNorm / InstanceNorm_v2 (tssep/train/net.py:250-330) along the middle axis of a contiguous
+ * (outer, cols, inner) f32 tensor (any single `dim` of a contiguous tensor is such a view).
+ * mode 0: (x - mean) / std  (population std, or Bessel-corrected when unbiased != 0)      InstanceNorm
+ * mode 1: x - mean;  mode 2: x / sqrt(mean(x^2))       the two steps of InstanceNorm_v2 when its axes differ */
+int tssep_instance_norm(const float* src, int64_t outer, int64_t cols, int64_t inner, int mode, int unbiased,
+                        float* dst, tssep_stream_t stream);
 
 /* ------------------------------------------------------------------------
  * (2) Conditioning + bulk contractions (torch.nn.Linear / LSTM input GEMMs,
@@ -91,13 +102,6 @@ int tssep_fold_embedding(int mode, const float* W, int64_t ldw, const float* b, 
                          int64_t Z, int N, int F, int A, uint16_t* Wk, int64_t ld_wk, float* bias_k,
                          tssep_stream_t stream);
 
-/* Conditioned input rows for the tcgen05 recurrence path (net.py:862-896), rows ordered
- * (group, t, b32) with z = group * 32 + b = item * K + speaker, groups = ceil(Z / 32):
- *   mode 0 ('mul'): out[r, :F] = bf16(xs[item, t, :] * e[z, :]);  mode 1 ('cat'): out[r] = [xs[item, t, :] | e[z, :]].
- * xs (items * T, ldx) bf16, e (Z, A) f32, out (groups * T * 32, ldo) bf16; rows with z >= Z are zero. */
-int tssep_condition_rows(int mode, const uint16_t* xs, int64_t ldx, const float* e, int64_t Z, int K,
-                         int64_t T, int F, int A, uint16_t* out, int64_t ldo, tssep_stream_t stream);
-
 /* Batched contraction on tcgen05/TMEM tensor cores:
  *   out[z] = act(alpha * A[z / a_div] . B[z % b_mod]^T + bias[z % b_mod])      z in [0, batch)
  * A (rows, K) bf16 row-major (lda), B (N, K) bf16 row-major (ldb); lda, ldb multiples
@@ -112,15 +116,8 @@ int tssep_condition_rows(int mode, const uint16_t* xs, int64_t ldx, const float*
  *   logit[(p * M + m) * row_len + f] = v and mask[...] = sigmoid(v); either may be NULL.
  *   The caller folds the speaker rotation / trial mean into B and bias (K = trials*projs)
  *   and the un-permutation into plane_map.
- * mode TSSEP_EPI_F32_BT / TSSEP_EPI_BF16_BT (input of tssep_blstm_recurrence_tc, f32 or bf16 elements): rows are ordered (group, t, b32), b = m % 32;
- *   out[((m/32)*N + (n/32)*32)*32 + (b/4)*128 + (n%32)*4 + b%4]: per (group, t) and per block of 32 columns
- *   a 4 KiB tile [b/4][column][b%4]  (batch == 1, M and N multiples of 32).
- * mode TSSEP_EPI_BF16_ROWMAP (speaker-concat rearrange net.py:606-612 after the tcgen05 recurrence):
- *   rows ordered (group, t, b32), z = group * 32 + b, item = z / rm_K, spk = z % rm_K; rows with
- *   z >= rm_Z are dropped; out[(item * rm_T + t) * ldo + spk * rm_P + n] as bf16.
  * impl: 0 = tcgen05 (product path), 1 = plain SIMT kernel (debug / bisecting only). */
-enum { TSSEP_EPI_F32 = 0, TSSEP_EPI_BF16 = 1, TSSEP_EPI_HEAD = 2, TSSEP_EPI_F32_BT = 3, TSSEP_EPI_BF16_ROWMAP = 4,
-       TSSEP_EPI_BF16_BT = 5 };
+enum { TSSEP_EPI_F32 = 0, TSSEP_EPI_BF16 = 1, TSSEP_EPI_HEAD = 2 };
 
 typedef struct tssep_gemm_desc {
   const uint16_t* A; int64_t lda; int64_t a_stride; int32_t a_div;
@@ -130,8 +127,7 @@ typedef struct tssep_gemm_desc {
   float alpha; int32_t act; int32_t mode;
   void* out; int64_t ldo; int64_t out_stride; int32_t out_div; int64_t out_stride_hi;
   float* mask; const int32_t* plane_map; int32_t n_blocks; int32_t row_len;
-  int64_t rm_T; int32_t rm_K; int32_t rm_Z; int32_t rm_P;
-  int32_t impl;
+  int32_t impl; int32_t max_ctas; /* max_ctas: 0 = one persistent CTA per SM, else an upper bound */
 } tssep_gemm_desc;
 
 int tssep_gemm(const tssep_gemm_desc* desc, tssep_stream_t stream);
@@ -146,49 +142,34 @@ int tssep_head_expand_t(const float* small, int64_t Z, int64_t T, int n_blocks, 
  * (3) BLSTM recurrence (torch.nn.LSTM inside RNNP_packed, rnnp.py:87-95, :143-159)
  * ---------------------------------------------------------------------- */
 
-/* Persistent cluster kernel: recurrent weights register/SM resident, h exchanged
- * through distributed shared memory, both directions concurrently.
- * G    (rows, T, 2, 4, Up) f32 (g_dtype 0) or bf16 (g_dtype 1): input projections + both biases,
- *      gate order i,f,g,o
- * Wfrag packed recurrent weights from tssep_pack_whh (2 * Up/4 * Up/16 * 128 u32)
+/* Tensor-memory cluster kernel (the product path for every row count): one cluster of ceil(Up/64) CTAs per
+ * (rows_per_cluster batch rows, direction), both directions concurrently.  The recurrent weights live in TENSOR
+ * MEMORY for the whole sequence as the A operand of tcgen05.mma; per step the tensor core computes
+ * P . G_t + W_hh . h_{t-1} (P: scaled permutation matrix, G_t: a TMA box of G in shared memory, h_{t-1}: exchanged
+ * through distributed shared memory with st.async), the epilogue warps apply the gates out of TMEM.
+ * G    (rows, T, 2, 4, Up) bf16: input projections + both biases, gate order i,f,g,o
+ * Wimg from tssep_pack_whh_ts: 2 * C * 2 * (Up/16) * 128 * 8 words, C = ceil(Up/64)
  * H    (rows, T, 2*Up) bf16 out: [h_fwd(Up) | h_bwd(Up)]
- * Up = hidden units rounded up to a multiple of 16 (<= 320); padded units stay 0.
- * cluster: CTAs per cluster (1,2,4,8), 0 = choose.  fast_math: 0 accurate
- * exp-based gates, 1 tanh.approx. */
-int tssep_blstm_recurrence(const void* G, int g_dtype, const uint32_t* Wfrag, uint16_t* H, int64_t rows,
-                           int64_t T, int Up, int cluster, int fast_math, tssep_stream_t stream);
-
-/* Throughput variant of the same recurrence for many batch rows: one cluster of ceil(Up/64) CTAs
- * per (32 rows, direction), recurrent weights resident in shared memory as UMMA operands,
- * tcgen05.mma (M=128, N=32, K=16) into TMEM, gates applied by 4 epilogue warps out of TMEM.
- * G f32 (g_dtype 0) or bf16 (g_dtype 1) in the tile layout written by tssep_gemm mode TSSEP_EPI_F32_BT /
- * TSSEP_EPI_BF16_BT with N = 8*Up columns ordered
- * n = dir*4*Up + (unit/8)*32 + (unit%8)*4 + gate (the caller packs W_ih rows in that order),
- * groups = ceil(rows / 32); H (groups, T, 32, 2*Up) bf16, i.e. rows ordered
- * (group, t, b).  Wimg from tssep_pack_whh_tc (2 * C * 2 * C * 16 KiB, C = ceil(Up/64)); Up <= 512. */
-int tssep_blstm_recurrence_tc(const void* G, int g_dtype, const uint16_t* Wimg, uint16_t* H, int64_t rows,
-                              int64_t T, int Up, int fast_math, tssep_stream_t stream);
-int tssep_pack_whh_tc(const float* whh_fwd, const float* whh_bwd, int U, int Up, uint16_t* Wimg,
-                      tssep_stream_t stream);
-
-/* Same recurrence, same G / H layouts as tssep_blstm_recurrence_tc, with the recurrent weights
- * resident in TENSOR MEMORY (A operand of tcgen05.mma read from TMEM, B = h_{t-1} from shared
- * memory): one cluster of ceil(Up/64) CTAs per (rows_per_cluster batch rows, direction),
- * rows_per_cluster = 16 or 32 (0 = choose: 16 while both directions fit in one wave of clusters).
- * G streamed with cp.async.bulk through an mbarrier ring.  Only the first
- * ceil(rows / rows_per_cluster) * rows_per_cluster rows of H are written.
- * layout TSSEP_REC_LAYOUT_ROWS: G (rows, T, 2, 4, Up) bf16 and H (rows, T, 2*Up), exactly the layouts of
- * tssep_blstm_recurrence (G streamed with one 5-D TMA box per step).
- * Wimg from tssep_pack_whh_ts: 2 * C * 2 * (Up/16) * 128 * 8 words, C = ceil(Up/64); Up <= 448. */
-enum { TSSEP_REC_LAYOUT_BT = 0, TSSEP_REC_LAYOUT_ROWS = 1 };
-int tssep_blstm_recurrence_ts(const void* G, int g_dtype, const uint32_t* Wimg, uint16_t* H, int64_t rows,
-                              int64_t T, int Up, int layout, int rows_per_cluster, int fast_math,
-                              tssep_stream_t stream);
+ * Up = hidden units rounded up to a multiple of 16; padded units stay 0.  Limits: Up <= 384, and
+ * 2 * roundup(Up/2, 32) + 64 + 2 * max(rows_per_cluster, 16) <= 512 tensor-memory columns (Up <= 320 at 32 rows).
+ * rows_per_cluster: 8, 16 or 32; 0 = choose (fewest rows per cluster whose clusters still fit in one wave).
+ * gate_math: 0 = exp-based sigmoid / tanh, 1 = tanh.approx.f32.
+ * k_split: 1 (and -1 = default) = the W_hh . h MMAs start on the half of h that arrives first; 0 = one phase. */
+int tssep_blstm_recurrence_ts(const uint16_t* G, const uint32_t* Wimg, uint16_t* H, int64_t rows, int64_t T, int Up,
+                              int rows_per_cluster, int gate_math, int k_split, tssep_stream_t stream);
 /* Batch rows that fit in ONE wave of co-resident clusters (both directions running) on the current
- * device at the given rows_per_cluster (16 or 32); < 0 on error. */
-int tssep_blstm_recurrence_ts_capacity(int Up, int rows_per_cluster, int g_dtype);
+ * device at the given rows_per_cluster (8, 16 or 32); < 0 on error. */
+int tssep_blstm_recurrence_ts_capacity(int Up, int rows_per_cluster);
 int tssep_pack_whh_ts(const float* whh_fwd, const float* whh_bwd, int U, int Up, uint32_t* Wimg,
                       tssep_stream_t stream);
+
+/* Register-resident variant of the same operator (mma.sync, recurrent weights in registers, cluster of up to 8,
+ * 8 rows per cluster): accepts f32 G, which the parity tests use to separate the rounding of G from the rest.
+ * G    (rows, T, 2, 4, Up) f32 (g_dtype 0) or bf16 (g_dtype 1)
+ * Wfrag packed recurrent weights from tssep_pack_whh (2 * Up/4 * Up/16 * 128 u32); Up <= 320.
+ * cluster: CTAs per cluster (1,2,4,8), 0 = choose.  fast_math: 0 accurate exp-based gates, 1 tanh.approx. */
+int tssep_blstm_recurrence(const void* G, int g_dtype, const uint32_t* Wfrag, uint16_t* H, int64_t rows,
+                           int64_t T, int Up, int cluster, int fast_math, tssep_stream_t stream);
 
 /* weight_hh_l0 / weight_hh_l0_reverse (4U, U) f32 -> mma fragment order. */
 int tssep_pack_whh(const float* whh_fwd, const float* whh_bwd, int U, int Up, uint32_t* Wfrag,
@@ -202,14 +183,16 @@ int tssep_pack_whh(const float* whh_fwd, const float* whh_bwd, int U, int Up, ui
 /* If mask != NULL:  Y[z,k] = X[z] * mask[z,k]  (X (Z,T,F) cfloat with item stride,
  * mask (Z,K,T,F) f32) else Y = X viewed as (Z*K, T, F) cfloat.
  * stft_estimate (Z,K,T,F) cfloat and time (Z,K,num_samples) f32 are optional outputs.
+ * activity (Z,K,T) f32, optional (needs mask): activity[z,k,t] = mean_f mask[z,k,t,f], the frame activity of the
+ * diarization stage (section 5), reduced from the mask rows this kernel reads anyway.
  * synwin (window_length) f32 synthesis window, twiddle as in tssep_stft.
  * size 1024 / shift 256 / window_length 1024 (every shipped config) takes a specialised kernel: 16 x 32
  * register FFT, two speakers per warp, overlap-add accumulator in registers; other geometries a generic
- * shared-memory kernel (TSSEP_ISTFT_GENERIC=1 forces it). */
+ * shared-memory kernel. */
 int tssep_mask_istft(const float* X, int64_t x_item_stride, const float* mask, int64_t Z, int n_spk,
                      int64_t T, int size, int shift, int window_length, int fading,
                      const float* synwin, const float* twiddle, float* stft_estimate, float* time,
-                     int64_t num_samples, tssep_stream_t stream);
+                     int64_t num_samples, float* activity, tssep_stream_t stream);
 
 /* ------------------------------------------------------------------------
  * (5) Diarization post-processing (no reference implementation; anchors

@@ -117,3 +117,19 @@ def test_instance_norm(cuda):
     got = InstanceNorm(dim=-1)(t.to(cuda)).cpu()
     want = O.instance_norm(t)
     assert (got - want).abs().max().item() < 1e-4
+
+
+def test_instance_norms_match_reference_goldens(cuda):
+    """InstanceNorm along any single axis (biased / unbiased) and InstanceNorm_v2 with equal and different axes against
+    outputs of the reference's own classes (tests/golden/reference_net_goldens.npz, tssep/train/net.py:250-330)."""
+    import os
+
+    from tssep_b200.net import InstanceNorm, InstanceNorm_v2
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_net_goldens.npz"))
+    x = torch.tensor(g["norm/x"]).to(cuda)
+    for dim in (-1, -2, 0):
+        assert np.abs(InstanceNorm(dim=dim)(x).cpu().numpy() - g[f"norm/v1/dim{dim}"]).max() < 2e-6
+        assert np.abs(InstanceNorm(dim=dim, unbiased=True)(x).cpu().numpy() - g[f"norm/v1u/dim{dim}"]).max() < 2e-6
+    for md, nd in ((-1, -1), (-2, -2), (-2, -1)):
+        assert np.abs(InstanceNorm_v2(md, nd)(x).cpu().numpy() - g[f"norm/v2/{md}/{nd}"]).max() < 2e-6

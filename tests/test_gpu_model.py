@@ -107,11 +107,10 @@ def test_reference_end_to_end_golden(cuda):
     dict(combination="mul", ts_vad=False, num_averaged_permutations=1, idim=513, nmask=2),
     dict(combination="mul", ts_vad=8, num_averaged_permutations=2, idim=513, explicit_vad=True),
 ])
-@pytest.mark.parametrize("kernel,layout", [("regs", "rows"), ("tc", "bt"), ("ts", "bt"), ("ts", "rows")])
-def test_mask_estimator_variants_batched(cuda, monkeypatch, kw, kernel, layout):
+@pytest.mark.parametrize("kernel", ["regs", "ts"])
+def test_mask_estimator_variants_batched(cuda, monkeypatch, kw, kernel):
     """MaskEstimator_v2 alone, batched (B, T, F) input, all option combinations the reference exposes,
-    through both recurrence kernels (register-resident mma.sync / shared-memory tcgen05)."""
-    monkeypatch.setenv("TSSEP_NET_LAYOUT", layout)
+    through both recurrence kernels (tensor-memory tcgen05 / register-resident mma.sync)."""
     monkeypatch.setenv("TSSEP_LSTM_KERNEL", kernel)
     ref, me = make_pair(_me_kwargs(**kw))
     B, T, K = 2, 120, 8
@@ -136,14 +135,12 @@ def test_mask_estimator_variants_batched(cuda, monkeypatch, kw, kernel, layout):
     assert (got.embedding.cpu() - want.embedding).abs().max().item() == 0.0
 
 
-@pytest.mark.parametrize("kernel,g_dtype,layout", [("regs", "bf16", "rows"), ("regs", "f32", "rows"), ("tc", "bf16", "bt"),
-                                                   ("ts", "bf16", "bt"), ("ts", "f32", "bt"), ("ts", "bf16", "rows")])
-def test_full_size_dims_short_meeting(cuda, monkeypatch, kernel, g_dtype, layout):
-    """C3 dims (U=300, P=320, mul, ts_vad=8, R=2) on 20 s of audio; separate() with two meetings; every
-    recurrence kernel, both storage types of the input projections, both row orders of the mask estimator."""
+@pytest.mark.parametrize("kernel,g_dtype", [("regs", "bf16"), ("regs", "f32"), ("ts", "bf16")])
+def test_full_size_dims_short_meeting(cuda, monkeypatch, kernel, g_dtype):
+    """C3 dims (U=300, P=320, mul, ts_vad=8, R=2) on 20 s of audio; separate() with two meetings; both
+    recurrence kernels, both storage types of the input projections."""
     monkeypatch.setenv("TSSEP_LSTM_KERNEL", kernel)
     monkeypatch.setenv("TSSEP_G_DTYPE", g_dtype)
-    monkeypatch.setenv("TSSEP_NET_LAYOUT", layout)
     ref, me = make_pair(_me_kwargs(units=300, projs=320))
     model = _product_model(me)
     tables = O.MFCCTables()
@@ -165,14 +162,11 @@ def test_full_size_dims_short_meeting(cuda, monkeypatch, kernel, g_dtype, layout
         assert (got.stft_estimate[i].cpu() - wants[i].stft_estimate).abs().max().item() < 5e-2
 
 
-@pytest.mark.parametrize("layout", ["rows", "bt"])
 @pytest.mark.parametrize("kw", [dict(), dict(ts_vad=False, num_averaged_permutations=1, combination="cat",
                                               aux_net_output_size=100)])
-def test_separate_waves_equals_one_batch(cuda, monkeypatch, kw, layout):
+def test_separate_waves_equals_one_batch(cuda, monkeypatch, kw):
     """Model.separate_waves shares the row-light layers across waves and runs the rest per wave; every output
     must be identical to the one-batch result (the rows of a recurrence launch are independent)."""
-    monkeypatch.setenv("TSSEP_LSTM_KERNEL", "ts")
-    monkeypatch.setenv("TSSEP_NET_LAYOUT", layout)
     _, me = make_pair(_me_kwargs(**kw))
     model = _product_model(me)
     n = 16000 * 3
@@ -219,3 +213,24 @@ def test_cpu_tensor_is_rejected(lib):
 
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         Log1pMaxNormAbsSTFT().stft(torch.zeros(2000))
+
+
+def test_runs_on_a_device_that_is_not_current(lib):
+    """Every C-ABI call makes the device of its stream current for the launch (tssep_b200/_lib.py::call): a model on
+    cuda:1 works while cuda:0 is the current device.  Needs two GPUs."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    dev = torch.device("cuda:1")
+    ref, me = make_pair(_me_kwargs(), device=dev)
+    model = _product_model(me)
+    e = _ex(0, 513)
+    obs, aux = torch.tensor(e["observation"]), torch.tensor(e["auxInput"])
+    np.random.seed(0)
+    want = O.forward_path(obs, aux, ref, feature="concat", tables=O.MFCCTables(), window="hann")
+    assert torch.cuda.current_device() == 0
+    np.random.seed(0)
+    got = model({"observation": obs.to(dev), "auxInput": aux.to(dev), "reference_channel": 0}, with_time_estimate=True)
+    assert torch.cuda.current_device() == 0
+    assert (got.mask.cpu() - want.mask).abs().max().item() < MASK_TOL
+    with pytest.raises(RuntimeError, match="different devices"):
+        me(torch.zeros((10, 553), device="cuda:0"), [a for a in aux.to(dev)])

@@ -49,3 +49,25 @@ def test_segments_edge_cases(cuda):
     assert got[0] == [] and got[1] == segs[1] and got[2] == segs[2]
     assert d.counts.cpu().numpy().tolist() == [0, 1, 2, 150]
     assert got[3] == segs[3][:64]
+
+
+@pytest.mark.parametrize("size,shift", [(1024, 256), (256, 64)])
+def test_activity_from_the_enhancement_kernel(cuda, size, shift):
+    """Masking.apply(activity_out=...) reduces the mask rows it reads anyway to the frame activity: same values as
+    the stand-alone reduction (fast 1024/256 kernel and the generic geometry)."""
+    from tssep_b200.enhancer import Masking
+    from tssep_b200.feature_extractor import Log1pMaxNormAbsSTFT
+    from tssep_b200.postprocess import diarize
+
+    fe = Log1pMaxNormAbsSTFT(size=size, shift=shift, window="hann")
+    g = torch.Generator().manual_seed(0)
+    B, K, T, F = 2, 5, 333, size // 2 + 1
+    mask = torch.rand((B, K, 1, T, F), generator=g).to(cuda)
+    X = torch.view_as_complex(torch.randn((B, 1, T, F, 2), generator=g)).to(cuda)
+    act = torch.empty((B, K, T), dtype=torch.float32, device=cuda)
+    Masking.apply(mask, X, 0, fe, want_estimate=True, want_time=True, activity_out=act)
+    want = mask[:, :, 0].mean(-1)
+    assert (act - want).abs().max().item() < 1e-6
+    a = diarize(mask, fe, threshold=0.5, median_width=5)
+    b = diarize(mask, fe, threshold=0.5, median_width=5, activity=act)
+    assert (a.activity - b.activity).abs().max().item() < 1e-6

@@ -183,16 +183,19 @@ def test_operand_leading_dimension_is_128_byte_aligned_for_long_rows():
 
 
 def test_recurrence_kernel_selection(monkeypatch):
-    """TSSEP_LSTM_KERNEL / TS_MIN_ROWS: the tensor-memory kernel from 17 batch rows on, the register kernel below."""
+    """TSSEP_LSTM_KERNEL: the tensor-memory kernel for every row count whenever the input projections are bf16 (the
+    default), the register kernel for f32 projections or on request."""
+    import torch
+
     from tssep_b200 import rnnp
 
     monkeypatch.delenv("TSSEP_LSTM_KERNEL", raising=False)
-    assert rnnp.rec_kernel(1) == "regs" and rnnp.rec_kernel(16) == "regs"
-    assert rnnp.rec_kernel(17) == "ts" and rnnp.rec_kernel(416) == "ts"
-    monkeypatch.setenv("TSSEP_LSTM_KERNEL", "tc")
-    assert rnnp.rec_kernel(1) == "tc" and rnnp.use_tc_recurrence(1)
+    assert rnnp.rec_kernel(torch.bfloat16, 304) == "ts" and rnnp.rec_kernel(torch.bfloat16, 16) == "ts"
+    assert rnnp.rec_kernel(torch.float32, 304) == "regs"
     monkeypatch.setenv("TSSEP_LSTM_KERNEL", "regs")
-    assert rnnp.rec_kernel(1000) == "regs" and not rnnp.use_tc_recurrence(1000)
+    assert rnnp.rec_kernel(torch.bfloat16, 304) == "regs"
+    monkeypatch.setenv("TSSEP_LSTM_KERNEL", "ts")
+    assert rnnp.rec_kernel(torch.bfloat16, 48) == "ts"
 
 
 def test_mask_estimator_can_be_deep_copied_and_pickled():
@@ -215,3 +218,27 @@ def test_mask_estimator_can_be_deep_copied_and_pickled():
     buf.seek(0)
     me3 = torch.load(buf, weights_only=False)
     assert list(me3.state_dict().keys()) == list(me.state_dict().keys())
+
+
+def test_stream_handle_carries_its_device():
+    """_lib.StreamHandle is the integer cudaStream_t plus the device it belongs to; _lib.call uses it as the device
+    guard of the launch (advisor finding of round 1: kernels used to launch on the current device with another
+    device's stream)."""
+    import ctypes
+
+    from tssep_b200 import _lib
+
+    h = _lib.StreamHandle(0x1234, 3)
+    assert int(h) == 0x1234 and h.device_index == 3 and isinstance(h, int)
+    assert ctypes.c_void_p(h).value == 0x1234  # converts like a plain integer at the ctypes boundary
+    args = (1, 2.0, None, h)
+    assert next((a.device_index for a in args if isinstance(a, _lib.StreamHandle)), -1) == 3
+
+
+def test_instance_norm_modules_mirror_the_reference_signatures():
+    from tssep_b200.configurable import FACTORY_ALIASES
+    from tssep_b200.net import InstanceNorm, InstanceNorm_v2
+
+    assert repr(InstanceNorm(dim=-1)) == "InstanceNorm(dim=-1, unbiased=False)"          # net.py:257-258
+    assert repr(InstanceNorm_v2(-1, -2)) == "InstanceNorm_v2(mean_dim=-1, norm_dim=-2)"
+    assert FACTORY_ALIASES["tssep.train.net.InstanceNorm_v2"] == "tssep_b200.net.InstanceNorm_v2"

@@ -28,7 +28,10 @@ def test_binding_table_covers_header(lib):
 
 
 def test_abi_version_and_error_channel(lib):
-    assert lib.tssep_abi_version() == 1
+    from tssep_b200 import _lib
+
+    header_version = int(re.search(r"#define TSSEP_ABI_VERSION (\d+)", open(HEADER).read()).group(1))
+    assert lib.tssep_abi_version() == header_version == _lib.ABI_VERSION
     # argument validation happens on the host before any launch: a null pointer is reported through
     # tssep_last_error without touching a device
     rc = lib.tssep_cast_bf16(None, 4, 4, 4, None, 8, None)
@@ -45,3 +48,17 @@ def test_gemm_descriptor_layout_matches_header():
     names = re.findall(r"[\s\*]([A-Za-z_]+);", body)
     assert names == [f[0] for f in GemmDesc._fields_]
     assert ctypes.sizeof(GemmDesc) % 8 == 0
+
+
+def test_library_reads_no_environment_and_exports_no_retired_symbols(lib):
+    """The shipped build has no getenv call sites (tuning knobs exist only with -DTSSEP_DEBUG_KNOBS) and the
+    superseded shared-memory recurrence is gone."""
+    assert not hasattr(lib, "tssep_blstm_recurrence_tc") and not hasattr(lib, "tssep_condition_rows")
+    csrc = os.path.join(os.path.dirname(HEADER), "..", "tssep_b200", "csrc")
+    for name in os.listdir(csrc):
+        text = open(os.path.join(csrc, name)).read()
+        if name == "common.cuh":
+            assert text.count("getenv(") == 1  # inside debug_env, under #ifdef TSSEP_DEBUG_KNOBS
+        else:
+            assert "getenv(" not in text.replace("debug_env(", ""), name
+    # (the linked CUDA runtime imports getenv for its own CUDA_* variables, so the symbol table says nothing)

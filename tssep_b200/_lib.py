@@ -29,12 +29,12 @@ class GemmDesc(C.Structure):
         ("alpha", c_f32), ("act", c_i32), ("mode", c_i32),
         ("out", c_vp), ("ldo", c_i64), ("out_stride", c_i64), ("out_div", c_i32), ("out_stride_hi", c_i64),
         ("mask", c_vp), ("plane_map", c_vp), ("n_blocks", c_i32), ("row_len", c_i32),
-        ("rm_T", c_i64), ("rm_K", c_i32), ("rm_Z", c_i32), ("rm_P", c_i32),
-        ("impl", c_i32),
+        ("impl", c_i32), ("max_ctas", c_i32),
     ]
 
 
-EPI_F32, EPI_BF16, EPI_HEAD, EPI_F32_BT, EPI_BF16_ROWMAP, EPI_BF16_BT = 0, 1, 2, 3, 4, 5
+EPI_F32, EPI_BF16, EPI_HEAD = 0, 1, 2
+ABI_VERSION = 2  # TSSEP_ABI_VERSION of include/tssep_b200.h this binding was written against
 
 _SIGNATURES = {
     "tssep_abi_version": ([], C.c_int),
@@ -45,21 +45,18 @@ _SIGNATURES = {
     "tssep_feature_write": ([c_vp, c_i64, c_i64, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_f32,
                              c_i32, c_vp, c_vp, c_i64, c_vp], C.c_int),
     "tssep_cast_bf16": ([c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp], C.c_int),
-    "tssep_instance_norm": ([c_vp, c_i64, c_i64, c_i32, c_vp, c_vp], C.c_int),
+    "tssep_instance_norm": ([c_vp, c_i64, c_i64, c_i64, c_i32, c_i32, c_vp, c_vp], C.c_int),
     "tssep_fold_embedding": ([c_i32, c_vp, c_i64, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_vp, c_i64, c_vp, c_vp],
                              C.c_int),
-    "tssep_condition_rows": ([c_i32, c_vp, c_i64, c_vp, c_i64, c_i32, c_i64, c_i32, c_i32, c_vp, c_i64, c_vp], C.c_int),
     "tssep_gemm": ([C.POINTER(GemmDesc), c_vp], C.c_int),
     "tssep_head_expand_t": ([c_vp, c_i64, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp], C.c_int),
     "tssep_blstm_recurrence": ([c_vp, c_i32, c_vp, c_vp, c_i64, c_i64, c_i32, c_i32, c_i32, c_vp], C.c_int),
     "tssep_pack_whh": ([c_vp, c_vp, c_i32, c_i32, c_vp, c_vp], C.c_int),
-    "tssep_blstm_recurrence_tc": ([c_vp, c_i32, c_vp, c_vp, c_i64, c_i64, c_i32, c_i32, c_vp], C.c_int),
-    "tssep_pack_whh_tc": ([c_vp, c_vp, c_i32, c_i32, c_vp, c_vp], C.c_int),
-    "tssep_blstm_recurrence_ts": ([c_vp, c_i32, c_vp, c_vp, c_i64, c_i64, c_i32, c_i32, c_i32, c_i32, c_vp], C.c_int),
-    "tssep_blstm_recurrence_ts_capacity": ([c_i32, c_i32, c_i32], C.c_int),
+    "tssep_blstm_recurrence_ts": ([c_vp, c_vp, c_vp, c_i64, c_i64, c_i32, c_i32, c_i32, c_i32, c_vp], C.c_int),
+    "tssep_blstm_recurrence_ts_capacity": ([c_i32, c_i32], C.c_int),
     "tssep_pack_whh_ts": ([c_vp, c_vp, c_i32, c_i32, c_vp, c_vp], C.c_int),
     "tssep_mask_istft": ([c_vp, c_i64, c_vp, c_i64, c_i32, c_i64, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp,
-                          c_i64, c_vp], C.c_int),
+                          c_i64, c_vp, c_vp], C.c_int),
     "tssep_activity": ([c_vp, c_i64, c_i64, c_i32, c_vp, c_vp], C.c_int),
     "tssep_median_threshold": ([c_vp, c_i64, c_i64, c_i32, c_f32, c_vp, c_vp, c_vp], C.c_int),
     "tssep_segments": ([c_vp, c_i64, c_i64, c_i32, c_i32, c_i32, c_i64, c_vp, c_vp, c_i32, c_vp], C.c_int),
@@ -89,6 +86,11 @@ def load():
         fn = getattr(lib, name)
         fn.argtypes = argtypes
         fn.restype = restype
+    got = lib.tssep_abi_version()
+    if got != ABI_VERSION:
+        # a stale .so left behind by an older checkout would be bound with mismatched argument layouts
+        raise RuntimeError(f"{_LIB_PATH} reports ABI version {got}, this binding needs {ABI_VERSION}: rebuild it with "
+                           "`python -m tssep_b200.build --force`")
     _lib = lib
     return lib
 
@@ -104,16 +106,39 @@ def ptr(t):
     return None if t is None else t.data_ptr()
 
 
-def stream_of(t: torch.Tensor = None):
-    return torch.cuda.current_stream(t.device if t is not None else None).cuda_stream
+class StreamHandle(int):
+    """``cudaStream_t`` as an integer that remembers its device: ``call`` makes that device current for the launch."""
+
+    device_index: int = -1
+
+    def __new__(cls, handle: int, device_index: int):
+        obj = super().__new__(cls, handle)
+        obj.device_index = device_index
+        return obj
+
+
+def stream_of(t: torch.Tensor = None) -> StreamHandle:
+    """The current stream of the tensor's device (not of the current device: they differ when a model lives on
+    cuda:1 while cuda:0 is current)."""
+    dev = t.device if t is not None else torch.device("cuda", torch.cuda.current_device())
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    return StreamHandle(torch.cuda.current_stream(idx).cuda_stream, idx)
 
 
 def require_cuda(*tensors):
+    """No CPU fallback, and every operand of one call lives on one device."""
+    dev = None
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise RuntimeError(
                 "tssep_b200 operators run on CUDA tensors only (no CPU fallback); got a tensor on " f"{t.device}"
             )
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError(f"tssep_b200 operator called with tensors on different devices: {dev} and {t.device}")
 
 
 # Optional per-call device timing (bench.py): when a list is installed here every C-ABI call is
@@ -128,10 +153,23 @@ def set_timeline(timeline):
 
 
 def call(name: str, *args, detail: str = None):
-    """Calls one C-ABI entry point; ``detail`` only refines the timeline entry (e.g. the GEMM shape)."""
+    """Calls one C-ABI entry point; ``detail`` only refines the timeline entry (e.g. the GEMM shape).
+
+    The kernels launch on the CURRENT device (occupancy queries, function attributes and the SM count are read from
+    it as well), so the device of the stream argument (a ``StreamHandle`` from ``stream_of``) is made current for
+    the call when it is not already."""
     global launch_count
     fn = getattr(load(), name)
     launch_count += 1
+    dev = next((a.device_index for a in args if isinstance(a, StreamHandle)), -1)
+    if dev >= 0 and dev != torch.cuda.current_device():
+        with torch.cuda.device(dev):
+            _call_on_current_device(fn, name, args, detail)
+        return
+    _call_on_current_device(fn, name, args, detail)
+
+
+def _call_on_current_device(fn, name, args, detail):
     if _timeline is None:
         check(fn(*args), name)
         return

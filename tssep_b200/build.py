@@ -21,6 +21,10 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
 ]
+# TSSEP_DEBUG_KNOBS=1 at BUILD time compiles the tuning / profiling knobs in (environment variables read by the
+# library, the per-phase cycle counters of the recurrence); the default library has none of them.
+if os.environ.get("TSSEP_DEBUG_KNOBS") == "1":
+    NVCC_FLAGS = NVCC_FLAGS + ["-DTSSEP_DEBUG_KNOBS"]
 
 
 def _nvcc() -> str:

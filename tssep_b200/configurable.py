@@ -30,6 +30,7 @@ FACTORY_ALIASES = {
     "tssep.train.feature_extractor_torchaudio.TorchMFCC": "tssep_b200.feature_extractor_torchaudio.TorchMFCC",
     "tssep.train.net.MaskEstimator_v2": "tssep_b200.net.MaskEstimator_v2",
     "tssep.train.net.InstanceNorm": "tssep_b200.net.InstanceNorm",
+    "tssep.train.net.InstanceNorm_v2": "tssep_b200.net.InstanceNorm_v2",
     "tssep.train.rnnp.RNNP_packed": "tssep_b200.rnnp.RNNP_packed",
     "tssep.train.enhancer.Masking": "tssep_b200.enhancer.Masking",
     "tssep.train.loss.LogMAE": "tssep_b200.loss.LogMAE",

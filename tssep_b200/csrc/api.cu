@@ -42,7 +42,7 @@ extern "C" {
 
 const char* tssep_last_error(void) { return tssep::g_error; }
 
-int tssep_abi_version(void) { return 1; }
+int tssep_abi_version(void) { return TSSEP_ABI_VERSION; }
 
 int tssep_device_info(int* sm_count, int* cc_major, int* cc_minor) {
   int dev = 0;

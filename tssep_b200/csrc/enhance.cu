@@ -9,8 +9,6 @@
 #include "common.cuh"
 #include "fft.cuh"
 
-#include <cstdlib>
-
 namespace tssep {
 
 // ---------------------------------------------------------------------------
@@ -45,40 +43,6 @@ __global__ void fold_cat_kernel(const float* __restrict__ W, int64_t ldw, const 
   for (int a = lane; a < A; a += 32) acc = fmaf(w[a], ez[a], acc);
   acc = warp_sum(acc);
   if (lane == 0) bias_k[zn] = b[n] + acc;
-}
-
-// ---------------------------------------------------------------------------
-// Conditioned input rows for the tcgen05 recurrence path: rows ordered (group, t, b32),
-// z = group * 32 + b = item * K + speaker.
-//   mul (net.py:871-874): row = xs[item, t, :] * e[z, :]
-//   cat (net.py:879-894): row = [xs[item, t, :] | e[z, :]]
-// ---------------------------------------------------------------------------
-__global__ void condition_rows_kernel(int mode, const __nv_bfloat16* __restrict__ xs, int64_t ldx,
-                                      const float* __restrict__ e, int64_t Z, int K, int64_t T, int F, int A,
-                                      __nv_bfloat16* __restrict__ out, int64_t ldo, int64_t n_rows) {
-  const int lane = threadIdx.x & 31;
-  const int wpb = blockDim.x >> 5;
-  const int kdim = mode == 0 ? F : F + A;
-  for (int64_t r = blockIdx.x * static_cast<int64_t>(wpb) + (threadIdx.x >> 5); r < n_rows;
-       r += static_cast<int64_t>(gridDim.x) * wpb) {
-    const int64_t gt = r >> 5;
-    const int64_t grp = gt / T, t = gt - grp * T;
-    const int64_t z = grp * 32 + (r & 31);
-    __nv_bfloat16* o = out + r * ldo;
-    if (z >= Z) {
-      for (int c = lane; c < kdim; c += 32) o[c] = __float2bfloat16_rn(0.f);
-      continue;
-    }
-    const int64_t item = z / K;
-    const __nv_bfloat16* x = xs + (item * T + t) * ldx;
-    const float* ez = e + z * A;
-    if (mode == 0) {
-      for (int c = lane; c < F; c += 32) o[c] = __float2bfloat16_rn(__bfloat162float(x[c]) * ez[c]);
-    } else {
-      for (int c = lane; c < F; c += 32) o[c] = x[c];
-      for (int c = lane; c < A; c += 32) o[F + c] = __float2bfloat16_rn(ez[c]);
-    }
-  }
 }
 
 // ---------------------------------------------------------------------------
@@ -275,7 +239,8 @@ __device__ __forceinline__ void idft_reg(float2 (&v)[N]) {
 __global__ void __launch_bounds__(32 * kFastWarps, 3)
 mask_istft_1024_kernel(const float2* __restrict__ X, int64_t x_item_stride, const float* __restrict__ mask, int n_spk,
                        int groups, int64_t T, int trim, const float* __restrict__ synwin, const float2* __restrict__ twiddle,
-                       float2* __restrict__ est, float* __restrict__ time_out, int64_t num_samples, int hops) {
+                       float2* __restrict__ est, float* __restrict__ time_out, int64_t num_samples, int hops,
+                       float* __restrict__ activity) {
   constexpr int M = 512, F = 513, R = 256;
   __shared__ float2 tw[M];                              // exp(-2 pi i k / 1024)
   __shared__ float2 twA[16 * 32];                       // exp(+2 pi i k2 n1 / 512) at [n1 * 32 + k2]
@@ -324,6 +289,7 @@ mask_istft_1024_kernel(const float2* __restrict__ X, int64_t x_item_stride, cons
       const float2* xrow_a = mask ? X + z * x_item_stride + t * F : X + row_a;
       const float2* xrow_b = mask ? xrow_a : X + row_b;
       const bool own = est != nullptr && t >= j_begin;
+      float msum_a = 0.f, msum_b = 0.f;  // frame activity: every bin is read as mask[kk] exactly once (+ bin 512)
 #pragma unroll
       for (int k1 = 0; k1 < 16; ++k1) {
         const int kk = 32 * k1 + lane;
@@ -332,6 +298,8 @@ mask_istft_1024_kernel(const float2* __restrict__ X, int64_t x_item_stride, cons
         if (mask) {
           const float mk = mask[row_a + kk], mm = mask[row_a + M - kk];
           const float mk2 = mask[row_b + kk], mm2 = mask[row_b + M - kk];
+          msum_a += mk + (kk == 0 ? mm : 0.f);
+          msum_b += mk2 + (kk == 0 ? mm2 : 0.f);
           yk = make_float2(yk.x * mk, yk.y * mk);
           ym = make_float2(ym.x * mm, ym.y * mm);
           yk2 = make_float2(yk2.x * mk2, yk2.y * mk2);
@@ -355,6 +323,14 @@ mask_istft_1024_kernel(const float2* __restrict__ X, int64_t x_item_stride, cons
         const float2 w = tw[kk];
         va[k1] = irfft_pack_w(yk, ym, w);
         vb[k1] = irfft_pack_w(yk2, ym2, w);
+      }
+      if (activity != nullptr && t >= j_begin) {  // halo frames belong to the previous range
+        msum_a = warp_sum(msum_a);
+        msum_b = warp_sum(msum_b);
+        if (lane == 0) {
+          activity[sig_a * T + t] = msum_a / static_cast<float>(F);
+          if (has_b) activity[sig_b * T + t] = msum_b / static_cast<float>(F);
+        }
       }
       idft_reg<16>(va);
       idft_reg<16>(vb);
@@ -434,21 +410,6 @@ int tssep_fold_embedding(int mode, const float* W, int64_t ldw, const float* b, 
   return check_launch("tssep_fold_embedding");
 }
 
-int tssep_condition_rows(int mode, const uint16_t* xs, int64_t ldx, const float* e, int64_t Z, int K, int64_t T,
-                         int F, int A, uint16_t* out, int64_t ldo, tssep_stream_t stream) {
-  TSSEP_REQUIRE(xs && e && out, "tssep_condition_rows: null pointer");
-  TSSEP_REQUIRE(mode == 0 || mode == 1, "tssep_condition_rows: mode must be 0 (mul) or 1 (cat)");
-  TSSEP_REQUIRE(mode == 1 || A == F, "tssep_condition_rows(mul): needs A == F");
-  TSSEP_REQUIRE(K >= 1 && ldx >= F && ldo >= (mode == 0 ? F : F + A), "tssep_condition_rows: bad extent");
-  if (Z == 0 || T == 0) return 0;
-  const int64_t n_rows = ((Z + 31) / 32) * T * 32;
-  const int blocks = static_cast<int>(imin64((n_rows + 7) / 8, 148 * 32));
-  condition_rows_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      mode, reinterpret_cast<const __nv_bfloat16*>(xs), ldx, e, Z, K, T, F, A, reinterpret_cast<__nv_bfloat16*>(out), ldo,
-      n_rows);
-  return check_launch("tssep_condition_rows");
-}
-
 int tssep_head_expand_t(const float* small, int64_t Z, int64_t T, int n_spk, int F, const int32_t* perm,
                         float* logit, float* mask, tssep_stream_t stream) {
   TSSEP_REQUIRE(small && perm && (logit || mask), "tssep_head_expand_t: null pointer");
@@ -461,16 +422,18 @@ int tssep_head_expand_t(const float* small, int64_t Z, int64_t T, int n_spk, int
 
 int tssep_mask_istft(const float* X, int64_t x_item_stride, const float* mask, int64_t Z, int n_spk, int64_t T,
                      int size, int shift, int window_length, int fading, const float* synwin, const float* twiddle,
-                     float* stft_estimate, float* time, int64_t num_samples, tssep_stream_t stream) {
+                     float* stft_estimate, float* time, int64_t num_samples, float* activity, tssep_stream_t stream) {
   TSSEP_REQUIRE(X && synwin && twiddle, "tssep_mask_istft: null pointer");
   TSSEP_REQUIRE(stft_estimate || time, "tssep_mask_istft: no output requested");
+  TSSEP_REQUIRE(activity == nullptr || mask != nullptr, "tssep_mask_istft: activity needs a mask");
   const int l2 = ilog2_exact(size);
   TSSEP_REQUIRE(l2 >= 3 && size <= 4096, "tssep_mask_istft: size must be a power of two in [8, 4096], got %d", size);
   TSSEP_REQUIRE(window_length <= size && shift >= 1 && window_length % shift == 0,
                 "tssep_mask_istft: need window_length <= size and window_length %% shift == 0");
   TSSEP_REQUIRE(Z >= 0 && Z < 65536 && n_spk >= 1 && T >= 0, "tssep_mask_istft: bad extent");
   if (Z == 0 || T == 0) return 0;
-  if (size == 1024 && shift == 256 && window_length == 1024 && getenv("TSSEP_ISTFT_GENERIC") == nullptr) {
+  if (size == 1024 && shift == 256 && window_length == 1024 && debug_env("TSSEP_ISTFT_GENERIC") == nullptr) {
+    // (the fast kernel loses nothing by also reducing the mask rows it reads to the frame activity)
     const int64_t J = T + 3;
     int hops = 128;
     const int groups = (n_spk + 2 * kFastWarps - 1) / (2 * kFastWarps);
@@ -478,8 +441,13 @@ int tssep_mask_istft(const float* X, int64_t x_item_stride, const float* mask, i
     dim3 grid(static_cast<unsigned>((J + hops - 1) / hops), static_cast<unsigned>(Z * groups));
     mask_istft_1024_kernel<<<grid, 32 * kFastWarps, 0, static_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<const float2*>(X), x_item_stride, mask, n_spk, groups, T, fading ? window_length - shift : 0, synwin,
-        reinterpret_cast<const float2*>(twiddle), reinterpret_cast<float2*>(stft_estimate), time, num_samples, hops);
+        reinterpret_cast<const float2*>(twiddle), reinterpret_cast<float2*>(stft_estimate), time, num_samples, hops,
+        activity);
     return check_launch("tssep_mask_istft");
+  }
+  // generic geometries: the frame activity comes from the stand-alone reduction
+  if (activity != nullptr) {
+    if (int r = tssep_activity(mask, Z * n_spk, T, size / 2 + 1, activity, stream)) return r;
   }
   const int M = size / 2, OV = window_length / shift;
   const size_t smem = sizeof(float2) * (M + (2 * kEWarps + OV - 1) * padded_len(M)) + sizeof(float) * window_length;

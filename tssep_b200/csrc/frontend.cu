@@ -173,23 +173,61 @@ __global__ void cast_bf16_kernel(const float* __restrict__ src, int64_t rows, in
   }
 }
 
-__global__ void instance_norm_kernel(const float* __restrict__ src, int64_t rows, int64_t cols, int unbiased,
-                                     float* __restrict__ dst) {
-  const int lane = threadIdx.x & 31;
-  const int64_t row = blockIdx.x * static_cast<int64_t>(blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  const float* x = src + row * cols;
-  float s = 0.f;
-  for (int64_t c = lane; c < cols; c += 32) s += x[c];
-  const float mean = warp_sum(s) / static_cast<float>(cols);
-  float v = 0.f;
-  for (int64_t c = lane; c < cols; c += 32) {
-    const float d = x[c] - mean;
-    v = fmaf(d, d, v);
+// Normalisation along one axis of a contiguous (outer, cols, inner) tensor (InstanceNorm / InstanceNorm_v2,
+// tssep/train/net.py:250-330).  mode 0: (x - mean) / std, mode 1: x - mean, mode 2: x / rms.
+// inner == 1: one warp per row (lanes stride the row); inner > 1: one thread per row (adjacent threads = adjacent
+// `inner` positions, so every load of the strided walk is coalesced across the warp).
+__device__ __forceinline__ float norm_apply(float x, float mean, float inv, int mode) {
+  return mode == 1 ? x - mean : (mode == 2 ? x * inv : (x - mean) * inv);
+}
+
+__global__ void instance_norm_kernel(const float* __restrict__ src, int64_t outer, int64_t cols, int64_t inner, int mode,
+                                     int unbiased, float* __restrict__ dst) {
+  const float denom = static_cast<float>(mode == 0 && unbiased ? cols - 1 : cols);
+  if (inner == 1) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = blockIdx.x * static_cast<int64_t>(blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= outer) return;
+    const float* x = src + row * cols;
+    float mean = 0.f;
+    if (mode != 2) {
+      float s = 0.f;
+      for (int64_t c = lane; c < cols; c += 32) s += x[c];
+      mean = warp_sum(s) / static_cast<float>(cols);
+    }
+    float inv = 1.f;
+    if (mode != 1) {
+      float v = 0.f;
+      for (int64_t c = lane; c < cols; c += 32) {
+        const float d = x[c] - mean;
+        v = fmaf(d, d, v);
+      }
+      inv = 1.0f / sqrtf(warp_sum(v) / denom);
+    }
+    for (int64_t c = lane; c < cols; c += 32) dst[row * cols + c] = norm_apply(x[c], mean, inv, mode);
+    return;
   }
-  const float var = warp_sum(v) / static_cast<float>(unbiased ? cols - 1 : cols);
-  const float inv = 1.0f / sqrtf(var);
-  for (int64_t c = lane; c < cols; c += 32) dst[row * cols + c] = (x[c] - mean) * inv;
+  const int64_t row = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (row >= outer * inner) return;
+  const int64_t o = row / inner, i = row - o * inner;
+  const float* x = src + o * cols * inner + i;
+  float* y = dst + o * cols * inner + i;
+  float mean = 0.f;
+  if (mode != 2) {
+    float s = 0.f;
+    for (int64_t c = 0; c < cols; ++c) s += x[c * inner];
+    mean = s / static_cast<float>(cols);
+  }
+  float inv = 1.f;
+  if (mode != 1) {
+    float v = 0.f;
+    for (int64_t c = 0; c < cols; ++c) {
+      const float d = x[c * inner] - mean;
+      v = fmaf(d, d, v);
+    }
+    inv = 1.0f / sqrtf(v / denom);
+  }
+  for (int64_t c = 0; c < cols; ++c) y[c * inner] = norm_apply(x[c * inner], mean, inv, mode);
 }
 
 static int ilog2_exact(int v) {
@@ -279,13 +317,16 @@ int tssep_cast_bf16(const float* src, int64_t rows, int64_t cols, int64_t ld_src
   return check_launch("tssep_cast_bf16");
 }
 
-int tssep_instance_norm(const float* src, int64_t rows, int64_t cols, int unbiased, float* dst,
+int tssep_instance_norm(const float* src, int64_t outer, int64_t cols, int64_t inner, int mode, int unbiased, float* dst,
                         tssep_stream_t stream) {
-  TSSEP_REQUIRE(src && dst && cols >= 1, "tssep_instance_norm: bad arguments");
-  if (rows == 0) return 0;
-  const int wpb = 8;
-  instance_norm_kernel<<<static_cast<unsigned>((rows + wpb - 1) / wpb), wpb * 32, 0,
-                         static_cast<cudaStream_t>(stream)>>>(src, rows, cols, unbiased, dst);
+  TSSEP_REQUIRE(src && dst && cols >= 1 && inner >= 1 && outer >= 0, "tssep_instance_norm: bad arguments");
+  TSSEP_REQUIRE(mode >= 0 && mode <= 2, "tssep_instance_norm: mode must be 0 (standardise), 1 (centre) or 2 (rms)");
+  if (outer == 0) return 0;
+  const int64_t rows = outer * inner;
+  const int64_t blocks = inner == 1 ? (rows + 7) / 8 : (rows + 255) / 256;
+  TSSEP_REQUIRE(blocks < (1ll << 31), "tssep_instance_norm: too many rows");
+  instance_norm_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, outer, cols, inner,
+                                                                                                    mode, unbiased, dst);
   return check_launch("tssep_instance_norm");
 }
 

@@ -15,8 +15,6 @@
 #include "../../include/tssep_b200.h"
 #include "common.cuh"
 
-#include <cstdlib>
-
 namespace tssep {
 
 constexpr int BM = 128;
@@ -27,7 +25,7 @@ constexpr int kGemmThreads = 64 + 32 * kEpiWarps;
 constexpr int kTmemCols = 512;
 constexpr int kAccCols = 256;
 
-enum EpiMode { EPI_F32 = 0, EPI_BF16 = 1, EPI_HEAD = 2, EPI_F32_BT = 3, EPI_BF16_ROWMAP = 4, EPI_BF16_BT = 5 };
+enum EpiMode { EPI_F32 = 0, EPI_BF16 = 1, EPI_HEAD = 2 };
 
 struct GemmArgs {
   int64_t M;
@@ -46,9 +44,6 @@ struct GemmArgs {
   float* mask;
   const int* plane_map;
   int n_blocks, row_len;
-  // row map of EPI_BF16_ROWMAP: input rows are ordered (group, t, b32); z = group*32 + b
-  int64_t rm_T;
-  int rm_K, rm_Z, rm_P;
   // tiling
   int bn, m_tiles, n_tiles, k_blocks, stages;
   int64_t total_tiles;
@@ -99,28 +94,6 @@ __device__ __forceinline__ void epilogue_store(const GemmArgs& g, int z, int64_t
         *reinterpret_cast<uint4*>(o + i) = v;
       }
     } else {
-#pragma unroll
-      for (int i = 0; i < 32; ++i)
-        if (i < nvalid) o[i] = __float2bfloat16_rn(apply_act(g.alpha * acc[i] + (bias ? bias[i] : 0.f), g.act));
-    }
-  } else if (g.mode == EPI_F32_BT || g.mode == EPI_BF16_BT) {
-    const int b = static_cast<int>(m & 31);
-    const int64_t o0 = ((m >> 5) * g.N + n0) * 32 + (b >> 2) * 128 + (b & 3);
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      if (i < nvalid) {
-        const float v = apply_act(g.alpha * acc[i] + (bias ? bias[i] : 0.f), g.act);
-        if (g.mode == EPI_F32_BT) static_cast<float*>(g.out)[o0 + i * 4] = v;
-        else static_cast<__nv_bfloat16*>(g.out)[o0 + i * 4] = __float2bfloat16_rn(v);
-      }
-    }
-  } else if (g.mode == EPI_BF16_ROWMAP) {
-    const int64_t gt = m >> 5;
-    const int64_t grp = gt / g.rm_T, t = gt - grp * g.rm_T;
-    const int64_t zz = grp * 32 + (m & 31);
-    if (zz < g.rm_Z) {
-      const int64_t item = zz / g.rm_K, spk = zz - item * g.rm_K;
-      __nv_bfloat16* o = static_cast<__nv_bfloat16*>(g.out) + (item * g.rm_T + t) * g.ldo + spk * g.rm_P + n0;
 #pragma unroll
       for (int i = 0; i < 32; ++i)
         if (i < nvalid) o[i] = __float2bfloat16_rn(apply_act(g.alpha * acc[i] + (bias ? bias[i] : 0.f), g.act));
@@ -179,11 +152,11 @@ __device__ __forceinline__ ChunkBias load_chunk_bias(const GemmArgs& g, const fl
   ChunkBias b;
   b.v[0] = b.v[1] = b.v[2] = b.v[3] = 0.f;
   b.plane = 0;
-  if (MODE == EPI_HEAD || MODE == EPI_F32_BT || MODE == EPI_BF16_BT) {
+  if (MODE == EPI_HEAD) {
     const int n = n0 + lane;
     if (n < g.N) {
       if (bias) b.v[0] = __ldg(bias + n);
-      if (MODE == EPI_HEAD) b.plane = __ldg(plane_row + n / g.row_len);
+      b.plane = __ldg(plane_row + n / g.row_len);
     }
   } else if (bias) {
     const int n = n0 + (lane & 7) * 4;
@@ -207,9 +180,7 @@ __device__ __forceinline__ ChunkBias load_chunk_bias(const GemmArgs& g, const fl
 // Per (tile, warp) invariants of the epilogue.
 struct EpiTile {
   int64_t rows_left;   // rows of this warp's 32-row block that exist
-  int64_t base;        // element offset of (row m0 + sub, column c4) [row modes] / of the tile [BT] in the output
-  int64_t row_off[8];  // EPI_BF16_ROWMAP: element offset of row pass*4 + sub
-  uint32_t row_ok;     // EPI_BF16_ROWMAP: bit pass set when that row is written
+  int64_t base;        // element offset of (row m0 + sub, column c4) in the output
   bool fast;           // vector-aligned full block: one LDS.128 + one vector store per pass
 };
 
@@ -217,7 +188,6 @@ template <int MODE>
 __device__ __forceinline__ EpiTile make_epi_tile(const GemmArgs& g, int z, int64_t m0, int lane) {
   EpiTile t;
   t.rows_left = g.M - m0;
-  t.row_ok = 0;
   t.base = 0;
   t.fast = false;
   const int sub = lane >> 3, c4 = (lane & 7) * 4;
@@ -228,21 +198,6 @@ __device__ __forceinline__ EpiTile make_epi_tile(const GemmArgs& g, int z, int64
     const uintptr_t amask = MODE == EPI_F32 ? 15 : 7;
     t.fast = t.rows_left >= 32 && ((reinterpret_cast<uintptr_t>(g.out) | static_cast<uintptr_t>(zoff * esz) |
                                     static_cast<uintptr_t>(g.ldo * esz)) & amask) == 0;
-  } else if (MODE == EPI_BF16_ROWMAP) {
-    // rows are ordered (group, t, b32) and m0 is a multiple of 32: group and t are the same for the whole block
-    const int64_t gt = m0 >> 5;
-    const int64_t grp = gt / g.rm_T, tt = gt - grp * g.rm_T;
-#pragma unroll
-    for (int pass = 0; pass < 8; ++pass) {
-      const int r = pass * 4 + sub;
-      const int zz = static_cast<int>(grp) * 32 + r;  // < 2^31: the launcher bounds the row count
-      const int item = zz / g.rm_K, spk = zz - item * g.rm_K;
-      t.row_off[pass] = (static_cast<int64_t>(item) * g.rm_T + tt) * g.ldo + static_cast<int64_t>(spk) * g.rm_P + c4;
-      if (zz < g.rm_Z && r < t.rows_left) t.row_ok |= 1u << pass;
-    }
-    t.fast = ((reinterpret_cast<uintptr_t>(g.out) | static_cast<uintptr_t>(g.ldo * 2) | static_cast<uintptr_t>(g.rm_P * 2)) & 7) == 0;
-  } else if (MODE == EPI_F32_BT || MODE == EPI_BF16_BT) {
-    t.base = (m0 >> 5) * static_cast<int64_t>(g.N) * 32 + lane * 4;
   }
   return t;
 }
@@ -256,7 +211,7 @@ __device__ __forceinline__ void stage_rows(uint32_t stage, int lane, const uint3
   __syncwarp();
 }
 
-// EPI_F32 / EPI_BF16 / EPI_BF16_ROWMAP: per pass 4 rows x (8 lanes x 4 columns)
+// EPI_F32 / EPI_BF16: per pass 4 rows x (8 lanes x 4 columns)
 template <int MODE, int ACT>
 __device__ __forceinline__ void epilogue_rows(const GemmArgs& g, const EpiTile& t, int n0, int limit, const uint32_t* v,
                                               const ChunkBias& cb, uint32_t stage, int lane) {
@@ -279,11 +234,8 @@ __device__ __forceinline__ void epilogue_rows(const GemmArgs& g, const EpiTile& 
       x.w = act_t<ACT>(fmaf(g.alpha, x.w, cb.v[3]));
       if (MODE == EPI_F32) {
         *reinterpret_cast<float4*>(static_cast<float*>(g.out) + t.base + pass * step + n0) = x;
-      } else if (MODE == EPI_BF16) {
+      } else {
         *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(g.out) + t.base + pass * step + n0) =
-            make_uint2(pack_bf16x2(x.x, x.y), pack_bf16x2(x.z, x.w));
-      } else if ((t.row_ok >> pass) & 1u) {
-        *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(g.out) + t.row_off[pass] + n0) =
             make_uint2(pack_bf16x2(x.x, x.y), pack_bf16x2(x.z, x.w));
       }
     }
@@ -297,8 +249,8 @@ __device__ __forceinline__ void epilogue_rows(const GemmArgs& g, const EpiTile& 
                    : "r"(stage + (r * kStageLd + c4) * 4));
 #pragma unroll
       for (int j = 0; j < 4; ++j) x[j] = act_t<ACT>(fmaf(g.alpha, x[j], cb.v[j]));
-      const bool row_ok = MODE == EPI_BF16_ROWMAP ? ((t.row_ok >> pass) & 1u) != 0 : r < t.rows_left;
-      const int64_t off = (MODE == EPI_BF16_ROWMAP ? t.row_off[pass] : t.base + pass * 4 * g.ldo) + n0;
+      const bool row_ok = r < t.rows_left;
+      const int64_t off = t.base + pass * 4 * g.ldo + n0;
       if (row_ok && c4 < nvalid) {
         if (MODE == EPI_F32) {
           float* o = static_cast<float*>(g.out) + off;
@@ -369,34 +321,6 @@ __device__ __forceinline__ void epilogue_head(const GemmArgs& g, const EpiTile& 
         if (mk) mk[idx] = sigmoid_acc(val);
       }
     }
-  }
-  __syncwarp();
-}
-
-// EPI_F32_BT / EPI_BF16_BT: rows are ordered (group, t, b32) and the output is the layout the tcgen05
-// recurrences stream: element (row m, column n) -> ((m/32)*N + (n/32)*32)*32 + (b/4)*128 + (n%32)*4 + b%4
-// with b = m % 32, i.e. per (group, t) and per block of 32 columns a tile [b/4][column][b%4].  The warp
-// transposes its 32 x 32 block through shared memory and writes eight fully coalesced rows (lane = column).
-template <int MODE, int ACT>
-__device__ __forceinline__ void epilogue_bt(const GemmArgs& g, const EpiTile& t, int n0, const uint32_t* v,
-                                            const ChunkBias& cb, uint32_t stage, int lane) {
-  if (n0 >= g.N) return;
-  stage_rows(stage, lane, v);
-  const int64_t o0 = t.base + static_cast<int64_t>(n0) * 32;
-  const uint32_t lds0 = stage + lane * 4;
-#pragma unroll
-  for (int bq = 0; bq < 8; ++bq) {
-    float x[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x[j]) : "r"(lds0 + (bq * 4 + j) * kStageLd * 4));
-      x[j] = act_t<ACT>(fmaf(g.alpha, x[j], cb.v[0]));
-    }
-    if (MODE == EPI_F32_BT)
-      *reinterpret_cast<float4*>(static_cast<float*>(g.out) + o0 + bq * 128) = make_float4(x[0], x[1], x[2], x[3]);
-    else
-      *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(g.out) + o0 + bq * 128) =
-          make_uint2(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]));
   }
   __syncwarp();
 }
@@ -533,8 +457,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const ChunkBias cb_next = load_chunk_bias<MODE>(g, bias, plane_row, nbase + c0 + 64, lane);  // for the next chunk
         tc_wait_ld();
         if (m0 < g.M) {
-          if (MODE == EPI_F32_BT || MODE == EPI_BF16_BT) epilogue_bt<MODE, ACT>(g, et, nbase + c0, v, cb, stage, lane);
-          else if (MODE == EPI_HEAD) epilogue_head(g, et, m0, nbase + c0, min(32, g.bn - c0), v, cb, stage, lane);
+          if (MODE == EPI_HEAD) epilogue_head(g, et, m0, nbase + c0, min(32, g.bn - c0), v, cb, stage, lane);
           else epilogue_rows<MODE, ACT>(g, et, nbase + c0, min(32, g.bn - c0), v, cb, stage, lane);
         }
         cb = cb_next;
@@ -595,8 +518,9 @@ static int make_map_2d(CUtensorMap* map, const void* base, uint64_t inner, uint6
   return 0;
 }
 
-static int choose_bn(int N, int step = 16) {
-  if (const char* e = getenv("TSSEP_GEMM_BN")) {
+static int choose_bn(int N) {
+  const int step = 16;
+  if (const char* e = debug_env("TSSEP_GEMM_BN")) {
     const int v = atoi(e);
     if (v >= 16 && v <= 256 && v % step == 0) return v;
   }
@@ -616,7 +540,7 @@ static int choose_bn(int N, int step = 16) {
 }
 
 static int launch_gemm(GemmArgs g, const uint16_t* A, int64_t lda, int64_t a_stride, const uint16_t* B, int64_t ldb,
-                       int64_t b_stride, int impl, cudaStream_t stream) {
+                       int64_t b_stride, int impl, int max_ctas, cudaStream_t stream) {
   TSSEP_REQUIRE(A && B, "gemm: null operand");
   TSSEP_REQUIRE(g.M >= 0 && g.N >= 1 && g.K >= 1 && g.batch >= 1 && g.a_div >= 1 && g.b_mod >= 1 && g.out_div >= 1,
                 "gemm: bad extent");
@@ -640,7 +564,7 @@ static int launch_gemm(GemmArgs g, const uint16_t* A, int64_t lda, int64_t a_str
                 (long long)ldb);
   TSSEP_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0,
                 "gemm: operands must be 16-byte aligned");
-  g.bn = choose_bn(g.N, (g.mode == EPI_F32_BT || g.mode == EPI_BF16_BT) ? 32 : 16);
+  g.bn = choose_bn(g.N);
   g.m_tiles = static_cast<int>((g.M + BM - 1) / BM);
   g.n_tiles = (g.N + g.bn - 1) / g.bn;
   g.k_blocks = (g.K + BK - 1) / BK;
@@ -660,13 +584,10 @@ static int launch_gemm(GemmArgs g, const uint16_t* A, int64_t lda, int64_t a_str
   TSSEP_REQUIRE(g.stages >= 2, "gemm: tile does not fit shared memory");
   const size_t smem = fixed + g.stages * stage_bytes;
   int grid = static_cast<int>(imin64(g.total_tiles, sms));
-  // TSSEP_GEMM_MAX_CTAS: run the persistent kernel on fewer SMs.  Under the board power cap a large GEMM is power
-  // limited, and the clocks it leaves behind decide the speed of the latency-bound recurrence that follows
+  // max_ctas: run the persistent kernel on fewer SMs.  Under the board power cap a large GEMM is power limited, and the
+  // clocks it leaves behind decide the speed of the latency-bound recurrence that follows
   // (profiles/r1_power_cap_probe.txt).
-  if (const char* e = getenv("TSSEP_GEMM_MAX_CTAS")) {
-    const int v = atoi(e);
-    if (v >= 1 && v < grid) grid = v;
-  }
+  if (max_ctas >= 1 && max_ctas < grid) grid = max_ctas;
 #define TSSEP_GEMM_CASE(MODE_, ACT_)                                                                                     \
   if (g.mode == MODE_ && g.act == ACT_) {                                                                                \
     TSSEP_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<MODE_, ACT_>, cudaFuncAttributeMaxDynamicSharedMemorySize,           \
@@ -679,12 +600,6 @@ static int launch_gemm(GemmArgs g, const uint16_t* A, int64_t lda, int64_t a_str
   TSSEP_GEMM_CASE(EPI_BF16, 0)
   TSSEP_GEMM_CASE(EPI_BF16, 1)
   TSSEP_GEMM_CASE(EPI_HEAD, 0)
-  TSSEP_GEMM_CASE(EPI_F32_BT, 0)
-  TSSEP_GEMM_CASE(EPI_F32_BT, 1)
-  TSSEP_GEMM_CASE(EPI_BF16_BT, 0)
-  TSSEP_GEMM_CASE(EPI_BF16_BT, 1)
-  TSSEP_GEMM_CASE(EPI_BF16_ROWMAP, 0)
-  TSSEP_GEMM_CASE(EPI_BF16_ROWMAP, 1)
 #undef TSSEP_GEMM_CASE
   set_error("gemm: no tensor-core instantiation for mode %d act %d", g.mode, g.act);
   return -1;
@@ -698,7 +613,7 @@ extern "C" {
 
 int tssep_gemm(const tssep_gemm_desc* d, tssep_stream_t stream) {
   TSSEP_REQUIRE(d != nullptr, "tssep_gemm: null descriptor");
-  TSSEP_REQUIRE(d->mode >= TSSEP_EPI_F32 && d->mode <= TSSEP_EPI_BF16_BT, "tssep_gemm: unknown epilogue mode %d",
+  TSSEP_REQUIRE(d->mode >= TSSEP_EPI_F32 && d->mode <= TSSEP_EPI_HEAD, "tssep_gemm: unknown epilogue mode %d",
                 d->mode);
   TSSEP_REQUIRE(d->act == 0 || d->act == 1, "tssep_gemm: act must be 0 (none) or 1 (tanh)");
   GemmArgs g{};
@@ -722,27 +637,17 @@ int tssep_gemm(const tssep_gemm_desc* d, tssep_stream_t stream) {
   g.plane_map = d->plane_map;
   g.n_blocks = d->n_blocks;
   g.row_len = d->row_len;
-  g.rm_T = d->rm_T;
-  g.rm_K = d->rm_K;
-  g.rm_Z = d->rm_Z;
-  g.rm_P = d->rm_P;
   if (d->mode == TSSEP_EPI_HEAD) {
     TSSEP_REQUIRE(d->out || d->mask, "tssep_gemm(head): no output");
     TSSEP_REQUIRE(d->plane_map && d->n_blocks >= 1 && d->row_len >= 1 && d->N == d->n_blocks * d->row_len,
                   "tssep_gemm(head): need plane_map and N == n_blocks * row_len");
     TSSEP_REQUIRE(d->act == 0, "tssep_gemm(head): act must be 0");
-  } else if (d->mode == TSSEP_EPI_F32_BT || d->mode == TSSEP_EPI_BF16_BT) {
-    TSSEP_REQUIRE(d->out != nullptr && d->batch == 1 && d->M % 32 == 0 && d->N % 32 == 0 &&
-                      (reinterpret_cast<uintptr_t>(d->out) & 15) == 0,
-                  "tssep_gemm(f32_bt): needs a 16-byte aligned output, batch == 1, M %% 32 == 0 and N %% 32 == 0");
-  } else if (d->mode == TSSEP_EPI_BF16_ROWMAP) {
-    TSSEP_REQUIRE(d->out != nullptr && d->batch == 1 && d->M % 32 == 0 && d->rm_T >= 1 && d->rm_K >= 1 && d->rm_Z >= 1,
-                  "tssep_gemm(bf16_rowmap): needs an output, batch == 1, M %% 32 == 0 and a row map");
   } else {
     TSSEP_REQUIRE(d->out != nullptr, "tssep_gemm: null output");
     TSSEP_REQUIRE(d->ldo >= d->N, "tssep_gemm: ldo < N");
   }
-  return launch_gemm(g, d->A, d->lda, d->a_stride, d->B, d->ldb, d->b_stride, d->impl,
+  TSSEP_REQUIRE(d->max_ctas >= 0, "tssep_gemm: max_ctas must be >= 0");
+  return launch_gemm(g, d->A, d->lda, d->a_stride, d->B, d->ldb, d->b_stride, d->impl, d->max_ctas,
                      static_cast<cudaStream_t>(stream));
 }
 

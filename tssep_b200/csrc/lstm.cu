@@ -22,8 +22,6 @@
 #include "../../include/tssep_b200.h"
 #include "common.cuh"
 
-#include <cstdlib>
-
 namespace tssep {
 
 constexpr int kGStages = 4;
@@ -384,7 +382,7 @@ int tssep_blstm_recurrence(const void* G, int g_dtype, const uint32_t* Wfrag, ui
   const int btiles = static_cast<int>((rows + 7) / 8);
   int NB = (2 * btiles + max_clusters - 1) / max_clusters;  // smallest NB that fits both directions in one wave
   NB = NB < 1 ? 1 : (NB > 4 ? 4 : NB);
-  if (const char* e = getenv("TSSEP_LSTM_NB")) {
+  if (const char* e = debug_env("TSSEP_LSTM_NB")) {
     const int v = atoi(e);
     if (v >= 1 && v <= 4) NB = v;
   }
@@ -406,9 +404,12 @@ int tssep_blstm_recurrence(const void* G, int g_dtype, const uint32_t* Wfrag, ui
   TSSEP_REQUIRE(r == CUDA_SUCCESS, "tssep_blstm_recurrence: cuTensorMapEncodeTiled failed with code %d", static_cast<int>(r));
 
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  // debugging aid: TSSEP_REC_PROF=<device pointer to 6 ints> makes one warp record per-phase cycle counts
+  // debug builds only (-DTSSEP_DEBUG_KNOBS): TSSEP_REC_PROF=<device pointer to 6 ints> makes one warp record
+  // per-phase cycle counts; the shipped library never takes an address from the environment
   int* prof = nullptr;
-  if (const char* e = getenv("TSSEP_REC_PROF")) prof = reinterpret_cast<int*>(strtoull(e, nullptr, 0));
+#ifdef TSSEP_DEBUG_KNOBS
+  if (const char* e = debug_env("TSSEP_REC_PROF")) prof = reinterpret_cast<int*>(strtoull(e, nullptr, 0));
+#endif
   switch (Up / 16) {
 #define TSSEP_CASE(kt)                                                                                  \
   case kt:                                                                                              \

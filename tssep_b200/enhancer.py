@@ -28,11 +28,13 @@ class Masking(ABC):
 
     @staticmethod
     def apply(masks, Observation, reference_channel, fe, want_estimate=True, want_time=False, num_samples=None,
-              time_out=None):
+              time_out=None, activity_out=None):
         """masks (K,1,T,F) or (B,K,1,T,F) f32; Observation ([B,] C, T, F) complex64 (or without the channel
         axis when ``reference_channel`` is None).  Returns (stft_estimate | None, time_estimate | None).
         ``time_out``: optional preallocated contiguous float32 device tensor ([B,] K, n) for time_estimate (a
-        serving loop that ships the audio to the host keeps its own buffers instead of churning the allocator)."""
+        serving loop that ships the audio to the host keeps its own buffers instead of churning the allocator).
+        ``activity_out``: optional float32 device tensor ([B,] K, T) that receives the frame activity
+        ``mean_f mask`` (the first stage of ``postprocess.diarize``), reduced from the mask rows the kernel reads anyway."""
         batched = {4: False, 5: True}[masks.dim()]
         if isinstance(Observation, np.ndarray):
             Observation = torch.as_tensor(Observation, device=masks.device)
@@ -64,8 +66,14 @@ class Masking(ABC):
                 time = time_out
             else:
                 time = torch.empty((*lead, n), dtype=torch.float32, device=m.device)
+        if activity_out is not None:
+            _lib.require_cuda(activity_out)
+            if (tuple(activity_out.shape) != (*lead, T) or activity_out.dtype != torch.float32
+                    or not activity_out.is_contiguous()):
+                raise ValueError(f"activity_out must be a contiguous float32 tensor of shape {(*lead, T)}")
         tab = fe._device_tables(m.device)
         _lib.call("tssep_mask_istft", obs.data_ptr(), T * F, m.data_ptr(), Z, K, T, fe.size, fe.shift,
                   fe.window_length, int(bool(fe.fading)), tab["synwin"].data_ptr(), tab["twiddle"].data_ptr(),
-                  _lib.ptr(est), _lib.ptr(time), time.shape[-1] if time is not None else 0, _lib.stream_of(m))
+                  _lib.ptr(est), _lib.ptr(time), time.shape[-1] if time is not None else 0, _lib.ptr(activity_out),
+                  _lib.stream_of(m))
         return est, time

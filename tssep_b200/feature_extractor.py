@@ -144,7 +144,7 @@ class STFT(Configurable):
         n_sig = int(np.prod(lead)) if lead else 1
         _lib.call("tssep_mask_istft", Xc.data_ptr(), 0, None, n_sig, 1, t, self.size, self.shift,
                   self.window_length, int(bool(self.fading)), tab["synwin"].data_ptr(), tab["twiddle"].data_ptr(),
-                  None, out.data_ptr(), n, _lib.stream_of(Xc))
+                  None, out.data_ptr(), n, None, _lib.stream_of(Xc))
         return out.cpu().numpy() if was_np else out
 
     # feature description consumed by `_compute_features`

@@ -19,8 +19,6 @@ materialises the reference's intermediate tensors:
 """
 from __future__ import annotations
 
-import os
-
 import collections
 import dataclasses
 
@@ -29,7 +27,7 @@ import torch
 
 from . import _lib, ops
 from .configurable import Configurable
-from .rnnp import RNNP_packed, param_key, use_tc_recurrence
+from .rnnp import RNNP_packed, param_key
 
 
 @dataclasses.dataclass
@@ -43,7 +41,7 @@ class Output:
 
 
 class InstanceNorm(torch.nn.Module):
-    """``(x - mean) / std`` over ``dim`` (tssep/train/net.py:250-285); CUDA path: last axis."""
+    """``(x - mean) / std`` over ``dim`` (tssep/train/net.py:250-285): population std unless ``unbiased``."""
 
     def __init__(self, dim=-1, unbiased=False):
         super().__init__()
@@ -54,9 +52,31 @@ class InstanceNorm(torch.nn.Module):
         return f"dim={self.dim!r}, unbiased={self.unbiased!r}"
 
     def forward(self, x):
-        if self.dim not in (-1, x.dim() - 1):
-            raise NotImplementedError("InstanceNorm on the CUDA path normalises the last axis only")
-        return ops.instance_norm(x, self.unbiased)
+        if not isinstance(self.dim, int):
+            raise NotImplementedError("InstanceNorm over several axes at once is not implemented on the CUDA path")
+        return ops.instance_norm(x, self.unbiased, dim=self.dim).to(x.dtype)
+
+
+class InstanceNorm_v2(torch.nn.Module):
+    """Mean removal over ``mean_dim``, then division by the root mean square over ``norm_dim``
+    (tssep/train/net.py:288-330; equals ``InstanceNorm`` when both axes coincide)."""
+
+    def __init__(self, mean_dim=-1, norm_dim=-1):
+        super().__init__()
+        self.mean_dim = mean_dim
+        self.norm_dim = norm_dim
+
+    def extra_repr(self):
+        return f"mean_dim={self.mean_dim!r}, norm_dim={self.norm_dim!r}"
+
+    def forward(self, x):
+        if not isinstance(self.mean_dim, int) or not isinstance(self.norm_dim, int):
+            # the reference itself cannot run this (x.shape[tuple] raises, net.py:326)
+            raise NotImplementedError("InstanceNorm_v2 over several axes at once")
+        if self.mean_dim % x.dim() == self.norm_dim % x.dim():
+            return ops.instance_norm(x, False, dim=self.mean_dim).to(x.dtype)
+        y = ops.instance_norm(x, dim=self.mean_dim, mode=1)
+        return ops.instance_norm(y, dim=self.norm_dim, mode=2).to(x.dtype)
 
 
 class _Einop(torch.nn.Module):
@@ -198,6 +218,14 @@ class MaskEstimator_v2(Configurable, torch.nn.Module):
     def extra_repr(self) -> str:
         return f"combination={self.combination!r},"
 
+    def invalidate_caches(self):
+        """Drops every packed weight copy.  The caches notice ``load_state_dict`` / ``.to()`` / optimizer steps on their
+        own (``rnnp.param_key``); in-place edits through ``.data`` are the one case that needs this call."""
+        self._head_cache = self._rot_cache = None
+        for m in self.modules():
+            if isinstance(m, RNNP_packed):
+                m.invalidate_caches()
+
     # -- derived weight caches -------------------------------------------------
     def _birnns(self):
         return [m for n, m in self.post_net.named_children() if n.startswith("birnn")]
@@ -229,7 +257,7 @@ class MaskEstimator_v2(Configurable, torch.nn.Module):
 
     def _rotated_input_weights(self, pk, K, R):
         """R column-rotated copies of the speaker-concat layer's W_ih, stacked on rows."""
-        key = (id(pk), K, R)
+        key = (param_key(self._birnns()[-1]), K, R)
         if self._rot_cache is None or self._rot_cache[0] != key:
             with torch.no_grad():
                 P = pk.I // K
@@ -255,10 +283,11 @@ class MaskEstimator_v2(Configurable, torch.nn.Module):
         a generator of ``(lo, hi, Output)`` for items [lo, hi).
 
         The recurrences cost T dependent steps whatever their batch; a step advances up to
-        ``ops.recurrence_ts_capacity`` rows at the same latency.  All recurrent layers therefore run ONCE
-        for all B items (with ``TSSEP_NET_LAYOUT=bt`` the K-rows-per-item layers run per ``wave`` items, which
-        bounds their G buffer), and the head writes each wave's logit / mask when the consumer asks for it, so the big
-        outputs of one wave can be dropped before the next is produced.  ``out_wave`` (default ``wave``)
+        ``ops.recurrence_ts_capacity`` rows at the same latency.  pre_net and the TS-VAD layer (1 and R rows per
+        item) run ONCE for all B items, the K-rows-per-item layers per ``wave`` items (their input projections G are
+        the largest buffer of the path: 0.36 GB per 10-min meeting, speaker and layer), and the head writes each output
+        wave's logit / mask when the consumer asks for it, so the big outputs of one wave can be dropped before the
+        next is produced.  ``out_wave`` (default ``wave``)
         is the number of items per yielded ``Output``: smaller output waves bound the memory of the
         GB-sized logit / mask tensors without touching the recurrence batching.  Results are independent
         of ``wave`` and ``out_wave``; speaker permutations are drawn for all items up front, in order.
@@ -330,124 +359,90 @@ class MaskEstimator_v2(Configurable, torch.nn.Module):
             F = Din
 
         birnns = self._birnns()
-        pk0 = birnns[0].layer_packs()[0]
+        packs = [m.layer_packs()[0] for m in birnns]
+        pk0 = packs[0]
         Up = pk0.Up
         e = aux_p.reshape(B * K, A).contiguous()
         stream = _lib.stream_of(xb)
         P = self.projs
         ldp = ops.operand_ld(P)
-        mode = {"mul": 0, "cat": 1}[self.combination]
         if self.combination == "mul":
             assert A == F, ("combination='mul' needs aux_size == odim", A, F)
         else:
             assert pk0.I == F + A, (pk0.I, F, A)
-        start_l = 0
-        y, y_ld, G = None, None, None
+        tsv = self.ts_vad is not False
+        n_indep = L - 1 if tsv else L  # layers that treat every (item, speaker) row on its own
         wave = B if wave is None else max(1, min(int(wave), B))
-        # Default: the fold-embedding path below for every batch size (plain (row, t) layouts all the way, the
-        # conditioning folded into birnn0's input weights, nothing materialised).  TSSEP_NET_LAYOUT=bt selects the
-        # (group, t, b32) tile layout from 17 rows on: conditioned rows materialised, one pass per wave of items
-        # (measured 5.7 % slower per step; kept for A/B runs and for devices where only a wave's G buffer fits).
-        if L >= 2 and use_tc_recurrence(wave * K) and os.environ.get("TSSEP_NET_LAYOUT", "rows") == "bt":
-            # ---- throughput path for the speaker-independent layers (all but the last) ---------------
-            # rows ordered (group, t, b32), z = group*32 + b = item*K + speaker: the conditioned rows are
-            # materialised once in bf16 (net.py:862-896), every input projection writes G with the batch
-            # row innermost, the recurrence runs on tcgen05 with the recurrent weights in tensor memory.
-            # One pass per wave of items; all waves write into the same output of the last of these layers.
-            if self.ts_vad is not False:
-                y_ld = ops.operand_ld(K * P)   # speaker-concat layout (B, T, K*P)   net.py:606-612
-                y = torch.empty((B * T, y_ld), dtype=torch.bfloat16, device=dev)
-            else:
-                y_ld = ldp
-                y = torch.empty((B * K * T, y_ld), dtype=torch.bfloat16, device=dev)
-            ld0 = ops.operand_ld(pk0.I)
-            for lo in range(0, B, wave):
-                hi = min(B, lo + wave)
-                Z = (hi - lo) * K
-                groups = (Z + 31) // 32
-                mrows = groups * T * 32
-                a0 = torch.empty((mrows, ld0), dtype=torch.bfloat16, device=dev)
-                _lib.call("tssep_condition_rows", mode, xb[lo * T:].data_ptr(), ld, e[lo * K:].data_ptr(), Z, K, T, F, A,
-                          a0.data_ptr(), ld0, stream)
-                yw, yw_ld = a0, ld0
-                del a0
-                for l in range(L - 1):
-                    pk = birnns[l].layer_packs()[0]
-                    G = pk.input_gemm_bt(yw, yw_ld, mrows)
-                    del yw  # the layer input is dead once its projection exists (G is the largest buffer of the path)
-                    H = pk.recurrence_tc(G, Z, T)
-                    del G
-                    if l < L - 2:
-                        yw_ld = ldp
-                        yw = torch.empty((mrows, yw_ld), dtype=torch.bfloat16, device=dev)
-                        pk.projection(H, mrows, yw, mode=ops.EPI_BF16, ldo=yw_ld, act=1)
-                    elif self.ts_vad is not False:
-                        pk.projection(H, mrows, y[lo * T:], mode=ops.EPI_BF16_ROWMAP, ldo=y_ld, act=1,
-                                      row_map=(T, K, Z, P))
-                    else:
-                        pk.projection(H, mrows, y[lo * K * T:], mode=ops.EPI_BF16_ROWMAP, ldo=y_ld, act=1,
-                                      row_map=(T, 1, Z, 0))
-                    del H
-                yw = None
-            start_l = L - 1
-        else:
-            # ---- latency path: conditioning folded into birnn0's input projection ----------------------
-            bias_k = torch.empty((B * K, 8 * Up), dtype=torch.float32, device=dev)
-            gd = ops.g_dtype()
-            gmode = ops.EPI_BF16 if gd == torch.bfloat16 else ops.EPI_F32
-            G = torch.empty((B * K * T, 8 * Up), dtype=gd, device=dev)
+        gd = ops.g_dtype()
+        gmode = ops.EPI_BF16 if gd == torch.bfloat16 else ops.EPI_F32
+        # output of the speaker-independent layers for ALL items: speaker-concat rows (B, T, K*P) for the TS-VAD layer
+        # (net.py:606-612), plain (B*K, T, P) rows otherwise
+        y_ld = ops.operand_ld(K * P) if tsv else ldp
+        y = torch.empty((B * T if tsv else B * K * T, y_ld), dtype=torch.bfloat16, device=dev)
+
+        # ---- speaker-independent layers, `wave` items at a time (their G buffer is the largest of the path) ----
+        for lo in range(0, B, wave):
+            hi = min(B, lo + wave)
+            Bw = hi - lo
+            rows = Bw * K
+            # birnn0 with the conditioning folded into its input projection (net.py:862-896): 'mul' scales the weight
+            # columns per speaker, 'cat' turns the embedding half of the weight into a per-speaker bias
+            bias_k = torch.empty((rows, 8 * Up), dtype=torch.float32, device=dev)
+            G = torch.empty((rows * T, 8 * Up), dtype=gd, device=dev)
+            e_w = e[lo * K:hi * K]
+            x_w = xb[lo * T:]
             if self.combination == "mul":
                 ldk = ops.operand_ld(F)
-                Wk = torch.empty((B * K * 8 * Up, ldk), dtype=torch.bfloat16, device=dev)
+                Wk = torch.empty((rows * 8 * Up, ldk), dtype=torch.bfloat16, device=dev)
                 _lib.call("tssep_fold_embedding", 0, pk0.w_ih_f32.data_ptr(), pk0.I, pk0.bias.data_ptr(),
-                          e.data_ptr(), B * K, 8 * Up, F, A, Wk.data_ptr(), ldk, bias_k.data_ptr(), stream)
-                ops.gemm(xb, ld, Wk, ldk, T, 8 * Up, F, G, mode=gmode, ldo=8 * Up, batch=B * K,
+                          e_w.data_ptr(), rows, 8 * Up, F, A, Wk.data_ptr(), ldk, bias_k.data_ptr(), stream)
+                ops.gemm(x_w, ld, Wk, ldk, T, 8 * Up, F, G, mode=gmode, ldo=8 * Up, batch=rows,
                          a_stride=T * ld, a_div=K, b_stride=8 * Up * ldk, bias=bias_k, bias_stride=8 * Up,
                          out_stride=T * 8 * Up)
                 del Wk
             else:  # cat
                 _lib.call("tssep_fold_embedding", 1, pk0.w_ih_f32.data_ptr(), pk0.I, pk0.bias.data_ptr(),
-                          e.data_ptr(), B * K, 8 * Up, F, A, None, 0, bias_k.data_ptr(), stream)
-                ops.gemm(xb, ld, pk0.w_ih, pk0.ld_in, T, 8 * Up, F, G, mode=gmode, ldo=8 * Up, batch=B * K,
+                          e_w.data_ptr(), rows, 8 * Up, F, A, None, 0, bias_k.data_ptr(), stream)
+                ops.gemm(x_w, ld, pk0.w_ih, pk0.ld_in, T, 8 * Up, F, G, mode=gmode, ldo=8 * Up, batch=rows,
                          a_stride=T * ld, a_div=K, b_stride=0, bias=bias_k, bias_stride=8 * Up,
                          out_stride=T * 8 * Up)
+            yw, yw_ld = None, None
+            for l in range(n_indep):
+                pk = packs[l]
+                if l > 0:
+                    G = pk.input_gemm(yw, yw_ld, rows * T)
+                    del yw
+                H = pk.recurrence(G, rows, T)
+                del G
+                if l < n_indep - 1:
+                    yw_ld = ldp
+                    yw = torch.empty((rows * T, yw_ld), dtype=torch.bfloat16, device=dev)
+                    pk.projection(H, rows * T, yw, mode=ops.EPI_BF16, ldo=yw_ld, act=1)
+                elif tsv:
+                    # tanh(proj) straight into the speaker-concat layout (B, T, K*P)   net.py:606-612
+                    pk.projection(H, 0, y[lo * T:], mode=ops.EPI_BF16, ldo=y_ld, act=1, batch=rows,
+                                  a_stride=T * 2 * pk.Up, M=T, out_stride=P, out_div=K, out_stride_hi=T * y_ld)
+                else:
+                    pk.projection(H, rows * T, y[lo * K * T:], mode=ops.EPI_BF16, ldo=y_ld, act=0)
+                del H
         del xb
 
-        rows = B * K
-        for l in range(start_l, L):
-            pk = birnns[l].layer_packs()[0]
-            last = l == L - 1
-            tsv_last = last and self.ts_vad is not False
-            if l > 0:
-                if tsv_last:
-                    rot = self._rotated_input_weights(pk, K, R)
-                    rows = B * R
-                    gd = ops.g_dtype()
-                    G = torch.empty((rows * T, 8 * pk.Up), dtype=gd, device=dev)
-                    ops.gemm(y, y_ld, rot["w"], rot["ld"], T, 8 * pk.Up, K * P, G,
-                             mode=ops.EPI_BF16 if gd == torch.bfloat16 else ops.EPI_F32, ldo=8 * pk.Up,
-                             batch=rows, a_stride=T * y_ld, a_div=R, b_stride=8 * pk.Up * rot["ld"], b_mod=R,
-                             bias=pk.bias, bias_stride=0, out_stride=T * 8 * pk.Up)
-                else:
-                    G = pk.input_gemm(y, y_ld, rows * T)
+        # ---- TS-VAD layer: all speakers of an item in one row, R cyclic speaker orders as R rotated weight copies ----
+        if tsv:
+            pk = packs[L - 1]
+            rot = self._rotated_input_weights(pk, K, R)
+            rows = B * R
+            G = torch.empty((rows * T, 8 * pk.Up), dtype=gd, device=dev)
+            ops.gemm(y, y_ld, rot["w"], rot["ld"], T, 8 * pk.Up, K * P, G, mode=gmode, ldo=8 * pk.Up,
+                     batch=rows, a_stride=T * y_ld, a_div=R, b_stride=8 * pk.Up * rot["ld"], b_mod=R,
+                     bias=pk.bias, bias_stride=0, out_stride=T * 8 * pk.Up)
             H = pk.recurrence(G, rows, T)
             del G
-            if not last and l == L - 2 and self.ts_vad is not False:
-                # write tanh(proj) straight into the speaker-concat layout (B, T, K*P)   net.py:606-612
-                y_ld = ops.operand_ld(K * P)
-                y = torch.empty((B * T, y_ld), dtype=torch.bfloat16, device=dev)
-                pk.projection(H, 0, y, mode=ops.EPI_BF16, ldo=y_ld, act=1, batch=rows, a_stride=T * 2 * pk.Up, M=T,
-                              out_stride=P, out_div=K, out_stride_hi=T * y_ld)
-            elif tsv_last:
-                # trial-concat layout (B, T, R*P) feeding the averaged head
-                y_ld = ops.operand_ld(R * P)
-                y = torch.empty((B * T, y_ld), dtype=torch.bfloat16, device=dev)
-                pk.projection(H, 0, y, mode=ops.EPI_BF16, ldo=y_ld, act=0, batch=rows, a_stride=T * 2 * pk.Up, M=T,
-                              out_stride=P, out_div=R, out_stride_hi=T * y_ld)
-            else:
-                y_ld = ldp
-                y = torch.empty((rows * T, y_ld), dtype=torch.bfloat16, device=dev)
-                pk.projection(H, rows * T, y, mode=ops.EPI_BF16, ldo=y_ld, act=0 if last else 1)
+            # trial-concat layout (B, T, R*P) feeding the averaged head
+            y_ld = ops.operand_ld(R * P)
+            y = torch.empty((B * T, y_ld), dtype=torch.bfloat16, device=dev)
+            pk.projection(H, 0, y, mode=ops.EPI_BF16, ldo=y_ld, act=0, batch=rows, a_stride=T * 2 * pk.Up, M=T,
+                          out_stride=P, out_div=R, out_stride_hi=T * y_ld)
             del H
 
         # head: Linear + rearrange + trial mean + un-permute + sigmoid (net.py:629-668, :928-986), per wave

@@ -12,7 +12,7 @@ import os
 import torch
 
 from . import _lib
-from ._lib import EPI_BF16, EPI_BF16_BT, EPI_BF16_ROWMAP, EPI_F32, EPI_F32_BT, EPI_HEAD, GemmDesc
+from ._lib import EPI_BF16, EPI_F32, EPI_HEAD, GemmDesc
 
 
 def round_up(x: int, m: int) -> int:
@@ -22,8 +22,9 @@ def round_up(x: int, m: int) -> int:
 def g_dtype() -> torch.dtype:
     """Storage type of the input projections G between the GEMM and the recurrence
     (TSSEP_G_DTYPE=bf16|f32, default bf16).  bf16 halves the largest intermediate of the path (2.9 GB per
-    meeting and layer in f32), which is what lets 28 ten-minute meetings share one 180 GB GPU; measured
-    parity is unchanged (max|dmask| 1.3e-4 toy / 5.4e-5 full size with either type)."""
+    meeting and layer in f32) and is what the tensor-memory recurrence consumes (G is an MMA operand there);
+    f32 routes every recurrence through the register-resident kernel (csrc/lstm.cu) -- a parity-test knob that
+    separates the rounding of G from everything else."""
     return torch.float32 if os.environ.get("TSSEP_G_DTYPE", "bf16") == "f32" else torch.bfloat16
 
 
@@ -40,7 +41,7 @@ def _gemm_impl() -> int:
 
 def gemm(A, lda, B, ldb, M, N, K, out, *, mode, ldo=0, batch=1, a_stride=0, a_div=1, b_stride=0, b_mod=None,
          bias=None, bias_stride=0, alpha=1.0, act=0, out_stride=0, out_div=None, out_stride_hi=0, mask=None,
-         plane_map=None, n_blocks=0, row_len=0, row_map=None, impl=None):
+         plane_map=None, n_blocks=0, row_len=0, impl=None, max_ctas=0):
     """``tssep_gemm``: out[z] = act(alpha * A[z / a_div] . B[z % b_mod]^T + bias[z % b_mod])."""
     _lib.require_cuda(A, B, out, bias, mask, plane_map)
     d = GemmDesc()
@@ -52,9 +53,8 @@ def gemm(A, lda, B, ldb, M, N, K, out, *, mode, ldo=0, batch=1, a_stride=0, a_di
     d.out, d.ldo, d.out_stride, d.out_stride_hi = _lib.ptr(out), ldo, out_stride, out_stride_hi
     d.out_div = batch if out_div is None else out_div
     d.mask, d.plane_map, d.n_blocks, d.row_len = _lib.ptr(mask), _lib.ptr(plane_map), n_blocks, row_len
-    if row_map is not None:  # (T, K, Z, P) of EPI_BF16_ROWMAP
-        d.rm_T, d.rm_K, d.rm_Z, d.rm_P = row_map
     d.impl = _gemm_impl() if impl is None else impl
+    d.max_ctas = max_ctas
     _lib.call("tssep_gemm", C.byref(d), _lib.stream_of(A), detail=f"M={M} N={N} K={K} batch={batch} mode={mode}")
 
 
@@ -85,7 +85,7 @@ def blstm_recurrence(G: torch.Tensor, wfrag: torch.Tensor, rows: int, T: int, Up
     if cluster is None:
         cluster = int(os.environ.get("TSSEP_LSTM_CLUSTER", "0"))
     if fast_math is None:
-        fast_math = os.environ.get("TSSEP_LSTM_FAST_MATH", "1") == "1"
+        fast_math = fast_math_default()
     H = torch.empty((rows, T, 2 * Up), dtype=torch.bfloat16, device=G.device)
     _lib.call("tssep_blstm_recurrence", G.data_ptr(), int(G.dtype == torch.bfloat16), wfrag.data_ptr(), H.data_ptr(),
               rows, T, Up, cluster,
@@ -93,28 +93,10 @@ def blstm_recurrence(G: torch.Tensor, wfrag: torch.Tensor, rows: int, T: int, Up
     return H
 
 
-def pack_whh_tc(w_fwd: torch.Tensor, w_bwd: torch.Tensor, U: int, Up: int) -> torch.Tensor:
-    """Shared-memory image of W_hh for the tcgen05 recurrence (pre-swizzled UMMA A operands)."""
-    _lib.require_cuda(w_fwd, w_bwd)
-    c = (Up + 63) // 64
-    out = torch.empty(2 * c * 2 * c * 8192, dtype=torch.bfloat16, device=w_fwd.device)
-    _lib.call("tssep_pack_whh_tc", w_fwd.contiguous().data_ptr(), w_bwd.contiguous().data_ptr(), U, Up,
-              out.data_ptr(), _lib.stream_of(w_fwd))
-    return out
-
-
-def blstm_recurrence_tc(G: torch.Tensor, wimg: torch.Tensor, rows: int, T: int, Up: int,
-                        fast_math: bool = None) -> torch.Tensor:
-    """tcgen05 variant: G in the EPI_F32_BT tile layout -> H (groups*T*32, 2*Up) bf16, rows (group, t, b)."""
-    _lib.require_cuda(G, wimg)
-    if fast_math is None:
-        fast_math = os.environ.get("TSSEP_LSTM_FAST_MATH", "1") == "1"
-    groups = (rows + 31) // 32
-    H = torch.empty((groups * T * 32, 2 * Up), dtype=torch.bfloat16, device=G.device)
-    _lib.call("tssep_blstm_recurrence_tc", G.data_ptr(), int(G.dtype == torch.bfloat16), wimg.data_ptr(), H.data_ptr(),
-              rows, T, Up, int(fast_math),
-              _lib.stream_of(G))
-    return H
+def fast_math_default() -> bool:
+    """Gate arithmetic of the recurrences: tanh.approx.f32 (max relative error 2^-11) unless TSSEP_LSTM_FAST_MATH=0
+    selects the exp-based sigmoid / tanh."""
+    return os.environ.get("TSSEP_LSTM_FAST_MATH", "1") == "1"
 
 
 def pack_whh_ts(w_fwd: torch.Tensor, w_bwd: torch.Tensor, U: int, Up: int) -> torch.Tensor:
@@ -128,44 +110,44 @@ def pack_whh_ts(w_fwd: torch.Tensor, w_bwd: torch.Tensor, U: int, Up: int) -> to
 
 
 def blstm_recurrence_ts(G: torch.Tensor, wimg: torch.Tensor, rows: int, T: int, Up: int,
-                        fast_math: bool = None, rows_per_cluster: int = 0, layout: str = "bt") -> torch.Tensor:
-    """Tensor-memory recurrence.  layout "bt": G in the BT tile layout -> H (groups*T*32, 2*Up) bf16, rows
-    (group, t, b), padding rows the kernel does not compute are zero.  layout "rows": G (rows, T, 8*Up) bf16
-    -> H (rows, T, 2*Up), the layouts of ``blstm_recurrence``."""
+                        fast_math: bool = None, rows_per_cluster: int = 0, k_split: int = -1) -> torch.Tensor:
+    """Tensor-memory recurrence: G (rows, T, 2, 4, Up) bf16 -> H (rows, T, 2*Up) bf16."""
     _lib.require_cuda(G, wimg)
+    if G.dtype != torch.bfloat16:
+        raise TypeError(f"the tensor-memory recurrence consumes bf16 input projections, got {G.dtype}")
     if fast_math is None:
-        fast_math = os.environ.get("TSSEP_LSTM_FAST_MATH", "1") == "1"
-    if layout == "rows":
-        H = torch.empty((rows, T, 2 * Up), dtype=torch.bfloat16, device=G.device)
-    else:
-        groups = (rows + 31) // 32
-        H = torch.empty((groups * T * 32, 2 * Up), dtype=torch.bfloat16, device=G.device)
-        done = ((rows + 15) // 16) * 16  # the kernel computes whole 16-row blocks at least
-        if done < groups * 32:
-            H.view(groups, T, 32, 2 * Up)[-1, :, done - (groups - 1) * 32:].zero_()
-    _lib.call("tssep_blstm_recurrence_ts", G.data_ptr(), int(G.dtype == torch.bfloat16), wimg.data_ptr(), H.data_ptr(),
-              rows, T, Up, {"bt": 0, "rows": 1}[layout], rows_per_cluster, int(fast_math), _lib.stream_of(G),
-              detail=f"rows={rows} T={T} layout={layout}")
+        fast_math = fast_math_default()
+    H = torch.empty((rows, T, 2 * Up), dtype=torch.bfloat16, device=G.device)
+    _lib.call("tssep_blstm_recurrence_ts", G.data_ptr(), wimg.data_ptr(), H.data_ptr(), rows, T, Up, rows_per_cluster,
+              int(fast_math), k_split, _lib.stream_of(G), detail=f"rows={rows} T={T}")
     return H
 
 
-def recurrence_ts_capacity(Up: int, rows_per_cluster: int = 16, g_bf16: bool = True) -> int:
+def recurrence_ts_capacity(Up: int, rows_per_cluster: int = 16) -> int:
     """Batch rows one launch of the tensor-memory recurrence advances in a single wave of clusters."""
-    n = _lib.load().tssep_blstm_recurrence_ts_capacity(Up, rows_per_cluster, int(g_bf16))
+    n = _lib.load().tssep_blstm_recurrence_ts_capacity(Up, rows_per_cluster)
     if n < 0:
         _lib.check(n, "tssep_blstm_recurrence_ts_capacity")
     return n
 
 
-def instance_norm(x: torch.Tensor, unbiased=False) -> torch.Tensor:
+def instance_norm(x: torch.Tensor, unbiased=False, dim: int = -1, mode: int = 0) -> torch.Tensor:
+    """Normalisation along ``dim`` (``tssep_instance_norm``): mode 0 (x - mean) / std, 1 x - mean, 2 x / rms."""
     _lib.require_cuda(x)
     x = x.contiguous().float()
-    cols = x.shape[-1]
-    rows = x.numel() // cols
+    dim = dim % x.dim()
+    cols = x.shape[dim]
+    outer = 1
+    for n in x.shape[:dim]:
+        outer *= n
+    inner = 1
+    for n in x.shape[dim + 1:]:
+        inner *= n
     out = torch.empty_like(x)
-    _lib.call("tssep_instance_norm", x.data_ptr(), rows, cols, int(bool(unbiased)), out.data_ptr(), _lib.stream_of(x))
+    _lib.call("tssep_instance_norm", x.data_ptr(), outer, cols, inner, mode, int(bool(unbiased)), out.data_ptr(),
+              _lib.stream_of(x))
     return out
 
 
-__all__ = ["gemm", "cast_bf16", "operand_ld", "pack_whh", "blstm_recurrence", "pack_whh_tc", "blstm_recurrence_tc", "pack_whh_ts", "blstm_recurrence_ts", "recurrence_ts_capacity", "instance_norm", "round_up", "EPI_F32", "EPI_BF16",
-           "EPI_HEAD", "EPI_F32_BT", "EPI_BF16_ROWMAP", "EPI_BF16_BT"]
+__all__ = ["gemm", "cast_bf16", "operand_ld", "pack_whh", "blstm_recurrence", "pack_whh_ts", "blstm_recurrence_ts",
+           "recurrence_ts_capacity", "instance_norm", "round_up", "fast_math_default", "EPI_F32", "EPI_BF16", "EPI_HEAD"]

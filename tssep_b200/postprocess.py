@@ -29,22 +29,29 @@ class Diarization:
         return [[(int(a), int(b)) for a, b in s[: min(c, s.shape[0])]] for s, c in zip(seg, cnt)]
 
 
-def diarize(mask: torch.Tensor, fe, *, num_samples=None, threshold=0.5, median_width=1, max_segments=256) -> Diarization:
-    """mask (..., K, 1, T, F) float32 on the device."""
-    _lib.require_cuda(mask)
+def diarize(mask: torch.Tensor, fe, *, num_samples=None, threshold=0.5, median_width=1, max_segments=256,
+            activity: torch.Tensor = None) -> Diarization:
+    """mask (..., K, 1, T, F) float32 on the device.  ``activity`` (..., K, T): the frame activity when the enhancement
+    kernel already produced it (``Masking.apply(activity_out=...)``); the mask is then not read again."""
+    _lib.require_cuda(mask, activity)
     if mask.shape[-3] != 1:
         raise ValueError(f"expected nmask == 1, got {tuple(mask.shape)}")
-    m = mask.float().contiguous()
-    lead = m.shape[:-3]
-    T, F = m.shape[-2:]
-    n = m.numel() // (T * F)
-    dev, stream = m.device, _lib.stream_of(m)
-    act = torch.empty((*lead, T), dtype=torch.float32, device=dev)
+    lead = mask.shape[:-3]
+    T, F = mask.shape[-2:]
+    n = mask.numel() // (T * F)
+    dev, stream = mask.device, _lib.stream_of(mask)
+    if activity is None:
+        m = mask.float().contiguous()
+        act = torch.empty((*lead, T), dtype=torch.float32, device=dev)
+        _lib.call("tssep_activity", m.data_ptr(), n, T, F, act.data_ptr(), stream)
+    else:
+        if tuple(activity.shape) != (*lead, T) or activity.dtype != torch.float32 or not activity.is_contiguous():
+            raise ValueError(f"activity must be a contiguous float32 tensor of shape {(*lead, T)}")
+        act = activity
     smooth = torch.empty_like(act)
     active = torch.empty((*lead, T), dtype=torch.uint8, device=dev)
     seg = torch.zeros((*lead, max_segments, 2), dtype=torch.int32, device=dev)
     cnt = torch.empty(lead, dtype=torch.int32, device=dev)
-    _lib.call("tssep_activity", m.data_ptr(), n, T, F, act.data_ptr(), stream)
     _lib.call("tssep_median_threshold", act.data_ptr(), n, T, int(median_width), float(threshold), smooth.data_ptr(),
               active.data_ptr(), stream)
     _lib.call("tssep_segments", active.data_ptr(), n, T, fe.window_length, fe.shift, int(bool(fe.fading)),

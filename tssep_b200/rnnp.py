@@ -6,8 +6,7 @@ Same constructor arguments, module list (so ``repr`` and ``state_dict`` keys
 parameters; ``forward`` runs
 
     x . W_ih^T (+ b_ih + b_hh)      tcgen05 GEMM, both directions at once
-    time recurrence                 persistent cluster kernel: W_hh resident in tensor memory (csrc/lstm_ts.cu)
-                                    from 17 batch rows on, in registers (csrc/lstm.cu) below
+    time recurrence                 persistent cluster kernel, W_hh resident in tensor memory (csrc/lstm_ts.cu)
     [h_fwd | h_bwd] . W_proj^T + b  tcgen05 GEMM with fused bias (+ tanh)
 
 on bf16 operands with fp32 accumulation and fp32 cell state.
@@ -20,24 +19,18 @@ import torch
 
 from . import _lib, ops
 
-# Recurrence kernels (all compute the same operator):
-#   regs  csrc/lstm.cu     W_hh in registers, mma.sync, rows in the plain (row, t) layout
-#   ts    csrc/lstm_ts.cu  W_hh in tensor memory, tcgen05.mma with A from TMEM, rows ordered (group, t, b32)
-#   tc    csrc/lstm_tc.cu  W_hh in shared memory, tcgen05.mma (kept for A/B measurements)
-# TSSEP_LSTM_KERNEL=regs|ts|tc|auto; auto takes the tensor-memory kernel from TS_MIN_ROWS batch rows on.
-TS_MIN_ROWS = int(os.environ.get("TSSEP_TS_MIN_ROWS", "17"))
+# Recurrence kernels (both compute the same operator on the plain (row, t) layouts):
+#   ts    csrc/lstm_ts.cu  W_hh in tensor memory, tcgen05.mma, bf16 G: the product path for every row count
+#   regs  csrc/lstm.cu     W_hh in registers, mma.sync, f32 or bf16 G (Up <= 320): parity-test variant
+# TSSEP_LSTM_KERNEL=auto|ts|regs; auto = ts whenever G is bf16 (the default storage type, ops.g_dtype).
+TS_MAX_UP = 384
 
 
-def rec_kernel(rows: int) -> str:
+def rec_kernel(g_dtype: torch.dtype = torch.bfloat16, Up: int = 0) -> str:
     choice = os.environ.get("TSSEP_LSTM_KERNEL", "auto")
     if choice == "auto":
-        return "ts" if rows >= TS_MIN_ROWS else "regs"
+        return "ts" if g_dtype == torch.bfloat16 and Up <= TS_MAX_UP else "regs"
     return choice
-
-
-def use_tc_recurrence(rows: int) -> bool:
-    """True when the recurrence runs on a tcgen05 kernel, i.e. on rows ordered (group, t, b32)."""
-    return rec_kernel(rows) in ("ts", "tc")
 
 
 class LayerPack:
@@ -46,8 +39,9 @@ class LayerPack:
     def __init__(self, lstm: torch.nn.LSTM, linear: torch.nn.Linear):
         U, I = lstm.hidden_size, lstm.input_size
         Up = ops.round_up(U, 16)
-        if Up > 320:
-            raise NotImplementedError(f"hidden size {U} > 320 is not supported by the recurrence kernel yet")
+        if Up > TS_MAX_UP:
+            raise NotImplementedError(f"hidden size {U} > {TS_MAX_UP} exceeds the tensor-memory budget of the recurrence "
+                                      "kernel (include/tssep_b200.h, tssep_blstm_recurrence_ts)")
         dev = lstm.weight_ih_l0.device
         _lib.require_cuda(lstm.weight_ih_l0)
         self.U, self.Up, self.I = U, Up, I
@@ -65,9 +59,7 @@ class LayerPack:
             self.w_ih = ops.cast_bf16(self.w_ih_f32, self.ld_in)
             self._whh_f32 = (lstm.weight_hh_l0.detach().float().contiguous(),
                              lstm.weight_hh_l0_reverse.detach().float().contiguous())
-            self.whh = ops.pack_whh(self._whh_f32[0], self._whh_f32[1], U, Up)
-            self.whh_tc = self.whh_ts = None  # built on first use by the tcgen05 recurrences
-            self.w_ih_tc = self.bias_tc = None
+            self.whh_regs = self.whh_ts = None  # packed on first use by the respective kernel
             wp = torch.zeros((self.hdim, 2 * Up), dtype=torch.float32, device=dev)
             wp[:, :U] = linear.weight.detach().float()[:, :U]
             wp[:, Up:Up + U] = linear.weight.detach().float()[:, U:]
@@ -76,7 +68,7 @@ class LayerPack:
 
     # -- the three stages ------------------------------------------------------
     def input_gemm(self, xb: torch.Tensor, ld: int, rows_t: int) -> torch.Tensor:
-        """xb (rows*T, ld) bf16 -> G (rows*T, 8*Up) f32."""
+        """xb (rows*T, ld) bf16 -> G (rows*T, 8*Up) bf16 (f32 with TSSEP_G_DTYPE=f32)."""
         gd = ops.g_dtype()
         G = torch.empty((rows_t, 8 * self.Up), dtype=gd, device=xb.device)
         ops.gemm(xb, ld, self.w_ih, self.ld_in, rows_t, 8 * self.Up, self.I, G,
@@ -84,48 +76,29 @@ class LayerPack:
         return G
 
     def recurrence(self, G: torch.Tensor, rows: int, T: int) -> torch.Tensor:
-        """G (rows, T, 8Up) -> H (rows, T, 2Up): the tensor-memory kernel (csrc/lstm_ts.cu, row layout) from
-        TS_MIN_ROWS rows on when G is bf16, else the register-resident mma.sync kernel (csrc/lstm.cu)."""
-        if rec_kernel(rows) == "ts" and G.dtype == torch.bfloat16:
+        """G (rows, T, 8Up) -> H (rows, T, 2Up)."""
+        if rec_kernel(G.dtype, self.Up) == "ts":
             if self.whh_ts is None:
                 self.whh_ts = ops.pack_whh_ts(self._whh_f32[0], self._whh_f32[1], self.U, self.Up)
-            return ops.blstm_recurrence_ts(G, self.whh_ts, rows, T, self.Up, layout="rows")
-        return ops.blstm_recurrence(G, self.whh, rows, T, self.Up)
-
-    # -- throughput path: rows ordered (group, t, b32), weights in shared memory, tcgen05 -------------
-    def input_gemm_bt(self, xb: torch.Tensor, ld: int, mrows: int, kdim: int = None) -> torch.Tensor:
-        """xb (groups*T*32, ld) bf16 -> G (groups, T, 8Up, 32) f32 (batch row innermost)."""
-        if self.w_ih_tc is None:
-            # column order of the tcgen05 recurrence: n = dir*4Up + (unit/8)*32 + (unit%8)*4 + gate
-            Up = self.Up
-            w = self.w_ih_f32.view(2, 4, Up // 8, 8, self.I).permute(0, 2, 3, 1, 4).reshape(8 * Up, self.I)
-            self.w_ih_tc = ops.cast_bf16(w.contiguous(), self.ld_in)
-            self.bias_tc = self.bias.view(2, 4, Up // 8, 8).permute(0, 2, 3, 1).reshape(8 * Up).contiguous()
-        gd = ops.g_dtype()
-        G = torch.empty((mrows * 8 * self.Up,), dtype=gd, device=xb.device)
-        ops.gemm(xb, ld, self.w_ih_tc, self.ld_in, mrows, 8 * self.Up, self.I if kdim is None else kdim, G,
-                 mode=ops.EPI_BF16_BT if gd == torch.bfloat16 else ops.EPI_F32_BT, bias=self.bias_tc)
-        return G
-
-    def recurrence_tc(self, G: torch.Tensor, rows: int, T: int) -> torch.Tensor:
-        """tcgen05 kernels (csrc/lstm_ts.cu, csrc/lstm_tc.cu): H (groups*T*32, 2Up), rows (group, t, b)."""
-        if rec_kernel(rows) == "tc":
-            if self.whh_tc is None:
-                self.whh_tc = ops.pack_whh_tc(self._whh_f32[0], self._whh_f32[1], self.U, self.Up)
-            return ops.blstm_recurrence_tc(G, self.whh_tc, rows, T, self.Up)
-        if self.whh_ts is None:
-            self.whh_ts = ops.pack_whh_ts(self._whh_f32[0], self._whh_f32[1], self.U, self.Up)
-        return ops.blstm_recurrence_ts(G, self.whh_ts, rows, T, self.Up)
+            # host-side tuning knobs, handed to the library as explicit arguments (0 / -1 = let it choose)
+            return ops.blstm_recurrence_ts(G, self.whh_ts, rows, T, self.Up,
+                                           rows_per_cluster=int(os.environ.get("TSSEP_TS_ROWS", "0")),
+                                           k_split=int(os.environ.get("TSSEP_TS_KSPLIT", "-1")))
+        if self.whh_regs is None:
+            self.whh_regs = ops.pack_whh(self._whh_f32[0], self._whh_f32[1], self.U, self.Up)
+        return ops.blstm_recurrence(G, self.whh_regs, rows, T, self.Up)
 
     def projection(self, H: torch.Tensor, rows_t: int, out: torch.Tensor, *, mode: int, ldo: int, act: int,
-                   batch=1, a_stride=0, M=None, out_stride=0, out_div=None, out_stride_hi=0, row_map=None):
+                   batch=1, a_stride=0, M=None, out_stride=0, out_div=None, out_stride_hi=0):
         """H (rows*T, 2*Up) bf16 -> out (bias and optional tanh fused)."""
         ops.gemm(H, 2 * self.Up, self.w_proj, 2 * self.Up, rows_t if M is None else M, self.hdim, 2 * self.Up, out,
                  mode=mode, ldo=ldo, bias=self.b_proj, act=act, batch=batch, a_stride=a_stride, b_mod=1,
-                 out_stride=out_stride, out_div=out_div, out_stride_hi=out_stride_hi, row_map=row_map)
+                 out_stride=out_stride, out_div=out_div, out_stride_hi=out_stride_hi)
 
 
 def param_key(module: torch.nn.Module):
+    """Identity + version + storage of every parameter.  In-place edits THROUGH ``.data`` (``p.data.copy_()``) bump
+    neither: call ``invalidate_caches()`` on the owning module after such an edit."""
     return tuple((id(p), p._version, p.data_ptr()) for p in module.parameters())
 
 
@@ -164,6 +137,10 @@ class RNNP_packed(torch.nn.Module):
         self.dropout, self.return_states = dropout, return_states
         self._packs, self._packs_key = None, None
 
+    def invalidate_caches(self):
+        """Drops the packed weight copies (needed only after in-place edits through ``.data``, see ``param_key``)."""
+        self._packs, self._packs_key = None, None
+
     def layer_packs(self):
         """Kernel-ready weights; rebuilt whenever a parameter was modified, moved or reloaded."""
         key = param_key(self)
@@ -192,11 +169,6 @@ class RNNP_packed(torch.nn.Module):
             rows *= s
         x = xs_pack.reshape(rows * T, D).float()
         packs = self.layer_packs()
-        # TSSEP_TS_LAYOUT=bt routes this generic entry point through the (group, t, b32) row order the mask
-        # estimator uses for its speaker-independent layers; by default the tensor-memory kernel reads and
-        # writes plain (row, t) layouts here and no re-ordering copies are needed.
-        if rec_kernel(rows) == "tc" or (rec_kernel(rows) == "ts" and os.environ.get("TSSEP_TS_LAYOUT", "rows") == "bt"):
-            return self._forward_tc(x, rows, T, D, packs).reshape(*shape[:-1], packs[-1].hdim)
         xb, ld = ops.cast_bf16(x), ops.operand_ld(D)
         out = None
         for li, pk in enumerate(packs):
@@ -212,29 +184,3 @@ class RNNP_packed(torch.nn.Module):
                 pk.projection(H, rows * T, xb, mode=ops.EPI_BF16, ldo=ld, act=1)
             del H
         return out.reshape(*shape[:-1], packs[-1].hdim)
-
-    def _forward_tc(self, x, rows, T, D, packs):
-        """Same stack through the tcgen05 recurrence.  The kernels want rows ordered (group, t, b32);
-        this generic entry point re-orders with torch copies (MaskEstimator_v2 produces that order
-        directly and never takes this route)."""
-        groups = (rows + 31) // 32
-        mrows = groups * T * 32
-        xp = torch.zeros((groups * 32, T, D), dtype=torch.float32, device=x.device)
-        xp[:rows] = x.view(rows, T, D)
-        xb = ops.cast_bf16(xp.view(groups, 32, T, D).permute(0, 2, 1, 3).reshape(mrows, D))
-        ld = ops.operand_ld(D)
-        out = None
-        for li, pk in enumerate(packs):
-            G = pk.input_gemm_bt(xb, ld, mrows)
-            H = pk.recurrence_tc(G, rows, T)
-            del G
-            if li == len(packs) - 1:
-                out = torch.empty((mrows, pk.hdim), dtype=torch.float32, device=x.device)
-                pk.projection(H, mrows, out, mode=ops.EPI_F32, ldo=pk.hdim, act=0)
-            else:
-                ld = ops.operand_ld(pk.hdim)
-                xb = torch.empty((mrows, ld), dtype=torch.bfloat16, device=x.device)
-                pk.projection(H, mrows, xb, mode=ops.EPI_BF16, ldo=ld, act=1)
-            del H
-        out = out.view(groups, T, 32, -1).permute(0, 2, 1, 3).reshape(groups * 32, T, -1)[:rows]
-        return out.reshape(rows * T, -1)
