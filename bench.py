@@ -4,12 +4,15 @@
     python bench.py --gpus N --steps K --warmup W          # product arm (this repo's CUDA path)
     python bench.py --impl reference ...                    # the reference's CPU arithmetic (oracle) on host cores
 
-Metric (BASELINE.json): audio-seconds processed per wall-second (RTF^-1), TS-SEP 8-speaker
-inference.  One "step" = one pass of the whole path (STFT -> features -> RNNP mask estimator ->
-mask x STFT -> iSTFT -> diarization) over the rank's batch of synthetic LibriCSS-shaped 10-min
-meetings; every output of the reference's ForwardOutput is materialised in HBM.  Scaling is weak
-(meetings are independent; each rank processes --meetings-per-gpu of them, no data-path collective,
-one NCCL gather of the segment tables per step).  Rank 0 prints ONE JSON line.
+Metric (BASELINE.json): audio-seconds processed per wall-second (RTF^-1), TS-SEP 8-speaker inference.
+
+Workload = BASELINE config 4: a batch of 64 synthetic LibriCSS-shaped 10-min meetings, sharded data-parallel across
+the N GPUs of one box (64/N meetings per GPU, `tssep_b200.dist.assign_meetings`), STRONG scaling.  One "step" = one
+pass of the whole path (STFT -> features -> RNNP mask estimator -> mask x STFT -> iSTFT -> diarization) over the
+rank's meetings; every output of the reference's ForwardOutput is materialised in HBM.  There is no data-path
+collective; one NCCL all-gather of the segment tables per step (`tssep_b200.dist.SegmentGather`).  Rank 0 prints ONE
+JSON line; at N = 1 it also carries BASELINE config 3 (ONE 10-min meeting alone: latency, audio-s/s) under
+`config3`, a live parity check against the oracle under `parity`, and the CPU baseline.
 """
 from __future__ import annotations
 
@@ -41,8 +44,7 @@ FE_CFG = {
     "fe2": {"factory": "tssep_b200.feature_extractor.Log1pMaxNormAbsSTFT"},
     "size": 1024, "shift": 256, "window": "hann",
 }
-# deduplicated algorithmic work of one 10-min meeting
-GFLOP_PER_AUDIO_S = 6.21
+WORKLOAD = "TS-SEP 8-speaker inference, LibriCSS-shaped synthetic 16 kHz meetings, U=300 P=320 mul ts_vad=8 R=2"
 
 
 def parse_args():
@@ -51,19 +53,18 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--meetings-per-gpu", type=int, default=int(os.environ.get("TSSEP_BENCH_MEETINGS", 0)),
-                    help="0 = as many as fit in memory (at most 28), trimmed to one wave of recurrence clusters")
+    ap.add_argument("--meetings", type=int, default=int(os.environ.get("TSSEP_BENCH_MEETINGS", 64)),
+                    help="meetings of the whole job (BASELINE config 4: 64), dealt to the ranks")
     ap.add_argument("--seconds", type=float, default=600.0, help="length of every synthetic meeting")
     ap.add_argument("--wave-meetings", type=int, default=int(os.environ.get("TSSEP_BENCH_WAVE", 0)),
-                    help="meetings per recurrence wave (0 = what fits in one wave of 32-row clusters)")
+                    help="meetings per pass of the K-rows-per-meeting layers (0 = planned from the recurrence capacity)")
     ap.add_argument("--out-wave-meetings", type=int, default=int(os.environ.get("TSSEP_BENCH_OUT_WAVE", 13)),
                     help="meetings per output wave (head -> mask x STFT -> iSTFT -> diarization)")
-    ap.add_argument("--waves", type=int, default=int(os.environ.get("TSSEP_BENCH_WAVES", 1)),
-                    help="with --meetings-per-gpu 0: waves of recurrence-capacity meetings per step (the row-light "
-                         "pre_net / speaker-concat recurrences are shared by all waves of a step)")
     ap.add_argument("--cpu-sample-seconds", type=float, default=60.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--profile-json", default=None, help="also write the per-kernel breakdown to this file")
+    ap.add_argument("--no-config3", action="store_true", help="skip the single-meeting (BASELINE config 3) measurement")
+    ap.add_argument("--no-parity", action="store_true", help="skip the live parity check against the oracle")
+    ap.add_argument("--profile-json", default=None, help="also write the line to this file")
     return ap.parse_args()
 
 
@@ -151,6 +152,34 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
+def measured_traffic():
+    """dram__bytes_read + dram__bytes_write per launch of the recurrence, from the committed ncu --set full capture
+    (profiles/r2_ncu_traffic.json, written by scripts/ncu_summary.py): {rows -> bytes per frame and row}."""
+    p = os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")
+    return json.load(open(p)) if os.path.exists(p) else None
+
+
+def bind_to_gpu_numa_node(local: int):
+    """Pins this process (and the pinned host buffers it allocates afterwards, by first touch) to the CPUs next to its
+    GPU: with several ranks on one host the device-to-host copies otherwise cross the socket interconnect."""
+    try:
+        props = torch.cuda.get_device_properties(local)
+        bdf = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        cpus = open(f"/sys/bus/pci/devices/{bdf}/local_cpulist").read().strip()
+        ids = set()
+        for part in cpus.split(","):
+            lo, _, hi = part.partition("-")
+            ids.update(range(int(lo), int(hi or lo) + 1))
+        ids &= os.sched_getaffinity(0)
+        if ids:
+            os.sched_setaffinity(0, ids)
+            node = open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip()
+            return {"cpus": cpus, "numa_node": int(node), "n_cpus": len(ids)}
+    except Exception as e:  # containers without sysfs PCI topology: leave the affinity alone
+        return {"error": f"{type(e).__name__}: {e}"}
+    return None
+
+
 # ----------------------------------------------------------------------------------------------
 def oracle_setup(units, projs):
     from oracle import tssep_oracle as O
@@ -166,7 +195,8 @@ def time_oracle(sample_seconds: float, reps: int, warmup: int = 1, threads: int 
     """The reference's CPU arithmetic (oracle restatement: torch.nn.LSTM/Linear, torchaudio, torch.fft)
     on all host cores (or ``threads``), on a bounded sample of the workload (the path is linear in the audio length)."""
     O, net, tables = oracle_setup(MODEL_KW["units"], MODEL_KW["projs"])
-    cores = threads or os.cpu_count() or 1
+    avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    cores = threads or avail
     torch.set_num_threads(cores)
     n = int(sample_seconds * SAMPLE_RATE)
     obs, aux = synth_meeting(0, n)
@@ -187,15 +217,18 @@ def run_reference(args):
     if rank != 0:
         return
     value, cores, times = time_oracle(args.cpu_sample_seconds, reps=max(1, args.steps), warmup=max(1, min(args.warmup, 1)))
-    sample = (f"oracle restatement of the reference CPU path on one {args.cpu_sample_seconds:.0f}-s slice of a synthetic "
-              f"8-speaker meeting per step (cost is linear in audio length), torch threads={cores}")
+    host = os.cpu_count() or cores
+    sample = (f"oracle restatement of the reference CPU path (torch.nn.LSTM/Linear, torchaudio, torch.fft; f32) on one "
+              f"{args.cpu_sample_seconds:.0f}-s slice of a synthetic 8-speaker meeting per step (cost is linear in audio "
+              f"length), torch threads={cores} of {host} host CPUs")
     line = {
         "impl": "reference", "metric": "audio_seconds_per_second", "value": value, "unit": "audio-s/s",
         "n_gpus": args.gpus, "steps": len(times), "warmup": 1, "ms_per_step": float(np.median(times)) * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "TS-SEP 8-speaker inference, LibriCSS-shaped synthetic meeting, U=300 P=320 mul ts_vad=8 R=2",
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD + f"; BASELINE config 4: {args.meetings} meetings of {args.seconds:.0f} s",
                    "sample_seconds": args.cpu_sample_seconds},
-        "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": cores, "host_cpus": host, "kind": "port",
+                         "sample": sample},
         "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -219,7 +252,7 @@ def build_product_model(device):
 
 
 def kernel_breakdown(timeline, steps):
-    """Per entry point, and per (entry point, detail) for the calls that carry one (the GEMM shapes)."""
+    """Per entry point, and per (entry point, detail) for the calls that carry one (GEMM shapes, recurrence rows)."""
     agg, fine = {}, {}
     for name, s, e, detail in timeline:
         ms = s.elapsed_time(e)
@@ -235,9 +268,46 @@ def kernel_breakdown(timeline, steps):
     return out, detail
 
 
+def parity_check(model, dev):
+    """Live check of the product path against the oracle (the checker, not the thing measured): C3 dims, a 20-s
+    meeting, same weights and permutation draws.  The full-length (T = 37 503) comparison is tests/test_gpu_full_size.py."""
+    from oracle import tssep_oracle as O
+
+    torch.manual_seed(0)
+    kw = {k: v for k, v in MODEL_KW.items() if k != "layers"}
+    ref = O.OracleMaskEstimator(**kw).eval()
+    ref.load_state_dict({k: v.detach().cpu() for k, v in model.mask_estimator.state_dict().items()}, strict=True)
+    n = 20 * SAMPLE_RATE
+    e = O.dummy_example(3, aux_size=513, num_samples=n)
+    obs, aux = torch.tensor(e["observation"]), torch.tensor(e["auxInput"])
+    np.random.seed(11)
+    want = O.forward_path(obs, aux, ref, feature="concat", tables=O.MFCCTables(), window="hann")
+    np.random.seed(11)
+    got = model.separate(obs.to(dev), aux[None].to(dev))
+    tgt = e["speaker_reverberation_early_ch0"]
+
+    def sdr(est):
+        return float(10 * np.log10((tgt ** 2).sum() / (((est - tgt) ** 2).sum() + 1e-20) + 1e-20))
+
+    return {
+        "against": "oracle/tssep_oracle.py (pinned to the reference's doctest goldens and, exactly, to its own net.py / "
+                   "rnnp.py / TorchMFCC: tests/test_oracle_vs_reference_net.py)",
+        "case": "C3 dims (U=300 P=320 mul ts_vad=8 R=2), one 20-s meeting, random-init weights",
+        "max_abs_dmask": float((got.mask[0].cpu() - want.mask).abs().max()),
+        "max_abs_dlogit": float((got.logit[0].cpu() - want.logit).abs().max()),
+        "max_abs_dtime": float((got.time_estimate[0].cpu() - want.time_estimate).abs().max()),
+        "sdr_delta_db": abs(sdr(got.time_estimate[0].cpu().numpy()) - sdr(want.time_estimate.numpy())),
+        "tolerance": {"max_abs_dmask": 1e-3, "sdr_delta_db": 0.05},
+        "full_length": "tests/test_gpu_full_size.py::test_full_length_meeting_matches_oracle (one 10-min meeting, T = 37503)",
+        "diarization": "parity unpinned: thresholding / median smoothing / segment extraction do not exist in the "
+                       "reference; checked against this repo's own spec (oracle.diarize_reference)",
+    }
+
+
 def run_b200(args):
     from tssep_b200 import _lib
     from tssep_b200 import dist as tdist
+    from tssep_b200 import ops as _ops
 
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -246,67 +316,61 @@ def run_b200(args):
     assert torch.cuda.is_available(), "bench.py needs CUDA (the product has no CPU fallback)"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(local)
     _lib.load()
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.distributed.init_process_group("nccl", device_id=dev)
 
-    M = args.meetings_per_gpu
     n = int(args.seconds * SAMPLE_RATE)
     model = build_product_model(dev)
-    # memory guard (model below): shrink the batch instead of failing on a smaller / busier device
+    K = 8
+
+    # ---- BASELINE config 4: `meetings` equal meetings dealt to the ranks (strong scaling) ------------------------
+    plan = tdist.assign_meetings([n] * args.meetings, world)
+    my_ids = plan[rank]
+    M = len(my_ids)
+    assert M >= 1, f"rank {rank} has no meeting: --meetings {args.meetings} < --gpus {world}"
+    # The K=8 speaker rows of every meeting advance together in the tensor-memory recurrence; pre_net (1 row per
+    # meeting) and the TS-VAD layer (R rows) run once for all meetings.  Waves of the K-row layers: as few dependent
+    # steps as possible given how many rows one wave of clusters holds at each cluster width.
+    Up = 304
+    cap = {w: _ops.recurrence_ts_capacity(Up, w) for w in (8, 16, 32)}
     free_b, _ = torch.cuda.mem_get_info(dev)
-    from tssep_b200 import ops as _ops
-    # The K=8 speaker rows of every meeting advance together in the tensor-memory recurrence.  One wave of 32-row
-    # clusters (52 meetings) steps in 2.5 us, one wave of 16-row clusters (26 meetings) in 1.3 us; a row more costs
-    # a second wave.  The row-light layers (pre_net, speaker-concat layer) always run once per step.
-    wave = args.wave_meetings if args.wave_meetings > 0 else max(1, _ops.recurrence_ts_capacity(304, 32) // 8)
-    # memory model per 10-min meeting, calibrated on torch.cuda.memory_stats (116 GB peak for 52 meetings in one wave
-    # plus the serving loop's buffers): 0.7 GB that lives for the whole step (audio, STFT, pre_net rows, the
-    # separated audio of the step and the serving loop's input / output buffers), 2.05 GB while its wave is in the
-    # K-rows-per-meeting layers (bf16 G + H + layer input), 2.5 GB while its output wave exists (logit, mask,
-    # stft_estimate)
+    # memory model per 10-min meeting (calibrated on torch.cuda.memory_stats in round 1): 0.7 GB that lives for the whole
+    # step (audio, STFT, pre_net rows, the step's separated audio and the serving loop's buffers), 2.05 GB while its wave
+    # is in the K-rows-per-meeting layers (bf16 G + H + layer input), 2.5 GB while its output wave exists
     scale = args.seconds / 600.0
     light, heavy, outs = 0.7e9 * scale, 2.05e9 * scale, 2.5e9 * scale
-    out_w = max(1, args.out_wave_meetings)
+    out_wave = min(M, max(1, args.out_wave_meetings))
+    max_wave = int((0.90 * free_b - M * light - 0 * outs) / heavy)
+    max_wave = max(1, min(M, max_wave))
+    if args.wave_meetings > 0:
+        waves = [min(args.wave_meetings, M - lo) for lo in range(0, M, args.wave_meetings)]
+    else:
+        waves = tdist.plan_recurrence_waves(M, K, cap, max_items=max_wave)
+    while out_wave > 1 and M * light + out_wave * outs > 0.90 * free_b:
+        out_wave -= 1
 
-    def fits(m, w):
-        return m * light + max(min(m, w) * heavy, min(m, out_w) * outs) <= 0.92 * free_b
-
-    if M <= 0:
-        M = wave * max(1, args.waves)
-    if not fits(M, wave) and args.wave_meetings <= 0:
-        # waves of 16-row clusters need half the G buffer; only the tile layout runs the K-row layers per wave
-        wave = max(1, _ops.recurrence_ts_capacity(304, 16) // 8)
-        os.environ["TSSEP_NET_LAYOUT"] = "bt"
-    while M > 1 and not fits(M, wave) and os.environ.get("TSSEP_BENCH_NO_MEM_GUARD") != "1":
-        M -= 1
-    wave = min(wave, M)
-    out_wave = min(M, max(1, args.out_wave_meetings))  # the GB-sized logit / mask / stft_estimate live per output wave
-    if world > 1:
-        mt = torch.tensor([M], device=dev)
-        torch.distributed.all_reduce(mt, op=torch.distributed.ReduceOp.MIN)
-        M = int(mt.item())
-    meetings = [synth_meeting(rank * M + i, n, device=dev) for i in range(M)]
+    meetings = [synth_meeting(i, n, device=dev) for i in my_ids]
     obs_host = torch.tensor(np.stack([m[0] for m in meetings])).pin_memory()
     aux_host = torch.tensor(np.stack([m[1] for m in meetings])).pin_memory()
     obs_dev, aux_dev = obs_host.to(dev), aux_host.to(dev)
     diar = dict(threshold=0.5, median_width=11, max_segments=256)
-    global_ids = list(range(rank * M, rank * M + M))
+    gather = tdist.SegmentGather(plan, rank, K, diar["max_segments"], dev)
 
     class StepOut:
         pass
 
-    def step(obs, aux, on_wave=None, time_out=None):
-        """One pass over the rank's meetings, ``wave`` meetings at a time (Model.separate_waves).  The big
-        per-wave outputs (mask, logit, stft_estimate) are fully written to HBM and released when the next wave
-        starts; time_estimate and the segment tables of all waves stay.  Speaker permutations are drawn on the
-        host in meeting order."""
+    def step(obs, aux, on_wave=None, time_out=None, wave_plan=None, do_gather=True):
+        """One pass over the rank's meetings (Model.separate_waves).  The big per-wave outputs (mask, logit,
+        stft_estimate) are fully written to HBM and released when the next output wave starts; time_estimate and the
+        segment tables of all waves stay.  Speaker permutations are drawn on the host in meeting order."""
         np.random.seed(0)
         out = StepOut()
-        out.groups, segs, cnts = [], [], []
-        for lo, hi, o in model.separate_waves(obs, aux, wave=wave, out_wave=out_wave, diarize=diar, time_out=time_out):
-            out.groups.append((lo, hi, o.time_estimate))
+        segs, cnts = [], []
+        for lo, hi, o in model.separate_waves(obs, aux, wave=waves if wave_plan is None else wave_plan, out_wave=out_wave,
+                                              diarize=diar, time_out=time_out):
             segs.append(o.segments.segments)
             cnts.append(o.segments.counts)
             if on_wave is not None:
@@ -314,8 +378,8 @@ def run_b200(args):
             del o
         out.segments = torch.cat(segs) if len(segs) > 1 else segs[0]
         out.counts = torch.cat(cnts) if len(cnts) > 1 else cnts[0]
-        if world > 1:
-            tdist.gather_segments(global_ids, out.segments, out.counts, world * M)
+        if do_gather and world > 1:
+            out.all_segments, out.all_counts = gather.start(out.segments, out.counts).result()
         return out
 
     def barrier():
@@ -347,42 +411,34 @@ def run_b200(args):
     breakdown, breakdown_detail = kernel_breakdown(timeline, args.steps)
 
     # ---- end-to-end: pinned host buffers in, separated audio + segments back on the host ----
-    k = 8
+    pinned = True
     try:
-        time_host = torch.empty((M, k, n), dtype=torch.float32).pin_memory()
-    except RuntimeError:  # not enough pinnable host memory (many ranks on one host): pageable destination, slower copies
-        time_host = torch.empty((M, k, n), dtype=torch.float32)
-    seg_host = torch.empty((M, k, diar["max_segments"], 2), dtype=torch.int32).pin_memory()
-    cnt_host = torch.empty((M, k), dtype=torch.int32).pin_memory()
+        time_host = torch.empty((M, K, n), dtype=torch.float32).pin_memory()
+    except RuntimeError:  # not enough pinnable host memory: pageable destination, slower copies -- recorded in the line
+        time_host = torch.empty((M, K, n), dtype=torch.float32)
+        pinned = False
+    seg_host = torch.empty((M, K, diar["max_segments"], 2), dtype=torch.int32).pin_memory()
+    cnt_host = torch.empty((M, K), dtype=torch.int32).pin_memory()
 
     # The copies run on their own streams, so the D2H read of step i overlaps the compute of step i+1 (what a
     # serving loop does); every step's H2D and D2H lie inside the timed region, which ends when the last result has
-    # landed in host memory.  One pinned host buffer suffices: a step's copies (0.33 s) are done long before the next
+    # landed in host memory.  One pinned host buffer suffices: a step's copies are done long before the next
     # step produces output (its output stages come last), and the copy stream is ordered anyway.
     copy_stream = torch.cuda.Stream(device=dev)   # device -> host
     in_stream = torch.cuda.Stream(device=dev)     # host -> device (separate, or it would queue behind the D2H)
     main_stream = torch.cuda.current_stream(dev)
-    time_hosts = [time_host, time_host]
 
-    dbg = os.environ.get("TSSEP_BENCH_E2E_DEBUG") == "1"
-    dbg_rows = []
-
-    # Persistent device buffers of the serving loop (two of each, used alternately): the inputs land in them by
-    # H2D copy, the separated audio is written into them by the enhancement kernel and read back by D2H copy.
-    # Nothing the copy streams touch goes through the caching allocator, so its footprint stays what the
-    # device-resident loop needs.
+    # Persistent device buffers of the serving loop (two of each input, used alternately): the inputs land in them by
+    # H2D copy, the separated audio is written into time_buf by the enhancement kernel and read back by D2H copy.
     torch.cuda.empty_cache()
     obs_bufs = [torch.empty_like(obs_dev) for _ in range(2)]
     aux_bufs = [torch.empty_like(aux_dev) for _ in range(2)]
-    time_buf = torch.empty((M, k, n), dtype=torch.float32, device=dev)  # one: it is written only at the end of a step
+    time_buf = torch.empty((M, K, n), dtype=torch.float32, device=dev)  # one: it is written only at the end of a step
     copied = [None]         # event: the D2H copies of the previous step out of time_buf are done
     in_free = [None, None]  # event: the step that read obs_bufs[j] / aux_bufs[j] is done
 
     def e2e_step(i):
-        h0 = time.perf_counter()
         j = i % 2
-        m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        c_ev = []
         ev_in = torch.cuda.Event()
         with torch.cuda.stream(in_stream):
             if in_free[j] is not None:
@@ -391,32 +447,20 @@ def run_b200(args):
             aux_bufs[j].copy_(aux_host, non_blocking=True)
             ev_in.record(in_stream)
         main_stream.wait_event(ev_in)
-        th = time_hosts[j]
 
         def time_out():  # called right before the first output wave of this step is written
             if copied[0] is not None:
                 main_stream.wait_event(copied[0])  # the previous step's audio has left time_buf
             return time_buf
-        if dbg:
-            m0.record(main_stream)
 
         def ship(lo, hi, time_estimate):  # D2H of a wave's separated audio as soon as it exists
             ev = torch.cuda.Event()
             ev.record(main_stream)
             copy_stream.wait_event(ev)
             with torch.cuda.stream(copy_stream):
-                if dbg:
-                    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    c0.record(copy_stream)
-                th[lo:hi].copy_(time_estimate, non_blocking=True)
-                if dbg:
-                    c1.record(copy_stream)
-                    c_ev.append((c0, c1))
+                time_host[lo:hi].copy_(time_estimate, non_blocking=True)
 
         out = step(obs_bufs[j], aux_bufs[j], on_wave=ship, time_out=time_out)
-        if dbg:
-            m1.record(main_stream)
-            dbg_rows.append((i, h0, time.perf_counter(), m0, m1, c_ev))
         ev_done = torch.cuda.Event()
         ev_done.record(main_stream)
         in_free[j] = ev_done  # the inputs of step i+2 may overwrite obs_bufs[j] only after this step
@@ -429,10 +473,11 @@ def run_b200(args):
             copied[0] = torch.cuda.Event()
             copied[0].record(copy_stream)
 
-    # plain D2H bandwidth of this box (what bounds the end-to-end number: 512 KB of separated audio per audio-second)
+    # plain D2H bandwidth of this rank with every rank copying at once (what bounds the end-to-end number: 512 KB of
+    # separated audio per audio-second)
     pm = min(M, out_wave)
-    probe = torch.empty((pm, k, n), dtype=torch.float32, device=dev)
-    torch.cuda.synchronize()
+    probe = torch.empty((pm, K, n), dtype=torch.float32, device=dev)
+    barrier()
     pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     pe0.record()
     time_host[:pm].copy_(probe, non_blocking=True)
@@ -441,12 +486,9 @@ def run_b200(args):
     d2h_gbs = probe.numel() * 4 / (pe0.elapsed_time(pe1) / 1e3) / 1e9
     del probe
 
-    # the end-to-end loop has its own buffers (host-to-device inputs, copies in flight): warm it up until the
-    # allocator has reached its steady state, or the first timed step pays for the growth
     for i in range(max(2, min(args.warmup, 3))):
         e2e_step(i)
     copy_stream.synchronize()
-    dbg_rows.clear()
     barrier()
     ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ee0.record(main_stream)
@@ -458,65 +500,106 @@ def run_b200(args):
     ee1.record(main_stream)
     barrier()
     e2e_ms = ee0.elapsed_time(ee1)
-    if dbg and rank == 0:
-        st = torch.cuda.memory_stats(dev)
-        print(f"[e2e debug] alloc_retries={st.get('num_alloc_retries')} peak_alloc={st.get('allocated_bytes.all.peak', 0) / 1e9:.1f} GB "
-              f"peak_reserved={st.get('reserved_bytes.all.peak', 0) / 1e9:.1f} GB", file=sys.stderr)
-        t00 = dbg_rows[0][1]
-        for i, h0, h1, m0, m1, c_ev in dbg_rows:
-            cs = " ".join(f"[{ee0.elapsed_time(c0):.0f}-{ee0.elapsed_time(c1):.0f}]" for c0, c1 in c_ev)
-            print(f"[e2e debug] step {i}: host enqueue {1e3 * (h0 - t00):.0f}-{1e3 * (h1 - t00):.0f} ms | main "
-                  f"{ee0.elapsed_time(m0):.0f}-{ee0.elapsed_time(m1):.0f} ms | copies {cs}", file=sys.stderr)
+    del obs_bufs, aux_bufs, time_buf, time_host
 
+    d2h_all = d2h_gbs
     if world > 1:
         t = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         ms, e2e_ms = float(t[0]), float(t[1])
+        s = torch.tensor([d2h_gbs, float(pinned)], device=dev, dtype=torch.float64)
+        torch.distributed.all_reduce(s, op=torch.distributed.ReduceOp.SUM)
+        d2h_all, pinned_ranks = float(s[0]), int(round(float(s[1])))
+    else:
+        pinned_ranks = int(pinned)
     if rank != 0:
         if world > 1:
             torch.distributed.destroy_process_group()
         return
 
-    audio_s = world * M * args.seconds * args.steps
+    # ---- BASELINE config 3: ONE meeting alone (latency), rank 0 at N = 1 ---------------------------------------------
+    config3 = None
+    if world == 1 and not args.no_config3:
+        o1, a1 = obs_dev[:1], aux_dev[:1]
+        h1 = torch.empty((1, K, n), dtype=torch.float32).pin_memory()
+        for _ in range(2):
+            step(o1, a1, wave_plan=[1], do_gather=False)
+        torch.cuda.synchronize()
+        tl3 = []
+        _lib.set_timeline(tl3)
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(args.steps):
+            step(o1, a1, wave_plan=[1], do_gather=False)
+        c1.record()
+        torch.cuda.synchronize()
+        _lib.set_timeline(None)
+        ms3 = c0.elapsed_time(c1) / args.steps
+        bd3, _ = kernel_breakdown(tl3, args.steps)
+        # end to end: host audio in, separated audio back on the host, nothing overlapped (a single request)
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(args.steps):
+            od, ad = obs_host[:1].to(dev, non_blocking=True), aux_host[:1].to(dev, non_blocking=True)
+            for lo, hi, o in model.separate_waves(od, ad, wave=[1], out_wave=1, diarize=diar):
+                h1.copy_(o.time_estimate, non_blocking=True)
+                del o
+        g1.record()
+        torch.cuda.synchronize()
+        e2e3 = g0.elapsed_time(g1) / args.steps
+        rec3 = sum(v["ms_per_step"] for k, v in bd3.items() if k.startswith("tssep_blstm_recurrence"))
+        T3 = model.fe.num_frames(n)
+        config3 = {"workload": f"BASELINE config 3: ONE {args.seconds:.0f}-s meeting alone on one B200",
+                   "ms": ms3, "value": args.seconds / (ms3 / 1e3), "unit": "audio-s/s",
+                   "e2e_ms": e2e3, "e2e_value": args.seconds / (e2e3 / 1e3),
+                   "recurrence_ms": rec3, "us_per_recurrent_step": rec3 * 1e3 / (4 * T3),
+                   "kernels": bd3}
+
+    parity = None
+    if world == 1 and not args.no_parity:
+        parity = parity_check(model, dev)
+
+    audio_s = args.meetings * args.seconds * args.steps
     value = audio_s / (ms / 1e3)
     e2e_value = audio_s / (e2e_ms / 1e3)
     peaks = measured_peaks()
     T = model.fe.num_frames(n)
-    Up = 304
     # dominant kernel: the BLSTM recurrence (latency bound; expressed against the tensor peak as asked)
     rec_parts = {k: v for k, v in breakdown.items() if k.startswith("tssep_blstm_recurrence")}
     rec = {"ms_per_step": sum(v["ms_per_step"] for v in rec_parts.values()),
            "launches_per_step": sum(v["launches_per_step"] for v in rec_parts.values()) or 1}
-    rec_rows = M * (1 + 8 + 8 + 2)  # pre_net, birnn0, birnn1, birnn2 (R=2) batch rows
-    rec_cfg = "tanh.approx gates" if os.environ.get("TSSEP_LSTM_FAST_MATH", "1") == "1" else "exp-based gates"
+    rec_rows = M * (1 + 8 + 8 + 2)  # pre_net, birnn0, birnn1, birnn2 (R=2) batch rows of this rank
+    rec_cfg = "tanh.approx gates" if _ops.fast_math_default() else "exp-based gates"
     rec_flops = 2.0 * rec_rows * T * 2 * (4 * 300 * 300)
     rec_tflops = rec_flops / (rec["ms_per_step"] / 1e3) / 1e12 if rec["ms_per_step"] else 0.0
     gemm = breakdown.get("tssep_gemm", {"ms_per_step": 0.0})
     gemm_flops = M * (3.726e12 - 2.0 * 19 * T * 2 * 4 * 300 * 300)
     gemm_tflops = gemm_flops / (gemm["ms_per_step"] / 1e3) / 1e12 if gemm["ms_per_step"] else 0.0
     top = max(breakdown.items(), key=lambda kv: kv[1]["ms_per_step"])[0] if breakdown else None
-    # HBM bytes of the recurrence launches of one step: G is streamed once, H written once.  ncu (--set full) of the
-    # 208-row launch measured dram read + write = 7.58 GB against 7.59 GB algorithmic (profiles/r1_ncu_rec_ts.txt).
-    g_bytes = 4 if os.environ.get("TSSEP_G_DTYPE", "bf16") == "f32" else 2
-    rec_bytes = rec_rows * T * (8 * Up * g_bytes + 2 * Up * 2)
+    # algorithmic HBM bytes of the recurrence launches of one step: G is streamed once (bf16), H written once
+    rec_bytes = rec_rows * T * (8 * Up * 2 + 2 * Up * 2)
     rec_launches = max(1.0, rec["launches_per_step"])
     rec_gbs = rec_bytes / (rec["ms_per_step"] / 1e3) / 1e9 if rec["ms_per_step"] else 0.0
+    traffic = measured_traffic()
+    traffic_per_launch, traffic_note = None, "no ncu --set full capture of the shipped recurrence committed yet"
+    if traffic and "bytes_per_row_frame" in traffic:
+        traffic_per_launch = traffic["bytes_per_row_frame"] * rec_rows * T / rec_launches
+        traffic_note = traffic.get("note")
     roofline = {
         "kernel": "blstm_rec_ts_kernel", "bound": "tensor", "achieved": rec_tflops, "peak": peaks["bf16_tflops_sustained"],
         "unit": "TFLOP/s", "frac": rec_tflops / peaks["bf16_tflops_sustained"],
-        "traffic": 1.00 * rec_bytes / rec_launches,
-        "traffic_note": "bytes per launch (mean over the recurrence launches of a step) = algorithmic bytes x 1.00, the "
-                        "dram read+write / algorithmic ratio ncu measured (profiles/r1_ncu_rec_ts.txt)",
+        "traffic": traffic_per_launch, "traffic_note": traffic_note,
         "algorithmic_flops_per_launch": rec_flops / rec_launches, "algorithmic_bytes_per_launch": rec_bytes / rec_launches,
         "avg_launch_ms": rec["ms_per_step"] / rec_launches,
         "peak_source": peaks["source"] + " (sustained)",
         "note": "the recurrence is bound by the latency of T dependent steps (per step: DSMEM exchange of h with st.async, "
-                "2 x Up/16 tcgen05.mma with W_hh resident in tensor memory, gate math), not by the tensor pipe or HBM; "
-                "see us_per_recurrent_step",
+                "tcgen05.mma with W_hh resident in tensor memory, gate math), not by the tensor pipe or HBM; "
+                "see us_per_recurrent_step and launches",
         "hbm_GBps": rec_gbs, "hbm_frac": rec_gbs / peaks["hbm_gbs"],
         "us_per_recurrent_step": rec["ms_per_step"] * 1e3 / (rec_launches * T) if rec["ms_per_step"] else None,
         "dependent_steps_per_step": rec_launches * T,
-        "launches": {k: v for k, v in rec_parts.items()},
+        "launches": {k: dict(v, us_per_dependent_step=v["ms_per_step"] * 1e3 / (v["launches_per_step"] * T))
+                     for k, v in breakdown_detail.items() if k.startswith("tssep_blstm_recurrence")},
         "gate_math": rec_cfg,
         "share_of_step": rec["ms_per_step"] / (ms / args.steps),
         "top_kernel_by_time": top,
@@ -540,38 +623,51 @@ def run_b200(args):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         v, cores, times = time_oracle(args.cpu_sample_seconds, reps=2)
-        cpu = {"value": v, "unit": "audio-s/s", "cores": cores, "kind": "port",
+        cpu = {"value": v, "unit": "audio-s/s", "cores": cores, "host_cpus": os.cpu_count(), "kind": "port",
                "sample": f"oracle (reference CPU arithmetic) on a {args.cpu_sample_seconds:.0f}-s slice of meeting 0, "
-                         f"median of 2 after 1 warm-up, torch threads={cores}; cost is linear in audio length"}
+                         f"median of 2 after 1 warm-up, torch threads={cores} (the CPUs this process may run on; the host "
+                         f"lists {os.cpu_count()}); cost is linear in audio length"}
         # the reference's documented setting (README.md:51-56, CI): one thread; a shorter slice keeps the run bounded
         s1 = max(5.0, args.cpu_sample_seconds / 2.0)
         v1, _, _ = time_oracle(s1, reps=2, warmup=1, threads=1)
         cpu["single_thread"] = {"value": v1, "unit": "audio-s/s", "cores": 1,
                                 "sample": f"same, {s1:.0f}-s slice, median of 2 after 1 warm-up, torch threads=1"}
-        torch.set_num_threads(os.cpu_count() or 1)
+        torch.set_num_threads(cores)
+        if config3 is not None:
+            config3["speedup_vs_cpu_baseline"] = config3["value"] / v
+            config3["e2e_speedup_vs_cpu_baseline"] = config3["e2e_value"] / v
 
+    d2h_bytes = int(M * K * n * 4 + seg_host.numel() * 4 + cnt_host.numel() * 4)
     line = {
         "metric": "audio_seconds_per_second", "value": value, "unit": "audio-s/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"{M} LibriCSS-shaped synthetic {args.seconds:.0f}-s 16 kHz meetings per GPU per step, "
-                               "8 speakers, TS-SEP (U=300, P=320, mul, ts_vad=8, 2 averaged permutations), "
-                               "random-init weights; every ForwardOutput field + time_estimate + segments written to HBM "
-                               f"(mask / logit / stft_estimate buffers are reused from one output wave of {out_wave} meetings to the next)",
+        "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"BASELINE config 4: {args.meetings} LibriCSS-shaped synthetic {args.seconds:.0f}-s 16 kHz "
+                               f"meetings per step, sharded over {world} GPU(s) ({M} per GPU), 8 speakers, TS-SEP (U=300, "
+                               "P=320, mul, ts_vad=8, 2 averaged permutations), random-init weights; every ForwardOutput "
+                               "field + time_estimate + segments written to HBM (mask / logit / stft_estimate buffers are "
+                               f"reused from one output wave of {out_wave} meetings to the next)",
                    "precision": "bf16 GEMM / recurrence operands, f32 accumulation, f32 cell state, f32 STFT / iSTFT",
-                   "meetings_per_gpu": M, "meetings_per_wave": wave, "meetings_per_output_wave": out_wave, "meeting_seconds": args.seconds, "frames": T,
+                   "meetings_total": args.meetings, "meetings_per_gpu": M, "recurrence_waves": waves,
+                   "recurrence_capacity_rows": cap, "meetings_per_output_wave": out_wave,
+                   "meeting_seconds": args.seconds, "frames": T,
                    "l2": "inputs and intermediates (GBs per step) far exceed the 126 MB L2; no explicit flush",
                    "parallelism": f"dp{world} over meetings"},
         "clocks": clocks.summary(),
         "e2e": {"value": e2e_value, "unit": "audio-s/s", "ms_per_step": e2e_ms / args.steps,
                 "h2d_bytes_per_step": int(obs_host.numel() * 4 + aux_host.numel() * 4),
-                "d2h_bytes_per_step": int(time_host.numel() * 4 + seg_host.numel() * 4 + cnt_host.numel() * 4),
-                "d2h_GBps_measured": d2h_gbs,
-                "note": "bounded by the device-to-host copy of the separated audio (8 speakers x f32 = 512 KB per audio-second)"},
+                "d2h_bytes_per_step": d2h_bytes,
+                "d2h_GBps_rank0": d2h_gbs, "d2h_GBps_all_ranks": d2h_all,
+                "host_buffers_pinned_ranks": pinned_ranks, "numa_binding_rank0": numa,
+                "note": "per-rank byte counts; bounded by the device-to-host copy of the separated audio (8 speakers x f32 = "
+                        "512 KB per audio-second); copies overlap the next step, the last step's copy tail is inside the "
+                        "timed region"},
         "gpu_launches": launches,
         "roofline": roofline, "roofline_gemm": roofline_gemm, "hbm_kernels": hbm,
         "cpu_baseline": cpu,
-        "kernels": breakdown, "gemm_shapes": breakdown_detail,
+        "config3": config3,
+        "parity": parity,
+        "kernels": breakdown, "gemm_shapes": {k: v for k, v in breakdown_detail.items() if k.startswith("tssep_gemm")},
     }
     print(json.dumps(line))
     if args.profile_json:

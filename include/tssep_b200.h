@@ -154,7 +154,8 @@ int tssep_head_expand_t(const float* small, int64_t Z, int64_t T, int n_blocks, 
  * 2 * roundup(Up/2, 32) + 64 + 2 * max(rows_per_cluster, 16) <= 512 tensor-memory columns (Up <= 320 at 32 rows).
  * rows_per_cluster: 8, 16 or 32; 0 = choose (fewest rows per cluster whose clusters still fit in one wave).
  * gate_math: 0 = exp-based sigmoid / tanh, 1 = tanh.approx.f32.
- * k_split: 1 (and -1 = default) = the W_hh . h MMAs start on the half of h that arrives first; 0 = one phase. */
+ * k_split: 1 = the W_hh . h MMAs start on the half of h that arrives first; 0 (and -1 = default) = one phase
+ * (measured: the second barrier wait + proxy fence cost more than the split hides). */
 int tssep_blstm_recurrence_ts(const uint16_t* G, const uint32_t* Wimg, uint16_t* H, int64_t rows, int64_t T, int Up,
                               int rows_per_cluster, int gate_math, int k_split, tssep_stream_t stream);
 /* Batch rows that fit in ONE wave of co-resident clusters (both directions running) on the current

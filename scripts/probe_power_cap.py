@@ -29,7 +29,7 @@ def burst(ms):
 def rec():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    ops.blstm_recurrence_ts(G, wts, rows, T, Up, layout="rows")
+    ops.blstm_recurrence_ts(G, wts, rows, T, Up)
     e1.record()
     return e0, e1
 

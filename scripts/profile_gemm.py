@@ -22,22 +22,18 @@ def main():
     Bm, T, K8, Up, P, F = a.meetings, a.frames, 8, 304, 320, 513
     shapes = [
         # name, batch, M, N, K, mode, a_div
-        ("pre_in   f32 ", 1, Bm * T, 8 * Up, 553, ops.EPI_F32),
+        ("pre_in   bf16", 1, Bm * T, 8 * Up, 553, ops.EPI_BF16),
         ("pre_proj bf16", 1, Bm * T, F, 2 * Up, ops.EPI_BF16),
-        ("b0_in    f32 ", Bm * K8, T, 8 * Up, 513, ops.EPI_F32),
+        ("b0_in    bf16", Bm * K8, T, 8 * Up, 513, ops.EPI_BF16),
         ("b0_proj  bf16", 1, Bm * K8 * T, P, 2 * Up, ops.EPI_BF16),
-        ("b1_in    f32 ", 1, Bm * K8 * T, 8 * Up, P, ops.EPI_F32),
-        ("b2_in    f32 ", Bm * 2, T, 8 * Up, K8 * P, ops.EPI_F32),
+        ("b1_in    bf16", 1, Bm * K8 * T, 8 * Up, P, ops.EPI_BF16),
+        ("b2_in    bf16", Bm * 2, T, 8 * Up, K8 * P, ops.EPI_BF16),
         ("head     head", Bm, T, K8 * F, 2 * P, ops.EPI_HEAD),
-        # throughput path: rows ordered (group, t, b32)
-        ("b0_in    bt  ", 1, ((Bm * K8 + 31) // 32) * T * 32, 8 * Up, 513, ops.EPI_BF16_BT),
-        ("b1_in    bt  ", 1, ((Bm * K8 + 31) // 32) * T * 32, 8 * Up, P, ops.EPI_BF16_BT),
-        ("b1_proj  rmap", 1, ((Bm * K8 + 31) // 32) * T * 32, P, 2 * Up, ops.EPI_BF16_ROWMAP),
     ]
     for name, batch, M, N, K, mode in shapes:
         if a.only and a.only not in name:
             continue
-        ld = ops.round_up(K, 8)
+        ld = ops.operand_ld(K)
         A = (torch.randn((batch * M if mode != ops.EPI_F32 or batch == 1 else batch * M, ld), device=dev) * 0.1).to(torch.bfloat16)
         B = (torch.randn((N, ld), device=dev) * 0.1).to(torch.bfloat16)
         bias = torch.randn(N, device=dev)
@@ -48,16 +44,6 @@ def main():
             pm = torch.arange(batch * K8, dtype=torch.int32, device=dev)
             run = lambda: ops.gemm(A, ld, B, ld, M, N, K, logit, mode=mode, mask=mask, plane_map=pm, n_blocks=K8, row_len=F, **kw)
             out_bytes = 2 * logit.numel() * 4
-        elif mode == ops.EPI_BF16_BT:
-            out = torch.empty((M * N,), dtype=torch.bfloat16, device=dev)
-            run = lambda: ops.gemm(A, ld, B, ld, M, N, K, out, mode=mode, bias=bias)
-            out_bytes = out.numel() * 2
-        elif mode == ops.EPI_BF16_ROWMAP:
-            Z = Bm * K8
-            ldo = ops.round_up(K8 * N, 8)
-            out = torch.empty((Bm * T, ldo), dtype=torch.bfloat16, device=dev)
-            run = lambda: ops.gemm(A, ld, B, ld, M, N, K, out, mode=mode, ldo=ldo, bias=bias, act=1, row_map=(T, K8, Z, N))
-            out_bytes = out.numel() * 2
         else:
             ldo = ops.round_up(N, 8)
             out = torch.empty((batch * M, ldo), dtype=torch.float32 if mode == ops.EPI_F32 else torch.bfloat16, device=dev)

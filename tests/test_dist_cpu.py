@@ -24,10 +24,11 @@ def _worker(rank, world, port, ret):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from tssep_b200.dist import assign_meetings, gather_segments
+    from tssep_b200.dist import SegmentGather, assign_meetings, gather_segments
 
     lengths = [100, 90, 80, 70, 60]
-    mine = assign_meetings(lengths, world)[rank]
+    plan = assign_meetings(lengths, world)
+    mine = plan[rank]
     K, S = 2, 4
     seg = torch.zeros((len(mine), K, S, 2), dtype=torch.int32)
     cnt = torch.zeros((len(mine), K), dtype=torch.int32)
@@ -38,6 +39,11 @@ def _worker(rank, world, port, ret):
     out_s, out_c = gather_segments(mine, seg, cnt, len(lengths))
     ok = all(int(out_s[m, 0, 0, 0]) == m * 10 and int(out_s[m, 1, 0, 1]) == m * 10 + 5 and int(out_c[m, 0]) == m + 1
              for m in range(len(lengths)))
+    # the serving form: plan known up front, one fixed-size collective per step, started asynchronously, reused
+    sg = SegmentGather(plan, rank, K, S, "cpu")
+    for step in range(2):
+        s2, c2 = sg.start(seg + step, cnt).result()
+        ok = ok and torch.equal(s2, out_s + step * (out_c[:, :, None, None] > 0)) and torch.equal(c2, out_c)
     ret[rank] = bool(ok) and len(mine) in (2, 3)
     dist.destroy_process_group()
 
@@ -66,3 +72,19 @@ def test_gather_segments_single_process():
     out_s, out_c = gather_segments([2, 0], seg, cnt, 3)
     assert torch.equal(out_s[2], seg[0]) and torch.equal(out_s[0], seg[1]) and int(out_s[1].abs().sum()) == 0
     assert out_c.tolist() == [[3, 0], [0, 0], [1, 2]]
+
+
+def test_plan_recurrence_waves():
+    """Wave planner of the K-rows-per-meeting layers: one launch while the rows fit one wave of clusters, else the
+    cheapest partition under the measured step costs."""
+    from tssep_b200.dist import plan_recurrence_waves
+
+    cap = {8: 104, 16: 208, 32: 416}
+    cost = {8: 1.0, 16: 1.35, 32: 2.3}
+    assert plan_recurrence_waves(8, 8, cap, cost=cost) == [8]            # 64 rows: one wave of 8-row clusters
+    assert plan_recurrence_waves(52, 8, cap, cost=cost) == [52]          # 416 rows: one wave of 32-row clusters
+    w = plan_recurrence_waves(64, 8, cap, cost=cost)
+    assert sum(w) == 64 and max(w) <= 52 and len(w) == 2                 # 512 rows do not fit one wave
+    assert plan_recurrence_waves(64, 8, cap, max_items=32, cost=cost) == [32, 32] or \
+        sum(plan_recurrence_waves(64, 8, cap, max_items=32, cost=cost)) == 64
+    assert plan_recurrence_waves(1, 8, cap, cost=cost) == [1]

@@ -12,7 +12,9 @@ from pathlib import Path
 
 import torch
 
-_LIB_PATH = Path(__file__).resolve().parent / "_lib" / "libtssep_b200.so"
+# TSSEP_DEBUG_KNOBS=1 binds the debug library (tuning knobs / cycle counters compiled in, tssep_b200/build.py)
+_LIB_PATH = Path(__file__).resolve().parent / "_lib" / (
+    "libtssep_b200_dbg.so" if os.environ.get("TSSEP_DEBUG_KNOBS") == "1" else "libtssep_b200.so")
 _lib = None
 
 c_i64, c_i32, c_f32, c_vp = C.c_int64, C.c_int32, C.c_float, C.c_void_p

@@ -16,15 +16,18 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent
 CSRC = ROOT / "csrc"
 OUT_DIR = ROOT / "_lib"
-LIB = OUT_DIR / "libtssep_b200.so"
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
 ]
-# TSSEP_DEBUG_KNOBS=1 at BUILD time compiles the tuning / profiling knobs in (environment variables read by the
-# library, the per-phase cycle counters of the recurrence); the default library has none of them.
-if os.environ.get("TSSEP_DEBUG_KNOBS") == "1":
+# TSSEP_DEBUG_KNOBS=1 selects the DEBUG library (libtssep_b200_dbg.so, built next to the product library): tuning /
+# profiling knobs compiled in (environment variables read by the library, per-phase cycle counters of the
+# recurrence).  The product library has none of them.  tssep_b200/_lib.py loads whichever this variable names.
+DEBUG = os.environ.get("TSSEP_DEBUG_KNOBS") == "1"
+if DEBUG:
     NVCC_FLAGS = NVCC_FLAGS + ["-DTSSEP_DEBUG_KNOBS"]
+TAG = "_dbg" if DEBUG else ""
+LIB = OUT_DIR / f"libtssep_b200{TAG}.so"
 
 
 def _nvcc() -> str:
@@ -49,7 +52,7 @@ def _fingerprint() -> str:
 
 def build(force: bool = False, verbose: bool = False) -> Path:
     OUT_DIR.mkdir(exist_ok=True)
-    stamp = OUT_DIR / "build.stamp"
+    stamp = OUT_DIR / f"build{TAG}.stamp"
     fp = _fingerprint()
     if not force and LIB.exists() and stamp.exists() and stamp.read_text() == fp:
         return LIB
@@ -57,7 +60,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     objs = []
 
     def compile_one(src: Path) -> Path:
-        obj = OUT_DIR / (src.stem + ".o")
+        obj = OUT_DIR / (src.stem + TAG + ".o")
         cmd = [nvcc, *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")

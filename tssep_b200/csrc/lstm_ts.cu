@@ -35,7 +35,8 @@ struct RecTsArgs {
   const uint4* Wimg;  // [dir][cta][tile][kstep][row 128][8 words], gate rows i,f,o pre-scaled by 1/2
   __nv_bfloat16* H;   // (rows, T, 2*Up)
   int rows, T, Up, NA, KS, stages;
-  int* prof;          // debug builds only (TSSEP_DEBUG_KNOBS): per-phase cycle counters of two epilogue warps
+  int flags;          // debug builds only: bit 0 = skip the proxy fence of the MMA warp (measurement, NOT correct)
+  int* prof;          // debug builds only (TSSEP_DEBUG_KNOBS): per-phase cycle counters of two epilogue warps + MMA warp
 };
 
 __device__ __forceinline__ uint64_t ts_desc_sw128(uint32_t saddr) {
@@ -72,6 +73,12 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t* v) {
         "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr)
       : "memory");
+}
+__device__ __forceinline__ void tc_ld4(uint32_t taddr, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
+               : "r"(taddr)
+               : "memory");
 }
 __device__ __forceinline__ void tc_ld8(uint32_t taddr, uint32_t* v) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -241,8 +248,17 @@ blstm_rec_ts_kernel(const RecTsArgs a, const __grid_constant__ CUtensorMap gmap)
         bk += kAtomB >> 4;
       }
     };
+#ifdef TSSEP_DEBUG_KNOBS
+    const bool mprof = a.prof != nullptr && blockIdx.y == 0 && blockIdx.z == 0 && crank == 0;
+    const bool no_fence = (a.flags & 1) != 0;
+    int mc[4] = {0, 0, 0, 0};
+#else
+    constexpr bool mprof = false, no_fence = false;
+#endif
     for (int s = 0; s < T; ++s) {
       const int rb = (s & 1) ^ 1;
+      int m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+      if (mprof) m0 = clock();
       // P . G_s: needs the G stage and the accumulators of step s-1 drained -- both long before h arrives
       mbar_wait(gfull0 + 8 * slot, gph);
       if (s > 0) {
@@ -261,14 +277,17 @@ blstm_rec_ts_kernel(const RecTsArgs a, const __grid_constant__ CUtensorMap gmap)
                            idesc, k > 0 ? 1u : 0u);
       }
       __syncwarp();
+      if (mprof) m1 = clock();
       const uint64_t bd = bdesc0 + static_cast<uint64_t>(rb ? buf_step : 0u);
       if (s > 0) {
         const uint32_t par = ((s - 1) >> 1) & 1;
         mbar_wait(hfull0 + 8 * (2 * rb), par);
+        if (mprof) m2 = clock();
         if (lane == 0) mbar_arrive_expect_tx(hfull0 + 8 * (2 * rb), tx_bytes);  // re-arm for the data of step s+1
         // h arrived through st.async (generic proxy); the MMA reads it through the async proxy
-        ts_fence_proxy_async();
+        if (!no_fence) ts_fence_proxy_async();
         tc_fence_after();
+        if (mprof) m3 = clock();
         if constexpr (SPLIT) {
           if (elect_one()) {
             issue_h(0, 0, bd);
@@ -289,11 +308,24 @@ blstm_rec_ts_kernel(const RecTsArgs a, const __grid_constant__ CUtensorMap gmap)
         tc_commit(gempty0 + 8 * slot);  // the stage is free once the MMAs that read it are done
       }
       __syncwarp();
+#ifdef TSSEP_DEBUG_KNOBS
+      if (mprof && s > 0) {
+        const int m4 = clock();
+        mc[0] += m1 - m0;  // G ring / accumulator-drained waits + P.G issue
+        mc[1] += m2 - m1;  // wait for h_{t-1}
+        mc[2] += m3 - m2;  // re-arm + proxy fence
+        mc[3] += m4 - m3;  // W_hh.h issue + commits
+      }
+#endif
       if (++slot == GS) {
         slot = 0;
         gph ^= 1;
       }
     }
+#ifdef TSSEP_DEBUG_KNOBS
+    if (mprof && lane == 0)
+      for (int i = 0; i < 4; ++i) a.prof[8 + i] = mc[i];
+#endif
   } else {
     // ---- epilogue: gates, cell update, h exchange --------------------------------------------------
     const int tl = ((warp - 2) >> 2) & 1;  // row tile handled by this warp
@@ -347,7 +379,8 @@ blstm_rec_ts_kernel(const RecTsArgs a, const __grid_constant__ CUtensorMap gmap)
       uint32_t v[NC];
       if constexpr (NC == 32) tc_ld32(t_acc, v);
       else if constexpr (NC == 16) tc_ld16(t_acc, v);
-      else tc_ld8(t_acc, v);
+      else if constexpr (NC == 8) tc_ld8(t_acc, v);
+      else tc_ld4(t_acc, v);
       tc_wait_ld();
       tc_fence_before();
       __syncwarp();
@@ -607,9 +640,11 @@ int tssep_blstm_recurrence_ts(const uint16_t* G, const uint32_t* Wimg, uint16_t*
   a.NA = C;
   a.KS = Up / 16;
   a.prof = nullptr;
+  a.flags = 0;
   int want_stages = 0;
 #ifdef TSSEP_DEBUG_KNOBS
   if (const char* e = debug_env("TSSEP_REC_PROF")) a.prof = reinterpret_cast<int*>(strtoull(e, nullptr, 0));
+  if (const char* e = debug_env("TSSEP_TS_NOFENCE")) a.flags |= atoi(e) ? 1 : 0;
   if (const char* e = debug_env("TSSEP_TS_STAGES")) want_stages = atoi(e);
 #endif
   int stages = 0;
@@ -621,9 +656,9 @@ int tssep_blstm_recurrence_ts(const uint16_t* G, const uint32_t* Wimg, uint16_t*
   int NC = NR < 16 ? NR : 16;
   if (const char* e = debug_env("TSSEP_TS_COLS")) {
     const int v = atoi(e);
-    if (v == NR || (v == NR / 2 && v >= 8)) NC = v;
+    if (v == NR || (v == NR / 2 && v >= 4)) NC = v;
   }
-  const bool split = k_split != 0;  // default: on
+  const bool split = k_split == 1;  // default: one phase (the second barrier + fence cost more than the split hides)
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 
   // G (rows, T, 2, 4, Up) bf16 viewed as (unit, row, gate, dir, t); box = 64 units x NR rows x 4 gates
@@ -647,6 +682,7 @@ int tssep_blstm_recurrence_ts(const uint16_t* G, const uint32_t* Wimg, uint16_t*
     return split ? launch_ts<NR_, NC_, 0, true>(a, gmap, C, nsub, smem, st)                              \
                  : launch_ts<NR_, NC_, 0, false>(a, gmap, C, nsub, smem, st);                            \
   }
+  TSSEP_TS_CASE(8, 4)
   TSSEP_TS_CASE(8, 8)
   TSSEP_TS_CASE(16, 8)
   TSSEP_TS_CASE(16, 16)

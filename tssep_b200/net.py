@@ -372,7 +372,15 @@ class MaskEstimator_v2(Configurable, torch.nn.Module):
             assert pk0.I == F + A, (pk0.I, F, A)
         tsv = self.ts_vad is not False
         n_indep = L - 1 if tsv else L  # layers that treat every (item, speaker) row on its own
-        wave = B if wave is None else max(1, min(int(wave), B))
+        # `wave`: items per pass of the speaker-independent layers -- one number, or the list of wave sizes
+        if wave is None:
+            wave_sizes = [B]
+        elif isinstance(wave, (list, tuple)):
+            wave_sizes = [int(w) for w in wave]
+            assert sum(wave_sizes) == B and min(wave_sizes) >= 1, (wave_sizes, B)
+        else:
+            w = max(1, min(int(wave), B))
+            wave_sizes = [min(w, B - lo) for lo in range(0, B, w)]
         gd = ops.g_dtype()
         gmode = ops.EPI_BF16 if gd == torch.bfloat16 else ops.EPI_F32
         # output of the speaker-independent layers for ALL items: speaker-concat rows (B, T, K*P) for the TS-VAD layer
@@ -381,9 +389,9 @@ class MaskEstimator_v2(Configurable, torch.nn.Module):
         y = torch.empty((B * T if tsv else B * K * T, y_ld), dtype=torch.bfloat16, device=dev)
 
         # ---- speaker-independent layers, `wave` items at a time (their G buffer is the largest of the path) ----
-        for lo in range(0, B, wave):
-            hi = min(B, lo + wave)
-            Bw = hi - lo
+        lo = 0
+        for Bw in wave_sizes:
+            hi = lo + Bw
             rows = Bw * K
             # birnn0 with the conditioning folded into its input projection (net.py:862-896): 'mul' scales the weight
             # columns per speaker, 'cat' turns the embedding half of the weight into a per-speaker bias
@@ -425,6 +433,7 @@ class MaskEstimator_v2(Configurable, torch.nn.Module):
                 else:
                     pk.projection(H, rows * T, y[lo * K * T:], mode=ops.EPI_BF16, ldo=y_ld, act=0)
                 del H
+            lo = hi
         del xb
 
         # ---- TS-VAD layer: all speakers of an item in one row, R cyclic speaker orders as R rotated weight copies ----
@@ -453,7 +462,7 @@ class MaskEstimator_v2(Configurable, torch.nn.Module):
         hp = self._head_pack(K, R, row_len)
         per_item, nb = (1, K * nmask) if self.ts_vad is not False else (K, nmask)  # GEMM batch entries / planes per item
         embedding_all = aux_p.unsqueeze(-2)
-        out_wave = wave if out_wave is None else max(1, min(int(out_wave), B))
+        out_wave = max(wave_sizes) if out_wave is None else max(1, min(int(out_wave), B))
         for lo in range(0, B, out_wave):
             hi = min(B, lo + out_wave)
             Bw = hi - lo
