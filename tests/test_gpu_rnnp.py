@@ -103,9 +103,10 @@ def test_rnnp_tmem_recurrence_accurate_and_fast_gates(cuda, monkeypatch, fast):
     assert err < 5e-3, err
 
 
-# Saturating regime (SURVEY.md §8d asks for it): every weight x4.  Bounds = 2x the error measured on B200
-# (round 2: see DESIGN.md §2) -- a real regression bound, not a courtesy.
-STRESS_BOUND = {("ts", "1"): 0.05, ("ts", "0"): 0.05, ("regs", "1"): 0.05, ("regs", "0"): 0.05}
+# Saturating regime (SURVEY.md §8d asks for it): every weight x4.  Bounds = 2x the error measured on B200 in round 2
+# (max abs err 1.6e-2 ... 1.8e-2 on outputs of range +-3.4, rms 3.0e-3, for both kernels and both gate arithmetics:
+# the error is the bf16 rounding of the operands, not the kernel or tanh.approx) -- a regression bound, not a courtesy.
+STRESS_BOUND = {("ts", "1"): 0.035, ("ts", "0"): 0.035, ("regs", "1"): 0.035, ("regs", "0"): 0.035}
 
 
 @pytest.mark.parametrize("kernel", ["ts", "regs"])

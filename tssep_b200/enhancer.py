@@ -9,7 +9,7 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from . import _lib
+from . import _lib, torch_ops
 from .configurable import Configurable
 
 
@@ -72,8 +72,7 @@ class Masking(ABC):
                     or not activity_out.is_contiguous()):
                 raise ValueError(f"activity_out must be a contiguous float32 tensor of shape {(*lead, T)}")
         tab = fe._device_tables(m.device)
-        _lib.call("tssep_mask_istft", obs.data_ptr(), T * F, m.data_ptr(), Z, K, T, fe.size, fe.shift,
-                  fe.window_length, int(bool(fe.fading)), tab["synwin"].data_ptr(), tab["twiddle"].data_ptr(),
-                  _lib.ptr(est), _lib.ptr(time), time.shape[-1] if time is not None else 0, _lib.ptr(activity_out),
-                  _lib.stream_of(m))
+        torch_ops.op.mask_istft(obs, T * F, m, Z, K, T, fe.size, fe.shift, fe.window_length, int(bool(fe.fading)),
+                                tab["synwin"], tab["twiddle"], est, time, time.shape[-1] if time is not None else 0,
+                                activity_out)
         return est, time

@@ -15,7 +15,7 @@ import numpy as np
 import scipy.signal
 import torch
 
-from . import _lib
+from . import _lib, torch_ops
 from .configurable import Configurable
 
 _TOP_DB = 80.0
@@ -123,9 +123,8 @@ class STFT(Configurable):
         tab = self._device_tables(x.device)
         out = torch.empty((*lead, t, self.frequencies), dtype=torch.complex64, device=x.device)
         n_sig = int(np.prod(lead)) if lead else 1
-        _lib.call("tssep_stft", x.data_ptr(), n_sig, n, tab["window"].data_ptr(), tab["twiddle"].data_ptr(),
-                  self.size, self.shift, self.window_length, int(bool(self.fading)), t, out.data_ptr(),
-                  _lib.stream_of(x))
+        torch_ops.op.stft(x, n_sig, n, tab["window"], tab["twiddle"], self.size, self.shift, self.window_length,
+                          int(bool(self.fading)), t, out)
         return out.cpu().numpy() if was_np else out
 
     def istft(self, X, num_samples=None):
@@ -142,9 +141,8 @@ class STFT(Configurable):
         tab = self._device_tables(Xc.device)
         out = torch.empty((*lead, n), dtype=torch.float32, device=Xc.device)
         n_sig = int(np.prod(lead)) if lead else 1
-        _lib.call("tssep_mask_istft", Xc.data_ptr(), 0, None, n_sig, 1, t, self.size, self.shift,
-                  self.window_length, int(bool(self.fading)), tab["synwin"].data_ptr(), tab["twiddle"].data_ptr(),
-                  None, out.data_ptr(), n, None, _lib.stream_of(Xc))
+        torch_ops.op.mask_istft(Xc, 0, None, n_sig, 1, t, self.size, self.shift, self.window_length,
+                                int(bool(self.fading)), tab["synwin"], tab["twiddle"], None, out, n, None)
         return out.cpu().numpy() if was_np else out
 
     # feature description consumed by `_compute_features`
@@ -175,7 +173,6 @@ def _compute_features(fe: STFT, X: torch.Tensor, want_f32=True, want_bf16=False,
     t, f = X.shape[-2:]
     n_items = int(np.prod(lead)) if lead else 1
     dev = X.device
-    stream = _lib.stream_of(X)
     n_mels = mfcc.n_mels if mfcc is not None else 0
     n_mfcc = mfcc.n_mfcc if mfcc is not None else 0
     din = n_mfcc + (f if with_log1p else 0)
@@ -185,24 +182,22 @@ def _compute_features(fe: STFT, X: torch.Tensor, want_f32=True, want_bf16=False,
     if couple and len(lead) >= 2:
         g = lead[-1]
         groups = [(i, g) for i in range(0, n_items, g)]
-    keys = torch.empty((2, n_items), dtype=torch.int32, device=dev)
+    keys = [torch.empty((n_items,), dtype=torch.int32, device=dev) for _ in range(2)]  # order-preserving max keys
     meldb = torch.empty((n_items, t, max(n_mels, 1)), dtype=torch.float32, device=dev) if n_mels else None
     mt = mfcc._mel_tables(dev) if mfcc is not None else None
-    _lib.call("tssep_feature_stats", X.data_ptr(), n_items, t * f, t, f,
-              _lib.ptr(mt["mel_t"]) if mt else None, _lib.ptr(mt["lo"]) if mt else None,
-              _lib.ptr(mt["hi"]) if mt else None, n_mels, keys[0].data_ptr(), keys[1].data_ptr(),
-              _lib.ptr(meldb), stream)
+    torch_ops.op.feature_stats(X, n_items, t * f, t, f, mt["mel_t"] if mt else None, mt["lo"] if mt else None,
+                               mt["hi"] if mt else None, n_mels, keys[0], keys[1], meldb)
     out = {}
     f32 = torch.empty((*lead, t, din), dtype=torch.float32, device=dev) if want_f32 else None
     ld = _round_up(din, 64) if din >= 64 else _round_up(din, 8)  # ops.operand_ld
     bf16 = torch.empty((n_items * t, ld), dtype=torch.bfloat16, device=dev) if want_bf16 else None
     xv = torch.view_as_real(X).reshape(n_items, t, f, 2)
     for start, count in groups:
-        _lib.call("tssep_feature_write", xv[start].data_ptr(), count, t * f, t, f, keys[0, start:].data_ptr(),
-                  keys[1, start:].data_ptr(), _lib.ptr(meldb[start:]) if meldb is not None else None,
-                  _lib.ptr(mt["dct"]) if mt else None, n_mels, n_mfcc, int(with_log1p), _TOP_DB, int(bool(couple)),
-                  _lib.ptr(f32.reshape(n_items, t, din)[start:]) if f32 is not None else None,
-                  _lib.ptr(bf16[start * t:]) if bf16 is not None else None, ld, stream)
+        torch_ops.op.feature_write(xv[start:], count, t * f, t, f, keys[0][start:], keys[1][start:],
+                                   meldb[start:] if meldb is not None else None, mt["dct"] if mt else None, n_mels, n_mfcc,
+                                   int(with_log1p), _TOP_DB, int(bool(couple)),
+                                   f32.reshape(n_items, t, din)[start:] if f32 is not None else None,
+                                   bf16[start * t:] if bf16 is not None else None, ld)
     out["f32"], out["bf16"], out["ld"], out["din"] = f32, bf16, ld, din
     return out
 

@@ -25,7 +25,7 @@ import dataclasses
 import numpy as np
 import torch
 
-from . import _lib, ops
+from . import _lib, ops, torch_ops
 from .configurable import Configurable
 from .rnnp import RNNP_packed, param_key
 
@@ -363,7 +363,6 @@ class MaskEstimator_v2(Configurable, torch.nn.Module):
         pk0 = packs[0]
         Up = pk0.Up
         e = aux_p.reshape(B * K, A).contiguous()
-        stream = _lib.stream_of(xb)
         P = self.projs
         ldp = ops.operand_ld(P)
         if self.combination == "mul":
@@ -402,15 +401,13 @@ class MaskEstimator_v2(Configurable, torch.nn.Module):
             if self.combination == "mul":
                 ldk = ops.operand_ld(F)
                 Wk = torch.empty((rows * 8 * Up, ldk), dtype=torch.bfloat16, device=dev)
-                _lib.call("tssep_fold_embedding", 0, pk0.w_ih_f32.data_ptr(), pk0.I, pk0.bias.data_ptr(),
-                          e_w.data_ptr(), rows, 8 * Up, F, A, Wk.data_ptr(), ldk, bias_k.data_ptr(), stream)
+                torch_ops.op.fold_embedding(0, pk0.w_ih_f32, pk0.I, pk0.bias, e_w, rows, 8 * Up, F, A, Wk, ldk, bias_k)
                 ops.gemm(x_w, ld, Wk, ldk, T, 8 * Up, F, G, mode=gmode, ldo=8 * Up, batch=rows,
                          a_stride=T * ld, a_div=K, b_stride=8 * Up * ldk, bias=bias_k, bias_stride=8 * Up,
                          out_stride=T * 8 * Up)
                 del Wk
             else:  # cat
-                _lib.call("tssep_fold_embedding", 1, pk0.w_ih_f32.data_ptr(), pk0.I, pk0.bias.data_ptr(),
-                          e_w.data_ptr(), rows, 8 * Up, F, A, None, 0, bias_k.data_ptr(), stream)
+                torch_ops.op.fold_embedding(1, pk0.w_ih_f32, pk0.I, pk0.bias, e_w, rows, 8 * Up, F, A, None, 0, bias_k)
                 ops.gemm(x_w, ld, pk0.w_ih, pk0.ld_in, T, 8 * Up, F, G, mode=gmode, ldo=8 * Up, batch=rows,
                          a_stride=T * ld, a_div=K, b_stride=0, bias=bias_k, bias_stride=8 * Up,
                          out_stride=T * 8 * Up)
@@ -480,8 +477,7 @@ class MaskEstimator_v2(Configurable, torch.nn.Module):
                 small = torch.empty((items * T, nb), dtype=torch.float32, device=dev)
                 ops.gemm(y_w, y_ld, hp["w"], hp["ld"], items * T, hp["n"], hp["kdim"], small, mode=ops.EPI_F32, ldo=nb,
                          b_mod=1, bias=hp["b"], alpha=1.0 / R)
-                _lib.call("tssep_head_expand_t", small.data_ptr(), items, T, nb, odim, pm.data_ptr(),
-                          logit.data_ptr(), mask.data_ptr(), stream)
+                torch_ops.op.head_expand_t(small, items, T, nb, odim, pm, logit, mask)
                 del small
             embedding = embedding_all[lo:hi]
             if hi == B:

@@ -1,8 +1,9 @@
-"""Thin typed wrappers around the C-ABI calls shared by several modules.
+"""Thin typed wrappers around the operators of ``torch.ops.tssep_b200`` shared by several modules.
 
 Nothing here computes on the host: each function validates, allocates the
 output with torch (device memory only) and enqueues one kernel from
-``libtssep_b200.so`` on the current CUDA stream.
+``libtssep_b200.so`` on the current CUDA stream through the custom-op layer
+(``tssep_b200/torch_ops.py``).
 """
 from __future__ import annotations
 
@@ -11,8 +12,8 @@ import os
 
 import torch
 
-from . import _lib
-from ._lib import EPI_BF16, EPI_F32, EPI_HEAD, GemmDesc
+from . import _lib, torch_ops
+from ._lib import EPI_BF16, EPI_F32, EPI_HEAD
 
 
 def round_up(x: int, m: int) -> int:
@@ -43,19 +44,9 @@ def gemm(A, lda, B, ldb, M, N, K, out, *, mode, ldo=0, batch=1, a_stride=0, a_di
          bias=None, bias_stride=0, alpha=1.0, act=0, out_stride=0, out_div=None, out_stride_hi=0, mask=None,
          plane_map=None, n_blocks=0, row_len=0, impl=None, max_ctas=0):
     """``tssep_gemm``: out[z] = act(alpha * A[z / a_div] . B[z % b_mod]^T + bias[z % b_mod])."""
-    _lib.require_cuda(A, B, out, bias, mask, plane_map)
-    d = GemmDesc()
-    d.A, d.lda, d.a_stride, d.a_div = A.data_ptr(), lda, a_stride, a_div
-    d.B, d.ldb, d.b_stride, d.b_mod = B.data_ptr(), ldb, b_stride, batch if b_mod is None else b_mod
-    d.bias, d.bias_stride = _lib.ptr(bias), bias_stride
-    d.M, d.N, d.K, d.batch = M, N, K, batch
-    d.alpha, d.act, d.mode = alpha, act, mode
-    d.out, d.ldo, d.out_stride, d.out_stride_hi = _lib.ptr(out), ldo, out_stride, out_stride_hi
-    d.out_div = batch if out_div is None else out_div
-    d.mask, d.plane_map, d.n_blocks, d.row_len = _lib.ptr(mask), _lib.ptr(plane_map), n_blocks, row_len
-    d.impl = _gemm_impl() if impl is None else impl
-    d.max_ctas = max_ctas
-    _lib.call("tssep_gemm", C.byref(d), _lib.stream_of(A), detail=f"M={M} N={N} K={K} batch={batch} mode={mode}")
+    torch_ops.op.gemm(A, lda, a_stride, a_div, B, ldb, b_stride, batch if b_mod is None else b_mod, bias, bias_stride,
+                      M, N, K, batch, float(alpha), act, mode, out, ldo, out_stride, batch if out_div is None else out_div,
+                      out_stride_hi, mask, plane_map, n_blocks, row_len, _gemm_impl() if impl is None else impl, max_ctas)
 
 
 def cast_bf16(src: torch.Tensor, ld_dst: int = None) -> torch.Tensor:
@@ -65,7 +56,7 @@ def cast_bf16(src: torch.Tensor, ld_dst: int = None) -> torch.Tensor:
     rows, cols = src.shape
     ld_dst = operand_ld(cols) if ld_dst is None else ld_dst
     dst = torch.empty((rows, ld_dst), dtype=torch.bfloat16, device=src.device)
-    _lib.call("tssep_cast_bf16", src.data_ptr(), rows, cols, cols, dst.data_ptr(), ld_dst, _lib.stream_of(src))
+    torch_ops.op.cast_bf16(src, rows, cols, cols, dst, ld_dst)
     return dst
 
 
@@ -73,8 +64,7 @@ def pack_whh(w_fwd: torch.Tensor, w_bwd: torch.Tensor, U: int, Up: int) -> torch
     _lib.require_cuda(w_fwd, w_bwd)
     n = 2 * (Up // 4) * (Up // 16) * 128
     out = torch.empty(n, dtype=torch.int32, device=w_fwd.device)
-    _lib.call("tssep_pack_whh", w_fwd.contiguous().data_ptr(), w_bwd.contiguous().data_ptr(), U, Up, out.data_ptr(),
-              _lib.stream_of(w_fwd))
+    torch_ops.op.pack_whh(w_fwd.contiguous(), w_bwd.contiguous(), U, Up, out)
     return out
 
 
@@ -87,9 +77,7 @@ def blstm_recurrence(G: torch.Tensor, wfrag: torch.Tensor, rows: int, T: int, Up
     if fast_math is None:
         fast_math = fast_math_default()
     H = torch.empty((rows, T, 2 * Up), dtype=torch.bfloat16, device=G.device)
-    _lib.call("tssep_blstm_recurrence", G.data_ptr(), int(G.dtype == torch.bfloat16), wfrag.data_ptr(), H.data_ptr(),
-              rows, T, Up, cluster,
-              int(fast_math), _lib.stream_of(G))
+    torch_ops.op.blstm_recurrence(G, int(G.dtype == torch.bfloat16), wfrag, H, rows, T, Up, cluster, int(fast_math))
     return H
 
 
@@ -104,8 +92,7 @@ def pack_whh_ts(w_fwd: torch.Tensor, w_bwd: torch.Tensor, U: int, Up: int) -> to
     _lib.require_cuda(w_fwd, w_bwd)
     c = (Up + 63) // 64
     out = torch.empty(2 * c * 2 * (Up // 16) * 128 * 8, dtype=torch.int32, device=w_fwd.device)
-    _lib.call("tssep_pack_whh_ts", w_fwd.contiguous().data_ptr(), w_bwd.contiguous().data_ptr(), U, Up,
-              out.data_ptr(), _lib.stream_of(w_fwd))
+    torch_ops.op.pack_whh_ts(w_fwd.contiguous(), w_bwd.contiguous(), U, Up, out)
     return out
 
 
@@ -118,8 +105,7 @@ def blstm_recurrence_ts(G: torch.Tensor, wimg: torch.Tensor, rows: int, T: int, 
     if fast_math is None:
         fast_math = fast_math_default()
     H = torch.empty((rows, T, 2 * Up), dtype=torch.bfloat16, device=G.device)
-    _lib.call("tssep_blstm_recurrence_ts", G.data_ptr(), wimg.data_ptr(), H.data_ptr(), rows, T, Up, rows_per_cluster,
-              int(fast_math), k_split, _lib.stream_of(G), detail=f"rows={rows} T={T}")
+    torch_ops.op.blstm_recurrence_ts(G, wimg, H, rows, T, Up, rows_per_cluster, int(fast_math), k_split)
     return H
 
 
@@ -144,8 +130,7 @@ def instance_norm(x: torch.Tensor, unbiased=False, dim: int = -1, mode: int = 0)
     for n in x.shape[dim + 1:]:
         inner *= n
     out = torch.empty_like(x)
-    _lib.call("tssep_instance_norm", x.data_ptr(), outer, cols, inner, mode, int(bool(unbiased)), out.data_ptr(),
-              _lib.stream_of(x))
+    torch_ops.op.instance_norm(x, outer, cols, inner, mode, int(bool(unbiased)), out)
     return out
 
 

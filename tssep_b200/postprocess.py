@@ -11,7 +11,7 @@ import dataclasses
 
 import torch
 
-from . import _lib
+from . import _lib, torch_ops
 
 
 @dataclasses.dataclass
@@ -39,11 +39,11 @@ def diarize(mask: torch.Tensor, fe, *, num_samples=None, threshold=0.5, median_w
     lead = mask.shape[:-3]
     T, F = mask.shape[-2:]
     n = mask.numel() // (T * F)
-    dev, stream = mask.device, _lib.stream_of(mask)
+    dev = mask.device
     if activity is None:
         m = mask.float().contiguous()
         act = torch.empty((*lead, T), dtype=torch.float32, device=dev)
-        _lib.call("tssep_activity", m.data_ptr(), n, T, F, act.data_ptr(), stream)
+        torch_ops.op.activity(m, n, T, F, act)
     else:
         if tuple(activity.shape) != (*lead, T) or activity.dtype != torch.float32 or not activity.is_contiguous():
             raise ValueError(f"activity must be a contiguous float32 tensor of shape {(*lead, T)}")
@@ -52,8 +52,7 @@ def diarize(mask: torch.Tensor, fe, *, num_samples=None, threshold=0.5, median_w
     active = torch.empty((*lead, T), dtype=torch.uint8, device=dev)
     seg = torch.zeros((*lead, max_segments, 2), dtype=torch.int32, device=dev)
     cnt = torch.empty(lead, dtype=torch.int32, device=dev)
-    _lib.call("tssep_median_threshold", act.data_ptr(), n, T, int(median_width), float(threshold), smooth.data_ptr(),
-              active.data_ptr(), stream)
-    _lib.call("tssep_segments", active.data_ptr(), n, T, fe.window_length, fe.shift, int(bool(fe.fading)),
-              -1 if num_samples is None else int(num_samples), seg.data_ptr(), cnt.data_ptr(), max_segments, stream)
+    torch_ops.op.median_threshold(act, n, T, int(median_width), float(threshold), smooth, active)
+    torch_ops.op.segments(active, n, T, fe.window_length, fe.shift, int(bool(fe.fading)),
+                          -1 if num_samples is None else int(num_samples), seg, cnt, max_segments)
     return Diarization(act, smooth, active, seg, cnt)
