@@ -142,8 +142,9 @@ int tssep_head_expand_t(const float* small, int64_t Z, int64_t T, int n_blocks, 
  * (3) BLSTM recurrence (torch.nn.LSTM inside RNNP_packed, rnnp.py:87-95, :143-159)
  * ---------------------------------------------------------------------- */
 
-/* Tensor-memory cluster kernel (the product path for every row count): one cluster of ceil(Up/64) CTAs per
- * (rows_per_cluster batch rows, direction), both directions concurrently.  The recurrent weights live in TENSOR
+/* Tensor-memory cluster kernel (the product path for every row count): one cluster per (rows_per_cluster batch
+ * rows, direction), both directions concurrently; every CTA owns tiles_per_cta row tiles of 32 hidden units, i.e.
+ * clusters of ceil(Up/64) CTAs at 2 tiles (throughput shape) or 2*ceil(Up/64) CTAs at 1 tile (latency shape).  The recurrent weights live in TENSOR
  * MEMORY for the whole sequence as the A operand of tcgen05.mma; per step the tensor core computes
  * P . G_t + W_hh . h_{t-1} (P: scaled permutation matrix, G_t: a TMA box of G in shared memory, h_{t-1}: exchanged
  * through distributed shared memory with st.async), the epilogue warps apply the gates out of TMEM.
@@ -151,16 +152,19 @@ int tssep_head_expand_t(const float* small, int64_t Z, int64_t T, int n_blocks, 
  * Wimg from tssep_pack_whh_ts: 2 * C * 2 * (Up/16) * 128 * 8 words, C = ceil(Up/64)
  * H    (rows, T, 2*Up) bf16 out: [h_fwd(Up) | h_bwd(Up)]
  * Up = hidden units rounded up to a multiple of 16; padded units stay 0.  Limits: Up <= 384, and
- * 2 * roundup(Up/2, 32) + 64 + 2 * max(rows_per_cluster, 16) <= 512 tensor-memory columns (Up <= 320 at 32 rows).
- * rows_per_cluster: 8, 16 or 32; 0 = choose (fewest rows per cluster whose clusters still fit in one wave).
+ * tiles * roundup(Up/2, 32) + 64 + tiles * max(rows_per_cluster, 16) <= 512 tensor-memory columns (Up <= 320 at 32
+ * rows and 2 tiles); clusters of at most 16 CTAs.
+ * rows_per_cluster: 8, 16 or 32; tiles_per_cta: 1 or 2; 0 = choose (the shape with the shortest step whose clusters
+ * still fit in one wave of co-resident clusters).
  * gate_math: 0 = exp-based sigmoid / tanh, 1 = tanh.approx.f32.
- * k_split: 1 = the W_hh . h MMAs start on the half of h that arrives first; 0 (and -1 = default) = one phase
+ * k_split: 1 = the W_hh . h MMAs start on the half of h that arrives first (2 tiles only); 0 (and -1 = default) = one phase
  * (measured: the second barrier wait + proxy fence cost more than the split hides). */
 int tssep_blstm_recurrence_ts(const uint16_t* G, const uint32_t* Wimg, uint16_t* H, int64_t rows, int64_t T, int Up,
-                              int rows_per_cluster, int gate_math, int k_split, tssep_stream_t stream);
+                              int rows_per_cluster, int tiles_per_cta, int gate_math, int k_split,
+                              tssep_stream_t stream);
 /* Batch rows that fit in ONE wave of co-resident clusters (both directions running) on the current
- * device at the given rows_per_cluster (8, 16 or 32); < 0 on error. */
-int tssep_blstm_recurrence_ts_capacity(int Up, int rows_per_cluster);
+ * device for the given cluster shape (rows_per_cluster 8 / 16 / 32, tiles_per_cta 1 / 2); < 0 on error. */
+int tssep_blstm_recurrence_ts_capacity(int Up, int rows_per_cluster, int tiles_per_cta);
 int tssep_pack_whh_ts(const float* whh_fwd, const float* whh_bwd, int U, int Up, uint32_t* Wimg,
                       tssep_stream_t stream);
 

@@ -25,20 +25,23 @@ def main():
     X = fe.stft(x)
     T, F = X.shape[-2:]
     mask = torch.rand((a.meetings, a.speakers, 1, T, F), device=dev)
-    run = lambda: Masking.apply(mask, X, 0, fe, want_estimate=True, want_time=True, num_samples=n)
-    for _ in range(2):
-        run()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(a.reps):
-        run()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / a.reps
-    nbytes = a.meetings * (8 * T * F + a.speakers * (4 * T * F + 8 * T * F + 4 * n))
-    print(f"mask_istft meetings={a.meetings} speakers={a.speakers} T={T}: {ms:.3f} ms  {nbytes / ms / 1e6:.0f} GB/s algorithmic "
-          f"({nbytes / 1e9:.2f} GB)")
+    act = torch.empty((a.meetings, a.speakers, T), device=dev)
+    for label, act_out in (("without activity", None), ("with fused activity", act), ("without activity", None),
+                           ("with fused activity", act)):
+        run = lambda: Masking.apply(mask, X, 0, fe, want_estimate=True, want_time=True, num_samples=n, activity_out=act_out)
+        for _ in range(2):
+            run()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(a.reps):
+            run()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / a.reps
+        nbytes = a.meetings * (8 * T * F + a.speakers * (4 * T * F + 8 * T * F + 4 * n))
+        print(f"mask_istft {label}: meetings={a.meetings} speakers={a.speakers} T={T}: {ms:.3f} ms  "
+              f"{nbytes / ms / 1e6:.0f} GB/s algorithmic ({nbytes / 1e9:.2f} GB)")
 
 
 if __name__ == "__main__":

@@ -62,7 +62,7 @@ def test_rnnp_register_recurrence_matches_torch(cuda, monkeypatch, idim, units, 
     assert err < 1e-2, err
 
 
-@pytest.mark.parametrize("k_split", ["0", "1"])
+@pytest.mark.parametrize("tiles,k_split", [("2", "0"), ("2", "1"), ("1", "0")])
 @pytest.mark.parametrize("rows_per_cluster", ["8", "16", "32"])
 @pytest.mark.parametrize("idim,units,hdim,shape", [
     (64, 40, 42, (3, 100, 64)),      # one CTA, 3 rows used
@@ -73,12 +73,14 @@ def test_rnnp_register_recurrence_matches_torch(cuda, monkeypatch, idim, units, 
     (72, 10, 12, (17, 60, 72)),      # one k-step, Up = 16
     (72, 20, 12, (1, 90, 72)),       # a single row, Up = 32
 ])
-def test_rnnp_tmem_recurrence_matches_torch(cuda, monkeypatch, k_split, rows_per_cluster, idim, units, hdim, shape):
-    """The tensor-memory recurrence (csrc/lstm_ts.cu) at every cluster width (8 / 16 / 32 rows), with and without
-    the two-phase K split of the W_hh . h MMAs."""
+def test_rnnp_tmem_recurrence_matches_torch(cuda, monkeypatch, tiles, k_split, rows_per_cluster, idim, units, hdim, shape):
+    """The tensor-memory recurrence (csrc/lstm_ts.cu) in every cluster shape: 8 / 16 / 32 rows per cluster, two row
+    tiles per CTA (clusters of ceil(Up/64) CTAs, with and without the two-phase K split of the W_hh . h MMAs) and one
+    row tile per CTA (clusters of 2*ceil(Up/64) CTAs: 10 at U = 300, a non-portable cluster size)."""
     monkeypatch.setenv("TSSEP_LSTM_KERNEL", "ts")
     monkeypatch.setenv("TSSEP_TS_ROWS", rows_per_cluster)
     monkeypatch.setenv("TSSEP_TS_KSPLIT", k_split)
+    monkeypatch.setenv("TSSEP_TS_TILES", tiles)
     ref, mine = _pair(idim, units, hdim)
     x = torch.randn(shape, generator=torch.Generator().manual_seed(1))
     with torch.no_grad():

@@ -3,9 +3,12 @@
 // The time loop of torch.nn.LSTM inside RNNP_packed (tssep/train/rnnp.py:87-95, :143-159): gate order
 // i,f,g,o, zero initial state, c_t = s(f) c_{t-1} + s(i) tanh(g), h_t = s(o) tanh(c_t), both directions.
 //
-// One cluster of C = ceil(Up/64) CTAs per (NR batch rows, direction), NR = 8, 16 or 32.  Each CTA owns 64 hidden
-// units = 256 gate rows (row = 4*unit + gate) as two M=128 A tiles of Up/2 TMEM columns each (two bf16 per 32-bit
-// column), written ONCE; per step the pre-activations of a tile are
+// One cluster per (NR batch rows, direction), NR = 8, 16 or 32.  Each CTA owns TILES row tiles of 32 hidden units =
+// 128 gate rows (row = 4*unit + gate), each an M=128 A tile of Up/2 TMEM columns (two bf16 per 32-bit column),
+// written ONCE.  TILES = 2: clusters of ceil(Up/64) CTAs (5 at U = 300), the throughput shape; TILES = 1: clusters
+// of 2*ceil(Up/64) CTAs (10 at U = 300, a non-portable cluster size), the latency shape -- a step is bound by the
+// tensor pipe (27 cycles per M=128,K=16 MMA whatever N, measured), and one tile per CTA halves the MMAs of a step.
+// Per step the pre-activations of a tile are
 //
 //     D[gate row, batch row] = P . G_t  +  W_hh . h_{t-1}
 //
@@ -96,23 +99,25 @@ __device__ __forceinline__ float ts_tanh(float x) {
 
 // NR batch rows per cluster, NC of them per epilogue warp (8 * NR/NC epilogue warps); MATH: gate arithmetic;
 // SPLIT: two K phases per step (see the header).  Everything the per-step loops branch on is a template parameter.
-template <int NR, int NC, int MATH, bool SPLIT>
-__global__ void __launch_bounds__(64 + 256 * (NR / NC), 1)
+template <int NR, int NC, int MATH, bool SPLIT, int TILES>
+__global__ void __launch_bounds__(64 + 128 * TILES * (NR / NC), 1)
 blstm_rec_ts_kernel(const RecTsArgs a, const __grid_constant__ CUtensorMap gmap) {
+  static_assert(TILES == 1 || TILES == 2, "one or two row tiles per CTA");
+  static_assert(TILES == 2 || !SPLIT, "the K split pairs the two row tiles of a CTA");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr int NB = NR < 16 ? 16 : NR;   // MMA N (M = 128 needs N % 16 == 0); rows NR..NB-1 of the operands stay zero
   constexpr uint32_t kAtomB = NB * 128;   // one 64-k atom of the h operand: NB rows x 128 bytes, 128-byte swizzle
   constexpr uint32_t kAtomG = NR * 128;   // one 64-k atom of the G operand as the TMA box lays it out
   constexpr int EW = NR / NC;             // epilogue warps per (row tile, TMEM lane quarter)
   constexpr int NQ = NC / 4;              // batch-row quads per epilogue warp
-  constexpr int kThreads = 64 + 256 * EW;
+  constexpr int kThreads = 64 + 128 * TILES * EW;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int NA = a.NA, KS = a.KS, GS = a.stages;
   constexpr uint32_t g_stage = 4u * kAtomG;         // [gate][row][64 units]
   const uint32_t sB = base;                         // [2 buffers][NA] x kAtomB
   const uint32_t sG = sB + 2u * NA * kAtomB;        // [GS] x g_stage (+ 1 KiB of zeros behind the last stage)
-  const uint32_t sT = sG + GS * g_stage + 1024u;    // [8 * EW warps] x NC x 16 B
-  const uint32_t sBar = sT + 8u * NR * 16u;
+  const uint32_t sT = sG + GS * g_stage + 1024u;    // [4 * TILES * EW warps] x NC x 16 B
+  const uint32_t sBar = sT + 4u * TILES * NR * 16u;
   const uint32_t hfull0 = sBar;                     // [buffer][phase]
   const uint32_t accfull0 = sBar + 32, accempty0 = sBar + 48, gfull0 = sBar + 64, gempty0 = gfull0 + 8 * kTsMaxStages,
                  tptr = gempty0 + 8 * kTsMaxStages;
@@ -123,8 +128,8 @@ blstm_rec_ts_kernel(const RecTsArgs a, const __grid_constant__ CUtensorMap gmap)
   const int dir = blockIdx.z;
   const int row0 = blockIdx.y * NR;  // first batch row of this cluster
   const int T = a.T, Up = a.Up;
-  // every CTA ships 64 units x NR rows per step; with SPLIT each row tile (32 units) completes its own barrier
-  const uint32_t tx_bytes = static_cast<uint32_t>(NR) * (SPLIT ? 64u : 128u) * C;
+  // every CTA ships TILES x 32 units x NR rows per step; with SPLIT each row tile completes its own barrier
+  const uint32_t tx_bytes = static_cast<uint32_t>(NR) * 64u * (SPLIT ? 1u : static_cast<uint32_t>(TILES)) * C;
 
   // ---- one-time setup ---------------------------------------------------------------------------
   for (uint32_t i = threadIdx.x; i < (sT - sB) / 16; i += kThreads)
@@ -154,13 +159,13 @@ blstm_rec_ts_kernel(const RecTsArgs a, const __grid_constant__ CUtensorMap gmap)
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tptr));
   const uint32_t a_tile_cols = (static_cast<uint32_t>(Up) / 2 + 31u) & ~31u;  // columns per A tile (32-aligned)
-  const uint32_t p_col = 2u * a_tile_cols;                                     // P behind the A tiles (64 columns)
+  const uint32_t p_col = TILES * a_tile_cols;                                  // P behind the A tiles (64 columns)
   const uint32_t acc_col = p_col + 64u;                                        // then the two accumulators
 
-  if (warp >= 2 && warp < 10) {
+  if (warp >= 2 && warp < 2 + 4 * TILES) {
     // W_hh -> TMEM: lane = gate row of the tile, 8 columns (16 k values) per store
     const int tl = (warp - 2) >> 2, q = warp & 3;
-    const uint4* src = a.Wimg + ((static_cast<size_t>(dir) * C + crank) * 2 + tl) * static_cast<size_t>(KS) * 256 +
+    const uint4* src = a.Wimg + ((static_cast<size_t>(dir) * C + crank) * TILES + tl) * static_cast<size_t>(KS) * 256 +
                        static_cast<size_t>(q * 32 + lane) * 2;
     const uint32_t t0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(tl) * a_tile_cols;
     for (int k = 0; k < KS; ++k) {
@@ -199,8 +204,9 @@ blstm_rec_ts_kernel(const RecTsArgs a, const __grid_constant__ CUtensorMap gmap)
   if (warp == 0) {
     // ---- G producer ---------------------------------------------------------------------------------
     // G (rows, T, 2, 4, Up) bf16 viewed as (unit, row, gate, dir, t): one box of 64 units x NR rows x 4 gates per
-    // step = [gate][row][128 bytes], per gate the canonical K-major SWIZZLE_128B operand layout (K = the CTA's 64
-    // units: k-steps 0,1 belong to row tile 0, k-steps 2,3 to row tile 1).
+    // step = [gate][row][128 bytes], per gate the canonical K-major SWIZZLE_128B operand layout (K = 64 units:
+    // k-steps 0,1 belong to the even row tile, k-steps 2,3 to the odd one; with one tile per CTA the two CTAs of a
+    // pair load the same box and each uses its half).
     if (lane == 0) {
       tma_prefetch_desc(&gmap);
       int slot = 0;
@@ -209,7 +215,7 @@ blstm_rec_ts_kernel(const RecTsArgs a, const __grid_constant__ CUtensorMap gmap)
         const int t = dir ? T - 1 - s : s;
         mbar_wait(gempty0 + 8 * slot, gph ^ 1);
         mbar_arrive_expect_tx(gfull0 + 8 * slot, g_stage);
-        tma_load_5d(sG + slot * g_stage, &gmap, gfull0 + 8 * slot, static_cast<int>(crank) * 64, row0, 0, dir, t);
+        tma_load_5d(sG + slot * g_stage, &gmap, gfull0 + 8 * slot, static_cast<int>(crank * TILES / 2) * 64, row0, 0, dir, t);
         if (++slot == GS) {
           slot = 0;
           gph ^= 1;
@@ -263,18 +269,20 @@ blstm_rec_ts_kernel(const RecTsArgs a, const __grid_constant__ CUtensorMap gmap)
       mbar_wait(gfull0 + 8 * slot, gph);
       if (s > 0) {
         mbar_wait(accempty0, (s - 1) & 1);
-        mbar_wait(accempty0 + 8, (s - 1) & 1);
+        if constexpr (TILES == 2) mbar_wait(accempty0 + 8, (s - 1) & 1);
       }
       tc_fence_after();
       if (elect_one()) {
         const uint64_t gd = gdesc0 + static_cast<uint64_t>(static_cast<uint32_t>(slot) * (g_stage >> 4));
 #pragma unroll
-        for (int tile = 0; tile < 2; ++tile)
+        for (int tile = 0; tile < TILES; ++tile) {
+          const uint32_t hx = (crank * TILES + tile) & 1u;  // which 32 units of the 64-unit box
 #pragma unroll
           for (int k = 0; k < 8; ++k)  // k-step k of P = gate k/2, half k%2 of the tile's 32 units
             tc_mma_bf16_ts(d0 + tile * NB, pt + k * 8,
-                           gd + static_cast<uint64_t>(static_cast<uint32_t>(k >> 1) * (kAtomG >> 4) + 2 * (2 * tile + (k & 1))),
+                           gd + static_cast<uint64_t>(static_cast<uint32_t>(k >> 1) * (kAtomG >> 4) + 2 * (2 * hx + (k & 1))),
                            idesc, k > 0 ? 1u : 0u);
+        }
       }
       __syncwarp();
       if (mprof) m1 = clock();
@@ -303,8 +311,10 @@ blstm_rec_ts_kernel(const RecTsArgs a, const __grid_constant__ CUtensorMap gmap)
       if (elect_one()) {
         if (s > 0) issue_h(0, SPLIT ? 1 : 0, bd);
         tc_commit(accfull0);
-        if (s > 0) issue_h(1, SPLIT ? 1 : 0, bd);
-        tc_commit(accfull0 + 8);
+        if constexpr (TILES == 2) {
+          if (s > 0) issue_h(1, SPLIT ? 1 : 0, bd);
+          tc_commit(accfull0 + 8);
+        }
         tc_commit(gempty0 + 8 * slot);  // the stage is free once the MMAs that read it are done
       }
       __syncwarp();
@@ -328,24 +338,25 @@ blstm_rec_ts_kernel(const RecTsArgs a, const __grid_constant__ CUtensorMap gmap)
 #endif
   } else {
     // ---- epilogue: gates, cell update, h exchange --------------------------------------------------
-    const int tl = ((warp - 2) >> 2) & 1;  // row tile handled by this warp
-    const int q = warp & 3;                // TMEM lane quarter
-    const int half = (warp - 2) >> 3;      // which NC columns (batch rows) of the tile
+    const int tl = ((warp - 2) >> 2) % TILES;  // row tile handled by this warp
+    const int q = warp & 3;                    // TMEM lane quarter
+    const int half = ((warp - 2) >> 2) / TILES;  // which NC columns (batch rows) of the tile
     const int gate = lane & 3;             // i, f, g, o
     const int ul = lane >> 2;              // unit within the warp's octet
     const bool is_g = gate == 2;
     // pre-activations arrive scaled by 1/2 for i, f, o:  sigmoid(x) = 0.5 tanh(x/2) + 0.5
     const float ka = is_g ? 1.0f : 0.5f, kb = is_g ? 0.0f : 0.5f;
     const uint32_t myT = sT + static_cast<uint32_t>(warp - 2) * (NC * 16);
-    const int oc = tl * 4 + q;  // unit octet inside the CTA = 16-byte chunk of the CTA's k-atom
-    const int unit0 = static_cast<int>(crank) * 64 + oc * 8;
+    const int gtile = static_cast<int>(crank) * TILES + tl;  // row tile of the whole layer: units 32 gtile ...
+    const int oc = (gtile & 1) * 4 + q;                      // unit octet = 16-byte chunk inside the 64-unit k-atom
+    const int unit0 = gtile * 32 + q * 8;
     const bool oct_ok = unit0 < Up;
     // sender role: lane ships batch row r to CTAs d0, d0 + 32/NC, ...
     constexpr int DG = 32 / NC;
     const int rl = lane % NC, r = half * NC + rl, d0 = lane / NC;
-    const uint32_t chunk_off = crank * kAtomB + static_cast<uint32_t>(r >> 3) * 1024 + static_cast<uint32_t>(r & 7) * 128 +
-                               ((static_cast<uint32_t>(oc) ^ static_cast<uint32_t>(r & 7)) << 4);
-    constexpr int ND = (8 + DG - 1) / DG;
+    const uint32_t chunk_off = static_cast<uint32_t>(gtile >> 1) * kAtomB + static_cast<uint32_t>(r >> 3) * 1024 +
+                               static_cast<uint32_t>(r & 7) * 128 + ((static_cast<uint32_t>(oc) ^ static_cast<uint32_t>(r & 7)) << 4);
+    constexpr int ND = ((TILES == 1 ? 16 : 8) + DG - 1) / DG;  // clusters of up to 16 CTAs with one tile per CTA
     uint32_t r_b[ND], r_bar[ND];
 #pragma unroll
     for (int j = 0; j < ND; ++j) {
@@ -500,14 +511,23 @@ __global__ void pack_whh_ts_kernel(const float* __restrict__ w_fwd, const float*
   }
 }
 
-template <int NR, int NC, int MATH, bool SPLIT>
+template <int NR, int NC, int MATH, bool SPLIT, int TILES>
+static cudaError_t prepare_ts(int C, size_t smem) {
+  auto* fn = blstm_rec_ts_kernel<NR, NC, MATH, SPLIT, TILES>;
+  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (e == cudaSuccess && C > 8) e = cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  return e;
+}
+
+template <int NR, int NC, int MATH, bool SPLIT, int TILES>
 static int max_clusters_ts(int C, size_t smem) {
-  if (cudaFuncSetAttribute(blstm_rec_ts_kernel<NR, NC, MATH, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           static_cast<int>(smem)) != cudaSuccess)
+  if (prepare_ts<NR, NC, MATH, SPLIT, TILES>(C, smem) != cudaSuccess) {
+    cudaGetLastError();
     return 0;
+  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(C, 64, 2);
-  cfg.blockDim = dim3(64 + 256 * (NR / NC));
+  cfg.blockDim = dim3(64 + 128 * TILES * (NR / NC));
   cfg.dynamicSmemBytes = smem;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -517,7 +537,7 @@ static int max_clusters_ts(int C, size_t smem) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   int n = 0;
-  if (cudaOccupancyMaxActiveClusters(&n, blstm_rec_ts_kernel<NR, NC, MATH, SPLIT>, &cfg) != cudaSuccess) {
+  if (cudaOccupancyMaxActiveClusters(&n, blstm_rec_ts_kernel<NR, NC, MATH, SPLIT, TILES>, &cfg) != cudaSuccess) {
     cudaGetLastError();
     return 0;
   }
@@ -525,10 +545,10 @@ static int max_clusters_ts(int C, size_t smem) {
 }
 
 // shared memory of one CTA and the depth of its G ring
-static size_t ts_smem(int C, int NR, int* stages_out, int want_stages) {
+static size_t ts_smem(int NA, int NR, int tiles, int* stages_out, int want_stages) {
   const int NB = NR < 16 ? 16 : NR;
   const size_t ring_stage = 4ull * NR * 128;
-  const size_t fixed_bytes = 1024 + 2ull * C * NB * 128 + 1024 + 8ull * NR * 16 + 64 + 16 * kTsMaxStages + 16;
+  const size_t fixed_bytes = 1024 + 2ull * NA * NB * 128 + 1024 + 4ull * tiles * NR * 16 + 64 + 16 * kTsMaxStages + 16;
   int stages = static_cast<int>((200 * 1024 - fixed_bytes) / ring_stage);
   stages = stages > kTsMaxStages ? kTsMaxStages : stages;
   if (want_stages >= 2 && want_stages <= stages) stages = want_stages;
@@ -539,21 +559,40 @@ static size_t ts_smem(int C, int NR, int* stages_out, int want_stages) {
   return smem < 120 * 1024 ? 120 * 1024 : smem;
 }
 
-static int clusters_for(int NR, int C) {
-  int st = 0;
-  const size_t smem = ts_smem(C, NR, &st, 0);
-  return NR == 8    ? max_clusters_ts<8, 8, 1, true>(C, smem)
-         : NR == 16 ? max_clusters_ts<16, 16, 1, true>(C, smem)
-                    : max_clusters_ts<32, 16, 1, true>(C, smem);
+// CTAs per cluster: every CTA owns `tiles` row tiles of 32 units; the tile count is even (two per 64-unit k-atom)
+static int cluster_ctas(int Up, int tiles) { return 2 * ((Up + 63) / 64) / tiles; }
+
+// co-resident clusters of one shape (cached per device: the query costs ~10 us and every launch asks)
+static int clusters_for(int NR, int Up, int tiles) {
+  static int cache[8][3][2][25];  // [device][NR 8/16/32][tiles 1/2][Up / 16]; 0 = not asked yet, -1 = none fit
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 8) dev = 0;
+  const int ri = NR == 8 ? 0 : (NR == 16 ? 1 : 2), ui = Up / 16;
+  int& slot = cache[dev][ri][tiles - 1][ui];
+  if (slot == 0) {
+    const int C = cluster_ctas(Up, tiles), NA = (Up + 63) / 64;
+    int st = 0;
+    const size_t smem = ts_smem(NA, NR, tiles, &st, 0);
+    int n = 0;
+    if (C <= 16) {
+      if (tiles == 2)
+        n = NR == 8 ? max_clusters_ts<8, 8, 1, false, 2>(C, smem)
+                    : (NR == 16 ? max_clusters_ts<16, 16, 1, false, 2>(C, smem) : max_clusters_ts<32, 16, 1, false, 2>(C, smem));
+      else
+        n = NR == 8 ? max_clusters_ts<8, 8, 1, false, 1>(C, smem)
+                    : (NR == 16 ? max_clusters_ts<16, 16, 1, false, 1>(C, smem) : max_clusters_ts<32, 16, 1, false, 1>(C, smem));
+    }
+    slot = n > 0 ? n : -1;
+  }
+  return slot > 0 ? slot : 0;
 }
 
-template <int NR, int NC, int MATH, bool SPLIT>
+template <int NR, int NC, int MATH, bool SPLIT, int TILES>
 static int launch_ts(const RecTsArgs& a, const CUtensorMap& gmap, int C, int nsub, size_t smem, cudaStream_t stream) {
-  TSSEP_CUDA(cudaFuncSetAttribute(blstm_rec_ts_kernel<NR, NC, MATH, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  static_cast<int>(smem)));
+  TSSEP_CUDA((prepare_ts<NR, NC, MATH, SPLIT, TILES>(C, smem)));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(C, static_cast<unsigned>(nsub), 2);
-  cfg.blockDim = dim3(64 + 256 * (NR / NC));
+  cfg.blockDim = dim3(64 + 128 * TILES * (NR / NC));
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -563,9 +602,17 @@ static int launch_ts(const RecTsArgs& a, const CUtensorMap& gmap, int C, int nsu
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  TSSEP_CUDA(cudaLaunchKernelEx(&cfg, blstm_rec_ts_kernel<NR, NC, MATH, SPLIT>, a, gmap));
+  TSSEP_CUDA(cudaLaunchKernelEx(&cfg, blstm_rec_ts_kernel<NR, NC, MATH, SPLIT, TILES>, a, gmap));
   return check_launch("blstm_rec_ts");
 }
+
+// Relative cost of one dependent step per cluster shape (tiles per CTA, rows per cluster), measured at U = 300 on B200
+// (profiles/r2_rec_ts_microbench.txt).  tssep_b200/dist.py::TS_STEP_COST mirrors the two-tile row.
+struct TsShape {
+  int tiles, rows;
+  double cost;
+};
+static const TsShape kTsShapes[] = {{1, 8, 0.78}, {2, 8, 1.0}, {1, 16, 1.15}, {2, 16, 1.35}, {2, 32, 2.3}};
 
 }  // namespace tssep
 
@@ -583,53 +630,65 @@ int tssep_pack_whh_ts(const float* whh_fwd, const float* whh_bwd, int U, int Up,
   return check_launch("tssep_pack_whh_ts");
 }
 
-int tssep_blstm_recurrence_ts_capacity(int Up, int rows_per_cluster) {
+int tssep_blstm_recurrence_ts_capacity(int Up, int rows_per_cluster, int tiles_per_cta) {
   TSSEP_REQUIRE(Up >= 16 && Up % 16 == 0 && Up <= 384, "tssep_blstm_recurrence_ts_capacity: bad Up");
   TSSEP_REQUIRE(rows_per_cluster == 8 || rows_per_cluster == 16 || rows_per_cluster == 32,
                 "tssep_blstm_recurrence_ts_capacity: rows_per_cluster must be 8, 16 or 32");
-  return (clusters_for(rows_per_cluster, (Up + 63) / 64) / 2) * rows_per_cluster;
+  TSSEP_REQUIRE(tiles_per_cta == 1 || tiles_per_cta == 2, "tssep_blstm_recurrence_ts_capacity: tiles_per_cta must be 1 or 2");
+  return (clusters_for(rows_per_cluster, Up, tiles_per_cta) / 2) * rows_per_cluster;
 }
 
 int tssep_blstm_recurrence_ts(const uint16_t* G, const uint32_t* Wimg, uint16_t* H, int64_t rows, int64_t T, int Up,
-                              int rows_per_cluster, int gate_math, int k_split, tssep_stream_t stream) {
+                              int rows_per_cluster, int tiles_per_cta, int gate_math, int k_split, tssep_stream_t stream) {
   TSSEP_REQUIRE(G && Wimg && H, "tssep_blstm_recurrence_ts: null pointer");
   TSSEP_REQUIRE(Up >= 16 && Up % 16 == 0 && Up <= 384, "tssep_blstm_recurrence_ts: Up must be a multiple of 16 in [16, 384]");
   TSSEP_REQUIRE(rows >= 0 && T >= 0 && T < (1ll << 30) && (rows + 7) / 8 <= 65535, "tssep_blstm_recurrence_ts: bad extent");
   TSSEP_REQUIRE(rows_per_cluster == 0 || rows_per_cluster == 8 || rows_per_cluster == 16 || rows_per_cluster == 32,
                 "tssep_blstm_recurrence_ts: rows_per_cluster must be 0 (auto), 8, 16 or 32");
+  TSSEP_REQUIRE(tiles_per_cta >= 0 && tiles_per_cta <= 2, "tssep_blstm_recurrence_ts: tiles_per_cta must be 0 (auto), 1 or 2");
   TSSEP_REQUIRE(gate_math == 0 || gate_math == 1, "tssep_blstm_recurrence_ts: gate_math must be 0 (exp based) or 1 (tanh.approx)");
   TSSEP_REQUIRE(k_split >= -1 && k_split <= 1, "tssep_blstm_recurrence_ts: k_split must be -1 (default), 0 or 1");
   TSSEP_REQUIRE((reinterpret_cast<uintptr_t>(H) & 15) == 0 && (reinterpret_cast<uintptr_t>(Wimg) & 15) == 0 &&
                     (reinterpret_cast<uintptr_t>(G) & 15) == 0,
                 "tssep_blstm_recurrence_ts: G, H and Wimg must be 16-byte aligned");
   if (rows == 0 || T == 0) return 0;
-  const int C = (Up + 63) / 64;
-  int NR = rows_per_cluster;
+  const int NA = (Up + 63) / 64;
+  int NR = rows_per_cluster, tiles = tiles_per_cta;
   if (const char* e = debug_env("TSSEP_TS_ROWS")) {
     const int v = atoi(e);
     if (v == 8 || v == 16 || v == 32) NR = v;
   }
-  if (NR == 0) {
-    // Fewer rows per cluster = shorter step (the epilogue math and the DSMEM exchange scale with the rows); a launch
-    // that does not fit in one wave of co-resident clusters runs its waves back to back.  Relative step costs
-    // 1 : 1.35 : 2.3 for 8 / 16 / 32 rows (measured at U = 300).
+  const bool split = k_split == 1;  // default: one phase (the second barrier + fence cost more than the split hides)
+  if (split) {
+    TSSEP_REQUIRE(tiles != 1, "tssep_blstm_recurrence_ts: k_split needs two row tiles per CTA");
+    tiles = 2;
+  }
+  if (NR == 0 || tiles == 0) {
+    // Fewer rows per cluster and fewer tiles per CTA = shorter step (epilogue math, DSMEM exchange and the MMAs of a
+    // step scale with them) but fewer rows per wave of co-resident clusters; a launch that does not fit in one wave
+    // runs its waves back to back.
     double best = 1e30;
-    const int cand[3] = {8, 16, 32};
-    const double cost[3] = {1.0, 1.35, 2.3};
-    for (int i = 0; i < 3; ++i) {
-      const int m = clusters_for(cand[i], C);
-      if (m <= 0) continue;
-      const int64_t n = 2 * ((rows + cand[i] - 1) / cand[i]);
-      const double t = cost[i] * static_cast<double>((n + m - 1) / m);
+    int best_nr = 0, best_tiles = 0;
+    for (const TsShape& sh : kTsShapes) {
+      if ((NR != 0 && sh.rows != NR) || (tiles != 0 && sh.tiles != tiles)) continue;
+      const int m = clusters_for(sh.rows, Up, sh.tiles);
+      if (m < 2) continue;
+      const int64_t n = 2 * ((rows + sh.rows - 1) / sh.rows);
+      const double t = sh.cost * static_cast<double>((n + m - 1) / m);
       if (t < best) {
         best = t;
-        NR = cand[i];
+        best_nr = sh.rows;
+        best_tiles = sh.tiles;
       }
     }
-    TSSEP_REQUIRE(NR != 0, "tssep_blstm_recurrence_ts: no cluster of %d CTAs fits on this device", C);
+    TSSEP_REQUIRE(best_nr != 0, "tssep_blstm_recurrence_ts: no cluster shape fits on this device (Up=%d)", Up);
+    NR = best_nr;
+    tiles = best_tiles;
   }
+  const int C = cluster_ctas(Up, tiles);
+  TSSEP_REQUIRE(C <= 16, "tssep_blstm_recurrence_ts: Up=%d needs clusters of %d CTAs with %d tile(s) per CTA (max 16)", Up, C, tiles);
   const uint32_t a_tile_cols = (static_cast<uint32_t>(Up) / 2 + 31u) & ~31u;
-  TSSEP_REQUIRE(2 * a_tile_cols + 64 + 2 * (NR < 16 ? 16 : NR) <= 512,
+  TSSEP_REQUIRE(tiles * a_tile_cols + 64 + tiles * (NR < 16 ? 16 : NR) <= 512,
                 "tssep_blstm_recurrence_ts: Up=%d with %d rows per cluster exceeds the 512 tensor-memory columns", Up, NR);
   RecTsArgs a;
   a.Wimg = reinterpret_cast<const uint4*>(Wimg);
@@ -637,7 +696,7 @@ int tssep_blstm_recurrence_ts(const uint16_t* G, const uint32_t* Wimg, uint16_t*
   a.rows = static_cast<int>(rows);
   a.T = static_cast<int>(T);
   a.Up = Up;
-  a.NA = C;
+  a.NA = NA;
   a.KS = Up / 16;
   a.prof = nullptr;
   a.flags = 0;
@@ -648,7 +707,7 @@ int tssep_blstm_recurrence_ts(const uint16_t* G, const uint32_t* Wimg, uint16_t*
   if (const char* e = debug_env("TSSEP_TS_STAGES")) want_stages = atoi(e);
 #endif
   int stages = 0;
-  const size_t smem = ts_smem(C, NR, &stages, want_stages);
+  const size_t smem = ts_smem(NA, NR, tiles, &stages, want_stages);
   TSSEP_REQUIRE(stages >= 2, "tssep_blstm_recurrence_ts: G ring does not fit shared memory");
   a.stages = stages;
   const int nsub = static_cast<int>((rows + NR - 1) / NR);
@@ -656,9 +715,8 @@ int tssep_blstm_recurrence_ts(const uint16_t* G, const uint32_t* Wimg, uint16_t*
   int NC = NR < 16 ? NR : 16;
   if (const char* e = debug_env("TSSEP_TS_COLS")) {
     const int v = atoi(e);
-    if (v == NR || (v == NR / 2 && v >= 4)) NC = v;
+    if (v == NR || (v == NR / 2 && v >= 8)) NC = v;
   }
-  const bool split = k_split == 1;  // default: one phase (the second barrier + fence cost more than the split hides)
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 
   // G (rows, T, 2, 4, Up) bf16 viewed as (unit, row, gate, dir, t); box = 64 units x NR rows x 4 gates
@@ -675,19 +733,20 @@ int tssep_blstm_recurrence_ts(const uint16_t* G, const uint32_t* Wimg, uint16_t*
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   TSSEP_REQUIRE(r == CUDA_SUCCESS, "tssep_blstm_recurrence_ts: cuTensorMapEncodeTiled failed with code %d", static_cast<int>(r));
 
-#define TSSEP_TS_CASE(NR_, NC_)                                                                          \
-  if (NR == NR_ && NC == NC_) {                                                                          \
-    if (gate_math) return split ? launch_ts<NR_, NC_, 1, true>(a, gmap, C, nsub, smem, st)               \
-                                : launch_ts<NR_, NC_, 1, false>(a, gmap, C, nsub, smem, st);             \
-    return split ? launch_ts<NR_, NC_, 0, true>(a, gmap, C, nsub, smem, st)                              \
-                 : launch_ts<NR_, NC_, 0, false>(a, gmap, C, nsub, smem, st);                            \
+#define TSSEP_TS_CASE(NR_, NC_)                                                                             \
+  if (NR == NR_ && NC == NC_) {                                                                             \
+    if (tiles == 1)                                                                                         \
+      return gate_math ? launch_ts<NR_, NC_, 1, false, 1>(a, gmap, C, nsub, smem, st)                       \
+                       : launch_ts<NR_, NC_, 0, false, 1>(a, gmap, C, nsub, smem, st);                      \
+    if (gate_math) return split ? launch_ts<NR_, NC_, 1, true, 2>(a, gmap, C, nsub, smem, st)               \
+                                : launch_ts<NR_, NC_, 1, false, 2>(a, gmap, C, nsub, smem, st);             \
+    return split ? launch_ts<NR_, NC_, 0, true, 2>(a, gmap, C, nsub, smem, st)                              \
+                 : launch_ts<NR_, NC_, 0, false, 2>(a, gmap, C, nsub, smem, st);                            \
   }
-  TSSEP_TS_CASE(8, 4)
   TSSEP_TS_CASE(8, 8)
   TSSEP_TS_CASE(16, 8)
   TSSEP_TS_CASE(16, 16)
   TSSEP_TS_CASE(32, 16)
-  TSSEP_TS_CASE(32, 32)
 #undef TSSEP_TS_CASE
   set_error("tssep_blstm_recurrence_ts: no instantiation for %d rows per cluster, %d columns per warp", NR, NC);
   return -1;

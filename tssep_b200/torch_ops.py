@@ -56,8 +56,8 @@ _OPS = {
         "(Tensor whh_fwd, Tensor whh_bwd, int U, int Up, Tensor(a!) Wfrag) -> ()",
         "tssep_pack_whh"),
     "blstm_recurrence_ts": (
-        "(Tensor G, Tensor Wimg, Tensor(a!) H, int rows, int T, int Up, int rows_per_cluster, int gate_math, "
-        "int k_split) -> ()",
+        "(Tensor G, Tensor Wimg, Tensor(a!) H, int rows, int T, int Up, int rows_per_cluster, int tiles_per_cta, "
+        "int gate_math, int k_split) -> ()",
         "tssep_blstm_recurrence_ts"),
     "pack_whh_ts": (
         "(Tensor whh_fwd, Tensor whh_bwd, int U, int Up, Tensor(a!) Wimg) -> ()",
