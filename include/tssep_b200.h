@@ -212,10 +212,20 @@ int tssep_median_threshold(const float* activity, int64_t n, int64_t T, int widt
                            float* smooth, uint8_t* active, tssep_stream_t stream);
 
 /* Maximal runs of active frames -> sample intervals.  segments (n, max_segments, 2)
- * i32, counts (n) i32 (the true number of runs, may exceed max_segments). */
+ * i32, counts (n) i32 (the true number of runs, may exceed max_segments).
+ * index_mode 0: run [t0, t1) -> samples [c(t0), c(t1)), c(t) = the first sample nearest to the centre of frame t
+ *               (this repo's diarization spec);
+ * index_mode 1: istft_vad (tssep/util/utils.py:80-129): [first(t0), last(t1)) with the paderbox index mapping
+ *               restated in csrc/postproc.cu (paderbox is absent: parity unpinned). */
 int tssep_segments(const uint8_t* active, int64_t n, int64_t T, int window_length, int shift, int fading,
-                   int64_t num_samples, int32_t* segments, int32_t* counts, int max_segments,
+                   int64_t num_samples, int32_t* segments, int32_t* counts, int max_segments, int index_mode,
                    tssep_stream_t stream);
+
+/* stft_vad (tssep/util/utils.py:11-77): sample activity vad (n, num_samples) u8 -> frame activity frames (n, T) u8,
+ * T = the STFT frame count of num_samples; a frame is active when a run of active samples [s, e) has
+ * frame(s) <= t < frame(e) (same index mapping as index_mode 1 above). */
+int tssep_stft_vad(const uint8_t* vad, int64_t n, int64_t num_samples, int window_length, int shift, int fading,
+                   int64_t T, uint8_t* frames, tssep_stream_t stream);
 
 #ifdef __cplusplus
 }

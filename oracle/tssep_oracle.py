@@ -548,16 +548,77 @@ def diarize_reference(mask: np.ndarray, *, threshold=0.5, median_width=1, window
     return act, sm, active, segments
 
 
+# paderbox index helpers used by tssep/util/utils.py (paderbox==0.0.8 is absent: restated from SURVEY.md App. A,
+# PARITY UNPINNED for these three functions; the control flow of utils.py around them is pinned by
+# tests/test_vad_utils.py, which runs the reference's own utils.py on top of them)
+
+
+def pb_samples_to_stft_frames(samples, size, shift, *, pad=True, fading=False):
+    """``paderbox.transform.module_stft._samples_to_stft_frames``."""
+    if fading:
+        samples = samples + 2 * (size - shift)
+    frames = (samples - size + shift) / shift
+    return int(math.ceil(frames)) if pad else int(math.floor(frames))
+
+
+def pb_sample_index_to_stft_frame_index(sample, window_length, shift, fading=True):
+    """``paderbox.transform.module_stft.sample_index_to_stft_frame_index``: 0 below ``ceil(wl/2)``, then one frame
+    per ``shift`` samples; ``+ ceil((wl - shift) / shift)`` frames of fading."""
+    sample = np.asarray(sample)
+    h = (window_length + 1) // 2
+    frame = np.where(sample < h, 0, (sample - h) // shift + 1)
+    if fading:
+        frame = frame + int(math.ceil((window_length - shift) / shift))
+    return frame
+
+
+def pb_stft_frame_index_to_sample_index(frame, window_length, shift, fading=True, mode="first"):
+    """Set inverse of ``pb_sample_index_to_stft_frame_index``: 'first' = smallest sample mapped to a frame >= ``frame``,
+    'last' = largest sample mapped to ``frame`` (= first(frame + 1) - 1)."""
+    frame = np.asarray(frame)
+    pad = int(math.ceil((window_length - shift) / shift)) if fading else 0
+    h = (window_length + 1) // 2
+
+    def first(f):
+        f = f - pad
+        return np.where(f <= 0, 0, h + (f - 1) * shift)
+
+    if mode == "first":
+        return first(frame)
+    if mode == "last":
+        return np.maximum(first(frame + 1) - 1, 0)
+    raise ValueError(mode)
+
+
+def _runs(a):
+    d = np.diff(np.concatenate([[False], np.asarray(a, dtype=bool), [False]]).astype(np.int8))
+    return list(zip(np.nonzero(d == 1)[0].tolist(), np.nonzero(d == -1)[0].tolist()))
+
+
 def stft_vad(vad: np.ndarray, window_length, shift, fading=True) -> np.ndarray:
-    """Sample activity -> frame activity (tssep/util/utils.py:11-77), using our index mapping."""
+    """Sample activity -> frame activity (tssep/util/utils.py:11-77)."""
     vad = np.asarray(vad, dtype=bool)
-    t = num_frames(vad.shape[-1], window_length, shift, True, fading)
+    t = pb_samples_to_stft_frames(vad.shape[-1], window_length, shift, pad=True, fading=fading)
     out = np.zeros(vad.shape[:-1] + (t,), dtype=bool)
     for idx in np.ndindex(vad.shape[:-1]):
-        a = np.concatenate([[False], vad[idx], [False]])
-        d = np.diff(a.astype(np.int8))
-        for s, e in zip(np.nonzero(d == 1)[0], np.nonzero(d == -1)[0]):
-            fs = int(sample_to_frame_index(s, window_length, shift, fading))
-            fe = int(sample_to_frame_index(e, window_length, shift, fading))
+        for s, e in _runs(vad[idx]):
+            fs = int(pb_sample_index_to_stft_frame_index(s, window_length, shift, fading))
+            fe = int(pb_sample_index_to_stft_frame_index(e, window_length, shift, fading))
             out[idx][fs:fe] = True
     return out
+
+
+def istft_vad(vad: np.ndarray, window_length, shift, fading=True, num_samples=None):
+    """Frame activity -> sample intervals (tssep/util/utils.py:80-129): nested list of merged ``(start, end)``."""
+    vad = np.asarray(vad, dtype=bool)
+    out = np.empty(vad.shape[:-1], dtype=object)
+    for idx in np.ndindex(vad.shape[:-1]):
+        iv = []
+        for s, e in _runs(vad[idx]):
+            a = int(pb_stft_frame_index_to_sample_index(s, window_length, shift, fading, mode="first"))
+            b = int(pb_stft_frame_index_to_sample_index(e, window_length, shift, fading, mode="last"))
+            if num_samples is not None:
+                a, b = min(a, num_samples), min(b, num_samples)
+            iv.append((a, b))
+        out[idx] = iv
+    return out.tolist()

@@ -61,7 +61,8 @@ _SIGNATURES = {
                           c_i64, c_vp, c_vp], C.c_int),
     "tssep_activity": ([c_vp, c_i64, c_i64, c_i32, c_vp, c_vp], C.c_int),
     "tssep_median_threshold": ([c_vp, c_i64, c_i64, c_i32, c_f32, c_vp, c_vp, c_vp], C.c_int),
-    "tssep_segments": ([c_vp, c_i64, c_i64, c_i32, c_i32, c_i32, c_i64, c_vp, c_vp, c_i32, c_vp], C.c_int),
+    "tssep_segments": ([c_vp, c_i64, c_i64, c_i32, c_i32, c_i32, c_i64, c_vp, c_vp, c_i32, c_i32, c_vp], C.c_int),
+    "tssep_stft_vad": ([c_vp, c_i64, c_i64, c_i32, c_i32, c_i32, c_i64, c_vp, c_vp], C.c_int),
 }
 
 EXPORTED_SYMBOLS = ["tssep_last_error", *_SIGNATURES]

@@ -236,6 +236,7 @@ __device__ __forceinline__ void idft_reg(float2 (&v)[N]) {
   }
 }
 
+template <bool ACT>
 __global__ void __launch_bounds__(32 * kFastWarps, 3)
 mask_istft_1024_kernel(const float2* __restrict__ X, int64_t x_item_stride, const float* __restrict__ mask, int n_spk,
                        int groups, int64_t T, int trim, const float* __restrict__ synwin, const float2* __restrict__ twiddle,
@@ -289,7 +290,30 @@ mask_istft_1024_kernel(const float2* __restrict__ X, int64_t x_item_stride, cons
       const float2* xrow_a = mask ? X + z * x_item_stride + t * F : X + row_a;
       const float2* xrow_b = mask ? xrow_a : X + row_b;
       const bool own = est != nullptr && t >= j_begin;
-      float msum_a = 0.f, msum_b = 0.f;  // frame activity: every bin is read as mask[kk] exactly once (+ bin 512)
+      if constexpr (ACT) {
+        // Frame activity mean_f mask[k, t, f] of the two speakers, from a prelude pass over the two mask rows: it
+        // doubles as the prefetch of the rows the transform below reads (the sums are dead before it starts, so the
+        // register budget of the transform -- 168 registers at 3 CTAs per SM -- is untouched; accumulating inside the
+        // transform loop cost 25 % of the kernel's speed).  Halo frames belong to the previous range.
+        if (t >= j_begin) {
+          float sa = 0.f, sb = 0.f;
+#pragma unroll
+          for (int k1 = 0; k1 < 16; ++k1) {
+            sa += mask[row_a + 32 * k1 + lane];
+            sb += mask[row_b + 32 * k1 + lane];
+          }
+          if (lane == 0) {
+            sa += mask[row_a + M];
+            sb += mask[row_b + M];
+          }
+          sa = warp_sum(sa);
+          sb = warp_sum(sb);
+          if (lane == 0) {
+            activity[sig_a * T + t] = sa / static_cast<float>(F);
+            if (has_b) activity[sig_b * T + t] = sb / static_cast<float>(F);
+          }
+        }
+      }
 #pragma unroll
       for (int k1 = 0; k1 < 16; ++k1) {
         const int kk = 32 * k1 + lane;
@@ -298,8 +322,6 @@ mask_istft_1024_kernel(const float2* __restrict__ X, int64_t x_item_stride, cons
         if (mask) {
           const float mk = mask[row_a + kk], mm = mask[row_a + M - kk];
           const float mk2 = mask[row_b + kk], mm2 = mask[row_b + M - kk];
-          msum_a += mk + (kk == 0 ? mm : 0.f);
-          msum_b += mk2 + (kk == 0 ? mm2 : 0.f);
           yk = make_float2(yk.x * mk, yk.y * mk);
           ym = make_float2(ym.x * mm, ym.y * mm);
           yk2 = make_float2(yk2.x * mk2, yk2.y * mk2);
@@ -323,14 +345,6 @@ mask_istft_1024_kernel(const float2* __restrict__ X, int64_t x_item_stride, cons
         const float2 w = tw[kk];
         va[k1] = irfft_pack_w(yk, ym, w);
         vb[k1] = irfft_pack_w(yk2, ym2, w);
-      }
-      if (activity != nullptr && t >= j_begin) {  // halo frames belong to the previous range
-        msum_a = warp_sum(msum_a);
-        msum_b = warp_sum(msum_b);
-        if (lane == 0) {
-          activity[sig_a * T + t] = msum_a / static_cast<float>(F);
-          if (has_b) activity[sig_b * T + t] = msum_b / static_cast<float>(F);
-        }
       }
       idft_reg<16>(va);
       idft_reg<16>(vb);
@@ -439,10 +453,16 @@ int tssep_mask_istft(const float* X, int64_t x_item_stride, const float* mask, i
     const int groups = (n_spk + 2 * kFastWarps - 1) / (2 * kFastWarps);
     while (hops > 16 && ((J + hops - 1) / hops) * Z * groups < 3 * 148) hops /= 2;
     dim3 grid(static_cast<unsigned>((J + hops - 1) / hops), static_cast<unsigned>(Z * groups));
-    mask_istft_1024_kernel<<<grid, 32 * kFastWarps, 0, static_cast<cudaStream_t>(stream)>>>(
-        reinterpret_cast<const float2*>(X), x_item_stride, mask, n_spk, groups, T, fading ? window_length - shift : 0, synwin,
-        reinterpret_cast<const float2*>(twiddle), reinterpret_cast<float2*>(stft_estimate), time, num_samples, hops,
-        activity);
+    if (activity != nullptr)
+      mask_istft_1024_kernel<true><<<grid, 32 * kFastWarps, 0, static_cast<cudaStream_t>(stream)>>>(
+          reinterpret_cast<const float2*>(X), x_item_stride, mask, n_spk, groups, T, fading ? window_length - shift : 0, synwin,
+          reinterpret_cast<const float2*>(twiddle), reinterpret_cast<float2*>(stft_estimate), time, num_samples, hops,
+          activity);
+    else
+      mask_istft_1024_kernel<false><<<grid, 32 * kFastWarps, 0, static_cast<cudaStream_t>(stream)>>>(
+          reinterpret_cast<const float2*>(X), x_item_stride, mask, n_spk, groups, T, fading ? window_length - shift : 0, synwin,
+          reinterpret_cast<const float2*>(twiddle), reinterpret_cast<float2*>(stft_estimate), time, num_samples, hops,
+          activity);
     return check_launch("tssep_mask_istft");
   }
   // generic geometries: the frame activity comes from the stand-alone reduction

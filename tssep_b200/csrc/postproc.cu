@@ -59,10 +59,33 @@ __device__ __forceinline__ int frame_to_sample(int64_t frame, int wl, int R, int
   return static_cast<int>(s);
 }
 
+// Index mapping of stft_vad / istft_vad (tssep/util/utils.py:11-129).  The reference delegates it to paderbox
+// (module_stft.sample_index_to_stft_frame_index / stft_frame_index_to_sample_index, paderbox==0.0.8, absent here);
+// restated from SURVEY.md App. A:
+//   frame(s)  = pad_frames + (s < ceil(wl/2) ? 0 : (s - ceil(wl/2)) / shift + 1),  pad_frames = ceil((wl-shift)/shift) | 0
+//   first(f)  = smallest sample mapped to a frame >= f;   last(f) = largest sample mapped to frame f = first(f+1) - 1
+__device__ __forceinline__ int64_t vad_first_sample(int64_t frame, int wl, int R, int pad_frames) {
+  const int64_t f = frame - pad_frames;
+  return f <= 0 ? 0 : (wl + 1) / 2 + (f - 1) * static_cast<int64_t>(R);
+}
+
+// frame f is covered by a run of active samples [s, e) with frame(s) <= f < frame(e)  <=>  the sample just below
+// first(f + 1) is active: a gather, no scan
+__global__ void stft_vad_kernel(const uint8_t* __restrict__ vad, int64_t n, int64_t N, int wl, int R, int pad_frames,
+                                int64_t T, uint8_t* __restrict__ out) {
+  const int64_t total = n * T;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t f = i % T, sig = i / T;
+    const int64_t a = vad_first_sample(f + 1, wl, R, pad_frames);
+    out[i] = (a >= 1 && a <= N && vad[sig * N + a - 1]) ? 1 : 0;
+  }
+}
+
 // one block per signal; starts and ends of runs are compacted with ballot + prefix sums
 __global__ void __launch_bounds__(256)
 segments_kernel(const uint8_t* __restrict__ active, int64_t T, int wl, int R, int pad, int64_t num_samples,
-                int* __restrict__ segments, int* __restrict__ counts, int max_segments) {
+                int* __restrict__ segments, int* __restrict__ counts, int max_segments, int index_mode) {
   __shared__ int warp_s[8], warp_e[8];
   __shared__ int base_s, base_e;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -95,11 +118,21 @@ segments_kernel(const uint8_t* __restrict__ active, int64_t T, int wl, int R, in
     const unsigned lt = (1u << lane) - 1;
     if (is_start) {
       const int i = off_s + __popc(ms & lt);
-      if (i < max_segments) seg[2 * i] = frame_to_sample(t, wl, R, pad, num_samples);
+      if (i < max_segments) {
+        int64_t v = index_mode ? vad_first_sample(t, wl, R, (pad + R - 1) / R) : frame_to_sample(t, wl, R, pad, num_samples);
+        if (num_samples >= 0 && v > num_samples) v = num_samples;
+        seg[2 * i] = static_cast<int>(v);
+      }
     }
     if (is_end) {
       const int i = off_e + __popc(me & lt);
-      if (i < max_segments) seg[2 * i + 1] = frame_to_sample(t + 1, wl, R, pad, num_samples);
+      if (i < max_segments) {
+        // istft_vad maps the exclusive frame end t + 1 with mode 'last' (utils.py:116-122): last(f) = first(f + 1) - 1
+        int64_t v = index_mode ? vad_first_sample(t + 2, wl, R, (pad + R - 1) / R) - 1 : frame_to_sample(t + 1, wl, R, pad, num_samples);
+        v = v < 0 ? 0 : v;
+        if (num_samples >= 0 && v > num_samples) v = num_samples;
+        seg[2 * i + 1] = static_cast<int>(v);
+      }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -143,13 +176,27 @@ int tssep_median_threshold(const float* activity, int64_t n, int64_t T, int widt
   return check_launch("tssep_median_threshold");
 }
 
+int tssep_stft_vad(const uint8_t* vad, int64_t n, int64_t num_samples, int window_length, int shift, int fading, int64_t T,
+                   uint8_t* frames, tssep_stream_t stream) {
+  TSSEP_REQUIRE(vad && frames, "tssep_stft_vad: null pointer");
+  TSSEP_REQUIRE(shift >= 1 && window_length >= shift && n >= 0 && num_samples >= 0 && T >= 0, "tssep_stft_vad: bad extent");
+  if (n == 0 || T == 0) return 0;
+  const int blocks = static_cast<int>(imin64((n * T + 255) / 256, 148 * 16));
+  stft_vad_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      vad, n, num_samples, window_length, shift, fading ? (window_length - shift + shift - 1) / shift : 0, T, frames);
+  return check_launch("tssep_stft_vad");
+}
+
 int tssep_segments(const uint8_t* active, int64_t n, int64_t T, int window_length, int shift, int fading,
-                   int64_t num_samples, int32_t* segments, int32_t* counts, int max_segments, tssep_stream_t stream) {
+                   int64_t num_samples, int32_t* segments, int32_t* counts, int max_segments, int index_mode,
+                   tssep_stream_t stream) {
   TSSEP_REQUIRE(active && segments && counts && max_segments >= 1, "tssep_segments: bad arguments");
+  TSSEP_REQUIRE(index_mode == 0 || index_mode == 1, "tssep_segments: index_mode must be 0 (window centre) or 1 (istft_vad)");
   TSSEP_REQUIRE(shift >= 1 && window_length >= shift, "tssep_segments: bad frame geometry");
   if (n == 0) return 0;
   segments_kernel<<<static_cast<unsigned>(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      active, T, window_length, shift, fading ? window_length - shift : 0, num_samples, segments, counts, max_segments);
+      active, T, window_length, shift, fading ? window_length - shift : 0, num_samples, segments, counts, max_segments,
+      index_mode);
   return check_launch("tssep_segments");
 }
 

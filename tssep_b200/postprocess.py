@@ -54,5 +54,5 @@ def diarize(mask: torch.Tensor, fe, *, num_samples=None, threshold=0.5, median_w
     cnt = torch.empty(lead, dtype=torch.int32, device=dev)
     torch_ops.op.median_threshold(act, n, T, int(median_width), float(threshold), smooth, active)
     torch_ops.op.segments(active, n, T, fe.window_length, fe.shift, int(bool(fe.fading)),
-                          -1 if num_samples is None else int(num_samples), seg, cnt, max_segments)
+                          -1 if num_samples is None else int(num_samples), seg, cnt, max_segments, 0)
     return Diarization(act, smooth, active, seg, cnt)

@@ -75,8 +75,11 @@ _OPS = {
         "tssep_median_threshold"),
     "segments": (
         "(Tensor active, int n, int T, int window_length, int shift, int fading, int num_samples, Tensor(a!) segments, "
-        "Tensor(b!) counts, int max_segments) -> ()",
+        "Tensor(b!) counts, int max_segments, int index_mode) -> ()",
         "tssep_segments"),
+    "stft_vad": (
+        "(Tensor vad, int n, int num_samples, int window_length, int shift, int fading, int T, Tensor(a!) frames) -> ()",
+        "tssep_stft_vad"),
     # tssep_gemm takes a descriptor struct: the operator carries its fields as arguments
     "gemm": (
         "(Tensor A, int lda, int a_stride, int a_div, Tensor B, int ldb, int b_stride, int b_mod, Tensor? bias, "
