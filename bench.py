@@ -335,7 +335,7 @@ def run_b200(args):
     # meeting) and the TS-VAD layer (R rows) run once for all meetings.  Waves of the K-row layers: as few dependent
     # steps as possible given how many rows one wave of clusters holds at each cluster width.
     Up = 304
-    cap = {w: _ops.recurrence_ts_capacity(Up, w) for w in (8, 16, 32)}
+    cap = {w: _ops.recurrence_ts_capacity(Up, w) for w in (8, 16, 32, 64)}
     free_b, _ = torch.cuda.mem_get_info(dev)
     # memory model per 10-min meeting (calibrated on torch.cuda.memory_stats in round 1): 0.7 GB that lives for the whole
     # step (audio, STFT, pre_net rows, the step's separated audio and the serving loop's buffers), 2.05 GB while its wave

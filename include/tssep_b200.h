@@ -154,8 +154,9 @@ int tssep_head_expand_t(const float* small, int64_t Z, int64_t T, int n_blocks, 
  * Up = hidden units rounded up to a multiple of 16; padded units stay 0.  Limits: Up <= 384, and
  * tiles * roundup(Up/2, 32) + 64 + tiles * max(rows_per_cluster, 16) <= 512 tensor-memory columns (Up <= 320 at 32
  * rows and 2 tiles); clusters of at most 16 CTAs.
- * rows_per_cluster: 8, 16 or 32; tiles_per_cta: 1 or 2; 0 = choose (the shape with the shortest step whose clusters
- * still fit in one wave of co-resident clusters).
+ * rows_per_cluster: 8, 16, 32, or 64 (two sub-batches of 32 rows advancing in anti-phase: while the h of one travels
+ * through DSMEM and its gate math runs, the tensor pipe works on the other; 2 tiles only); tiles_per_cta: 1 or 2;
+ * 0 = choose (the shape with the shortest step whose clusters still fit in one wave of co-resident clusters).
  * gate_math: 0 = exp-based sigmoid / tanh, 1 = tanh.approx.f32.
  * k_split: 1 = the W_hh . h MMAs start on the half of h that arrives first (2 tiles only); 0 (and -1 = default) = one phase
  * (measured: the second barrier wait + proxy fence cost more than the split hides). */
@@ -163,7 +164,7 @@ int tssep_blstm_recurrence_ts(const uint16_t* G, const uint32_t* Wimg, uint16_t*
                               int rows_per_cluster, int tiles_per_cta, int gate_math, int k_split,
                               tssep_stream_t stream);
 /* Batch rows that fit in ONE wave of co-resident clusters (both directions running) on the current
- * device for the given cluster shape (rows_per_cluster 8 / 16 / 32, tiles_per_cta 1 / 2); < 0 on error. */
+ * device for the given cluster shape (rows_per_cluster 8 / 16 / 32 / 64, tiles_per_cta 1 / 2); < 0 on error. */
 int tssep_blstm_recurrence_ts_capacity(int Up, int rows_per_cluster, int tiles_per_cta);
 int tssep_pack_whh_ts(const float* whh_fwd, const float* whh_bwd, int U, int Up, uint32_t* Wimg,
                       tssep_stream_t stream);

@@ -97,38 +97,45 @@ __device__ __forceinline__ float ts_tanh(float x) {
   else return tanh_acc(x);
 }
 
-// NR batch rows per cluster, NC of them per epilogue warp (8 * NR/NC epilogue warps); MATH: gate arithmetic;
-// SPLIT: two K phases per step (see the header).  Everything the per-step loops branch on is a template parameter.
-template <int NR, int NC, int MATH, bool SPLIT, int TILES>
-__global__ void __launch_bounds__(64 + 128 * TILES * (NR / NC), 1)
+// NR batch rows per sub-batch, NC of them per epilogue warp; MATH: gate arithmetic; SPLIT: two K phases per step (see
+// the header); TILES: row tiles per CTA; SUBS: independent sub-batches of NR rows per cluster.  SUBS = 2 is the
+// throughput shape: the cluster advances two recurrences in anti-phase -- while one sub-batch's h travels through
+// DSMEM and its epilogue warps run, the tensor pipe works on the other (an MMA costs ~27 cycles whatever its N, so 64
+// rows per cluster at N = 32 halve the tensor-pipe time per row, and the ping-pong hides the exchange).
+// Everything the per-step loops branch on is a template parameter.
+template <int NR, int NC, int MATH, bool SPLIT, int TILES, int SUBS>
+__global__ void __launch_bounds__(64 + 128 * TILES * SUBS * (NR / NC), 1)
 blstm_rec_ts_kernel(const RecTsArgs a, const __grid_constant__ CUtensorMap gmap) {
   static_assert(TILES == 1 || TILES == 2, "one or two row tiles per CTA");
-  static_assert(TILES == 2 || !SPLIT, "the K split pairs the two row tiles of a CTA");
+  static_assert(SUBS == 1 || SUBS == 2, "one or two sub-batches per cluster");
+  static_assert((TILES == 2 && SUBS == 1) || !SPLIT, "the K split pairs the two row tiles of a CTA");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr int NB = NR < 16 ? 16 : NR;   // MMA N (M = 128 needs N % 16 == 0); rows NR..NB-1 of the operands stay zero
+  constexpr int NRT = NR * SUBS;          // batch rows per cluster
   constexpr uint32_t kAtomB = NB * 128;   // one 64-k atom of the h operand: NB rows x 128 bytes, 128-byte swizzle
-  constexpr uint32_t kAtomG = NR * 128;   // one 64-k atom of the G operand as the TMA box lays it out
-  constexpr int EW = NR / NC;             // epilogue warps per (row tile, TMEM lane quarter)
+  constexpr uint32_t kAtomG = NRT * 128;  // one 64-k atom of the G operand as the TMA box lays it out (all sub-batches)
+  constexpr int EW = NR / NC;             // epilogue warps per (sub-batch, row tile, TMEM lane quarter)
   constexpr int NQ = NC / 4;              // batch-row quads per epilogue warp
-  constexpr int kThreads = 64 + 128 * TILES * EW;
+  constexpr int kThreads = 64 + 128 * TILES * SUBS * EW;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int NA = a.NA, KS = a.KS, GS = a.stages;
-  constexpr uint32_t g_stage = 4u * kAtomG;         // [gate][row][64 units]
-  const uint32_t sB = base;                         // [2 buffers][NA] x kAtomB
-  const uint32_t sG = sB + 2u * NA * kAtomB;        // [GS] x g_stage (+ 1 KiB of zeros behind the last stage)
-  const uint32_t sT = sG + GS * g_stage + 1024u;    // [4 * TILES * EW warps] x NC x 16 B
-  const uint32_t sBar = sT + 4u * TILES * NR * 16u;
-  const uint32_t hfull0 = sBar;                     // [buffer][phase]
-  const uint32_t accfull0 = sBar + 32, accempty0 = sBar + 48, gfull0 = sBar + 64, gempty0 = gfull0 + 8 * kTsMaxStages,
-                 tptr = gempty0 + 8 * kTsMaxStages;
+  constexpr uint32_t g_stage = 4u * kAtomG;                 // [gate][row][64 units]
+  const uint32_t sB = base;                                 // [sub-batch][2 buffers][NA] x kAtomB
+  const uint32_t sub_bytes = 2u * NA * kAtomB;
+  const uint32_t sG = sB + SUBS * sub_bytes;                // [GS] x g_stage (+ 1 KiB of zeros behind the last stage)
+  const uint32_t sT = sG + GS * g_stage + 1024u;            // [epilogue warps] x NC x 16 B
+  const uint32_t sBar = sT + 4u * TILES * NRT * 16u;
+  const uint32_t hfull0 = sBar;                             // [sub-batch][buffer][phase]
+  const uint32_t accfull0 = sBar + 64, accempty0 = sBar + 96;  // [sub-batch][tile]
+  const uint32_t gfull0 = sBar + 128, gempty0 = gfull0 + 8 * kTsMaxStages, tptr = gempty0 + 8 * kTsMaxStages;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t crank = cluster_ctarank();
   const uint32_t C = cluster_nctarank();
   const int dir = blockIdx.z;
-  const int row0 = blockIdx.y * NR;  // first batch row of this cluster
+  const int row0 = blockIdx.y * NRT;  // first batch row of this cluster
   const int T = a.T, Up = a.Up;
-  // every CTA ships TILES x 32 units x NR rows per step; with SPLIT each row tile completes its own barrier
+  // every CTA ships TILES x 32 units x NR rows per step and sub-batch; with SPLIT each row tile completes its own barrier
   const uint32_t tx_bytes = static_cast<uint32_t>(NR) * 64u * (SPLIT ? 1u : static_cast<uint32_t>(TILES)) * C;
 
   // ---- one-time setup ---------------------------------------------------------------------------
@@ -136,8 +143,8 @@ blstm_rec_ts_kernel(const RecTsArgs a, const __grid_constant__ CUtensorMap gmap)
     asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(sB + 16 * i), "r"(0u) : "memory");
   if (warp == 1) {
     if (lane == 0) {
-      for (int i = 0; i < 4; ++i) mbar_init(hfull0 + 8 * i, 1);
-      for (int i = 0; i < 2; ++i) {
+      for (int i = 0; i < 8; ++i) mbar_init(hfull0 + 8 * i, 1);
+      for (int i = 0; i < 4; ++i) {
         mbar_init(accfull0 + 8 * i, 1);
         mbar_init(accempty0 + 8 * i, 4 * EW);
       }
@@ -146,7 +153,9 @@ blstm_rec_ts_kernel(const RecTsArgs a, const __grid_constant__ CUtensorMap gmap)
         mbar_init(gempty0 + 8 * i, 1);
       }
       mbar_fence_init();
-      for (int i = 0; i < (SPLIT ? 4 : 2); ++i) mbar_arrive_expect_tx(hfull0 + 8 * (SPLIT ? i : 2 * i), tx_bytes);
+      for (int sb = 0; sb < SUBS; ++sb)
+        for (int bf = 0; bf < 2; ++bf)
+          for (int ph = 0; ph < (SPLIT ? 2 : 1); ++ph) mbar_arrive_expect_tx(hfull0 + 8 * ((sb * 2 + bf) * 2 + ph), tx_bytes);
     }
     __syncwarp();
     tc_alloc(tptr, 512);
@@ -160,7 +169,7 @@ blstm_rec_ts_kernel(const RecTsArgs a, const __grid_constant__ CUtensorMap gmap)
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tptr));
   const uint32_t a_tile_cols = (static_cast<uint32_t>(Up) / 2 + 31u) & ~31u;  // columns per A tile (32-aligned)
   const uint32_t p_col = TILES * a_tile_cols;                                  // P behind the A tiles (64 columns)
-  const uint32_t acc_col = p_col + 64u;                                        // then the two accumulators
+  const uint32_t acc_col = p_col + 64u;                                        // then the accumulators [sub][tile]
 
   if (warp >= 2 && warp < 2 + 4 * TILES) {
     // W_hh -> TMEM: lane = gate row of the tile, 8 columns (16 k values) per store
@@ -203,10 +212,10 @@ blstm_rec_ts_kernel(const RecTsArgs a, const __grid_constant__ CUtensorMap gmap)
 
   if (warp == 0) {
     // ---- G producer ---------------------------------------------------------------------------------
-    // G (rows, T, 2, 4, Up) bf16 viewed as (unit, row, gate, dir, t): one box of 64 units x NR rows x 4 gates per
+    // G (rows, T, 2, 4, Up) bf16 viewed as (unit, row, gate, dir, t): one box of 64 units x NRT rows x 4 gates per
     // step = [gate][row][128 bytes], per gate the canonical K-major SWIZZLE_128B operand layout (K = 64 units:
     // k-steps 0,1 belong to the even row tile, k-steps 2,3 to the odd one; with one tile per CTA the two CTAs of a
-    // pair load the same box and each uses its half).
+    // pair load the same box and each uses its half; the sub-batches are row ranges of the box).
     if (lane == 0) {
       tma_prefetch_desc(&gmap);
       int slot = 0;
@@ -233,15 +242,14 @@ blstm_rec_ts_kernel(const RecTsArgs a, const __grid_constant__ CUtensorMap gmap)
                            (static_cast<uint32_t>(128 >> 4) << 24);
     const uint64_t bdesc0 = ts_desc_sw128(sB);
     const uint64_t gdesc0 = ts_desc_sw128(sG);
-    const uint32_t buf_step = static_cast<uint32_t>(NA) * (kAtomB >> 4);  // encoded distance of the two h buffers
+    const uint32_t buf_step = static_cast<uint32_t>(NA) * (kAtomB >> 4);  // encoded distance of two h buffers
     const uint32_t d0 = tmem_base + acc_col;
     const uint32_t pt = tmem_base + p_col;
     int slot = 0;
     uint32_t gph = 0;
     // W_hh . h for one tile and one K phase: phase 0 = k-steps 0,1 of every atom (units of the senders' first
     // row tile), phase 1 = k-steps 2,3; without SPLIT phase 0 covers all four
-    auto issue_h = [&](int tile, int phase, uint64_t bd) {
-      const uint32_t d = d0 + tile * NB;
+    auto issue_h = [&](uint32_t d, int tile, int phase, uint64_t bd) {
       uint32_t at = tmem_base + static_cast<uint32_t>(tile) * a_tile_cols;
       uint64_t bk = bd;
       const int k_lo = phase * 2, k_hi = SPLIT ? k_lo + 2 : 4;
@@ -263,70 +271,76 @@ blstm_rec_ts_kernel(const RecTsArgs a, const __grid_constant__ CUtensorMap gmap)
 #endif
     for (int s = 0; s < T; ++s) {
       const int rb = (s & 1) ^ 1;
-      int m0 = 0, m1 = 0, m2 = 0, m3 = 0;
-      if (mprof) m0 = clock();
-      // P . G_s: needs the G stage and the accumulators of step s-1 drained -- both long before h arrives
       mbar_wait(gfull0 + 8 * slot, gph);
-      if (s > 0) {
-        mbar_wait(accempty0, (s - 1) & 1);
-        if constexpr (TILES == 2) mbar_wait(accempty0 + 8, (s - 1) & 1);
-      }
-      tc_fence_after();
-      if (elect_one()) {
-        const uint64_t gd = gdesc0 + static_cast<uint64_t>(static_cast<uint32_t>(slot) * (g_stage >> 4));
+      const uint64_t gd = gdesc0 + static_cast<uint64_t>(static_cast<uint32_t>(slot) * (g_stage >> 4));
 #pragma unroll
-        for (int tile = 0; tile < TILES; ++tile) {
-          const uint32_t hx = (crank * TILES + tile) & 1u;  // which 32 units of the 64-unit box
-#pragma unroll
-          for (int k = 0; k < 8; ++k)  // k-step k of P = gate k/2, half k%2 of the tile's 32 units
-            tc_mma_bf16_ts(d0 + tile * NB, pt + k * 8,
-                           gd + static_cast<uint64_t>(static_cast<uint32_t>(k >> 1) * (kAtomG >> 4) + 2 * (2 * hx + (k & 1))),
-                           idesc, k > 0 ? 1u : 0u);
+      for (int sb = 0; sb < SUBS; ++sb) {
+        int m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+        if (mprof) m0 = clock();
+        const uint32_t dsub = d0 + static_cast<uint32_t>(sb * TILES) * NB;
+        // P . G_s: needs the accumulators of step s-1 drained -- long before h arrives
+        if (s > 0) {
+          mbar_wait(accempty0 + 8 * (sb * 2), (s - 1) & 1);
+          if constexpr (TILES == 2) mbar_wait(accempty0 + 8 * (sb * 2 + 1), (s - 1) & 1);
         }
-      }
-      __syncwarp();
-      if (mprof) m1 = clock();
-      const uint64_t bd = bdesc0 + static_cast<uint64_t>(rb ? buf_step : 0u);
-      if (s > 0) {
-        const uint32_t par = ((s - 1) >> 1) & 1;
-        mbar_wait(hfull0 + 8 * (2 * rb), par);
-        if (mprof) m2 = clock();
-        if (lane == 0) mbar_arrive_expect_tx(hfull0 + 8 * (2 * rb), tx_bytes);  // re-arm for the data of step s+1
-        // h arrived through st.async (generic proxy); the MMA reads it through the async proxy
-        if (!no_fence) ts_fence_proxy_async();
         tc_fence_after();
-        if (mprof) m3 = clock();
-        if constexpr (SPLIT) {
-          if (elect_one()) {
-            issue_h(0, 0, bd);
-            issue_h(1, 0, bd);
+        if (elect_one()) {
+#pragma unroll
+          for (int tile = 0; tile < TILES; ++tile) {
+            const uint32_t hx = (crank * TILES + tile) & 1u;  // which 32 units of the 64-unit box
+#pragma unroll
+            for (int k = 0; k < 8; ++k)  // k-step k of P = gate k/2, half k%2 of the tile's 32 units; rows of sub-batch sb
+              tc_mma_bf16_ts(dsub + tile * NB, pt + k * 8,
+                             gd + static_cast<uint64_t>(static_cast<uint32_t>(k >> 1) * (kAtomG >> 4) +
+                                                        static_cast<uint32_t>(sb) * (NR * 8) + 2 * (2 * hx + (k & 1))),
+                             idesc, k > 0 ? 1u : 0u);
           }
-          __syncwarp();
-          mbar_wait(hfull0 + 8 * (2 * rb + 1), par);
-          if (lane == 0) mbar_arrive_expect_tx(hfull0 + 8 * (2 * rb + 1), tx_bytes);
-          ts_fence_proxy_async();
+        }
+        __syncwarp();
+        if (mprof) m1 = clock();
+        const uint64_t bd = bdesc0 + static_cast<uint64_t>(static_cast<uint32_t>(sb * 2 + rb) * buf_step);
+        const uint32_t hbar = hfull0 + 8 * ((sb * 2 + rb) * 2);
+        if (s > 0) {
+          const uint32_t par = ((s - 1) >> 1) & 1;
+          mbar_wait(hbar, par);
+          if (mprof) m2 = clock();
+          if (lane == 0) mbar_arrive_expect_tx(hbar, tx_bytes);  // re-arm for the data of step s+1
+          // h arrived through st.async (generic proxy); the MMA reads it through the async proxy
+          if (!no_fence) ts_fence_proxy_async();
           tc_fence_after();
+          if (mprof) m3 = clock();
+          if constexpr (SPLIT) {
+            if (elect_one()) {
+              issue_h(dsub, 0, 0, bd);
+              issue_h(dsub + NB, 1, 0, bd);
+            }
+            __syncwarp();
+            mbar_wait(hbar + 8, par);
+            if (lane == 0) mbar_arrive_expect_tx(hbar + 8, tx_bytes);
+            ts_fence_proxy_async();
+            tc_fence_after();
+          }
         }
-      }
-      if (elect_one()) {
-        if (s > 0) issue_h(0, SPLIT ? 1 : 0, bd);
-        tc_commit(accfull0);
-        if constexpr (TILES == 2) {
-          if (s > 0) issue_h(1, SPLIT ? 1 : 0, bd);
-          tc_commit(accfull0 + 8);
+        if (elect_one()) {
+          if (s > 0) issue_h(dsub, 0, SPLIT ? 1 : 0, bd);
+          tc_commit(accfull0 + 8 * (sb * 2));
+          if constexpr (TILES == 2) {
+            if (s > 0) issue_h(dsub + NB, 1, SPLIT ? 1 : 0, bd);
+            tc_commit(accfull0 + 8 * (sb * 2 + 1));
+          }
+          if (sb == SUBS - 1) tc_commit(gempty0 + 8 * slot);  // the stage is free once the MMAs that read it are done
         }
-        tc_commit(gempty0 + 8 * slot);  // the stage is free once the MMAs that read it are done
-      }
-      __syncwarp();
+        __syncwarp();
 #ifdef TSSEP_DEBUG_KNOBS
-      if (mprof && s > 0) {
-        const int m4 = clock();
-        mc[0] += m1 - m0;  // G ring / accumulator-drained waits + P.G issue
-        mc[1] += m2 - m1;  // wait for h_{t-1}
-        mc[2] += m3 - m2;  // re-arm + proxy fence
-        mc[3] += m4 - m3;  // W_hh.h issue + commits
-      }
+        if (mprof && s > 0 && sb == 0) {
+          const int m4 = clock();
+          mc[0] += m1 - m0;  // accumulator-drained waits + P.G issue
+          mc[1] += m2 - m1;  // wait for h_{t-1}
+          mc[2] += m3 - m2;  // re-arm + proxy fence
+          mc[3] += m4 - m3;  // W_hh.h issue + commits
+        }
 #endif
+      }
       if (++slot == GS) {
         slot = 0;
         gph ^= 1;
@@ -338,9 +352,11 @@ blstm_rec_ts_kernel(const RecTsArgs a, const __grid_constant__ CUtensorMap gmap)
 #endif
   } else {
     // ---- epilogue: gates, cell update, h exchange --------------------------------------------------
-    const int tl = ((warp - 2) >> 2) % TILES;  // row tile handled by this warp
+    const int wx = (warp - 2) >> 2;            // (tile, column group) of this warp
+    const int tl = wx % TILES;                 // row tile handled by this warp
     const int q = warp & 3;                    // TMEM lane quarter
-    const int half = ((warp - 2) >> 2) / TILES;  // which NC columns (batch rows) of the tile
+    const int cg = wx / TILES;                 // column group: NC batch rows
+    const int sb = cg / EW, half = cg % EW;    // sub-batch and which NC columns of its tile
     const int gate = lane & 3;             // i, f, g, o
     const int ul = lane >> 2;              // unit within the warp's octet
     const bool is_g = gate == 2;
@@ -351,24 +367,27 @@ blstm_rec_ts_kernel(const RecTsArgs a, const __grid_constant__ CUtensorMap gmap)
     const int oc = (gtile & 1) * 4 + q;                      // unit octet = 16-byte chunk inside the 64-unit k-atom
     const int unit0 = gtile * 32 + q * 8;
     const bool oct_ok = unit0 < Up;
-    // sender role: lane ships batch row r to CTAs d0, d0 + 32/NC, ...
+    // sender role: lane ships batch row r (of its sub-batch) to CTAs d0, d0 + 32/NC, ...
     constexpr int DG = 32 / NC;
     const int rl = lane % NC, r = half * NC + rl, d0 = lane / NC;
-    const uint32_t chunk_off = static_cast<uint32_t>(gtile >> 1) * kAtomB + static_cast<uint32_t>(r >> 3) * 1024 +
-                               static_cast<uint32_t>(r & 7) * 128 + ((static_cast<uint32_t>(oc) ^ static_cast<uint32_t>(r & 7)) << 4);
+    const uint32_t chunk_off = static_cast<uint32_t>(sb) * sub_bytes + static_cast<uint32_t>(gtile >> 1) * kAtomB +
+                               static_cast<uint32_t>(r >> 3) * 1024 + static_cast<uint32_t>(r & 7) * 128 +
+                               ((static_cast<uint32_t>(oc) ^ static_cast<uint32_t>(r & 7)) << 4);
     constexpr int ND = ((TILES == 1 ? 16 : 8) + DG - 1) / DG;  // clusters of up to 16 CTAs with one tile per CTA
     uint32_t r_b[ND], r_bar[ND];
 #pragma unroll
     for (int j = 0; j < ND; ++j) {
       const uint32_t d = static_cast<uint32_t>(d0 + j * DG);
       r_b[j] = d < C ? mapa(sB, d) + chunk_off : 0;
-      r_bar[j] = d < C ? mapa(hfull0 + (SPLIT ? 8u * tl : 0u), d) : 0;
+      r_bar[j] = d < C ? mapa(hfull0 + 32u * sb + (SPLIT ? 8u * tl : 0u), d) : 0;
     }
-    __nv_bfloat16* hptr = a.H + (static_cast<int64_t>(row0 + r) * T) * (2 * static_cast<int64_t>(Up)) + dir * Up + unit0 +
+    const int grow = row0 + sb * NR + r;  // batch row of the launch
+    __nv_bfloat16* hptr = a.H + (static_cast<int64_t>(grow) * T) * (2 * static_cast<int64_t>(Up)) + dir * Up + unit0 +
                           (dir ? static_cast<int64_t>(T - 1) * 2 * Up : 0);  // frame of step 0
     const int64_t h_step = dir ? -2ll * Up : 2ll * Up;
-    const bool h_store = oct_ok && d0 == 0 && row0 + r < a.rows;
-    const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc_col + tl * NB + half * NC;
+    const bool h_store = oct_ok && d0 == 0 && grow < a.rows;
+    const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc_col + (sb * TILES + tl) * NB + half * NC;
+    const uint32_t my_accfull = accfull0 + 8 * (sb * 2 + tl), my_accempty = accempty0 + 8 * (sb * 2 + tl);
 
     float cst[NQ];
 #pragma unroll
@@ -384,7 +403,7 @@ blstm_rec_ts_kernel(const RecTsArgs a, const __grid_constant__ CUtensorMap gmap)
       const int wb = s & 1;
       int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
       if (do_prof) c0 = clock();
-      mbar_wait(accfull0 + 8 * tl, s & 1);
+      mbar_wait(my_accfull, s & 1);
       if (do_prof) c1 = clock();
       tc_fence_after();
       uint32_t v[NC];
@@ -395,7 +414,7 @@ blstm_rec_ts_kernel(const RecTsArgs a, const __grid_constant__ CUtensorMap gmap)
       tc_wait_ld();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(accempty0 + 8 * tl);  // the next step's P.G MMAs may overwrite the accumulator
+      if (lane == 0) mbar_arrive(my_accempty);  // the next step's P.G MMAs may overwrite the accumulator
       if (do_prof) c2 = clock();
 
       // gate non-linearity of this lane's row for the warp's NC batch rows
@@ -511,23 +530,23 @@ __global__ void pack_whh_ts_kernel(const float* __restrict__ w_fwd, const float*
   }
 }
 
-template <int NR, int NC, int MATH, bool SPLIT, int TILES>
+template <int NR, int NC, int MATH, bool SPLIT, int TILES, int SUBS>
 static cudaError_t prepare_ts(int C, size_t smem) {
-  auto* fn = blstm_rec_ts_kernel<NR, NC, MATH, SPLIT, TILES>;
+  auto* fn = blstm_rec_ts_kernel<NR, NC, MATH, SPLIT, TILES, SUBS>;
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e == cudaSuccess && C > 8) e = cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
   return e;
 }
 
-template <int NR, int NC, int MATH, bool SPLIT, int TILES>
+template <int NR, int NC, int MATH, bool SPLIT, int TILES, int SUBS>
 static int max_clusters_ts(int C, size_t smem) {
-  if (prepare_ts<NR, NC, MATH, SPLIT, TILES>(C, smem) != cudaSuccess) {
+  if (prepare_ts<NR, NC, MATH, SPLIT, TILES, SUBS>(C, smem) != cudaSuccess) {
     cudaGetLastError();
     return 0;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(C, 64, 2);
-  cfg.blockDim = dim3(64 + 128 * TILES * (NR / NC));
+  cfg.blockDim = dim3(64 + 128 * TILES * SUBS * (NR / NC));
   cfg.dynamicSmemBytes = smem;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -537,18 +556,19 @@ static int max_clusters_ts(int C, size_t smem) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   int n = 0;
-  if (cudaOccupancyMaxActiveClusters(&n, blstm_rec_ts_kernel<NR, NC, MATH, SPLIT, TILES>, &cfg) != cudaSuccess) {
+  if (cudaOccupancyMaxActiveClusters(&n, blstm_rec_ts_kernel<NR, NC, MATH, SPLIT, TILES, SUBS>, &cfg) != cudaSuccess) {
     cudaGetLastError();
     return 0;
   }
   return n;
 }
 
-// shared memory of one CTA and the depth of its G ring
-static size_t ts_smem(int NA, int NR, int tiles, int* stages_out, int want_stages) {
+// shared memory of one CTA and the depth of its G ring; rows = batch rows per cluster (64 = two sub-batches of 32)
+static size_t ts_smem(int NA, int rows, int tiles, int* stages_out, int want_stages) {
+  const int subs = rows > 32 ? 2 : 1, NR = rows / subs;
   const int NB = NR < 16 ? 16 : NR;
-  const size_t ring_stage = 4ull * NR * 128;
-  const size_t fixed_bytes = 1024 + 2ull * NA * NB * 128 + 1024 + 4ull * tiles * NR * 16 + 64 + 16 * kTsMaxStages + 16;
+  const size_t ring_stage = 4ull * rows * 128;
+  const size_t fixed_bytes = 1024 + 2ull * subs * NA * NB * 128 + 1024 + 4ull * tiles * rows * 16 + 128 + 16 * kTsMaxStages + 16;
   int stages = static_cast<int>((200 * 1024 - fixed_bytes) / ring_stage);
   stages = stages > kTsMaxStages ? kTsMaxStages : stages;
   if (want_stages >= 2 && want_stages <= stages) stages = want_stages;
@@ -562,37 +582,40 @@ static size_t ts_smem(int NA, int NR, int tiles, int* stages_out, int want_stage
 // CTAs per cluster: every CTA owns `tiles` row tiles of 32 units; the tile count is even (two per 64-unit k-atom)
 static int cluster_ctas(int Up, int tiles) { return 2 * ((Up + 63) / 64) / tiles; }
 
-// co-resident clusters of one shape (cached per device: the query costs ~10 us and every launch asks)
-static int clusters_for(int NR, int Up, int tiles) {
-  static int cache[8][3][2][25];  // [device][NR 8/16/32][tiles 1/2][Up / 16]; 0 = not asked yet, -1 = none fit
+// co-resident clusters of one shape (cached per device: the query costs ~10 us and every launch asks);
+// rows = batch rows per cluster: 8, 16, 32 or 64 (two sub-batches of 32)
+static int clusters_for(int rows, int Up, int tiles) {
+  static int cache[8][4][2][25];  // [device][rows 8/16/32/64][tiles 1/2][Up / 16]; 0 = not asked yet, -1 = none fit
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 8) dev = 0;
-  const int ri = NR == 8 ? 0 : (NR == 16 ? 1 : 2), ui = Up / 16;
+  const int ri = rows == 8 ? 0 : (rows == 16 ? 1 : (rows == 32 ? 2 : 3)), ui = Up / 16;
   int& slot = cache[dev][ri][tiles - 1][ui];
   if (slot == 0) {
     const int C = cluster_ctas(Up, tiles), NA = (Up + 63) / 64;
     int st = 0;
-    const size_t smem = ts_smem(NA, NR, tiles, &st, 0);
+    const size_t smem = ts_smem(NA, rows, tiles, &st, 0);
     int n = 0;
-    if (C <= 16) {
-      if (tiles == 2)
-        n = NR == 8 ? max_clusters_ts<8, 8, 1, false, 2>(C, smem)
-                    : (NR == 16 ? max_clusters_ts<16, 16, 1, false, 2>(C, smem) : max_clusters_ts<32, 16, 1, false, 2>(C, smem));
+    if (C <= 16 && st >= 2) {
+      if (rows == 64)
+        n = tiles == 2 ? max_clusters_ts<32, 32, 1, false, 2, 2>(C, smem) : 0;
+      else if (tiles == 2)
+        n = rows == 8 ? max_clusters_ts<8, 8, 1, false, 2, 1>(C, smem)
+                      : (rows == 16 ? max_clusters_ts<16, 16, 1, false, 2, 1>(C, smem) : max_clusters_ts<32, 16, 1, false, 2, 1>(C, smem));
       else
-        n = NR == 8 ? max_clusters_ts<8, 8, 1, false, 1>(C, smem)
-                    : (NR == 16 ? max_clusters_ts<16, 16, 1, false, 1>(C, smem) : max_clusters_ts<32, 16, 1, false, 1>(C, smem));
+        n = rows == 8 ? max_clusters_ts<8, 8, 1, false, 1, 1>(C, smem)
+                      : (rows == 16 ? max_clusters_ts<16, 16, 1, false, 1, 1>(C, smem) : max_clusters_ts<32, 16, 1, false, 1, 1>(C, smem));
     }
     slot = n > 0 ? n : -1;
   }
   return slot > 0 ? slot : 0;
 }
 
-template <int NR, int NC, int MATH, bool SPLIT, int TILES>
+template <int NR, int NC, int MATH, bool SPLIT, int TILES, int SUBS>
 static int launch_ts(const RecTsArgs& a, const CUtensorMap& gmap, int C, int nsub, size_t smem, cudaStream_t stream) {
-  TSSEP_CUDA((prepare_ts<NR, NC, MATH, SPLIT, TILES>(C, smem)));
+  TSSEP_CUDA((prepare_ts<NR, NC, MATH, SPLIT, TILES, SUBS>(C, smem)));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(C, static_cast<unsigned>(nsub), 2);
-  cfg.blockDim = dim3(64 + 128 * TILES * (NR / NC));
+  cfg.blockDim = dim3(64 + 128 * TILES * SUBS * (NR / NC));
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -602,7 +625,7 @@ static int launch_ts(const RecTsArgs& a, const CUtensorMap& gmap, int C, int nsu
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  TSSEP_CUDA(cudaLaunchKernelEx(&cfg, blstm_rec_ts_kernel<NR, NC, MATH, SPLIT, TILES>, a, gmap));
+  TSSEP_CUDA(cudaLaunchKernelEx(&cfg, blstm_rec_ts_kernel<NR, NC, MATH, SPLIT, TILES, SUBS>, a, gmap));
   return check_launch("blstm_rec_ts");
 }
 
@@ -612,7 +635,7 @@ struct TsShape {
   int tiles, rows;
   double cost;
 };
-static const TsShape kTsShapes[] = {{1, 8, 0.78}, {2, 8, 1.0}, {1, 16, 1.15}, {2, 16, 1.35}, {2, 32, 2.3}};
+static const TsShape kTsShapes[] = {{1, 8, 0.9}, {2, 8, 1.0}, {2, 16, 1.35}, {2, 32, 2.3}, {2, 64, 2.6}};
 
 }  // namespace tssep
 
@@ -632,8 +655,8 @@ int tssep_pack_whh_ts(const float* whh_fwd, const float* whh_bwd, int U, int Up,
 
 int tssep_blstm_recurrence_ts_capacity(int Up, int rows_per_cluster, int tiles_per_cta) {
   TSSEP_REQUIRE(Up >= 16 && Up % 16 == 0 && Up <= 384, "tssep_blstm_recurrence_ts_capacity: bad Up");
-  TSSEP_REQUIRE(rows_per_cluster == 8 || rows_per_cluster == 16 || rows_per_cluster == 32,
-                "tssep_blstm_recurrence_ts_capacity: rows_per_cluster must be 8, 16 or 32");
+  TSSEP_REQUIRE(rows_per_cluster == 8 || rows_per_cluster == 16 || rows_per_cluster == 32 || rows_per_cluster == 64,
+                "tssep_blstm_recurrence_ts_capacity: rows_per_cluster must be 8, 16, 32 or 64");
   TSSEP_REQUIRE(tiles_per_cta == 1 || tiles_per_cta == 2, "tssep_blstm_recurrence_ts_capacity: tiles_per_cta must be 1 or 2");
   return (clusters_for(rows_per_cluster, Up, tiles_per_cta) / 2) * rows_per_cluster;
 }
@@ -643,8 +666,9 @@ int tssep_blstm_recurrence_ts(const uint16_t* G, const uint32_t* Wimg, uint16_t*
   TSSEP_REQUIRE(G && Wimg && H, "tssep_blstm_recurrence_ts: null pointer");
   TSSEP_REQUIRE(Up >= 16 && Up % 16 == 0 && Up <= 384, "tssep_blstm_recurrence_ts: Up must be a multiple of 16 in [16, 384]");
   TSSEP_REQUIRE(rows >= 0 && T >= 0 && T < (1ll << 30) && (rows + 7) / 8 <= 65535, "tssep_blstm_recurrence_ts: bad extent");
-  TSSEP_REQUIRE(rows_per_cluster == 0 || rows_per_cluster == 8 || rows_per_cluster == 16 || rows_per_cluster == 32,
-                "tssep_blstm_recurrence_ts: rows_per_cluster must be 0 (auto), 8, 16 or 32");
+  TSSEP_REQUIRE(rows_per_cluster == 0 || rows_per_cluster == 8 || rows_per_cluster == 16 || rows_per_cluster == 32 ||
+                    rows_per_cluster == 64,
+                "tssep_blstm_recurrence_ts: rows_per_cluster must be 0 (auto), 8, 16, 32 or 64");
   TSSEP_REQUIRE(tiles_per_cta >= 0 && tiles_per_cta <= 2, "tssep_blstm_recurrence_ts: tiles_per_cta must be 0 (auto), 1 or 2");
   TSSEP_REQUIRE(gate_math == 0 || gate_math == 1, "tssep_blstm_recurrence_ts: gate_math must be 0 (exp based) or 1 (tanh.approx)");
   TSSEP_REQUIRE(k_split >= -1 && k_split <= 1, "tssep_blstm_recurrence_ts: k_split must be -1 (default), 0 or 1");
@@ -656,7 +680,7 @@ int tssep_blstm_recurrence_ts(const uint16_t* G, const uint32_t* Wimg, uint16_t*
   int NR = rows_per_cluster, tiles = tiles_per_cta;
   if (const char* e = debug_env("TSSEP_TS_ROWS")) {
     const int v = atoi(e);
-    if (v == 8 || v == 16 || v == 32) NR = v;
+    if (v == 8 || v == 16 || v == 32 || v == 64) NR = v;
   }
   const bool split = k_split == 1;  // default: one phase (the second barrier + fence cost more than the split hides)
   if (split) {
@@ -685,10 +709,11 @@ int tssep_blstm_recurrence_ts(const uint16_t* G, const uint32_t* Wimg, uint16_t*
     NR = best_nr;
     tiles = best_tiles;
   }
+  TSSEP_REQUIRE(!(NR == 64 && (tiles == 1 || split)), "tssep_blstm_recurrence_ts: 64 rows per cluster need two row tiles per CTA, one K phase");
   const int C = cluster_ctas(Up, tiles);
   TSSEP_REQUIRE(C <= 16, "tssep_blstm_recurrence_ts: Up=%d needs clusters of %d CTAs with %d tile(s) per CTA (max 16)", Up, C, tiles);
   const uint32_t a_tile_cols = (static_cast<uint32_t>(Up) / 2 + 31u) & ~31u;
-  TSSEP_REQUIRE(tiles * a_tile_cols + 64 + tiles * (NR < 16 ? 16 : NR) <= 512,
+  TSSEP_REQUIRE(tiles * a_tile_cols + 64 + tiles * (NR < 16 ? 16 : NR) <= 512,  /* 64 rows = 2 sub-batches x 32 columns per tile */
                 "tssep_blstm_recurrence_ts: Up=%d with %d rows per cluster exceeds the 512 tensor-memory columns", Up, NR);
   RecTsArgs a;
   a.Wimg = reinterpret_cast<const uint4*>(Wimg);
@@ -712,10 +737,10 @@ int tssep_blstm_recurrence_ts(const uint16_t* G, const uint32_t* Wimg, uint16_t*
   a.stages = stages;
   const int nsub = static_cast<int>((rows + NR - 1) / NR);
   // batch columns per epilogue warp (debug knob TSSEP_TS_COLS): 16 measured best for 32 rows per cluster
-  int NC = NR < 16 ? NR : 16;
+  int NC = NR < 16 ? NR : (NR == 64 ? 32 : 16);
   if (const char* e = debug_env("TSSEP_TS_COLS")) {
     const int v = atoi(e);
-    if (v == NR || (v == NR / 2 && v >= 8)) NC = v;
+    if (NR != 64 && (v == NR || (v == NR / 2 && v >= 8))) NC = v;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 
@@ -733,21 +758,24 @@ int tssep_blstm_recurrence_ts(const uint16_t* G, const uint32_t* Wimg, uint16_t*
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   TSSEP_REQUIRE(r == CUDA_SUCCESS, "tssep_blstm_recurrence_ts: cuTensorMapEncodeTiled failed with code %d", static_cast<int>(r));
 
-#define TSSEP_TS_CASE(NR_, NC_)                                                                             \
-  if (NR == NR_ && NC == NC_) {                                                                             \
-    if (tiles == 1)                                                                                         \
-      return gate_math ? launch_ts<NR_, NC_, 1, false, 1>(a, gmap, C, nsub, smem, st)                       \
-                       : launch_ts<NR_, NC_, 0, false, 1>(a, gmap, C, nsub, smem, st);                      \
-    if (gate_math) return split ? launch_ts<NR_, NC_, 1, true, 2>(a, gmap, C, nsub, smem, st)               \
-                                : launch_ts<NR_, NC_, 1, false, 2>(a, gmap, C, nsub, smem, st);             \
-    return split ? launch_ts<NR_, NC_, 0, true, 2>(a, gmap, C, nsub, smem, st)                              \
-                 : launch_ts<NR_, NC_, 0, false, 2>(a, gmap, C, nsub, smem, st);                            \
+#define TSSEP_TS_CASE(NR_, NC_)                                                                                \
+  if (NR == NR_ && NC == NC_) {                                                                                \
+    if (tiles == 1)                                                                                            \
+      return gate_math ? launch_ts<NR_, NC_, 1, false, 1, 1>(a, gmap, C, nsub, smem, st)                       \
+                       : launch_ts<NR_, NC_, 0, false, 1, 1>(a, gmap, C, nsub, smem, st);                      \
+    if (gate_math) return split ? launch_ts<NR_, NC_, 1, true, 2, 1>(a, gmap, C, nsub, smem, st)               \
+                                : launch_ts<NR_, NC_, 1, false, 2, 1>(a, gmap, C, nsub, smem, st);             \
+    return split ? launch_ts<NR_, NC_, 0, true, 2, 1>(a, gmap, C, nsub, smem, st)                              \
+                 : launch_ts<NR_, NC_, 0, false, 2, 1>(a, gmap, C, nsub, smem, st);                            \
   }
   TSSEP_TS_CASE(8, 8)
   TSSEP_TS_CASE(16, 8)
   TSSEP_TS_CASE(16, 16)
   TSSEP_TS_CASE(32, 16)
 #undef TSSEP_TS_CASE
+  if (NR == 64 && NC == 32)  // two sub-batches of 32 rows in anti-phase
+    return gate_math ? launch_ts<32, 32, 1, false, 2, 2>(a, gmap, C, nsub, smem, st)
+                     : launch_ts<32, 32, 0, false, 2, 2>(a, gmap, C, nsub, smem, st);
   set_error("tssep_blstm_recurrence_ts: no instantiation for %d rows per cluster, %d columns per warp", NR, NC);
   return -1;
 }

@@ -108,9 +108,10 @@ def gather_segments(local_ids: Sequence[int], segments: torch.Tensor, counts: to
     return SegmentGather(plan, rank, K, S, dev, group, n_total=n_total).start(segments, counts).result()
 
 
-# Relative cost of one dependent step of the tensor-memory recurrence at 8 / 16 / 32 rows per cluster (measured at
-# U = 300 on B200, profiles/r2_rec_ts_microbench.txt); the same ratios steer the kernel's own choice (csrc/lstm_ts.cu).
-TS_STEP_COST: Dict[int, float] = {8: 1.0, 16: 1.35, 32: 2.3}
+# Relative cost of one dependent step of the tensor-memory recurrence at 8 / 16 / 32 / 64 rows per cluster, two row
+# tiles per CTA (measured at U = 300 on B200, profiles/r2_rec_ts_microbench.txt); the same ratios steer the kernel's own
+# choice (csrc/lstm_ts.cu::kTsShapes).
+TS_STEP_COST: Dict[int, float] = {8: 1.0, 16: 1.35, 32: 2.3, 64: 2.6}
 
 
 def plan_recurrence_waves(n_items: int, rows_per_item: int, capacity: Dict[int, int], max_items: Optional[int] = None,
