@@ -85,7 +85,7 @@ def test_plan_recurrence_waves():
     assert plan_recurrence_waves(52, 8, cap, cost=cost) == [52]          # 416 rows: one wave of 32-row clusters
     w = plan_recurrence_waves(64, 8, cap, cost=cost)
     assert sum(w) == 64 and max(w) <= 52 and len(w) == 2                 # 512 rows do not fit one wave
-    cap64, cost64 = {**cap, 64: 832}, {**cost, 64: 2.6}
+    cap64, cost64 = {**cap, 64: 832}, {**cost, 64: 3.18}
     assert plan_recurrence_waves(64, 8, cap64, cost=cost64) == [64]      # ... unless clusters take 64 rows each
     assert plan_recurrence_waves(64, 8, cap, max_items=32, cost=cost) == [32, 32] or \
         sum(plan_recurrence_waves(64, 8, cap, max_items=32, cost=cost)) == 64

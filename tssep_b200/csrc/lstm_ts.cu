@@ -635,7 +635,7 @@ struct TsShape {
   int tiles, rows;
   double cost;
 };
-static const TsShape kTsShapes[] = {{1, 8, 0.9}, {2, 8, 1.0}, {2, 16, 1.35}, {2, 32, 2.3}, {2, 64, 2.6}};
+static const TsShape kTsShapes[] = {{1, 8, 0.9}, {2, 8, 1.0}, {2, 16, 1.37}, {2, 32, 2.3}, {2, 64, 3.18}};
 
 }  // namespace tssep
 
