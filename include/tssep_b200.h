@@ -169,6 +169,26 @@ int tssep_blstm_recurrence_ts_capacity(int Up, int rows_per_cluster, int tiles_p
 int tssep_pack_whh_ts(const float* whh_fwd, const float* whh_bwd, int U, int Up, uint32_t* Wimg,
                       tssep_stream_t stream);
 
+/* Training step (BASELINE config 5: forward + backward through torch.nn.LSTM, tssep/train/rnnp.py:143-159 under
+ * tssep/train/loss.py:219-247).  tssep_blstm_recurrence_train = tssep_blstm_recurrence_ts (two row tiles per CTA) that
+ * also stores the gate activations and cell states:
+ *   gates  (rows, T, 2, Up) x {i, f, g, o} bf16  (4 x uint16 per hidden unit),  cstate (rows, T, 2, Up) f32.
+ * tssep_blstm_recurrence_bwd = the reverse-time recurrence  dh_t = dH_t + W_hh^T da_{t+1},  dc_t = dc_{t+1} f_{t+1} +
+ * dh_t o_t (1 - tanh^2 c_t),  da_t = gate derivatives:  dH (rows, T, 2*Up) bf16 in (the gradient of H),
+ *   dG (rows, T, 2, Up) x {i, f, g, o} bf16 out: the gradient of the gate pre-activations, [unit][gate] innermost
+ *   (a (rows*T, 8*Up) K-major operand for the input-projection dgrad / wgrad with correspondingly ordered weights).
+ * Cluster of ceil(Up/64) CTAs per (8 rows, direction); every CTA keeps the transposed rows of W_hh it owns in tensor
+ * memory (WTimg from tssep_pack_whh_bwd: 2 * C * ceil(C/2) * 16 * 128 * 8 words), multiplies them with its own da and
+ * ships partial sums to the owning CTAs through distributed shared memory.  The gradients of W_hh, W_ih, biases are
+ * plain GEMMs / reductions over dG and are left to the caller. */
+int tssep_blstm_recurrence_train(const uint16_t* G, const uint32_t* Wimg, uint16_t* H, uint16_t* gates, float* cstate,
+                                 int64_t rows, int64_t T, int Up, int rows_per_cluster, int gate_math,
+                                 tssep_stream_t stream);
+int tssep_blstm_recurrence_bwd(const uint16_t* gates, const float* cstate, const uint16_t* dH, const uint32_t* WTimg,
+                               uint16_t* dG, int64_t rows, int64_t T, int Up, tssep_stream_t stream);
+int tssep_pack_whh_bwd(const float* whh_fwd, const float* whh_bwd, int U, int Up, uint32_t* WTimg,
+                       tssep_stream_t stream);
+
 /* Register-resident variant of the same operator (mma.sync, recurrent weights in registers, cluster of up to 8,
  * 8 rows per cluster): accepts f32 G, which the parity tests use to separate the rounding of G from the rest.
  * G    (rows, T, 2, 4, Up) f32 (g_dtype 0) or bf16 (g_dtype 1)

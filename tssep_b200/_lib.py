@@ -57,6 +57,9 @@ _SIGNATURES = {
     "tssep_blstm_recurrence_ts": ([c_vp, c_vp, c_vp, c_i64, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp], C.c_int),
     "tssep_blstm_recurrence_ts_capacity": ([c_i32, c_i32, c_i32], C.c_int),
     "tssep_pack_whh_ts": ([c_vp, c_vp, c_i32, c_i32, c_vp, c_vp], C.c_int),
+    "tssep_blstm_recurrence_train": ([c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i32, c_i32, c_i32, c_vp], C.c_int),
+    "tssep_blstm_recurrence_bwd": ([c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i32, c_vp], C.c_int),
+    "tssep_pack_whh_bwd": ([c_vp, c_vp, c_i32, c_i32, c_vp, c_vp], C.c_int),
     "tssep_mask_istft": ([c_vp, c_i64, c_vp, c_i64, c_i32, c_i64, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp,
                           c_i64, c_vp, c_vp], C.c_int),
     "tssep_activity": ([c_vp, c_i64, c_i64, c_i32, c_vp, c_vp], C.c_int),

@@ -34,6 +34,9 @@ FACTORY_ALIASES = {
     "tssep.train.rnnp.RNNP_packed": "tssep_b200.rnnp.RNNP_packed",
     "tssep.train.enhancer.Masking": "tssep_b200.enhancer.Masking",
     "tssep.train.loss.LogMAE": "tssep_b200.loss.LogMAE",
+    "tssep.train.loss.MAE": "tssep_b200.loss.MAE",
+    "tssep.train.init_ckpt.InitCheckPoint": "tssep_b200.init_ckpt.InitCheckPoint",
+    "tssep.train.init_ckpt.InitCheckPointVAD2Sep": "tssep_b200.init_ckpt.InitCheckPointVAD2Sep",
     "tssep.train.loss.VADSigmoidBCE": "tssep_b200.loss.VADSigmoidBCE",
     "tssep.data.DummyReader": "tssep_b200.data.DummyReader",
 }

@@ -38,6 +38,8 @@ struct RecTsArgs {
   const uint4* Wimg;  // [dir][cta][tile][kstep][row 128][8 words], gate rows i,f,o pre-scaled by 1/2
   __nv_bfloat16* H;   // (rows, T, 2*Up)
   int rows, T, Up, NA, KS, stages;
+  uint2* gates_out;   // SAVE variant (training): (rows, T, 2, Up) x {i, f, g, o} bf16 gate activations, else null
+  float* c_out;       // SAVE variant: (rows, T, 2, Up) f32 cell states
   int flags;          // debug builds only: bit 0 = skip the proxy fence of the MMA warp (measurement, NOT correct)
   int* prof;          // debug builds only (TSSEP_DEBUG_KNOBS): per-phase cycle counters of two epilogue warps + MMA warp
 };
@@ -103,7 +105,7 @@ __device__ __forceinline__ float ts_tanh(float x) {
 // DSMEM and its epilogue warps run, the tensor pipe works on the other (an MMA costs ~27 cycles whatever its N, so 64
 // rows per cluster at N = 32 halve the tensor-pipe time per row, and the ping-pong hides the exchange).
 // Everything the per-step loops branch on is a template parameter.
-template <int NR, int NC, int MATH, bool SPLIT, int TILES, int SUBS>
+template <int NR, int NC, int MATH, bool SPLIT, int TILES, int SUBS, bool SAVE = false>
 __global__ void __launch_bounds__(64 + 128 * TILES * SUBS * (NR / NC), 1)
 blstm_rec_ts_kernel(const RecTsArgs a, const __grid_constant__ CUtensorMap gmap) {
   static_assert(TILES == 1 || TILES == 2, "one or two row tiles per CTA");
@@ -456,6 +458,15 @@ blstm_rec_ts_kernel(const RecTsArgs a, const __grid_constant__ CUtensorMap gmap)
         cst[i] = c;
         const float h = og * ts_tanh<MATH>(c);
         const int b = 4 * i + gate;
+        if constexpr (SAVE) {
+          // training: the backward recurrence (csrc/lstm_bwd.cu) needs the gate activations and c_t of every step
+          const int srow = row0 + sb * NR + half * NC + b;
+          if (oct_ok && srow < a.rows) {
+            const int64_t e = ((static_cast<int64_t>(srow) * T + (dir ? T - 1 - s : s)) * 2 + dir) * Up + unit0 + ul;
+            a.gates_out[e] = make_uint2(pack_bf16x2(ig, fg), pack_bf16x2(gg, og));
+            a.c_out[e] = c;
+          }
+        }
         const __nv_bfloat16 hb = __float2bfloat16_rn(h);
         asm volatile("st.shared.u16 [%0], %1;" ::"r"(myT + static_cast<uint32_t>(b * 8 + ul) * 2),
                      "h"(*reinterpret_cast<const unsigned short*>(&hb))
@@ -530,9 +541,9 @@ __global__ void pack_whh_ts_kernel(const float* __restrict__ w_fwd, const float*
   }
 }
 
-template <int NR, int NC, int MATH, bool SPLIT, int TILES, int SUBS>
+template <int NR, int NC, int MATH, bool SPLIT, int TILES, int SUBS, bool SAVE = false>
 static cudaError_t prepare_ts(int C, size_t smem) {
-  auto* fn = blstm_rec_ts_kernel<NR, NC, MATH, SPLIT, TILES, SUBS>;
+  auto* fn = blstm_rec_ts_kernel<NR, NC, MATH, SPLIT, TILES, SUBS, SAVE>;
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e == cudaSuccess && C > 8) e = cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
   return e;
@@ -610,9 +621,9 @@ static int clusters_for(int rows, int Up, int tiles) {
   return slot > 0 ? slot : 0;
 }
 
-template <int NR, int NC, int MATH, bool SPLIT, int TILES, int SUBS>
+template <int NR, int NC, int MATH, bool SPLIT, int TILES, int SUBS, bool SAVE = false>
 static int launch_ts(const RecTsArgs& a, const CUtensorMap& gmap, int C, int nsub, size_t smem, cudaStream_t stream) {
-  TSSEP_CUDA((prepare_ts<NR, NC, MATH, SPLIT, TILES, SUBS>(C, smem)));
+  TSSEP_CUDA((prepare_ts<NR, NC, MATH, SPLIT, TILES, SUBS, SAVE>(C, smem)));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(C, static_cast<unsigned>(nsub), 2);
   cfg.blockDim = dim3(64 + 128 * TILES * SUBS * (NR / NC));
@@ -625,7 +636,7 @@ static int launch_ts(const RecTsArgs& a, const CUtensorMap& gmap, int C, int nsu
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  TSSEP_CUDA(cudaLaunchKernelEx(&cfg, blstm_rec_ts_kernel<NR, NC, MATH, SPLIT, TILES, SUBS>, a, gmap));
+  TSSEP_CUDA(cudaLaunchKernelEx(&cfg, blstm_rec_ts_kernel<NR, NC, MATH, SPLIT, TILES, SUBS, SAVE>, a, gmap));
   return check_launch("blstm_rec_ts");
 }
 
@@ -661,9 +672,18 @@ int tssep_blstm_recurrence_ts_capacity(int Up, int rows_per_cluster, int tiles_p
   return (clusters_for(rows_per_cluster, Up, tiles_per_cta) / 2) * rows_per_cluster;
 }
 
-int tssep_blstm_recurrence_ts(const uint16_t* G, const uint32_t* Wimg, uint16_t* H, int64_t rows, int64_t T, int Up,
-                              int rows_per_cluster, int tiles_per_cta, int gate_math, int k_split, tssep_stream_t stream) {
+static int recurrence_ts_impl(const uint16_t* G, const uint32_t* Wimg, uint16_t* H, int64_t rows, int64_t T, int Up,
+                              int rows_per_cluster, int tiles_per_cta, int gate_math, int k_split, uint16_t* gates_out,
+                              float* c_out, tssep_stream_t stream) {
   TSSEP_REQUIRE(G && Wimg && H, "tssep_blstm_recurrence_ts: null pointer");
+  const bool save = gates_out != nullptr;
+  TSSEP_REQUIRE(save == (c_out != nullptr), "tssep_blstm_recurrence_train: gates and cstate go together");
+  TSSEP_REQUIRE(!save || (reinterpret_cast<uintptr_t>(gates_out) & 7) == 0, "tssep_blstm_recurrence_train: gates must be 8-byte aligned");
+  if (save) {  // the training variant is instantiated for the two-tile shapes of up to 32 rows, one K phase
+    TSSEP_REQUIRE(tiles_per_cta != 1 && k_split != 1 && rows_per_cluster != 64,
+                  "tssep_blstm_recurrence_train: needs two row tiles per CTA, at most 32 rows per cluster, one K phase");
+    tiles_per_cta = 2;
+  }
   TSSEP_REQUIRE(Up >= 16 && Up % 16 == 0 && Up <= 384, "tssep_blstm_recurrence_ts: Up must be a multiple of 16 in [16, 384]");
   TSSEP_REQUIRE(rows >= 0 && T >= 0 && T < (1ll << 30) && (rows + 7) / 8 <= 65535, "tssep_blstm_recurrence_ts: bad extent");
   TSSEP_REQUIRE(rows_per_cluster == 0 || rows_per_cluster == 8 || rows_per_cluster == 16 || rows_per_cluster == 32 ||
@@ -694,7 +714,7 @@ int tssep_blstm_recurrence_ts(const uint16_t* G, const uint32_t* Wimg, uint16_t*
     double best = 1e30;
     int best_nr = 0, best_tiles = 0;
     for (const TsShape& sh : kTsShapes) {
-      if ((NR != 0 && sh.rows != NR) || (tiles != 0 && sh.tiles != tiles)) continue;
+      if ((NR != 0 && sh.rows != NR) || (tiles != 0 && sh.tiles != tiles) || (save && sh.rows == 64)) continue;
       const int m = clusters_for(sh.rows, Up, sh.tiles);
       if (m < 2) continue;
       const int64_t n = 2 * ((rows + sh.rows - 1) / sh.rows);
@@ -725,6 +745,8 @@ int tssep_blstm_recurrence_ts(const uint16_t* G, const uint32_t* Wimg, uint16_t*
   a.KS = Up / 16;
   a.prof = nullptr;
   a.flags = 0;
+  a.gates_out = reinterpret_cast<uint2*>(gates_out);
+  a.c_out = c_out;
   int want_stages = 0;
 #ifdef TSSEP_DEBUG_KNOBS
   if (const char* e = debug_env("TSSEP_REC_PROF")) a.prof = reinterpret_cast<int*>(strtoull(e, nullptr, 0));
@@ -760,6 +782,9 @@ int tssep_blstm_recurrence_ts(const uint16_t* G, const uint32_t* Wimg, uint16_t*
 
 #define TSSEP_TS_CASE(NR_, NC_)                                                                                \
   if (NR == NR_ && NC == NC_) {                                                                                \
+    if (save)                                                                                                  \
+      return gate_math ? launch_ts<NR_, NC_, 1, false, 2, 1, true>(a, gmap, C, nsub, smem, st)                 \
+                       : launch_ts<NR_, NC_, 0, false, 2, 1, true>(a, gmap, C, nsub, smem, st);                \
     if (tiles == 1)                                                                                            \
       return gate_math ? launch_ts<NR_, NC_, 1, false, 1, 1>(a, gmap, C, nsub, smem, st)                       \
                        : launch_ts<NR_, NC_, 0, false, 1, 1>(a, gmap, C, nsub, smem, st);                      \
@@ -778,6 +803,17 @@ int tssep_blstm_recurrence_ts(const uint16_t* G, const uint32_t* Wimg, uint16_t*
                      : launch_ts<32, 32, 0, false, 2, 2>(a, gmap, C, nsub, smem, st);
   set_error("tssep_blstm_recurrence_ts: no instantiation for %d rows per cluster, %d columns per warp", NR, NC);
   return -1;
+}
+
+int tssep_blstm_recurrence_ts(const uint16_t* G, const uint32_t* Wimg, uint16_t* H, int64_t rows, int64_t T, int Up,
+                              int rows_per_cluster, int tiles_per_cta, int gate_math, int k_split, tssep_stream_t stream) {
+  return recurrence_ts_impl(G, Wimg, H, rows, T, Up, rows_per_cluster, tiles_per_cta, gate_math, k_split, nullptr, nullptr, stream);
+}
+
+int tssep_blstm_recurrence_train(const uint16_t* G, const uint32_t* Wimg, uint16_t* H, uint16_t* gates, float* cstate,
+                                 int64_t rows, int64_t T, int Up, int rows_per_cluster, int gate_math, tssep_stream_t stream) {
+  TSSEP_REQUIRE(gates && cstate, "tssep_blstm_recurrence_train: null pointer");
+  return recurrence_ts_impl(G, Wimg, H, rows, T, Up, rows_per_cluster, 2, gate_math, 0, gates, cstate, stream);
 }
 
 }  // extern "C"

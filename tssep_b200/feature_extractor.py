@@ -111,8 +111,9 @@ class STFT(Configurable):
         _lib.require_cuda(x)
         return x.to(dtype), False
 
-    def stft(self, signal):
-        """(..., N) float -> (..., T, F) complex64."""
+    def stft(self, signal, _window="window"):
+        """(..., N) float -> (..., T, F) complex64.  (``_window="synwin"``: frames weighted with the synthesis window, the
+        adjoint of ``istft`` up to a per-bin scale -- used by ``tssep_b200.autograd.ISTFTFn``.)"""
         x, was_np = self._to_cuda(signal, torch.float32)
         if not self.pad:
             raise NotImplementedError("pad=False is not supported by the CUDA STFT")
@@ -123,7 +124,7 @@ class STFT(Configurable):
         tab = self._device_tables(x.device)
         out = torch.empty((*lead, t, self.frequencies), dtype=torch.complex64, device=x.device)
         n_sig = int(np.prod(lead)) if lead else 1
-        torch_ops.op.stft(x, n_sig, n, tab["window"], tab["twiddle"], self.size, self.shift, self.window_length,
+        torch_ops.op.stft(x, n_sig, n, tab[_window], tab["twiddle"], self.size, self.shift, self.window_length,
                           int(bool(self.fading)), t, out)
         return out.cpu().numpy() if was_np else out
 

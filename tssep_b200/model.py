@@ -88,6 +88,8 @@ class Model(Configurable, torch.nn.Module):
         """tssep/train/model.py:465-536.  ``with_time_estimate=True`` additionally runs the iSTFT of
         ``Model.review`` (model.py:661-664) in the same enhancement kernel."""
         ex["AuxInput"] = [a for a in ex["auxInput"]]
+        if self.training and torch.is_grad_enabled():
+            return self._forward_train(ex, feature_transform)
         bf16 = None
         if "Input" not in ex:
             feats = self._features(ex)
@@ -110,6 +112,31 @@ class Model(Configurable, torch.nn.Module):
         return ForwardOutput(mask=me_out.mask, logit=me_out.logit, vad_mask=me_out.vad_mask,
                              vad_logit=me_out.vad_logit, embedding=me_out.embedding, stft_estimate=stft_estimate,
                              time_estimate=time_estimate)
+
+    def _forward_train(self, ex, feature_transform=None) -> ForwardOutput:
+        """Training step forward (BASELINE config 5): the same path with autograd through it -- features (inputs, no
+        gradient), mask estimator (``MaskEstimator_v2.forward_train``), Masking as a torch product, and the iSTFT of
+        ``Model.review`` (model.py:661-664) through ``tssep_b200.autograd.ISTFTFn`` so that ``LogMAE`` on
+        ``time_estimate`` back-propagates."""
+        from .autograd import ISTFTFn
+
+        if "Input" not in ex:
+            with torch.no_grad():
+                ex["Input"] = self._features(ex)["f32"]
+        if feature_transform is not None:
+            ex["Input"] = feature_transform(ex["Input"])
+        ex = self.reader.data_hooks.pre_net(ex) if self.reader is not None else ex
+        me_out = self.mask_estimator(ex["Input"], ex["AuxInput"])
+        stft_estimate = time_estimate = None
+        if "Observation" in ex:
+            if not isinstance(self.enhancer, Masking):
+                raise NotImplementedError("training through enhancers other than Masking")
+            obs = ex["Observation"][..., ex["reference_channel"], :, :]
+            stft_estimate = obs[..., None, :, :] * torch.squeeze(me_out.mask, dim=-3)   # enhancer.py:73-100
+            if "observation" in ex:
+                time_estimate = ISTFTFn.apply(stft_estimate, self.fe, ex["observation"].shape[-1])
+        return ForwardOutput(mask=me_out.mask, logit=me_out.logit, vad_mask=me_out.vad_mask, vad_logit=me_out.vad_logit,
+                             embedding=me_out.embedding, stft_estimate=stft_estimate, time_estimate=time_estimate)
 
     def istft(self, out: ForwardOutput, num_samples: Optional[int]):
         """The time-domain step of ``Model.review`` (tssep/train/model.py:661-664)."""

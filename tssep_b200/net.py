@@ -275,8 +275,87 @@ class MaskEstimator_v2(Configurable, torch.nn.Module):
         ``_features_bf16=(tensor, ld)`` lets ``Model.forward`` hand over the bf16 feature rows the
         feature kernel already produced.
         """
+        if self.training and torch.is_grad_enabled():
+            return self.forward_train(xs, aux)
         (_, _, out), = self.forward_waves(xs, aux, wave=None, _features_bf16=_features_bf16)
         return out
+
+    def forward_train(self, xs, aux) -> Output:
+        """Differentiable forward for the training step (BASELINE config 5; tssep/train/net.py:809-986 followed line by
+        line, autograd through it).  The projected BLSTM layers run on this package's kernels forward AND backward
+        (``tssep_b200.autograd.RNNPLayerFn``: tcgen05 GEMMs, tensor-memory recurrence, BPTT kernel); the speaker
+        conditioning, the rearrangements, the head ``Linear`` and the sigmoid are torch ops (elementwise / plain
+        library GEMM).  birnn0 / birnn1 treat every (item, speaker) row on its own, so the permutation-averaging
+        trials are expanded AFTER them instead of before (identical values, 1/R of the work)."""
+        _lib.require_cuda(xs)
+        if xs.dim() == 2:
+            batched = False
+            K = len(aux)
+            perm = np.random.permutation(K) if self.random_speaker_order else np.arange(K)
+            aux_t = torch.stack([aux[i] for i in perm], dim=0)[None]
+            perms = perm[None]
+            xs = xs[None]
+        elif xs.dim() == 3:
+            batched = True
+            K = len(aux[0])
+            perms = np.stack([np.random.permutation(K) if self.random_speaker_order else np.arange(K)
+                              for _ in range(len(aux))])
+            aux_t = torch.stack([torch.stack([a[i] for i in p], dim=0) for a, p in zip(aux, perms)], dim=0)
+            if self.aux_normalizer is not None:
+                aux_t = self.aux_normalizer(aux_t)
+        else:
+            raise RuntimeError(xs.shape)
+        B, T = xs.shape[:2]
+        if self.input_normalizer is not None:
+            xs = self.input_normalizer(xs)
+        xs = self.pre_net(xs.float()) if isinstance(self.pre_net, RNNP_packed) else xs.float()   # (B, T, F)
+        emb = aux_t.float().unsqueeze(-2)                                                         # (B, K, 1, A)
+        if self.combination == "mul":
+            h = xs[:, None] * emb                                                                 # (B, K, T, F)
+        else:
+            h = torch.cat([xs[:, None].expand(B, K, T, xs.shape[-1]), emb.expand(B, K, T, emb.shape[-1])], dim=-1)
+        birnns = self._birnns()
+        L, R = self.layers, self.num_averaged_permutations
+        tsv = self.ts_vad is not False
+        n_indep = L - 1 if tsv else L
+        for l in range(n_indep):
+            h = birnns[l](h)
+            if l < L - 1:
+                h = torch.tanh(h)
+        if tsv:
+            idx = ((np.arange(K)[:, None] + np.arange(K)[None, :]) % K)[:R].ravel()              # net.py:913-916
+            he = h[:, torch.as_tensor(idx, device=h.device)].reshape(B * R, K, T, h.shape[-1])
+            he = he.movedim(1, 2).reshape(B * R, T, K * h.shape[-1])                              # '(spk feature)'
+            h = birnns[L - 1](he)                                                                 # (B*R, T, P)
+        logit = self._head_linear()(h)
+        nmask = self.nmask
+        if self.output_resolution == "tf":
+            fh = self.odim + int(self.explicit_vad)
+            if tsv:
+                logit = logit.reshape(B * R, T, K, nmask, fh).permute(0, 2, 3, 1, 4)              # spk mask time freq
+            else:
+                logit = logit.reshape(B, K, T, nmask, fh).permute(0, 1, 3, 2, 4)
+        else:
+            if tsv:
+                logit = logit.reshape(B * R, T, K, nmask).permute(0, 2, 3, 1)
+            else:
+                logit = logit.reshape(B, K, T, nmask).permute(0, 1, 3, 2)
+            logit = logit[..., None].expand(*logit.shape, self.odim)
+        if tsv and R > 1:                                                                         # net.py:928-955
+            revert = torch.as_tensor(np.argsort(idx), device=logit.device)
+            logit = logit.reshape(B, R * K, *logit.shape[2:])[:, revert]
+            logit = logit.reshape(B, K, R, *logit.shape[2:]).mean(dim=2)
+        iperm = torch.as_tensor(np.argsort(perms, axis=-1), device=logit.device)
+        logit = logit[torch.arange(B, device=logit.device)[:, None], iperm]                      # net.py:957-967
+        embedding = emb
+        if not batched:
+            logit, embedding = logit[0], embedding[0]
+        if self.explicit_vad:
+            mask = torch.sigmoid(logit)
+            vad = mask[..., 0]
+            return Output(mask=mask[..., 1:] * vad[..., None], logit=None, vad_mask=vad, vad_logit=logit[..., 0],
+                          embedding=embedding)
+        return Output(mask=torch.sigmoid(logit), logit=logit, embedding=embedding)
 
     def forward_waves(self, xs, aux=None, wave=None, _features_bf16=None, out_wave=None):
         """Same computation as ``forward`` for a batch of B items, produced in waves of ``wave`` items:

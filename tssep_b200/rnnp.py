@@ -17,7 +17,7 @@ import os
 
 import torch
 
-from . import _lib, ops
+from . import _lib, ops, torch_ops
 
 # Recurrence kernels (both compute the same operator on the plain (row, t) layouts):
 #   ts    csrc/lstm_ts.cu  W_hh in tensor memory, tcgen05.mma, bf16 G: the product path for every row count
@@ -63,7 +63,9 @@ class LayerPack:
             wp = torch.zeros((self.hdim, 2 * Up), dtype=torch.float32, device=dev)
             wp[:, :U] = linear.weight.detach().float()[:, :U]
             wp[:, Up:Up + U] = linear.weight.detach().float()[:, U:]
+            self._w_proj_f32 = wp
             self.w_proj = ops.cast_bf16(wp, 2 * Up)
+            self._w_proj_t = self._w_ih_t = self._whh_bwd = None  # backward operands, built on first use
             self.b_proj = linear.bias.detach().float().contiguous()
 
     # -- the three stages ------------------------------------------------------
@@ -75,11 +77,41 @@ class LayerPack:
                  mode=ops.EPI_BF16 if gd == torch.bfloat16 else ops.EPI_F32, ldo=8 * self.Up, bias=self.bias)
         return G
 
+    def whh_ts_image(self) -> torch.Tensor:
+        if self.whh_ts is None:
+            self.whh_ts = ops.pack_whh_ts(self._whh_f32[0], self._whh_f32[1], self.U, self.Up)
+        return self.whh_ts
+
+    # -- operands of the backward pass (tssep_b200/autograd.py) ------------------------------------------------
+    def whh_bwd_image(self) -> torch.Tensor:
+        """Transposed tensor-memory image of W_hh for the BPTT kernel (csrc/lstm_bwd.cu)."""
+        if self._whh_bwd is None:
+            c = (self.Up + 63) // 64
+            out = torch.empty(2 * c * ((c + 1) // 2) * 16 * 128 * 8, dtype=torch.int32, device=self.bias.device)
+            torch_ops.op.pack_whh_bwd(self._whh_f32[0], self._whh_f32[1], self.U, self.Up, out)
+            self._whh_bwd = out
+        return self._whh_bwd
+
+    def w_proj_t(self):
+        """(2Up, P) bf16: B operand of dH = dproj . W_proj."""
+        if self._w_proj_t is None:
+            ld = ops.operand_ld(self.hdim)
+            self._w_proj_t = (ops.cast_bf16(self._w_proj_f32.t().contiguous(), ld), ld)
+        return self._w_proj_t
+
+    def w_ih_t(self):
+        """(I, 8Up) bf16 with columns ordered [dir][unit][gate] (the order of dG): B operand of dx = dG . W_ih."""
+        if self._w_ih_t is None:
+            Up = self.Up
+            w = self.w_ih_f32.view(2, 4, Up, self.I).permute(0, 2, 1, 3).reshape(8 * Up, self.I)
+            ld = ops.operand_ld(8 * Up)
+            self._w_ih_t = (ops.cast_bf16(w.t().contiguous(), ld), ld)
+        return self._w_ih_t
+
     def recurrence(self, G: torch.Tensor, rows: int, T: int) -> torch.Tensor:
         """G (rows, T, 8Up) -> H (rows, T, 2Up)."""
         if rec_kernel(G.dtype, self.Up) == "ts":
-            if self.whh_ts is None:
-                self.whh_ts = ops.pack_whh_ts(self._whh_f32[0], self._whh_f32[1], self.U, self.Up)
+            self.whh_ts_image()
             # host-side tuning knobs, handed to the library as explicit arguments (0 / -1 = let it choose)
             return ops.blstm_recurrence_ts(G, self.whh_ts, rows, T, self.Up,
                                            rows_per_cluster=int(os.environ.get("TSSEP_TS_ROWS", "0")),
@@ -168,6 +200,8 @@ class RNNP_packed(torch.nn.Module):
         rows = 1
         for s in shape[:-2]:
             rows *= s
+        if self.training and torch.is_grad_enabled():
+            return self.forward_train(xs_pack.reshape(rows, T, D)).reshape(*shape[:-1], self.hdim)
         x = xs_pack.reshape(rows * T, D).float()
         packs = self.layer_packs()
         xb, ld = ops.cast_bf16(x), ops.operand_ld(D)
@@ -185,3 +219,16 @@ class RNNP_packed(torch.nn.Module):
                 pk.projection(H, rows * T, xb, mode=ops.EPI_BF16, ldo=ld, act=1)
             del H
         return out.reshape(*shape[:-1], packs[-1].hdim)
+
+    def forward_train(self, x: torch.Tensor) -> torch.Tensor:
+        """Differentiable forward (training mode): x (rows, T, idim) f32 -> (rows, T, hdim) f32 through
+        ``tssep_b200.autograd.RNNPLayerFn`` (own kernels forward and backward, BPTT in csrc/lstm_bwd.cu)."""
+        from .autograd import rnnp_layer
+
+        packs = self.layer_packs()
+        mods = list(self.net)
+        pairs = [(m, mods[i + 1]) for i, m in enumerate(mods) if isinstance(m, torch.nn.LSTM)]
+        h = x.float()
+        for li, ((lstm, lin), pk) in enumerate(zip(pairs, packs)):
+            h = rnnp_layer(lstm, lin, pk, h, act_tanh=li < len(packs) - 1)
+        return h

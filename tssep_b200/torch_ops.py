@@ -62,6 +62,16 @@ _OPS = {
     "pack_whh_ts": (
         "(Tensor whh_fwd, Tensor whh_bwd, int U, int Up, Tensor(a!) Wimg) -> ()",
         "tssep_pack_whh_ts"),
+    "blstm_recurrence_train": (
+        "(Tensor G, Tensor Wimg, Tensor(a!) H, Tensor(b!) gates, Tensor(c!) cstate, int rows, int T, int Up, "
+        "int rows_per_cluster, int gate_math) -> ()",
+        "tssep_blstm_recurrence_train"),
+    "blstm_recurrence_bwd": (
+        "(Tensor gates, Tensor cstate, Tensor dH, Tensor WTimg, Tensor(a!) dG, int rows, int T, int Up) -> ()",
+        "tssep_blstm_recurrence_bwd"),
+    "pack_whh_bwd": (
+        "(Tensor whh_fwd, Tensor whh_bwd, int U, int Up, Tensor(a!) WTimg) -> ()",
+        "tssep_pack_whh_bwd"),
     "mask_istft": (
         "(Tensor X, int x_item_stride, Tensor? mask, int Z, int n_spk, int T, int size, int shift, int window_length, "
         "int fading, Tensor synwin, Tensor twiddle, Tensor(a!)? stft_estimate, Tensor(b!)? time, int num_samples, "
@@ -104,6 +114,8 @@ def _first_tensor(args):
 _DETAIL = {
     "tssep_blstm_recurrence_ts": lambda a: f"rows={a[3]} T={a[4]}",
     "tssep_blstm_recurrence": lambda a: f"rows={a[4]} T={a[5]} regs",
+    "tssep_blstm_recurrence_train": lambda a: f"rows={a[5]} T={a[6]} train",
+    "tssep_blstm_recurrence_bwd": lambda a: f"rows={a[5]} T={a[6]} bwd",
 }
 
 
