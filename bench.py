@@ -53,6 +53,10 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="c4", choices=["c4", "c5"],
+                    help="c4 (default): BASELINE config 4, inference of 64 meetings; c5: BASELINE config 5, one training "
+                         "forward + backward step on a batch of 60-s segments (extra mode, its own JSON line)")
+    ap.add_argument("--segments", type=int, default=8, help="c5: 60-s segments per training step")
     ap.add_argument("--meetings", type=int, default=int(os.environ.get("TSSEP_BENCH_MEETINGS", 64)),
                     help="meetings of the whole job (BASELINE config 4: 64), dealt to the ranks")
     ap.add_argument("--seconds", type=float, default=600.0, help="length of every synthetic meeting")
@@ -677,9 +681,134 @@ def run_b200(args):
         torch.distributed.destroy_process_group()
 
 
+# ----------------------------------------------------------------------------------------------
+# BASELINE config 5: TS-SEP training forward / backward step, bf16 operands, synthetic 8-speaker 60-s segments, 1 GPU
+def c5_batch(n_segments: int, seconds: float):
+    from tssep_b200.data import DummyReader
+
+    reader = DummyReader(sample_rate=SAMPLE_RATE, aux_size=513)
+    n = int(seconds * SAMPLE_RATE)
+    exs = [reader.get_example(s, num_samples=n, with_targets=True) for s in range(n_segments)]
+    obs = torch.tensor(np.stack([e["audio_data"]["observation"] for e in exs]).astype(np.float32))       # (B, 1, n)
+    tgt = torch.tensor(np.stack([e["audio_data"]["speaker_reverberation_early_ch0"] for e in exs]).astype(np.float32))
+    aux = torch.tensor(np.stack([e["auxInput"] for e in exs]).astype(np.float32))
+    return obs, aux, tgt
+
+
+def run_c5(args):
+    from tssep_b200 import _lib
+
+    assert args.gpus == 1 and int(os.environ.get("WORLD_SIZE", 1)) == 1, "config 5 is a single-GPU configuration"
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    _lib.load()
+    seconds = 60.0
+    model = build_product_model(dev).train()
+    obs, aux, tgt = c5_batch(args.segments, seconds)
+    obs, aux, tgt = obs.to(dev), aux.to(dev), tgt.to(dev)
+
+    def step():
+        np.random.seed(0)
+        for p in model.parameters():
+            p.grad = None
+        ex = {"observation": obs, "auxInput": aux, "reference_channel": 0}
+        out = model(ex)
+        loss = model.loss(out.time_estimate, tgt).sum()
+        loss.backward()
+        return loss
+
+    for _ in range(args.warmup):
+        loss = step()
+    torch.cuda.synchronize()
+    timeline = []
+    _lib.set_timeline(timeline)
+    l0 = _lib.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(0) as clocks:
+        e0.record()
+        for _ in range(args.steps):
+            loss = step()
+        e1.record()
+        torch.cuda.synchronize()
+    _lib.set_timeline(None)
+    ms = e0.elapsed_time(e1) / args.steps
+    breakdown, detail = kernel_breakdown(timeline, args.steps)
+    own_ms = sum(v["ms_per_step"] for v in breakdown.values())
+    T = model.fe.num_frames(int(seconds * SAMPLE_RATE))
+    grads = sum(int(p.grad is not None) for p in model.parameters())
+    line = {
+        "metric": "audio_seconds_per_second", "value": args.segments * seconds / (ms / 1e3), "unit": "audio-s/s",
+        "segments_per_second": args.segments / (ms / 1e3), "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {"workload": f"BASELINE config 5: TS-SEP training forward + backward step (LogMAE, no optimizer) on a batch "
+                               f"of {args.segments} synthetic 8-speaker {seconds:.0f}-s segments, U=300 P=320 mul ts_vad=8 R=2, "
+                               "random-init weights, 1 B200",
+                   "precision": "bf16 GEMM / recurrence operands, f32 accumulation, f32 cell state, f32 parameter gradients",
+                   "segments": args.segments, "frames": T, "parameters_with_gradient": grads,
+                   "library_parts": "weight-gradient GEMMs, the head Linear and the elementwise glue run through torch "
+                                    "(cuBLAS / ATen); the recurrences (forward and BPTT), the input / projection GEMMs and "
+                                    "their data gradients, STFT / iSTFT and its adjoint are this repo's kernels"},
+        "clocks": clocks.summary(), "loss": float(loss), "gpu_launches": _lib.launch_count - l0,
+        "own_kernel_ms_per_step": own_ms, "kernels": breakdown,
+        "recurrence_launches": {k: dict(v, us_per_dependent_step=v["ms_per_step"] * 1e3 / (v["launches_per_step"] * T))
+                                for k, v in detail.items() if "recurrence" in k},
+    }
+    if not args.no_cpu_baseline:
+        line["cpu_baseline"] = time_oracle_c5(seconds)
+    print(json.dumps(line))
+    if args.profile_json:
+        json.dump(line, open(args.profile_json, "w"), indent=1)
+
+
+def time_oracle_c5(seconds: float, reps: int = 2):
+    """The reference's training arithmetic (oracle restatement, torch autograd, f32) on the host cores: forward + backward
+    of ONE 60-s segment per repetition."""
+    O, net, tables = oracle_setup(MODEL_KW["units"], MODEL_KW["projs"])
+    net.train()
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    torch.set_num_threads(cores)
+    obs, aux, tgt = c5_batch(1, seconds)
+    n = obs.shape[-1]
+    times = []
+    for i in range(1 + reps):
+        np.random.seed(0)
+        net.zero_grad()
+        t0 = time.perf_counter()
+        X = O.stft(obs[0], size=1024, shift=256, window="hann")
+        inp = O.concat_feature(X[0], tables).float()
+        out = net(inp, [a for a in aux[0]])
+        est = O.masking(out.mask, X, 0)
+        t_est = O.istft(est, size=1024, shift=256, window="hann", num_samples=n)
+        O.log_mae(t_est, tgt[0]).backward()
+        dt = time.perf_counter() - t0
+        if i > 0:
+            times.append(dt)
+    v = seconds / float(np.median(times))
+    return {"value": v, "unit": "audio-s/s", "segments_per_second": v / seconds, "cores": cores, "host_cpus": os.cpu_count(),
+            "kind": "port", "sample": f"oracle forward + backward (torch autograd, f32) of one {seconds:.0f}-s segment, median "
+                                      f"of {reps} after 1 warm-up, torch threads={cores}"}
+
+
+def run_reference_c5(args):
+    if int(os.environ.get("RANK", 0)) != 0:
+        return
+    cpu = time_oracle_c5(60.0, reps=max(1, args.steps))
+    line = {"impl": "reference", "metric": "audio_seconds_per_second", "value": cpu["value"], "unit": "audio-s/s",
+            "segments_per_second": cpu["segments_per_second"], "n_gpus": args.gpus, "steps": max(1, args.steps), "warmup": 1,
+            "ms_per_step": 60.0 / cpu["value"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "BASELINE config 5: TS-SEP training forward + backward step, one 60-s segment per step"},
+            "cpu_baseline": cpu, "e2e": {"value": cpu["value"], "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
 if __name__ == "__main__":
     a = parse_args()
-    if a.impl == "reference":
+    if a.config == "c5":
+        run_reference_c5(a) if a.impl == "reference" else run_c5(a)
+    elif a.impl == "reference":
         run_reference(a)
     else:
         run_b200(a)
