@@ -220,6 +220,22 @@ int tssep_mask_istft(const float* X, int64_t x_item_stride, const float* mask, i
                      const float* synwin, const float* twiddle, float* stft_estimate, float* time,
                      int64_t num_samples, float* activity, tssep_stream_t stream);
 
+/* Mask-based MVDR beamformer, Souden formulation: TorchBF.__call__ (tssep/train/enhancer.py:140-283).
+ * Y (Z, D, T, F) cfloat multi-channel STFT, D <= 8 channels; mask (Z, K, nmask, T, F) f32, nmask 1 (interference
+ * weight = 1 - mask) or 2 (target, interference); K * nmask (+1) <= 17.
+ * tssep_bf_psd: psd (Z, planes, F, D(D+1)/2) complex float64 = upper triangles of sum_t w Y Y^H, planes = K * nmask
+ *   weights in mask order, plus the all-ones weight as the last plane when nmask == 1 (the buffer is zeroed by the call).
+ * tssep_bf_mvdr_souden: w (Z, K, F, D) cfloat = phi[:, ref] / max(Re trace(phi), eps), phi = interference^-1 target
+ *   (Gaussian elimination with partial pivoting, complex float64).
+ * tssep_bf_apply: out (Z, K, T, F) cfloat = sum_d conj(w) Y, times max(mask[:, :, 0], masking_eps) when mask != NULL
+ *   (TorchBF(masking=True), enhancer.py:276-281). */
+int tssep_bf_psd(const float* Y, const float* mask, int64_t Z, int K, int nmask, int D, int64_t T, int F, double* psd,
+                 tssep_stream_t stream);
+int tssep_bf_mvdr_souden(const double* psd, int64_t Z, int K, int nmask, int D, int F, int reference_channel, double eps,
+                         float* w, tssep_stream_t stream);
+int tssep_bf_apply(const float* Y, const float* w, const float* mask, int64_t Z, int K, int nmask, int D, int64_t T, int F,
+                   float masking_eps, float* out, tssep_stream_t stream);
+
 /* ------------------------------------------------------------------------
  * (5) Diarization post-processing (no reference implementation; anchors
  *     tssep/util/utils.py:11-129, tssep/train/loss.py:343)

@@ -386,6 +386,30 @@ def masking(mask: torch.Tensor, observation_stft: torch.Tensor, reference_channe
     return obs[..., None, :, :] * torch.squeeze(mask, dim=-3)
 
 
+def torch_bf(masks: torch.Tensor, observation_stft: torch.Tensor, reference_channel=0, masking=False, masking_eps=0.0,
+             eps=None) -> torch.Tensor:
+    """``TorchBF('mvdr_souden').__call__`` (tssep/train/enhancer.py:226-283), complex128 as the reference demands."""
+    Y = observation_stft.to(torch.complex128)
+    if masks.shape[-3] == 2:
+        psds = torch.einsum("...kmtf,...dtf,...Dtf->...mkfdD", masks.to(torch.complex128), Y, Y.conj())
+        target_psd, interference_psd = psds[..., 0, :, :, :, :], psds[..., 1, :, :, :, :]
+    elif masks.shape[-3] == 1:
+        m = torch.squeeze(masks, dim=-3).to(torch.complex128)
+        target_psd = torch.einsum("...ktf,...dtf,...Dtf->...kfdD", m, Y, Y.conj())
+        interference_psd = torch.einsum("...ktf,...dtf,...Dtf->...kfdD", 1 - m, Y, Y.conj())
+    else:
+        raise ValueError(masks.shape)
+    phi = torch.linalg.solve(interference_psd, target_psd)
+    lambda_ = torch.diagonal(phi, dim1=-2, dim2=-1).sum(-1)[..., None, None]
+    eps = torch.finfo(lambda_.real.dtype).tiny if eps is None else eps
+    mat = phi / torch.clamp(lambda_.real, min=eps)
+    beamformer = mat[..., reference_channel]
+    enh = torch.einsum("...kfd,...dtf->...ktf", beamformer.conj(), Y)
+    if masking:
+        enh = enh * torch.clamp(masks[..., :, 0, :, :], min=masking_eps)
+    return enh
+
+
 def log_mae(estimate: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
     """``LogMAE.loss_fn`` (tssep/train/loss.py:244-247)."""
     return torch.log10((estimate - target).abs().mean(dim=-1).sum(dim=-1))

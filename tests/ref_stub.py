@@ -137,3 +137,17 @@ def case_inputs(name: str, batched: bool):
 
 def aux_argument(aux, batched: bool):
     return [[a for a in item] for item in aux] if batched else [a for a in aux]
+
+
+def load_enhancer():
+    """The reference's ``tssep/train/enhancer.py`` (TorchBF is pure torch; pb_bss / paderbox are only needed by the
+    numpy beamformers and WPE, which are not exercised)."""
+    if "enh" in _cache:
+        return _cache["enh"]
+    load()
+    for name in ("pb_bss", "pb_bss.testing", "pb_bss.testing.random_utils", "pb_bss.extraction", "pb_bss.extraction.beamformer"):
+        sys.modules.setdefault(name, _module(name))
+    sys.modules["pb_bss"].testing = sys.modules["pb_bss.testing"]
+    sys.modules["pb_bss.testing"].random_utils = sys.modules["pb_bss.testing.random_utils"]
+    _cache["enh"] = importlib.import_module("tssep.train.enhancer")
+    return _cache["enh"]

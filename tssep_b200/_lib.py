@@ -62,6 +62,9 @@ _SIGNATURES = {
     "tssep_pack_whh_bwd": ([c_vp, c_vp, c_i32, c_i32, c_vp, c_vp], C.c_int),
     "tssep_mask_istft": ([c_vp, c_i64, c_vp, c_i64, c_i32, c_i64, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp,
                           c_i64, c_vp, c_vp], C.c_int),
+    "tssep_bf_psd": ([c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i64, c_i32, c_vp, c_vp], C.c_int),
+    "tssep_bf_mvdr_souden": ([c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, C.c_double, c_vp, c_vp], C.c_int),
+    "tssep_bf_apply": ([c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i64, c_i32, c_f32, c_vp, c_vp], C.c_int),
     "tssep_activity": ([c_vp, c_i64, c_i64, c_i32, c_vp, c_vp], C.c_int),
     "tssep_median_threshold": ([c_vp, c_i64, c_i64, c_i32, c_f32, c_vp, c_vp, c_vp], C.c_int),
     "tssep_segments": ([c_vp, c_i64, c_i64, c_i32, c_i32, c_i32, c_i64, c_vp, c_vp, c_i32, c_i32, c_vp], C.c_int),

@@ -33,6 +33,7 @@ FACTORY_ALIASES = {
     "tssep.train.net.InstanceNorm_v2": "tssep_b200.net.InstanceNorm_v2",
     "tssep.train.rnnp.RNNP_packed": "tssep_b200.rnnp.RNNP_packed",
     "tssep.train.enhancer.Masking": "tssep_b200.enhancer.Masking",
+    "tssep.train.enhancer.TorchBF": "tssep_b200.enhancer.TorchBF",
     "tssep.train.loss.LogMAE": "tssep_b200.loss.LogMAE",
     "tssep.train.loss.MAE": "tssep_b200.loss.MAE",
     "tssep.train.init_ckpt.InitCheckPoint": "tssep_b200.init_ckpt.InitCheckPoint",

@@ -76,3 +76,46 @@ class Masking(ABC):
                                 tab["synwin"], tab["twiddle"], est, time, time.shape[-1] if time is not None else 0,
                                 activity_out)
         return est, time
+
+
+class TorchBF(ABC):
+    """Mask-based MVDR beamformer, Souden formulation (tssep/train/enhancer.py:140-283): spatial covariance matrices of
+    target and interference from the masks, ``w = (Phi_i^-1 Phi_t)[:, ref] / trace(Phi_i^-1 Phi_t)``, ``enh = w^H Y``.
+
+    Same constructor and call contract as the reference: ``masks`` (K, nmask, T, F) or (B, K, nmask, T, F) with
+    ``nmask`` 1 (interference weight = 1 - mask) or 2 (target, interference); ``ex['Observation']`` ([B,] D, T, F)
+    complex.  The covariance sums and the D x D solves run in float64 (the reference works in complex128 throughout),
+    the beamformer is applied in float32; the result has the dtype of ``Observation``."""
+
+    def __init__(self, bf="mvdr_souden", masking=False, masking_eps=0.0, eps=None):
+        super().__init__()
+        assert bf == "mvdr_souden", (bf, "Only mvdr_souden is implemented")
+        self.bf, self.eps, self.masking, self.masking_eps = bf, eps, masking, masking_eps
+
+    def __call__(self, masks, ex, model=None):
+        batched = {4: False, 5: True}[masks.dim()]
+        ref = ex["reference_channel"]
+        Obs = ex["Observation"]
+        if isinstance(Obs, np.ndarray):
+            Obs = torch.as_tensor(Obs, device=masks.device)
+        assert Obs.dim() == (4 if batched else 3), Obs.shape
+        _lib.require_cuda(masks, Obs)
+        out_dtype = Obs.dtype
+        Y = Obs.to(torch.complex64).contiguous()
+        m = masks.float().contiguous()
+        if not batched:
+            Y, m = Y[None], m[None]
+        Z, D, T, F = Y.shape
+        K, nmask = m.shape[1], m.shape[2]
+        assert m.shape == (Z, K, nmask, T, F), (m.shape, Y.shape)
+        planes = K * nmask + (1 if nmask == 1 else 0)
+        psd = torch.empty((Z, planes, F, D * (D + 1) // 2, 2), dtype=torch.float64, device=Y.device)
+        torch_ops.op.bf_psd(Y, m, Z, K, nmask, D, T, F, psd)
+        w = torch.empty((Z, K, F, D), dtype=torch.complex64, device=Y.device)
+        eps = float(torch.finfo(torch.float64).tiny) if self.eps is None else float(self.eps)
+        torch_ops.op.bf_mvdr_souden(psd, Z, K, nmask, D, F, int(ref), eps, w)
+        enh = torch.empty((Z, K, T, F), dtype=torch.complex64, device=Y.device)
+        torch_ops.op.bf_apply(Y, w, m if self.masking else None, Z, K, nmask, D, T, F, float(self.masking_eps), enh)
+        self.last_beamformer = w if batched else w[0]
+        enh = enh.to(out_dtype) if out_dtype.is_complex else enh
+        return enh if batched else enh[0]

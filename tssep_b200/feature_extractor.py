@@ -128,22 +128,24 @@ class STFT(Configurable):
                           int(bool(self.fading)), t, out)
         return out.cpu().numpy() if was_np else out
 
-    def istft(self, X, num_samples=None):
-        """(..., T, F) complex -> (..., N) float32."""
+    def istft(self, X, num_samples=None, _fading=None):
+        """(..., T, F) complex -> (..., N) float32.  (``_fading=False``: keep the leading / trailing
+        ``window_length - shift`` samples, for a frame RANGE of a longer signal -- ``tssep_b200.eval``.)"""
+        fading = self.fading if _fading is None else _fading
         Xc, was_np = self._to_cuda(X, torch.complex64)
         Xc = Xc.contiguous()
         lead = Xc.shape[:-2]
         t = Xc.shape[-2]
         assert Xc.shape[-1] == self.frequencies, (Xc.shape, self.frequencies)
         total = (t - 1) * self.shift + self.window_length
-        if self.fading:
+        if fading:
             total -= 2 * (self.window_length - self.shift)
         n = total if num_samples is None else min(int(num_samples), total)
         tab = self._device_tables(Xc.device)
         out = torch.empty((*lead, n), dtype=torch.float32, device=Xc.device)
         n_sig = int(np.prod(lead)) if lead else 1
         torch_ops.op.mask_istft(Xc, 0, None, n_sig, 1, t, self.size, self.shift, self.window_length,
-                                int(bool(self.fading)), tab["synwin"], tab["twiddle"], None, out, n, None)
+                                int(bool(fading)), tab["synwin"], tab["twiddle"], None, out, n, None)
         return out.cpu().numpy() if was_np else out
 
     # feature description consumed by `_compute_features`

@@ -77,6 +77,16 @@ _OPS = {
         "int fading, Tensor synwin, Tensor twiddle, Tensor(a!)? stft_estimate, Tensor(b!)? time, int num_samples, "
         "Tensor(c!)? activity) -> ()",
         "tssep_mask_istft"),
+    "bf_psd": (
+        "(Tensor Y, Tensor mask, int Z, int K, int nmask, int D, int T, int F, Tensor(a!) psd) -> ()",
+        "tssep_bf_psd"),
+    "bf_mvdr_souden": (
+        "(Tensor psd, int Z, int K, int nmask, int D, int F, int reference_channel, float eps, Tensor(a!) w) -> ()",
+        "tssep_bf_mvdr_souden"),
+    "bf_apply": (
+        "(Tensor Y, Tensor w, Tensor? mask, int Z, int K, int nmask, int D, int T, int F, float masking_eps, "
+        "Tensor(a!) out) -> ()",
+        "tssep_bf_apply"),
     "activity": (
         "(Tensor mask, int n, int T, int F, Tensor(a!) activity) -> ()",
         "tssep_activity"),
