@@ -77,6 +77,15 @@ int tssep_feature_write(const float* X, int64_t n_items, int64_t x_item_stride, 
                         int couple_batch, float* feat_f32, uint16_t* feat_bf16, int64_t ld_bf16,
                         tssep_stream_t stream);
 
+/* Multi-channel / normalised feature variants of the reference (tssep/train/feature_extractor.py:13-168, :266-287):
+ * tssep_log1p_abs: out[i] = log1p(|X[i]|) for n complex values (Log1pAbsSTFT; MVNLog1pAbsSTFT subtracts the mean over
+ *   frames afterwards: tssep_instance_norm mode 1 along the frame axis);
+ * tssep_ipd: inter-channel phase differences of X (lead, D, TF) cfloat against channel second_channel[d] (D int32):
+ *   cos_out / sin_out (lead, D, TF) f32 = Re / Im of X[d] conj(X[second[d]]) / |.|. */
+int tssep_log1p_abs(const float* X, int64_t n, float* out, tssep_stream_t stream);
+int tssep_ipd(const float* X, int64_t lead, int D, int64_t TF, const int32_t* second_channel, float* cos_out,
+              float* sin_out, tssep_stream_t stream);
+
 /* f32 (rows, cols) -> bf16 (rows, ld) conversion (zero padded columns). */
 int tssep_cast_bf16(const float* src, int64_t rows, int64_t cols, int64_t ld_src, uint16_t* dst,
                     int64_t ld_dst, tssep_stream_t stream);

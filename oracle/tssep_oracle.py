@@ -154,6 +154,45 @@ def log1p_maxnorm_feature(X, statistics_axis="tf"):
     return torch.log1p(s)
 
 
+def interchannel_phase_differences(signal: np.ndarray, second_channel=None, concatenate=False):
+    """tssep/train/feature_extractor.py:13-80.  signal (..., channels, frames, features) complex (numpy).
+
+    ``interchannel_phase_differences_op`` is padertorch's (absent package, padertorch==0.0.1): the unit phasor of
+    ``a * conj(b)``; pinned by the reference's doctest values (tests/test_ipd_features.py).  The partner channels are
+    drawn from the global NumPy RNG exactly as feature_extractor.py:58-66 does."""
+    import itertools
+
+    signal = np.asarray(signal)
+    if second_channel is None:
+        D = signal.shape[-3]
+        assert D >= 2, (D, signal.shape)
+        pairs = list(itertools.permutations(range(D), 2))
+        np.random.shuffle(pairs)
+        second_channel = np.array(sorted(dict(pairs).items()))[:, 1]
+    z = signal * np.conj(signal[..., second_channel, :, :])
+    z = z / np.abs(z)
+    if concatenate:
+        return np.concatenate([np.abs(signal), z.real, z.imag], axis=-1)
+    return z.real, z.imag
+
+
+def log1p_abs_ipd_feature(X: np.ndarray) -> np.ndarray:
+    """``Log1pAbsIPDSTFT.stft_to_feature`` (feature_extractor.py:96-109)."""
+    return np.concatenate([np.log1p(np.abs(X)), *interchannel_phase_differences(X)], axis=-1)
+
+
+def log1p_maxnorm_ipd_feature(X: np.ndarray, statistics_axis="tf") -> np.ndarray:
+    """``Log1pMaxNormAbsIPDSTFT.stft_to_feature`` (feature_extractor.py:277-287)."""
+    base = log1p_maxnorm_feature(np.asarray(X), statistics_axis)
+    return np.concatenate([base, *interchannel_phase_differences(X)], axis=-1)
+
+
+def mvn_log1p_abs_feature(X: np.ndarray) -> np.ndarray:
+    """``MVNLog1pAbsSTFT.stft_to_feature`` (feature_extractor.py:154-168): log1p|X| minus its mean over the frames."""
+    f = np.log1p(np.abs(X))
+    return f - np.mean(f, axis=-2, keepdims=True)
+
+
 class MFCCTables:
     """Constant tables of ``TorchMFCC`` (tssep/train/feature_extractor_torchaudio.py:22-85)."""
 

@@ -133,7 +133,8 @@ def test_segment_wise_beamforming(cuda):
     np.random.seed(0)
     X = O.stft(torch.tensor(obs.astype(np.float32)), size=1024, shift=256, window="hann")
     inp = O.concat_feature(X[0], O.MFCCTables()).float()
-    mask = ref(inp, [a for a in torch.tensor(e["auxInput"])]).mask
+    with torch.no_grad():
+        mask = ref(inp, [a for a in torch.tensor(e["auxInput"])]).mask
     pad = 768
     for s in got[:3]:
         f0 = max(0, int(fe.sample_index_to_frame_index(s.start)) - 2)

@@ -46,6 +46,8 @@ _SIGNATURES = {
                             C.c_int),
     "tssep_feature_write": ([c_vp, c_i64, c_i64, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_f32,
                              c_i32, c_vp, c_vp, c_i64, c_vp], C.c_int),
+    "tssep_log1p_abs": ([c_vp, c_i64, c_vp, c_vp], C.c_int),
+    "tssep_ipd": ([c_vp, c_i64, c_i32, c_i64, c_vp, c_vp, c_vp, c_vp], C.c_int),
     "tssep_cast_bf16": ([c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp], C.c_int),
     "tssep_instance_norm": ([c_vp, c_i64, c_i64, c_i64, c_i32, c_i32, c_vp, c_vp], C.c_int),
     "tssep_fold_embedding": ([c_i32, c_vp, c_i64, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_vp, c_i64, c_vp, c_vp],

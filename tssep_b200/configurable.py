@@ -27,6 +27,10 @@ FACTORY_ALIASES = {
     "tssep.train.feature_extractor.ConcaternatedSTFTFeatures": "tssep_b200.feature_extractor.ConcaternatedSTFTFeatures",
     "tssep.train.feature_extractor.Log1pMaxNormAbsSTFT": "tssep_b200.feature_extractor.Log1pMaxNormAbsSTFT",
     "tssep.train.feature_extractor.TorchMFCC": "tssep_b200.feature_extractor_torchaudio.TorchMFCC",
+    "tssep.train.feature_extractor.Log1pAbsIPDSTFT": "tssep_b200.feature_extractor.Log1pAbsIPDSTFT",
+    "tssep.train.feature_extractor.Log1pMaxNormAbsIPDSTFT": "tssep_b200.feature_extractor.Log1pMaxNormAbsIPDSTFT",
+    "tssep.train.feature_extractor.MVNLog1pAbsSTFT": "tssep_b200.feature_extractor.MVNLog1pAbsSTFT",
+    "tssep.train.feature_extractor.NoFeatureSTFT": "tssep_b200.feature_extractor.NoFeatureSTFT",
     "tssep.train.feature_extractor_torchaudio.TorchMFCC": "tssep_b200.feature_extractor_torchaudio.TorchMFCC",
     "tssep.train.net.MaskEstimator_v2": "tssep_b200.net.MaskEstimator_v2",
     "tssep.train.net.InstanceNorm": "tssep_b200.net.InstanceNorm",

@@ -230,6 +230,33 @@ __global__ void instance_norm_kernel(const float* __restrict__ src, int64_t oute
   for (int64_t c = 0; c < cols; ++c) y[c * inner] = norm_apply(x[c * inner], mean, inv, mode);
 }
 
+// log1p(|X|) (Log1pAbsSTFT of padertorch, base of MVNLog1pAbsSTFT / Log1pAbsIPDSTFT, tssep/train/feature_extractor.py:83-168)
+__global__ void log1p_abs_kernel(const float2* __restrict__ X, int64_t n, float* __restrict__ out) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float2 v = X[i];
+    out[i] = log1pf(sqrtf(v.x * v.x + v.y * v.y));
+  }
+}
+
+// inter-channel phase differences (tssep/train/feature_extractor.py:13-80): z = X[d] conj(X[second[d]]),
+// cos = Re z / |z|, sin = Im z / |z|; X (lead, D, TF)
+__global__ void ipd_kernel(const float2* __restrict__ X, int64_t lead, int D, int64_t TF, const int* __restrict__ second,
+                           float* __restrict__ cos_out, float* __restrict__ sin_out) {
+  const int64_t total = lead * D * TF;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t e = i % TF;
+    const int64_t ld = i / TF;
+    const int d = static_cast<int>(ld % D);
+    const int64_t l = ld / D;
+    const float2 a = X[i], b = X[(l * D + second[d]) * TF + e];
+    const float re = a.x * b.x + a.y * b.y, im = a.y * b.x - a.x * b.y;
+    const float inv = 1.0f / sqrtf(re * re + im * im);
+    cos_out[i] = re * inv;
+    sin_out[i] = im * inv;
+  }
+}
+
 static int ilog2_exact(int v) {
   int l = 0;
   while ((1 << l) < v) ++l;
@@ -315,6 +342,25 @@ int tssep_cast_bf16(const float* src, int64_t rows, int64_t cols, int64_t ld_src
   cast_bf16_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, rows, cols, ld_src,
                                                                            reinterpret_cast<__nv_bfloat16*>(dst), ld_dst);
   return check_launch("tssep_cast_bf16");
+}
+
+int tssep_log1p_abs(const float* X, int64_t n, float* out, tssep_stream_t stream) {
+  TSSEP_REQUIRE(X && out && n >= 0, "tssep_log1p_abs: bad arguments");
+  if (n == 0) return 0;
+  const int blocks = static_cast<int>(imin64((n + 255) / 256, 148 * 16));
+  log1p_abs_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const float2*>(X), n, out);
+  return check_launch("tssep_log1p_abs");
+}
+
+int tssep_ipd(const float* X, int64_t lead, int D, int64_t TF, const int32_t* second_channel, float* cos_out, float* sin_out,
+              tssep_stream_t stream) {
+  TSSEP_REQUIRE(X && second_channel && cos_out && sin_out && D >= 2 && lead >= 0 && TF >= 0, "tssep_ipd: bad arguments");
+  if (lead == 0 || TF == 0) return 0;
+  const int64_t total = lead * D * TF;
+  const int blocks = static_cast<int>(imin64((total + 255) / 256, 148 * 16));
+  ipd_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const float2*>(X), lead, D, TF, second_channel,
+                                                                    cos_out, sin_out);
+  return check_launch("tssep_ipd");
 }
 
 int tssep_instance_norm(const float* src, int64_t outer, int64_t cols, int64_t inner, int mode, int unbiased, float* dst,

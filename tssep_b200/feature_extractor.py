@@ -223,6 +223,96 @@ class Log1pMaxNormAbsSTFT(STFT):
         return {"log1p": True}
 
 
+def interchannel_phase_differences(signal, second_channel=None, concatenate=False):
+    """cos / sin of ``angle(channel * second_channel.conj())`` (tssep/train/feature_extractor.py:13-80).
+
+    signal (..., channels, frames, features) complex.  Without ``second_channel`` the partner channels are sampled
+    exactly as the reference does -- ``np.random.shuffle`` of all ordered channel pairs, last pair per first channel
+    wins -- so the global NumPy RNG is consumed identically."""
+    import itertools
+
+    X, was_np = STFT._to_cuda(signal, torch.complex64)
+    if X.dim() < 3:
+        raise IndexError(tuple(X.shape))
+    D = X.shape[-3]
+    if second_channel is None:
+        assert D >= 2, (D, X.shape)
+        pairs = list(itertools.permutations(range(D), 2))
+        np.random.shuffle(pairs)
+        second_channel = np.array(sorted(dict(pairs).items()))[:, 1]
+    X = X.contiguous()
+    TF = X.shape[-2] * X.shape[-1]
+    lead = X.numel() // (D * TF)
+    sc = torch.as_tensor(np.asarray(second_channel, dtype=np.int32), device=X.device)
+    cos = torch.empty(X.shape, dtype=torch.float32, device=X.device)
+    sin = torch.empty_like(cos)
+    torch_ops.op.ipd(X, lead, D, TF, sc, cos, sin)
+    if concatenate:
+        out = torch.cat([X.abs(), cos, sin], dim=-1)
+        return out.cpu().numpy() if was_np else out
+    return (cos.cpu().numpy(), sin.cpu().numpy()) if was_np else (cos, sin)
+
+
+class Log1pAbsSTFT(STFT):
+    """``log1p(|X|)`` (padertorch ``Log1pAbsSTFT``, the base of the two classes below)."""
+
+    def stft_to_feature(self, stft_signals):
+        X, was_np = self._to_cuda(stft_signals, torch.complex64)
+        X = X.contiguous()
+        out = torch.empty(X.shape, dtype=torch.float32, device=X.device)
+        torch_ops.op.log1p_abs(X, X.numel(), out)
+        return out.cpu().numpy() if was_np else out
+
+
+class MVNLog1pAbsSTFT(Log1pAbsSTFT):
+    """``log1p(|X|)`` minus its mean over the frames (tssep/train/feature_extractor.py:112-168): the utterance-level
+    mean normalisation of the front end."""
+
+    def __init__(self, size=1024, shift=256, window_length=None, pad=True, fading=True, output_size=None,
+                 window="blackman", norm_means: bool = True, norm_vars: bool = False, eps: float = 1.0e-20):
+        super().__init__(size=size, shift=shift, window_length=window_length, pad=pad, fading=fading,
+                         output_size=output_size, window=window)
+        self.norm_means, self.norm_vars, self.eps = norm_means, norm_vars, eps
+
+    def stft_to_feature(self, stft_signals):
+        if not self.norm_means or self.norm_vars:
+            raise NotImplementedError()  # as the reference (feature_extractor.py:160-166)
+        X, was_np = self._to_cuda(stft_signals, torch.complex64)
+        feature = Log1pAbsSTFT.stft_to_feature(self, X)
+        from . import ops
+
+        out = ops.instance_norm(feature, dim=-2, mode=1)
+        return out.cpu().numpy() if was_np else out
+
+
+class Log1pAbsIPDSTFT(Log1pAbsSTFT):
+    """``[log1p|X| , cos IPD , sin IPD]`` per channel (tssep/train/feature_extractor.py:83-109); input (channels, T, F)."""
+
+    def _get_output_size(self, output_size):
+        return (self.size // 2 + 1) * 3 if output_size is None else output_size
+
+    def stft_to_feature(self, stft_signals):
+        was_np = isinstance(stft_signals, np.ndarray)
+        X, _ = self._to_cuda(stft_signals, torch.complex64)
+        base = Log1pAbsSTFT.stft_to_feature(self, X)
+        cos, sin = interchannel_phase_differences(X, concatenate=False)
+        out = torch.cat([base, cos, sin], dim=-1)
+        return out.cpu().numpy() if was_np else out
+
+
+class NoFeatureSTFT(STFT):
+    """Zero features (tssep/train/feature_extractor.py:171-180)."""
+
+    def stft_to_feature(self, stft_signals):
+        return stft_signals[..., :0]
+
+    def _get_output_size(self, output_size):
+        if output_size is None:
+            return 0
+        assert output_size == 0, (output_size, self.frequencies)
+        return output_size
+
+
 class ConcaternatedSTFTFeatures(STFT, torch.nn.Module):
     """Concatenation ``[fe1 | fe2]`` of two STFT features (tssep/train/feature_extractor.py:290-367).
 
@@ -267,3 +357,21 @@ class ConcaternatedSTFTFeatures(STFT, torch.nn.Module):
             "ConcaternatedSTFTFeatures: the CUDA path implements fe1=TorchMFCC, fe2=Log1pMaxNormAbsSTFT "
             f"(got {type(self.fe1).__name__}, {type(self.fe2).__name__})"
         )
+
+
+class Log1pMaxNormAbsIPDSTFT(Log1pMaxNormAbsSTFT):
+    """``[log1p-max-norm |X| , cos IPD , sin IPD]`` per channel (tssep/train/feature_extractor.py:266-287)."""
+
+    def _get_output_size(self, output_size):
+        if output_size is None:
+            return (self.size // 2 + 1) * 3
+        assert output_size == self.frequencies * 3, (output_size, self.frequencies * 3)
+        return output_size
+
+    def stft_to_feature(self, stft_signals):
+        was_np = isinstance(stft_signals, np.ndarray)
+        X, _ = self._to_cuda(stft_signals, torch.complex64)
+        base = _compute_features(self, X, want_f32=True)["f32"]
+        cos, sin = interchannel_phase_differences(X, concatenate=False)
+        out = torch.cat([base, cos, sin], dim=-1)
+        return out.cpu().numpy() if was_np else out

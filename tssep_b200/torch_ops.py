@@ -36,6 +36,10 @@ _OPS = {
         "Tensor? dct, int n_mels, int n_mfcc, int with_log1p, float top_db, int couple_batch, Tensor(a!)? feat_f32, "
         "Tensor(b!)? feat_bf16, int ld_bf16) -> ()",
         "tssep_feature_write"),
+    "log1p_abs": ("(Tensor X, int n, Tensor(a!) out) -> ()", "tssep_log1p_abs"),
+    "ipd": (
+        "(Tensor X, int lead, int D, int TF, Tensor second_channel, Tensor(a!) cos_out, Tensor(b!) sin_out) -> ()",
+        "tssep_ipd"),
     "cast_bf16": (
         "(Tensor src, int rows, int cols, int ld_src, Tensor(a!) dst, int ld_dst) -> ()",
         "tssep_cast_bf16"),
