@@ -33,7 +33,7 @@ typedef void* tssep_stream_t; /* cudaStream_t */
 
 /* Bumped whenever a signature or struct layout below changes; tssep_b200/_lib.py refuses a library that
  * reports another value. */
-#define TSSEP_ABI_VERSION 2
+#define TSSEP_ABI_VERSION 3
 
 const char* tssep_last_error(void);
 int tssep_abi_version(void);
@@ -76,6 +76,19 @@ int tssep_feature_write(const float* X, int64_t n_items, int64_t x_item_stride, 
                         const float* dct, int n_mels, int n_mfcc, int with_log1p, float top_db,
                         int couple_batch, float* feat_f32, uint16_t* feat_bf16, int64_t ld_bf16,
                         tssep_stream_t stream);
+
+/* Weighted prediction error dereverberation (tssep/train/enhancer.py:292-367: WPE / ChannelWiseWPE, wrappers around
+ * nara_wpe.wpe.wpe_v8 -- nara_wpe>=0.0.11 is a third-party dependency absent from the reference tree; the kernels
+ * restate its published algorithm).  Y, X: (D, T, F) complex64 (interleaved float pairs), D <= 8, D * taps small enough
+ * for the shared-memory solve ((D*taps) * (D*taps + D) * 16 bytes <= 200 KiB).  Per frequency and iteration:
+ * lambda_t = mean_d |X|^2 (mean over +-psd_context frames, floor 1e-10 * max_t), R = sum_t Yt Yt^H / lambda_t,
+ * P = sum_t Yt Y^H / lambda_t with Yt the taps delayed frames (delay, ..., delay + taps - 1), G = R^-1 P in f64,
+ * X = Y - G^H Yt.  statistics_mode: 0 = 'full' (every frame), 1 = 'valid' (frames >= delay + taps - 1).
+ * workspace: device memory of tssep_wpe_workspace_bytes(...) bytes, 256-byte aligned (scratch, no state between calls).
+ * ChannelWiseWPE = the same call on the (1, T, D*F) view of the channel-major signal. */
+int64_t tssep_wpe_workspace_bytes(int D, int64_t T, int F, int taps);
+int tssep_wpe(const float* Y, int D, int64_t T, int F, int taps, int delay, int iterations, int psd_context,
+              int statistics_mode, float* X, void* workspace, int64_t workspace_bytes, tssep_stream_t stream);
 
 /* Multi-channel / normalised feature variants of the reference (tssep/train/feature_extractor.py:13-168, :266-287):
  * tssep_log1p_abs: out[i] = log1p(|X[i]|) for n complex values (Log1pAbsSTFT; MVNLog1pAbsSTFT subtracts the mean over
@@ -161,20 +174,23 @@ int tssep_head_expand_t(const float* small, int64_t Z, int64_t T, int n_blocks, 
  * Wimg from tssep_pack_whh_ts: 2 * C * 2 * (Up/16) * 128 * 8 words, C = ceil(Up/64)
  * H    (rows, T, 2*Up) bf16 out: [h_fwd(Up) | h_bwd(Up)]
  * Up = hidden units rounded up to a multiple of 16; padded units stay 0.  Limits: Up <= 384, and
- * tiles * roundup(Up/2, 32) + 64 + tiles * max(rows_per_cluster, 16) <= 512 tensor-memory columns (Up <= 320 at 32
- * rows and 2 tiles); clusters of at most 16 CTAs.
- * rows_per_cluster: 8, 16, 32, or 64 (two sub-batches of 32 rows advancing in anti-phase: while the h of one travels
- * through DSMEM and its gate math runs, the tensor pipe works on the other; 2 tiles only); tiles_per_cta: 1 or 2;
- * 0 = choose (the shape with the shortest step whose clusters still fit in one wave of co-resident clusters).
+ * tiles * roundup(Up/2, 32) + 64 + tiles * sub_batches * max(rows_per_cluster / sub_batches, 16) <= 512 tensor-memory
+ * columns (Up <= 320 at 2 tiles and 32 rows per sub-batch); clusters of at most 16 CTAs.
+ * rows_per_cluster: 8, 16, 32 or 64; tiles_per_cta: 1 or 2; sub_batches: 1, or 2 (2 tiles only; 16, 32 or 64 rows per
+ * cluster): the cluster advances two independent halves of its rows in anti-phase -- while the h of one travels through
+ * DSMEM and its gate math runs, the tensor pipe works on the other (64 rows per cluster exist only in this form).
+ * 0 for any of the three = choose (the shape with the shortest step whose clusters still fit in one wave of
+ * co-resident clusters, from a cost table measured on B200).
  * gate_math: 0 = exp-based sigmoid / tanh, 1 = tanh.approx.f32.
  * k_split: 1 = the W_hh . h MMAs start on the half of h that arrives first (2 tiles only); 0 (and -1 = default) = one phase
  * (measured: the second barrier wait + proxy fence cost more than the split hides). */
 int tssep_blstm_recurrence_ts(const uint16_t* G, const uint32_t* Wimg, uint16_t* H, int64_t rows, int64_t T, int Up,
-                              int rows_per_cluster, int tiles_per_cta, int gate_math, int k_split,
+                              int rows_per_cluster, int tiles_per_cta, int sub_batches, int gate_math, int k_split,
                               tssep_stream_t stream);
 /* Batch rows that fit in ONE wave of co-resident clusters (both directions running) on the current
- * device for the given cluster shape (rows_per_cluster 8 / 16 / 32 / 64, tiles_per_cta 1 / 2); < 0 on error. */
-int tssep_blstm_recurrence_ts_capacity(int Up, int rows_per_cluster, int tiles_per_cta);
+ * device for the given cluster shape (rows_per_cluster 8 / 16 / 32 / 64, tiles_per_cta 1 / 2, sub_batches 1 / 2);
+ * 0 if the shape does not exist or does not fit, < 0 on error. */
+int tssep_blstm_recurrence_ts_capacity(int Up, int rows_per_cluster, int tiles_per_cta, int sub_batches);
 int tssep_pack_whh_ts(const float* whh_fwd, const float* whh_bwd, int U, int Up, uint32_t* Wimg,
                       tssep_stream_t stream);
 

@@ -449,6 +449,59 @@ def torch_bf(masks: torch.Tensor, observation_stft: torch.Tensor, reference_chan
     return enh
 
 
+def _wpe_window_mean(x: np.ndarray, ctx: int) -> np.ndarray:
+    """nara_wpe's ``window_mean(x, (ctx, ctx))``: mean over frames [t - ctx, t + ctx], normalised by the number of
+    frames that exist."""
+    if ctx == 0:
+        return x
+    T = x.shape[-1]
+    c = np.concatenate([np.zeros(x.shape[:-1] + (1,)), np.cumsum(x, axis=-1)], axis=-1)
+    lo = np.maximum(np.arange(T) - ctx, 0)
+    hi = np.minimum(np.arange(T) + ctx, T - 1) + 1
+    return (c[..., hi] - c[..., lo]) / (hi - lo)
+
+
+def wpe(Y: np.ndarray, taps=10, delay=2, iterations=3, psd_context=0, statistics_mode="full") -> np.ndarray:
+    """``WPE.__call__`` (tssep/train/enhancer.py:292-345): Y (D, T, F) complex -> dereverberated (D, T, F).
+
+    PARITY UNPINNED: the arithmetic lives in ``nara_wpe.wpe.wpe_v8`` (requirements.txt: nara_wpe>=0.0.11), a
+    third-party package absent from the reference tree and from this image; the reference holds no golden values for
+    it (its doctest only compares its own numpy and torch paths).  This restates nara_wpe's published algorithm
+    (Drude et al., "NARA-WPE", ITG 2018; wpe_v6/wpe_v8): per frequency, ``iterations`` times,
+    lambda_t = mean_d |X[d,t]|^2 (window mean over +-psd_context), floored at 1e-10 max_t lambda;
+    R = sum_t Yt_t Yt_t^H / lambda_t, P = sum_t Yt_t Y_t^H / lambda_t over all frames ('full') or the frames
+    >= delay + taps - 1 ('valid'); G = solve(R, P); X = Y - G^H Yt, where Yt stacks the frames delayed by
+    delay ... delay + taps - 1 (zeros before the first frame).  float64 / complex128 throughout.
+    """
+    Y = np.asarray(Y).astype(np.complex128)
+    D, T, F = Y.shape
+    Yf = np.transpose(Y, (2, 0, 1))                                  # (F, D, T)
+    Yt = np.zeros((F, taps, D, T), dtype=np.complex128)
+    for tau in range(taps):
+        sh = delay + tau
+        if sh < T:
+            Yt[:, tau, :, sh:] = Yf[:, :, :T - sh]
+    Yt = Yt.reshape(F, taps * D, T)
+    s0 = delay + taps - 1 if statistics_mode == "valid" else 0
+    assert statistics_mode in ("full", "valid"), statistics_mode
+    X = Yf.copy()
+    for _ in range(iterations):
+        power = _wpe_window_mean(np.mean(X.real ** 2 + X.imag ** 2, axis=-2), int(psd_context))   # (F, T)
+        eps = 1e-10 * np.max(power, axis=-1, keepdims=True)
+        inv = 1.0 / np.maximum(power, eps)
+        Yw = Yt * inv[:, None, :]
+        R = Yw[..., s0:] @ np.conj(np.swapaxes(Yt[..., s0:], -1, -2))
+        P = Yw[..., s0:] @ np.conj(np.swapaxes(Yf[..., s0:], -1, -2))
+        G = np.linalg.solve(R, P)
+        X = Yf - np.conj(np.swapaxes(G, -1, -2)) @ Yt
+    return np.transpose(X, (1, 2, 0))
+
+
+def channel_wise_wpe(Y: np.ndarray, **kw) -> np.ndarray:
+    """``ChannelWiseWPE.__call__`` (tssep/train/enhancer.py:348-367): every channel dereverberated on its own."""
+    return np.stack([wpe(y[None], **kw)[0] for y in np.asarray(Y)])
+
+
 def log_mae(estimate: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
     """``LogMAE.loss_fn`` (tssep/train/loss.py:244-247)."""
     return torch.log10((estimate - target).abs().mean(dim=-1).sum(dim=-1))

@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--fast", type=int, nargs="+", default=[1])
     ap.add_argument("--ksplit", type=int, nargs="+", default=[0])
     ap.add_argument("--tiles", type=int, nargs="+", default=[2], help="row tiles per CTA of the tensor-memory kernel (0 = auto)")
+    ap.add_argument("--subs", type=int, nargs="+", default=[0], help="sub-batches per cluster (0 = auto)")
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--kernel", default="ts", choices=["regs", "ts"])
     a = ap.parse_args()
@@ -37,16 +38,18 @@ def main():
 
     def run(G, rows, C, fast, ks):
         if a.kernel == "ts":
-            tiles, ksp = ks
+            tiles, ksp, subs = ks
             return ops.blstm_recurrence_ts(G, wts, rows, a.frames, Up, fast_math=bool(fast), rows_per_cluster=C, k_split=ksp,
-                                           tiles_per_cta=tiles)
+                                           tiles_per_cta=tiles, sub_batches=subs)
         return ops.blstm_recurrence(G, whh, rows, a.frames, Up, cluster=C, fast_math=bool(fast))
 
     for rows in a.rows:
         G = torch.empty((rows, a.frames, 8 * Up), device=dev, dtype=torch.bfloat16).normal_(0.0, 0.3)
         for C in a.clusters:
             for fast in a.fast:
-                for ks in ([(tl, k) for tl in a.tiles for k in a.ksplit if not (tl == 1 and k == 1)] if a.kernel == "ts" else [0]):
+                for ks in ([(tl, k, sb) for tl in a.tiles for k in a.ksplit for sb in a.subs
+                            if not (tl == 1 and k == 1) and not (sb == 2 and (tl == 1 or k == 1 or C == 8))
+                            and not (sb == 1 and C == 64)] if a.kernel == "ts" else [0]):
                     for _ in range(2):
                         run(G, rows, C, fast, ks)
                     torch.cuda.synchronize()
@@ -72,7 +75,7 @@ def main():
                         else:
                             ph = " | cycles/step " + " ".join(
                                 f"{n}={v / max(pc[5], 1):.0f}" for n, v in zip(["gwait", "hwait", "mma", "gates", "send"], pc[:5]))
-                    print(f"U={U} rows={rows:4d} kernel={a.kernel} cluster={C} fast={fast} (tiles, ksplit)={ks}: {us:.3f} us/step{ph}",
+                    print(f"U={U} rows={rows:4d} kernel={a.kernel} cluster={C} fast={fast} (tiles, ksplit, subs)={ks}: {us:.3f} us/step{ph}",
                           flush=True)
         del G
 

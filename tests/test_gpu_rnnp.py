@@ -62,9 +62,10 @@ def test_rnnp_register_recurrence_matches_torch(cuda, monkeypatch, idim, units, 
     assert err < 1e-2, err
 
 
-@pytest.mark.parametrize("rows_per_cluster,tiles,k_split", [
-    ("8", "2", "0"), ("16", "2", "0"), ("32", "2", "0"), ("8", "2", "1"), ("16", "2", "1"), ("32", "2", "1"),
-    ("8", "1", "0"), ("16", "1", "0"), ("32", "1", "0"), ("64", "2", "0")])
+@pytest.mark.parametrize("rows_per_cluster,tiles,k_split,subs", [
+    ("8", "2", "0", "1"), ("16", "2", "0", "1"), ("32", "2", "0", "1"), ("8", "2", "1", "1"), ("16", "2", "1", "1"),
+    ("32", "2", "1", "1"), ("8", "1", "0", "1"), ("16", "1", "0", "1"), ("32", "1", "0", "1"),
+    ("16", "2", "0", "2"), ("32", "2", "0", "2"), ("64", "2", "0", "2"), ("0", "0", "-1", "0")])
 @pytest.mark.parametrize("idim,units,hdim,shape", [
     (64, 40, 42, (3, 100, 64)),      # one CTA, 3 rows used
     (96, 64, 48, (40, 150, 96)),     # exactly 64 units, several row groups, the last one partly filled
@@ -75,15 +76,16 @@ def test_rnnp_register_recurrence_matches_torch(cuda, monkeypatch, idim, units, 
     (72, 10, 12, (17, 60, 72)),      # one k-step, Up = 16
     (72, 20, 12, (1, 90, 72)),       # a single row, Up = 32
 ])
-def test_rnnp_tmem_recurrence_matches_torch(cuda, monkeypatch, tiles, k_split, rows_per_cluster, idim, units, hdim, shape):
+def test_rnnp_tmem_recurrence_matches_torch(cuda, monkeypatch, tiles, k_split, subs, rows_per_cluster, idim, units, hdim, shape):
     """The tensor-memory recurrence (csrc/lstm_ts.cu) in every cluster shape: 8 / 16 / 32 rows per cluster, two row
     tiles per CTA (clusters of ceil(Up/64) CTAs, with and without the two-phase K split of the W_hh . h MMAs), one
-    row tile per CTA (clusters of 2*ceil(Up/64) CTAs: 10 at U = 300, a non-portable cluster size), and 64 rows per
-    cluster as two sub-batches of 32 advancing in anti-phase."""
+    row tile per CTA (clusters of 2*ceil(Up/64) CTAs: 10 at U = 300, a non-portable cluster size), 16 / 32 / 64 rows per
+    cluster as two sub-batches of 8 / 16 / 32 advancing in anti-phase, and the library's own choice."""
     monkeypatch.setenv("TSSEP_LSTM_KERNEL", "ts")
     monkeypatch.setenv("TSSEP_TS_ROWS", rows_per_cluster)
     monkeypatch.setenv("TSSEP_TS_KSPLIT", k_split)
     monkeypatch.setenv("TSSEP_TS_TILES", tiles)
+    monkeypatch.setenv("TSSEP_TS_SUBS", subs)
     ref, mine = _pair(idim, units, hdim)
     x = torch.randn(shape, generator=torch.Generator().manual_seed(1))
     with torch.no_grad():

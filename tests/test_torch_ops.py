@@ -7,7 +7,8 @@ import torch
 
 from tests.test_lib_exports import declared_symbols
 
-HOST_QUERIES = {"tssep_last_error", "tssep_abi_version", "tssep_device_info", "tssep_blstm_recurrence_ts_capacity"}
+HOST_QUERIES = {"tssep_last_error", "tssep_abi_version", "tssep_device_info", "tssep_blstm_recurrence_ts_capacity",
+                "tssep_wpe_workspace_bytes"}
 
 
 class RnnpLayer(torch.nn.Module):

@@ -36,7 +36,7 @@ class GemmDesc(C.Structure):
 
 
 EPI_F32, EPI_BF16, EPI_HEAD = 0, 1, 2
-ABI_VERSION = 2  # TSSEP_ABI_VERSION of include/tssep_b200.h this binding was written against
+ABI_VERSION = 3  # TSSEP_ABI_VERSION of include/tssep_b200.h this binding was written against
 
 _SIGNATURES = {
     "tssep_abi_version": ([], C.c_int),
@@ -46,6 +46,8 @@ _SIGNATURES = {
                             C.c_int),
     "tssep_feature_write": ([c_vp, c_i64, c_i64, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_f32,
                              c_i32, c_vp, c_vp, c_i64, c_vp], C.c_int),
+    "tssep_wpe_workspace_bytes": ([c_i32, c_i64, c_i32, c_i32], c_i64),
+    "tssep_wpe": ([c_vp, c_i32, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_i64, c_vp], C.c_int),
     "tssep_log1p_abs": ([c_vp, c_i64, c_vp, c_vp], C.c_int),
     "tssep_ipd": ([c_vp, c_i64, c_i32, c_i64, c_vp, c_vp, c_vp, c_vp], C.c_int),
     "tssep_cast_bf16": ([c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp], C.c_int),
@@ -56,8 +58,8 @@ _SIGNATURES = {
     "tssep_head_expand_t": ([c_vp, c_i64, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp], C.c_int),
     "tssep_blstm_recurrence": ([c_vp, c_i32, c_vp, c_vp, c_i64, c_i64, c_i32, c_i32, c_i32, c_vp], C.c_int),
     "tssep_pack_whh": ([c_vp, c_vp, c_i32, c_i32, c_vp, c_vp], C.c_int),
-    "tssep_blstm_recurrence_ts": ([c_vp, c_vp, c_vp, c_i64, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp], C.c_int),
-    "tssep_blstm_recurrence_ts_capacity": ([c_i32, c_i32, c_i32], C.c_int),
+    "tssep_blstm_recurrence_ts": ([c_vp, c_vp, c_vp, c_i64, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp], C.c_int),
+    "tssep_blstm_recurrence_ts_capacity": ([c_i32, c_i32, c_i32, c_i32], C.c_int),
     "tssep_pack_whh_ts": ([c_vp, c_vp, c_i32, c_i32, c_vp, c_vp], C.c_int),
     "tssep_blstm_recurrence_train": ([c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i32, c_i32, c_i32, c_vp], C.c_int),
     "tssep_blstm_recurrence_bwd": ([c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i32, c_vp], C.c_int),

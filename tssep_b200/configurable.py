@@ -27,6 +27,8 @@ FACTORY_ALIASES = {
     "tssep.train.feature_extractor.ConcaternatedSTFTFeatures": "tssep_b200.feature_extractor.ConcaternatedSTFTFeatures",
     "tssep.train.feature_extractor.Log1pMaxNormAbsSTFT": "tssep_b200.feature_extractor.Log1pMaxNormAbsSTFT",
     "tssep.train.feature_extractor.TorchMFCC": "tssep_b200.feature_extractor_torchaudio.TorchMFCC",
+    "tssep.train.enhancer.WPE": "tssep_b200.enhancer.WPE",
+    "tssep.train.enhancer.ChannelWiseWPE": "tssep_b200.enhancer.ChannelWiseWPE",
     "tssep.train.feature_extractor.Log1pAbsIPDSTFT": "tssep_b200.feature_extractor.Log1pAbsIPDSTFT",
     "tssep.train.feature_extractor.Log1pMaxNormAbsIPDSTFT": "tssep_b200.feature_extractor.Log1pMaxNormAbsIPDSTFT",
     "tssep.train.feature_extractor.MVNLog1pAbsSTFT": "tssep_b200.feature_extractor.MVNLog1pAbsSTFT",

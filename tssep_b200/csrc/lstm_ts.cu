@@ -250,7 +250,10 @@ blstm_rec_ts_kernel(const RecTsArgs a, const __grid_constant__ CUtensorMap gmap)
     int slot = 0;
     uint32_t gph = 0;
     // W_hh . h for one tile and one K phase: phase 0 = k-steps 0,1 of every atom (units of the senders' first
-    // row tile), phase 1 = k-steps 2,3; without SPLIT phase 0 covers all four
+    // row tile), phase 1 = k-steps 2,3; without SPLIT phase 0 covers all four.  Tile after tile, not alternating:
+    // an MMA costs its ~27 cycles of tensor pipe whatever accumulator it targets (alternating the tiles was measured:
+    // no faster to issue, and it makes both tiles' epilogues start together instead of the first one overlapping the
+    // second tile's MMAs -- 1.29 instead of 0.99 us per step at 8 rows per cluster).
     auto issue_h = [&](uint32_t d, int tile, int phase, uint64_t bd) {
       uint32_t at = tmem_base + static_cast<uint32_t>(tile) * a_tile_cols;
       uint64_t bk = bd;
@@ -574,9 +577,9 @@ static int max_clusters_ts(int C, size_t smem) {
   return n;
 }
 
-// shared memory of one CTA and the depth of its G ring; rows = batch rows per cluster (64 = two sub-batches of 32)
-static size_t ts_smem(int NA, int rows, int tiles, int* stages_out, int want_stages) {
-  const int subs = rows > 32 ? 2 : 1, NR = rows / subs;
+// shared memory of one CTA and the depth of its G ring; rows = batch rows per cluster = subs sub-batches of rows / subs
+static size_t ts_smem(int NA, int rows, int tiles, int subs, int* stages_out, int want_stages) {
+  const int NR = rows / subs;
   const int NB = NR < 16 ? 16 : NR;
   const size_t ring_stage = 4ull * rows * 128;
   const size_t fixed_bytes = 1024 + 2ull * subs * NA * NB * 128 + 1024 + 4ull * tiles * rows * 16 + 128 + 16 * kTsMaxStages + 16;
@@ -594,27 +597,30 @@ static size_t ts_smem(int NA, int rows, int tiles, int* stages_out, int want_sta
 static int cluster_ctas(int Up, int tiles) { return 2 * ((Up + 63) / 64) / tiles; }
 
 // co-resident clusters of one shape (cached per device: the query costs ~10 us and every launch asks);
-// rows = batch rows per cluster: 8, 16, 32 or 64 (two sub-batches of 32)
-static int clusters_for(int rows, int Up, int tiles) {
-  static int cache[8][4][2][25];  // [device][rows 8/16/32/64][tiles 1/2][Up / 16]; 0 = not asked yet, -1 = none fit
+// rows = batch rows per cluster (8, 16, 32 or 64) = subs sub-batches of rows / subs (8, 16 or 32)
+static int clusters_for(int rows, int Up, int tiles, int subs) {
+  static int cache[8][4][2][2][25];  // [device][rows 8/16/32/64][tiles 1/2][subs 1/2][Up / 16]; 0 = not asked yet, -1 = none fit
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 8) dev = 0;
   const int ri = rows == 8 ? 0 : (rows == 16 ? 1 : (rows == 32 ? 2 : 3)), ui = Up / 16;
-  int& slot = cache[dev][ri][tiles - 1][ui];
+  int& slot = cache[dev][ri][tiles - 1][subs - 1][ui];
   if (slot == 0) {
-    const int C = cluster_ctas(Up, tiles), NA = (Up + 63) / 64;
+    const int C = cluster_ctas(Up, tiles), NA = (Up + 63) / 64, NR = rows / subs;
     int st = 0;
-    const size_t smem = ts_smem(NA, rows, tiles, &st, 0);
+    const size_t smem = ts_smem(NA, rows, tiles, subs, &st, 0);
     int n = 0;
-    if (C <= 16 && st >= 2) {
-      if (rows == 64)
-        n = tiles == 2 ? max_clusters_ts<32, 32, 1, false, 2, 2>(C, smem) : 0;
+    if (C <= 16 && st >= 2 && (NR == 8 || NR == 16 || NR == 32)) {
+      if (subs == 2)  // two tiles per CTA only (with one tile the ping-pong was measured slower than the two-tile shapes)
+        n = tiles != 2 ? 0
+                       : (NR == 8 ? max_clusters_ts<8, 8, 1, false, 2, 2>(C, smem)
+                                  : (NR == 16 ? max_clusters_ts<16, 16, 1, false, 2, 2>(C, smem)
+                                              : max_clusters_ts<32, 32, 1, false, 2, 2>(C, smem)));
       else if (tiles == 2)
-        n = rows == 8 ? max_clusters_ts<8, 8, 1, false, 2, 1>(C, smem)
-                      : (rows == 16 ? max_clusters_ts<16, 16, 1, false, 2, 1>(C, smem) : max_clusters_ts<32, 16, 1, false, 2, 1>(C, smem));
+        n = NR == 8 ? max_clusters_ts<8, 8, 1, false, 2, 1>(C, smem)
+                    : (NR == 16 ? max_clusters_ts<16, 16, 1, false, 2, 1>(C, smem) : max_clusters_ts<32, 16, 1, false, 2, 1>(C, smem));
       else
-        n = rows == 8 ? max_clusters_ts<8, 8, 1, false, 1, 1>(C, smem)
-                      : (rows == 16 ? max_clusters_ts<16, 16, 1, false, 1, 1>(C, smem) : max_clusters_ts<32, 16, 1, false, 1, 1>(C, smem));
+        n = NR == 8 ? max_clusters_ts<8, 8, 1, false, 1, 1>(C, smem)
+                    : (NR == 16 ? max_clusters_ts<16, 16, 1, false, 1, 1>(C, smem) : max_clusters_ts<32, 16, 1, false, 1, 1>(C, smem));
     }
     slot = n > 0 ? n : -1;
   }
@@ -640,13 +646,17 @@ static int launch_ts(const RecTsArgs& a, const CUtensorMap& gmap, int C, int nsu
   return check_launch("blstm_rec_ts");
 }
 
-// Relative cost of one dependent step per cluster shape (tiles per CTA, rows per cluster), measured at U = 300 on B200
-// (profiles/r2_rec_ts_microbench.txt).  tssep_b200/dist.py::TS_STEP_COST mirrors the two-tile row.
+// Relative cost of one dependent step per cluster shape (tiles per CTA, rows per cluster, sub-batches), measured at
+// U = 300 on B200 (profiles/r2_rec_ts_microbench.txt): ~us per step.  tssep_b200/dist.py::TS_STEP_COST mirrors the best
+// shape per rows-per-cluster.  32 rows per cluster run fastest as two sub-batches of 16 in anti-phase (1.83 us against
+// 2.03-2.36 us as one sub-batch: the step is then bound by the tensor pipe instead of the exchange + gate-math chain);
+// 16 rows as 2 x 8 are slower than one sub-batch (the MMAs of a step cost the same for 8 and 16 columns).
 struct TsShape {
-  int tiles, rows;
+  int tiles, rows, subs;  // rows per cluster = subs sub-batches (advanced in anti-phase) of rows / subs
   double cost;
 };
-static const TsShape kTsShapes[] = {{1, 8, 0.9}, {2, 8, 1.0}, {2, 16, 1.37}, {2, 32, 2.3}, {2, 64, 3.18}};
+static const TsShape kTsShapes[] = {{1, 8, 1, 0.9},   {2, 8, 1, 1.0},  {1, 16, 1, 1.4},  {2, 16, 1, 1.37}, {2, 16, 2, 1.68},
+                                    {1, 32, 1, 2.6},  {2, 32, 1, 2.3}, {2, 32, 2, 1.86}, {2, 64, 2, 3.18}};
 
 }  // namespace tssep
 
@@ -664,25 +674,28 @@ int tssep_pack_whh_ts(const float* whh_fwd, const float* whh_bwd, int U, int Up,
   return check_launch("tssep_pack_whh_ts");
 }
 
-int tssep_blstm_recurrence_ts_capacity(int Up, int rows_per_cluster, int tiles_per_cta) {
+int tssep_blstm_recurrence_ts_capacity(int Up, int rows_per_cluster, int tiles_per_cta, int sub_batches) {
   TSSEP_REQUIRE(Up >= 16 && Up % 16 == 0 && Up <= 384, "tssep_blstm_recurrence_ts_capacity: bad Up");
   TSSEP_REQUIRE(rows_per_cluster == 8 || rows_per_cluster == 16 || rows_per_cluster == 32 || rows_per_cluster == 64,
                 "tssep_blstm_recurrence_ts_capacity: rows_per_cluster must be 8, 16, 32 or 64");
   TSSEP_REQUIRE(tiles_per_cta == 1 || tiles_per_cta == 2, "tssep_blstm_recurrence_ts_capacity: tiles_per_cta must be 1 or 2");
-  return (clusters_for(rows_per_cluster, Up, tiles_per_cta) / 2) * rows_per_cluster;
+  TSSEP_REQUIRE(sub_batches == 1 || sub_batches == 2, "tssep_blstm_recurrence_ts_capacity: sub_batches must be 1 or 2");
+  if ((sub_batches == 2 && (tiles_per_cta == 1 || rows_per_cluster == 8)) || (sub_batches == 1 && rows_per_cluster == 64)) return 0;
+  return (clusters_for(rows_per_cluster, Up, tiles_per_cta, sub_batches) / 2) * rows_per_cluster;
 }
 
 static int recurrence_ts_impl(const uint16_t* G, const uint32_t* Wimg, uint16_t* H, int64_t rows, int64_t T, int Up,
-                              int rows_per_cluster, int tiles_per_cta, int gate_math, int k_split, uint16_t* gates_out,
-                              float* c_out, tssep_stream_t stream) {
+                              int rows_per_cluster, int tiles_per_cta, int sub_batches, int gate_math, int k_split,
+                              uint16_t* gates_out, float* c_out, tssep_stream_t stream) {
   TSSEP_REQUIRE(G && Wimg && H, "tssep_blstm_recurrence_ts: null pointer");
   const bool save = gates_out != nullptr;
   TSSEP_REQUIRE(save == (c_out != nullptr), "tssep_blstm_recurrence_train: gates and cstate go together");
   TSSEP_REQUIRE(!save || (reinterpret_cast<uintptr_t>(gates_out) & 7) == 0, "tssep_blstm_recurrence_train: gates must be 8-byte aligned");
-  if (save) {  // the training variant is instantiated for the two-tile shapes of up to 32 rows, one K phase
-    TSSEP_REQUIRE(tiles_per_cta != 1 && k_split != 1 && rows_per_cluster != 64,
+  if (save) {  // the training variant is instantiated for the two-tile shapes of up to 32 rows, one sub-batch, one K phase
+    TSSEP_REQUIRE(tiles_per_cta != 1 && k_split != 1 && rows_per_cluster != 64 && sub_batches != 2,
                   "tssep_blstm_recurrence_train: needs two row tiles per CTA, at most 32 rows per cluster, one K phase");
     tiles_per_cta = 2;
+    sub_batches = 1;
   }
   TSSEP_REQUIRE(Up >= 16 && Up % 16 == 0 && Up <= 384, "tssep_blstm_recurrence_ts: Up must be a multiple of 16 in [16, 384]");
   TSSEP_REQUIRE(rows >= 0 && T >= 0 && T < (1ll << 30) && (rows + 7) / 8 <= 65535, "tssep_blstm_recurrence_ts: bad extent");
@@ -690,6 +703,7 @@ static int recurrence_ts_impl(const uint16_t* G, const uint32_t* Wimg, uint16_t*
                     rows_per_cluster == 64,
                 "tssep_blstm_recurrence_ts: rows_per_cluster must be 0 (auto), 8, 16, 32 or 64");
   TSSEP_REQUIRE(tiles_per_cta >= 0 && tiles_per_cta <= 2, "tssep_blstm_recurrence_ts: tiles_per_cta must be 0 (auto), 1 or 2");
+  TSSEP_REQUIRE(sub_batches >= 0 && sub_batches <= 2, "tssep_blstm_recurrence_ts: sub_batches must be 0 (auto), 1 or 2");
   TSSEP_REQUIRE(gate_math == 0 || gate_math == 1, "tssep_blstm_recurrence_ts: gate_math must be 0 (exp based) or 1 (tanh.approx)");
   TSSEP_REQUIRE(k_split >= -1 && k_split <= 1, "tssep_blstm_recurrence_ts: k_split must be -1 (default), 0 or 1");
   TSSEP_REQUIRE((reinterpret_cast<uintptr_t>(H) & 15) == 0 && (reinterpret_cast<uintptr_t>(Wimg) & 15) == 0 &&
@@ -697,44 +711,49 @@ static int recurrence_ts_impl(const uint16_t* G, const uint32_t* Wimg, uint16_t*
                 "tssep_blstm_recurrence_ts: G, H and Wimg must be 16-byte aligned");
   if (rows == 0 || T == 0) return 0;
   const int NA = (Up + 63) / 64;
-  int NR = rows_per_cluster, tiles = tiles_per_cta;
+  int RPC = rows_per_cluster, tiles = tiles_per_cta, subs = sub_batches;  // RPC: batch rows per cluster
   if (const char* e = debug_env("TSSEP_TS_ROWS")) {
     const int v = atoi(e);
-    if (v == 8 || v == 16 || v == 32 || v == 64) NR = v;
+    if (v == 8 || v == 16 || v == 32 || v == 64) RPC = v;
   }
   const bool split = k_split == 1;  // default: one phase (the second barrier + fence cost more than the split hides)
   if (split) {
-    TSSEP_REQUIRE(tiles != 1, "tssep_blstm_recurrence_ts: k_split needs two row tiles per CTA");
+    TSSEP_REQUIRE(tiles != 1 && subs != 2, "tssep_blstm_recurrence_ts: k_split needs two row tiles per CTA and one sub-batch");
     tiles = 2;
+    subs = 1;
   }
-  if (NR == 0 || tiles == 0) {
+  {
     // Fewer rows per cluster and fewer tiles per CTA = shorter step (epilogue math, DSMEM exchange and the MMAs of a
     // step scale with them) but fewer rows per wave of co-resident clusters; a launch that does not fit in one wave
-    // runs its waves back to back.
+    // runs its waves back to back.  Whatever the caller fixed narrows the candidates.
     double best = 1e30;
-    int best_nr = 0, best_tiles = 0;
+    const TsShape* pick = nullptr;
     for (const TsShape& sh : kTsShapes) {
-      if ((NR != 0 && sh.rows != NR) || (tiles != 0 && sh.tiles != tiles) || (save && sh.rows == 64)) continue;
-      const int m = clusters_for(sh.rows, Up, sh.tiles);
+      if ((RPC != 0 && sh.rows != RPC) || (tiles != 0 && sh.tiles != tiles) || (subs != 0 && sh.subs != subs) ||
+          (save && sh.subs != 1) || (split && (sh.tiles != 2 || sh.subs != 1)))
+        continue;
+      const int m = clusters_for(sh.rows, Up, sh.tiles, sh.subs);
       if (m < 2) continue;
       const int64_t n = 2 * ((rows + sh.rows - 1) / sh.rows);
       const double t = sh.cost * static_cast<double>((n + m - 1) / m);
       if (t < best) {
         best = t;
-        best_nr = sh.rows;
-        best_tiles = sh.tiles;
+        pick = &sh;
       }
     }
-    TSSEP_REQUIRE(best_nr != 0, "tssep_blstm_recurrence_ts: no cluster shape fits on this device (Up=%d)", Up);
-    NR = best_nr;
-    tiles = best_tiles;
+    TSSEP_REQUIRE(pick != nullptr,
+                  "tssep_blstm_recurrence_ts: no cluster shape with rows_per_cluster=%d tiles_per_cta=%d sub_batches=%d fits (Up=%d)",
+                  rows_per_cluster, tiles_per_cta, sub_batches, Up);
+    RPC = pick->rows;
+    tiles = pick->tiles;
+    subs = pick->subs;
   }
-  TSSEP_REQUIRE(!(NR == 64 && (tiles == 1 || split)), "tssep_blstm_recurrence_ts: 64 rows per cluster need two row tiles per CTA, one K phase");
+  const int NR = RPC / subs;  // batch rows per sub-batch
   const int C = cluster_ctas(Up, tiles);
   TSSEP_REQUIRE(C <= 16, "tssep_blstm_recurrence_ts: Up=%d needs clusters of %d CTAs with %d tile(s) per CTA (max 16)", Up, C, tiles);
   const uint32_t a_tile_cols = (static_cast<uint32_t>(Up) / 2 + 31u) & ~31u;
-  TSSEP_REQUIRE(tiles * a_tile_cols + 64 + tiles * (NR < 16 ? 16 : NR) <= 512,  /* 64 rows = 2 sub-batches x 32 columns per tile */
-                "tssep_blstm_recurrence_ts: Up=%d with %d rows per cluster exceeds the 512 tensor-memory columns", Up, NR);
+  TSSEP_REQUIRE(tiles * a_tile_cols + 64 + tiles * subs * (NR < 16 ? 16 : NR) <= 512,
+                "tssep_blstm_recurrence_ts: Up=%d with %d rows per cluster exceeds the 512 tensor-memory columns", Up, RPC);
   RecTsArgs a;
   a.Wimg = reinterpret_cast<const uint4*>(Wimg);
   a.H = reinterpret_cast<__nv_bfloat16*>(H);
@@ -754,15 +773,15 @@ static int recurrence_ts_impl(const uint16_t* G, const uint32_t* Wimg, uint16_t*
   if (const char* e = debug_env("TSSEP_TS_STAGES")) want_stages = atoi(e);
 #endif
   int stages = 0;
-  const size_t smem = ts_smem(NA, NR, tiles, &stages, want_stages);
+  const size_t smem = ts_smem(NA, RPC, tiles, subs, &stages, want_stages);
   TSSEP_REQUIRE(stages >= 2, "tssep_blstm_recurrence_ts: G ring does not fit shared memory");
   a.stages = stages;
-  const int nsub = static_cast<int>((rows + NR - 1) / NR);
+  const int nsub = static_cast<int>((rows + RPC - 1) / RPC);
   // batch columns per epilogue warp (debug knob TSSEP_TS_COLS): 16 measured best for 32 rows per cluster
-  int NC = NR < 16 ? NR : (NR == 64 ? 32 : 16);
+  int NC = NR < 16 ? NR : (subs == 2 ? NR : 16);
   if (const char* e = debug_env("TSSEP_TS_COLS")) {
     const int v = atoi(e);
-    if (NR != 64 && (v == NR || (v == NR / 2 && v >= 8))) NC = v;
+    if (subs == 1 && (v == NR || (v == NR / 2 && v >= 8))) NC = v;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 
@@ -773,7 +792,7 @@ static int recurrence_ts_impl(const uint16_t* G, const uint32_t* Wimg, uint16_t*
   const cuuint64_t up = static_cast<cuuint64_t>(Up);
   cuuint64_t dims[5] = {up, static_cast<cuuint64_t>(rows), 4, 2, static_cast<cuuint64_t>(T)};
   cuuint64_t strides[4] = {static_cast<cuuint64_t>(T) * 8 * up * 2, up * 2, 4 * up * 2, 8 * up * 2};
-  cuuint32_t box[5] = {64, static_cast<cuuint32_t>(NR), 4, 1, 1};
+  cuuint32_t box[5] = {64, static_cast<cuuint32_t>(RPC), 4, 1, 1};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = enc(&gmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<uint16_t*>(G), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -781,7 +800,7 @@ static int recurrence_ts_impl(const uint16_t* G, const uint32_t* Wimg, uint16_t*
   TSSEP_REQUIRE(r == CUDA_SUCCESS, "tssep_blstm_recurrence_ts: cuTensorMapEncodeTiled failed with code %d", static_cast<int>(r));
 
 #define TSSEP_TS_CASE(NR_, NC_)                                                                                \
-  if (NR == NR_ && NC == NC_) {                                                                                \
+  if (subs == 1 && NR == NR_ && NC == NC_) {                                                                              \
     if (save)                                                                                                  \
       return gate_math ? launch_ts<NR_, NC_, 1, false, 2, 1, true>(a, gmap, C, nsub, smem, st)                 \
                        : launch_ts<NR_, NC_, 0, false, 2, 1, true>(a, gmap, C, nsub, smem, st);                \
@@ -798,22 +817,30 @@ static int recurrence_ts_impl(const uint16_t* G, const uint32_t* Wimg, uint16_t*
   TSSEP_TS_CASE(16, 16)
   TSSEP_TS_CASE(32, 16)
 #undef TSSEP_TS_CASE
-  if (NR == 64 && NC == 32)  // two sub-batches of 32 rows in anti-phase
-    return gate_math ? launch_ts<32, 32, 1, false, 2, 2>(a, gmap, C, nsub, smem, st)
-                     : launch_ts<32, 32, 0, false, 2, 2>(a, gmap, C, nsub, smem, st);
-  set_error("tssep_blstm_recurrence_ts: no instantiation for %d rows per cluster, %d columns per warp", NR, NC);
+  // two sub-batches in anti-phase
+#define TSSEP_TS_CASE2(NR_, TILES_)                                                                \
+  if (subs == 2 && tiles == TILES_ && NR == NR_ && NC == NR_)                                      \
+    return gate_math ? launch_ts<NR_, NR_, 1, false, TILES_, 2>(a, gmap, C, nsub, smem, st)        \
+                     : launch_ts<NR_, NR_, 0, false, TILES_, 2>(a, gmap, C, nsub, smem, st);
+  TSSEP_TS_CASE2(8, 2)
+  TSSEP_TS_CASE2(16, 2)
+  TSSEP_TS_CASE2(32, 2)
+#undef TSSEP_TS_CASE2
+  set_error("tssep_blstm_recurrence_ts: no instantiation for %d x %d rows per cluster, %d columns per warp", subs, NR, NC);
   return -1;
 }
 
 int tssep_blstm_recurrence_ts(const uint16_t* G, const uint32_t* Wimg, uint16_t* H, int64_t rows, int64_t T, int Up,
-                              int rows_per_cluster, int tiles_per_cta, int gate_math, int k_split, tssep_stream_t stream) {
-  return recurrence_ts_impl(G, Wimg, H, rows, T, Up, rows_per_cluster, tiles_per_cta, gate_math, k_split, nullptr, nullptr, stream);
+                              int rows_per_cluster, int tiles_per_cta, int sub_batches, int gate_math, int k_split,
+                              tssep_stream_t stream) {
+  return recurrence_ts_impl(G, Wimg, H, rows, T, Up, rows_per_cluster, tiles_per_cta, sub_batches, gate_math, k_split, nullptr,
+                            nullptr, stream);
 }
 
 int tssep_blstm_recurrence_train(const uint16_t* G, const uint32_t* Wimg, uint16_t* H, uint16_t* gates, float* cstate,
                                  int64_t rows, int64_t T, int Up, int rows_per_cluster, int gate_math, tssep_stream_t stream) {
   TSSEP_REQUIRE(gates && cstate, "tssep_blstm_recurrence_train: null pointer");
-  return recurrence_ts_impl(G, Wimg, H, rows, T, Up, rows_per_cluster, 2, gate_math, 0, gates, cstate, stream);
+  return recurrence_ts_impl(G, Wimg, H, rows, T, Up, rows_per_cluster, 2, 1, gate_math, 0, gates, cstate, stream);
 }
 
 }  // extern "C"

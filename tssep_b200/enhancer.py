@@ -119,3 +119,68 @@ class TorchBF(ABC):
         self.last_beamformer = w if batched else w[0]
         enh = enh.to(out_dtype) if out_dtype.is_complex else enh
         return enh if batched else enh[0]
+
+
+class WPE:
+    """Weighted-prediction-error dereverberation in front of the feature extraction
+    (tssep/train/enhancer.py:292-345; same constructor and call signature).
+
+    ``Observation`` (D, T, F) complex, numpy (moved to the current CUDA device, result returned as numpy of the input's
+    dtype) or a CUDA tensor.  One ``tssep_wpe`` call: statistics / solve / filter kernels of csrc/wpe.cu -- complex64
+    signals, f64 accumulation of the correlation matrices and an f64 solve.  The arithmetic the reference delegates to
+    ``nara_wpe`` (absent package) is restated from its publication: parity is pinned to the repo's own oracle only
+    (oracle/tssep_oracle.py::wpe says so).
+    """
+
+    def __init__(self, taps=10, delay=2, iterations=3, psd_context=0, statistics_mode="full"):
+        self.taps, self.delay, self.iterations = taps, delay, iterations
+        self.psd_context, self.statistics_mode = psd_context, statistics_mode
+
+    def _run(self, Y: torch.Tensor) -> torch.Tensor:
+        if self.statistics_mode not in ("full", "valid"):
+            raise ValueError(self.statistics_mode)
+        D, T, F = Y.shape
+        Y = Y.contiguous()
+        lib = _lib.load()
+        nbytes = lib.tssep_wpe_workspace_bytes(D, T, F, self.taps)
+        if nbytes < 0:
+            _lib.check(-1, "tssep_wpe_workspace_bytes")
+        ws = torch.empty((nbytes + 255,), dtype=torch.uint8, device=Y.device)
+        ws = ws[(-ws.data_ptr()) % 256:][:nbytes]
+        X = torch.empty_like(Y)
+        torch_ops.op.wpe(Y, D, T, F, int(self.taps), int(self.delay), int(self.iterations), int(self.psd_context),
+                         int(self.statistics_mode == "valid"), X, ws, nbytes)
+        return X
+
+    def __call__(self, Observation, inplace=False):
+        if isinstance(Observation, np.ndarray):
+            if not torch.cuda.is_available():
+                raise RuntimeError("tssep_b200 needs a CUDA device (no CPU fallback)")
+            out = self._run(torch.as_tensor(Observation).to(device="cuda", dtype=torch.complex64)).cpu().numpy()
+            out = out.astype(Observation.dtype if np.iscomplexobj(Observation) else np.complex128)
+            if inplace:
+                Observation[...] = out
+                return Observation
+            return out
+        if isinstance(Observation, torch.Tensor):
+            _lib.require_cuda(Observation)
+            return self._run(Observation.to(torch.complex64)).to(
+                Observation.dtype if Observation.is_complex() else torch.complex64)
+        raise NotImplementedError(type(Observation), Observation)
+
+
+class ChannelWiseWPE(WPE):
+    """Every channel dereverberated on its own (tssep/train/enhancer.py:348-367): the (D, T, F) signal is handed to
+    ``WPE`` as one channel with D * F independent frequencies."""
+
+    def __call__(self, Observation, inplace=False):
+        D, T, F = Observation.shape
+        if isinstance(Observation, np.ndarray):
+            flat = np.ascontiguousarray(np.transpose(Observation, (1, 0, 2)).reshape(1, T, D * F))
+            out = np.transpose(super().__call__(flat).reshape(T, D, F), (1, 0, 2))
+            if inplace:
+                Observation[...] = out
+                return Observation
+            return np.ascontiguousarray(out)
+        flat = Observation.permute(1, 0, 2).reshape(1, T, D * F)
+        return super().__call__(flat).reshape(T, D, F).permute(1, 0, 2).contiguous()

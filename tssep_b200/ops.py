@@ -98,7 +98,7 @@ def pack_whh_ts(w_fwd: torch.Tensor, w_bwd: torch.Tensor, U: int, Up: int) -> to
 
 def blstm_recurrence_ts(G: torch.Tensor, wimg: torch.Tensor, rows: int, T: int, Up: int,
                         fast_math: bool = None, rows_per_cluster: int = 0, k_split: int = -1,
-                        tiles_per_cta: int = 0) -> torch.Tensor:
+                        tiles_per_cta: int = 0, sub_batches: int = 0) -> torch.Tensor:
     """Tensor-memory recurrence: G (rows, T, 2, 4, Up) bf16 -> H (rows, T, 2*Up) bf16."""
     _lib.require_cuda(G, wimg)
     if G.dtype != torch.bfloat16:
@@ -106,13 +106,18 @@ def blstm_recurrence_ts(G: torch.Tensor, wimg: torch.Tensor, rows: int, T: int, 
     if fast_math is None:
         fast_math = fast_math_default()
     H = torch.empty((rows, T, 2 * Up), dtype=torch.bfloat16, device=G.device)
-    torch_ops.op.blstm_recurrence_ts(G, wimg, H, rows, T, Up, rows_per_cluster, tiles_per_cta, int(fast_math), k_split)
+    torch_ops.op.blstm_recurrence_ts(G, wimg, H, rows, T, Up, rows_per_cluster, tiles_per_cta, sub_batches, int(fast_math),
+                                     k_split)
     return H
 
 
-def recurrence_ts_capacity(Up: int, rows_per_cluster: int = 16, tiles_per_cta: int = 2) -> int:
-    """Batch rows one launch of the tensor-memory recurrence advances in a single wave of clusters."""
-    n = _lib.load().tssep_blstm_recurrence_ts_capacity(Up, rows_per_cluster, tiles_per_cta)
+def recurrence_ts_capacity(Up: int, rows_per_cluster: int = 16, tiles_per_cta: int = 2, sub_batches: int = None) -> int:
+    """Batch rows one launch of the tensor-memory recurrence advances in a single wave of clusters (``sub_batches``
+    None: 2 for 64 rows per cluster, which exist only as two sub-batches, else 1; the capacity of a shape does not
+    depend on it otherwise -- the clusters are the same size)."""
+    if sub_batches is None:
+        sub_batches = 2 if rows_per_cluster == 64 else 1
+    n = _lib.load().tssep_blstm_recurrence_ts_capacity(Up, rows_per_cluster, tiles_per_cta, sub_batches)
     if n < 0:
         _lib.check(n, "tssep_blstm_recurrence_ts_capacity")
     return n

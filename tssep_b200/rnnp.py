@@ -116,7 +116,8 @@ class LayerPack:
             return ops.blstm_recurrence_ts(G, self.whh_ts, rows, T, self.Up,
                                            rows_per_cluster=int(os.environ.get("TSSEP_TS_ROWS", "0")),
                                            k_split=int(os.environ.get("TSSEP_TS_KSPLIT", "-1")),
-                                           tiles_per_cta=int(os.environ.get("TSSEP_TS_TILES", "0")))
+                                           tiles_per_cta=int(os.environ.get("TSSEP_TS_TILES", "0")),
+                                           sub_batches=int(os.environ.get("TSSEP_TS_SUBS", "0")))
         if self.whh_regs is None:
             self.whh_regs = ops.pack_whh(self._whh_f32[0], self._whh_f32[1], self.U, self.Up)
         return ops.blstm_recurrence(G, self.whh_regs, rows, T, self.Up)

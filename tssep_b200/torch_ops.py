@@ -36,6 +36,10 @@ _OPS = {
         "Tensor? dct, int n_mels, int n_mfcc, int with_log1p, float top_db, int couple_batch, Tensor(a!)? feat_f32, "
         "Tensor(b!)? feat_bf16, int ld_bf16) -> ()",
         "tssep_feature_write"),
+    "wpe": (
+        "(Tensor Y, int D, int T, int F, int taps, int delay, int iterations, int psd_context, int statistics_mode, "
+        "Tensor(a!) X, Tensor(b!) workspace, int workspace_bytes) -> ()",
+        "tssep_wpe"),
     "log1p_abs": ("(Tensor X, int n, Tensor(a!) out) -> ()", "tssep_log1p_abs"),
     "ipd": (
         "(Tensor X, int lead, int D, int TF, Tensor second_channel, Tensor(a!) cos_out, Tensor(b!) sin_out) -> ()",
@@ -60,7 +64,7 @@ _OPS = {
         "(Tensor whh_fwd, Tensor whh_bwd, int U, int Up, Tensor(a!) Wfrag) -> ()",
         "tssep_pack_whh"),
     "blstm_recurrence_ts": (
-        "(Tensor G, Tensor Wimg, Tensor(a!) H, int rows, int T, int Up, int rows_per_cluster, int tiles_per_cta, "
+        "(Tensor G, Tensor Wimg, Tensor(a!) H, int rows, int T, int Up, int rows_per_cluster, int tiles_per_cta, int sub_batches, "
         "int gate_math, int k_split) -> ()",
         "tssep_blstm_recurrence_ts"),
     "pack_whh_ts": (
