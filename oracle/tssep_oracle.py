@@ -449,6 +449,70 @@ def torch_bf(masks: torch.Tensor, observation_stft: torch.Tensor, reference_chan
     return enh
 
 
+def sum_cross_talker(masks: np.ndarray, eps=0.0001) -> np.ndarray:
+    """``SumCrossTalker.__call__`` (tssep/train/enhancer_distortion_mask.py:41-55)."""
+    assert masks.shape[0] == 1, masks.shape
+    noise = np.stack([np.sum(np.delete(masks, k, axis=1), axis=1) for k in range(masks.shape[1])], axis=1)
+    return np.concatenate([masks, np.maximum(noise, eps)], axis=0)
+
+
+def one_minus(masks: np.ndarray) -> np.ndarray:
+    """``OneMinus.__call__`` (tssep/train/enhancer_distortion_mask.py:17-21)."""
+    assert masks.shape[0] == 1, masks.shape
+    return np.concatenate([masks, np.maximum(1 - masks, 0)], axis=0)
+
+
+def _get_psd(mask, observation, mask_power=1):
+    """``_get_psd`` (tssep/train/enhancer.py:267-289): mask (..., t), observation (..., d, t).  The last line adds the
+    plain transpose, not the conjugate one: what remains of the Hermitian matrix is its real part."""
+    if mask_power != 1:
+        mask = mask ** mask_power
+    psd = np.einsum("...t,...dt,...Dt->...dD", mask, observation, observation.conj()) / observation.shape[-1]
+    return (psd + np.swapaxes(psd, -2, -1)) / 2
+
+
+def mvdr_souden_vector(target_psd, noise_psd, ref_channel=0, eps=None):
+    """``pb_bss.extraction.beamformer.get_mvdr_vector_souden`` (pb_bss@99eb6c8, absent third-party package; the
+    published Souden MVDR): w = (Phi_n^-1 Phi_t)[:, ref] / max(Re trace(Phi_n^-1 Phi_t), eps)."""
+    phi = np.linalg.solve(noise_psd, target_psd)
+    lam = np.trace(phi, axis1=-1, axis2=-2)[..., None, None]
+    eps = np.finfo(lam.real.dtype).tiny if eps is None else eps
+    return (phi / np.maximum(lam.real, eps))[..., ref_channel]
+
+
+def classic_bf_np(masks, Observation, dia, bf="mvdr_souden", masking=False, masking_eps=0, eps=0.0001, mask_power=1,
+                  segment_bf=True):
+    """``ClassicBF_np.__call__(..., numpy_out=True)`` (tssep/train/enhancer.py:455-590) with the default
+    ``SumCrossTalker`` distortion mask: masks (spk, 1, T, F), Observation (mics, T, F), dia = per speaker a list of
+    (start, end) frame intervals (the ``normalized_intervals`` of the reference's ArrayInterval) -> (spk, T, F).
+
+    PARITY UNPINNED for the beamforming vector: ``pb_bss`` is absent, the reference's golden values for this class
+    (SDR of its toy example, enhancer.py:411-418) need pb_bss / mir_eval to be reproduced.  ``_get_psd`` and the
+    distortion masks are the reference's own code restated, the latter pinned by its doctest values."""
+    masks = np.asarray(masks, dtype=np.float64)
+    Y = np.transpose(np.asarray(Observation).astype(np.complex128), (2, 0, 1))       # freq mic time
+    m = np.transpose(masks, (1, 0, 3, 2))                                            # mask spk freq time
+    _, K, F, T = m.shape
+    m = sum_cross_talker(m[:1], eps)
+    out = np.zeros((K, T, F), dtype=np.complex128)
+    for k in range(K):
+        ivs = dia[k] if segment_bf else [(0, T)]
+        for s, e in ivs:
+            Yl = Y[:, :, s:e]
+            if bf in ("ch0", "ch1"):
+                est = Yl[:, int(bf[2]), :]
+            else:
+                pt = _get_psd(m[0, k, :, s:e], Yl, mask_power)
+                pn = _get_psd(m[1, k, :, s:e], Yl, mask_power)
+                w = mvdr_souden_vector(pt, pn, 0)
+                est = np.einsum("...a,...at->...t", w.conj(), Yl)
+            est = est.T
+            if masking:
+                est = est * np.maximum(m[0, k, :, s:e].T, masking_eps)
+            out[k, s:e] = est
+    return out
+
+
 def _wpe_window_mean(x: np.ndarray, ctx: int) -> np.ndarray:
     """nara_wpe's ``window_mean(x, (ctx, ctx))``: mean over frames [t - ctx, t + ctx], normalised by the number of
     frames that exist."""

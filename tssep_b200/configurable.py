@@ -27,6 +27,9 @@ FACTORY_ALIASES = {
     "tssep.train.feature_extractor.ConcaternatedSTFTFeatures": "tssep_b200.feature_extractor.ConcaternatedSTFTFeatures",
     "tssep.train.feature_extractor.Log1pMaxNormAbsSTFT": "tssep_b200.feature_extractor.Log1pMaxNormAbsSTFT",
     "tssep.train.feature_extractor.TorchMFCC": "tssep_b200.feature_extractor_torchaudio.TorchMFCC",
+    "tssep.train.enhancer.ClassicBF_np": "tssep_b200.enhancer.ClassicBF_np",
+    "tssep.train.enhancer_distortion_mask.SumCrossTalker": "tssep_b200.enhancer_distortion_mask.SumCrossTalker",
+    "tssep.train.enhancer_distortion_mask.OneMinus": "tssep_b200.enhancer_distortion_mask.OneMinus",
     "tssep.train.enhancer.WPE": "tssep_b200.enhancer.WPE",
     "tssep.train.enhancer.ChannelWiseWPE": "tssep_b200.enhancer.ChannelWiseWPE",
     "tssep.train.feature_extractor.Log1pAbsIPDSTFT": "tssep_b200.feature_extractor.Log1pAbsIPDSTFT",

@@ -184,3 +184,115 @@ class ChannelWiseWPE(WPE):
             return np.ascontiguousarray(out)
         flat = Observation.permute(1, 0, 2).reshape(1, T, D * F)
         return super().__call__(flat).reshape(T, D, F).permute(1, 0, 2).contiguous()
+
+
+def _intervals(ai):
+    """(start, end) frame pairs of one speaker's activity: an ``ArrayInterval``-like object (``normalized_intervals``),
+    an iterable of pairs, or a boolean activity vector."""
+    if hasattr(ai, "normalized_intervals"):
+        return [(int(s), int(e)) for s, e in ai.normalized_intervals]
+    a = np.asarray(ai.cpu() if isinstance(ai, torch.Tensor) else ai)
+    if a.dtype == bool:
+        d = np.diff(np.concatenate([[0], a.astype(np.int8), [0]]))
+        return list(zip(np.flatnonzero(d == 1).tolist(), np.flatnonzero(d == -1).tolist()))
+    return [(int(s), int(e)) for s, e in a.reshape(-1, 2)]
+
+
+class ClassicBF_np(ABC):
+    """Segment-wise mask-based beamformer of the evaluation (tssep/train/enhancer.py:370-590): for every speaker and
+    every interval of its diarization, spatial covariance matrices of target / distortion over the frames of the
+    interval (``_get_psd``, enhancer.py:267-289 -- including its symmetrisation ``(psd + psd^T) / 2``, which keeps the
+    real part of the Hermitian matrix), Souden MVDR towards channel 0, applied to the interval.
+
+    Same constructor and call contract as the reference; ``Observation`` (mics, T, F) and ``masks``
+    (spk, 1, T, F) may be numpy (moved to the current CUDA device) or CUDA tensors; ``dia`` a list (one entry per
+    speaker) of ``ArrayInterval``-like objects, (start, end) lists or boolean vectors.  The statistics, the D x D
+    solves and the filtering run in the kernels of csrc/beamform.cu (f64 statistics and solve, f32 signal);
+    ``pb_bss`` (absent third-party package) is restated for ``mvdr_souden``, ``ch0`` and ``ch1`` -- the eigenvector
+    beamformers (``scaled_gev_atf+mvdr``, ``rank1_gev+mvdr_souden``, ``wmwf``) raise ``NotImplementedError``.
+    """
+
+    def __init__(self, bf="mvdr_souden", masking=False, masking_eps=0, distortion_mask=None, pre_wpe: "WPE" = None,
+                 segment_wpe: "WPE" = None, mask_power=1):
+        super().__init__()
+        if distortion_mask is None:   # the reference's finalize_dogmatic_config default
+            from .enhancer_distortion_mask import SumCrossTalker
+
+            distortion_mask = SumCrossTalker()
+        self.bf, self.masking, self.masking_eps = bf, masking, masking_eps
+        self.distortion_mask, self.mask_power = distortion_mask, mask_power
+        self.pre_wpe, self.segment_wpe = pre_wpe, segment_wpe
+
+    def _beamform(self, m2: torch.Tensor, Y: torch.Tensor) -> torch.Tensor:
+        """m2 (2, T', F) target / distortion weights of one speaker, Y (D, T', F) -> (T', F)."""
+        D, T, F = Y.shape
+        if self.bf in ("ch0", "ch1"):
+            enh = Y[int(self.bf[2])]
+        else:
+            m = m2 if self.mask_power == 1 else m2 ** self.mask_power
+            m = m.float().contiguous()[None, None]                       # (Z=1, K=1, 2, T', F)
+            Yc = Y.contiguous()[None]
+            psd = torch.empty((1, 2, F, D * (D + 1) // 2, 2), dtype=torch.float64, device=Y.device)
+            torch_ops.op.bf_psd(Yc, m, 1, 1, 2, D, T, F, psd)
+            psd[..., 1] = 0.0                                            # (psd + psd^T) / 2 of a Hermitian matrix
+            w = torch.empty((1, 1, F, D), dtype=torch.complex64, device=Y.device)
+            torch_ops.op.bf_mvdr_souden(psd, 1, 1, 2, D, F, 0, float(torch.finfo(torch.float64).tiny), w)
+            out = torch.empty((1, 1, T, F), dtype=torch.complex64, device=Y.device)
+            torch_ops.op.bf_apply(Yc, w, None, 1, 1, 2, D, T, F, 0.0, out)
+            enh = out[0, 0]
+        if self.masking:
+            enh = enh * torch.clamp(m2[0].to(torch.float32), min=self.masking_eps)
+        return enh
+
+    def __call__(self, masks, Observation, dia, segment_bf=True, numpy_out=False):
+        if self.bf not in ("mvdr_souden", "ch0", "ch1"):
+            raise NotImplementedError(self.bf)
+        if not torch.cuda.is_available():
+            raise RuntimeError("tssep_b200 needs a CUDA device (no CPU fallback)")
+        obs_np = isinstance(Observation, np.ndarray)
+        dev = masks.device if isinstance(masks, torch.Tensor) and masks.is_cuda else (
+            Observation.device if isinstance(Observation, torch.Tensor) and Observation.is_cuda else torch.device("cuda"))
+        out_dtype = Observation.dtype
+        masks = torch.as_tensor(masks).to(dev)
+        Y = torch.as_tensor(Observation).to(dev)
+        mics = Y.shape[0]
+        assert mics >= 6 or self.bf in ("ch0", "ch1"), Y.shape     # all channels loaded (enhancer.py:466-472)
+        if self.pre_wpe:
+            Y = self.pre_wpe(Y)
+        Y = Y.to(torch.complex64)
+        masks = masks.permute(1, 0, 2, 3)                                # spk mask time freq -> mask spk time freq
+        _, K, T, F = masks.shape
+        if masks.shape[0] == 1 or self.bf == "ch0":
+            masks = self.distortion_mask(masks[:1])
+        else:
+            assert masks.shape[0] == 2, masks.shape
+            raise NotImplementedError(masks.shape)
+        if dia is None:
+            assert segment_bf is False and self.segment_wpe is None and numpy_out is True, (segment_bf, numpy_out)
+            dia = [None] * K
+        assert isinstance(dia, (tuple, list)), ("Expect list of ArrayInterval", type(dia), dia)
+        ret = []
+        out = torch.zeros((K, T, F), dtype=torch.complex64, device=dev) if numpy_out else None
+        for k, ai in enumerate(dia):
+            ret_spk = {}
+            if segment_bf:
+                for s, e in _intervals(ai):
+                    Yl = Y[:, s:e]
+                    if self.segment_wpe:
+                        Yl = self.segment_wpe(Yl.contiguous())
+                    ret_spk[(s, e)] = self._beamform(masks[:, k, s:e], Yl)
+                    if numpy_out:
+                        out[k, s:e] = ret_spk[(s, e)]
+            else:
+                assert self.segment_wpe is None, self.segment_wpe
+                if ai is not None:
+                    raise NotImplementedError("ToDo")                    # as the reference (enhancer.py:585)
+                out[k] = self._beamform(masks[:, k], Y)
+            ret.append(ret_spk)
+        if numpy_out:
+            if obs_np:
+                return out.cpu().numpy().astype(out_dtype if np.issubdtype(out_dtype, np.complexfloating) else np.complex128)
+            return out.to(out_dtype) if out_dtype.is_complex else out
+        if obs_np:
+            return [{k: v.cpu().numpy().astype(out_dtype) for k, v in r.items()} for r in ret]
+        return ret
