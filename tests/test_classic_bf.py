@@ -107,7 +107,7 @@ class _AI:  # what the call needs of paderbox's ArrayInterval
 def test_classic_bf_against_oracle(kw, cuda):
     from tssep_b200.enhancer import ClassicBF_np
 
-    obs, src, mask, dia = toy_scene(seed=3, F=33, T=140, D=7)
+    obs, src, mask, dia = toy_scene(seed=3, F=33, T=140, D=6)
     dia = [[(0, 55), (90, 140)], [(45, 100)]]
     want = O.classic_bf_np(mask[:-1, None], obs, dia, **kw)
     enh = ClassicBF_np(**kw)

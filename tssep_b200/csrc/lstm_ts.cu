@@ -30,6 +30,8 @@
 #include "../../include/tssep_b200.h"
 #include "common.cuh"
 
+#include <type_traits>
+
 namespace tssep {
 
 constexpr int kTsMaxStages = 8;
@@ -62,6 +64,18 @@ __device__ __forceinline__ void tc_mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem,
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
       "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// the same with the shared-memory descriptor as two words (only the low one -- start address -- differs between the
+// operands of a kernel): the caller's address arithmetic stays 32 bits wide
+__device__ __forceinline__ void tc_mma_bf16_ts2(uint32_t d_tmem, uint32_t a_tmem, uint32_t bdesc_lo, uint32_t bdesc_hi,
+                                                uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 bd;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "mov.b64 bd, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], bd, %4, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "r"(bdesc_lo), "r"(bdesc_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 __device__ __forceinline__ void tc_st8(uint32_t taddr, const uint4& a, const uint4& b) {
@@ -105,7 +119,12 @@ __device__ __forceinline__ float ts_tanh(float x) {
 // DSMEM and its epilogue warps run, the tensor pipe works on the other (an MMA costs ~27 cycles whatever its N, so 64
 // rows per cluster at N = 32 halve the tensor-pipe time per row, and the ping-pong hides the exchange).
 // Everything the per-step loops branch on is a template parameter.
-template <int NR, int NC, int MATH, bool SPLIT, int TILES, int SUBS, bool SAVE = false>
+// GEPI (the default for two sub-batches of 8 rows): the epilogue adds G_t from shared memory instead of the P . G MMAs;
+// the loads are issued while the warp waits for the accumulator anyway.  Measured after the MMA issue was unrolled
+// (profiles/r2_rec_ts_microbench.txt): 2 x 8 rows 0.96-1.00 us per step with GEPI against 1.14 without; 2 x 16 rows
+// 1.79-1.81 with against 1.48-1.54 without (16 conflicting 2-byte loads per lane cost the epilogue -- which bounds that
+// shape -- more than 16 MMAs cost the tensor pipe); 2 x 32 rows spill with it.
+template <int NR, int NC, int MATH, bool SPLIT, int TILES, int SUBS, bool SAVE = false, bool GEPI = (SUBS == 2 && NR == 8)>
 __global__ void __launch_bounds__(64 + 128 * TILES * SUBS * (NR / NC), 1)
 blstm_rec_ts_kernel(const RecTsArgs a, const __grid_constant__ CUtensorMap gmap) {
   static_assert(TILES == 1 || TILES == 2, "one or two row tiles per CTA");
@@ -152,7 +171,7 @@ blstm_rec_ts_kernel(const RecTsArgs a, const __grid_constant__ CUtensorMap gmap)
       }
       for (int i = 0; i < GS; ++i) {
         mbar_init(gfull0 + 8 * i, 1);
-        mbar_init(gempty0 + 8 * i, 1);
+        mbar_init(gempty0 + 8 * i, GEPI ? 4 * TILES * SUBS * EW : 1);  // GEPI: every epilogue warp reads the stage
       }
       mbar_fence_init();
       for (int sb = 0; sb < SUBS; ++sb)
@@ -183,7 +202,7 @@ blstm_rec_ts_kernel(const RecTsArgs a, const __grid_constant__ CUtensorMap gmap)
       const uint4 w0 = __ldg(src + static_cast<size_t>(k) * 256), w1 = __ldg(src + static_cast<size_t>(k) * 256 + 1);
       tc_st8(t0 + k * 8, w0, w1);
     }
-    if (tl == 0) {
+    if (tl == 0 && !GEPI) {
       // P: row m = 4*unit + gate of a tile picks k = gate*32 + unit of the tile's G operand (two k-steps of 16
       // units from each of the four gate atoms), scaled by 1/2 for the sigmoid gates
       const int m = q * 32 + lane, gate = m & 3, unit = m >> 2;
@@ -239,122 +258,140 @@ blstm_rec_ts_kernel(const RecTsArgs a, const __grid_constant__ CUtensorMap gmap)
     // The whole warp runs the loop convergently and elect.sync guards only the MMA blocks: inside a
     // divergent `if (lane == 0)` ptxas wraps every UTCHMMA in an ELECT / BRA.U.ANY waterfall and
     // rebuilds the descriptor through a long uniform-datapath chain (~70 cycles per MMA, measured).
-    // Descriptors advance by adding a constant to the encoded start address (16-byte units).
+    // The tensor pipe itself needs only max(8, N/2) cycles per M=128, K=16 MMA with A in tensor memory
+    // (scripts/probes/mma_probe.cu: 9 cycles at N=16, 16 at N=32) -- what a step pays per MMA is the ISSUE
+    // sequence.  So for the product size (KSC = 19 k-steps) the k loop is unrolled completely, every operand address
+    // is "base + compile-time constant", and the 64-bit shared-memory descriptor is kept as two words of which only
+    // the low one (start address, 16-byte units) ever changes: 2 adds + 2 R2UR per MMA instead of a 64-bit add
+    // chain, per-atom loop control and predicates (27-30 cycles per MMA before).  Other sizes take the loop form.
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(NB >> 3) << 17) |
                            (static_cast<uint32_t>(128 >> 4) << 24);
     const uint64_t bdesc0 = ts_desc_sw128(sB);
     const uint64_t gdesc0 = ts_desc_sw128(sG);
+    const uint32_t desc_hi = static_cast<uint32_t>(bdesc0 >> 32);  // SBO, version, swizzle: the same for every operand
+    const uint32_t bdesc_lo0 = static_cast<uint32_t>(bdesc0), gdesc_lo0 = static_cast<uint32_t>(gdesc0);
     const uint32_t buf_step = static_cast<uint32_t>(NA) * (kAtomB >> 4);  // encoded distance of two h buffers
     const uint32_t d0 = tmem_base + acc_col;
     const uint32_t pt = tmem_base + p_col;
-    int slot = 0;
-    uint32_t gph = 0;
-    // W_hh . h for one tile and one K phase: phase 0 = k-steps 0,1 of every atom (units of the senders' first
-    // row tile), phase 1 = k-steps 2,3; without SPLIT phase 0 covers all four.  Tile after tile, not alternating:
-    // an MMA costs its ~27 cycles of tensor pipe whatever accumulator it targets (alternating the tiles was measured:
-    // no faster to issue, and it makes both tiles' epilogues start together instead of the first one overlapping the
-    // second tile's MMAs -- 1.29 instead of 0.99 us per step at 8 rows per cluster).
-    auto issue_h = [&](uint32_t d, int tile, int phase, uint64_t bd) {
-      uint32_t at = tmem_base + static_cast<uint32_t>(tile) * a_tile_cols;
-      uint64_t bk = bd;
-      const int k_lo = phase * 2, k_hi = SPLIT ? k_lo + 2 : 4;
-      for (int atom = 0; atom < NA; ++atom) {
-        const int n = KS - 4 * atom;  // k-steps of this atom (>= 1)
-#pragma unroll
-        for (int k4 = 0; k4 < 4; ++k4)
-          if (k4 >= k_lo && k4 < k_hi && k4 < n) tc_mma_bf16_ts(d, at + k4 * 8, bk + 2 * k4, idesc, 1u);
-        at += 32;
-        bk += kAtomB >> 4;
-      }
-    };
 #ifdef TSSEP_DEBUG_KNOBS
     const bool mprof = a.prof != nullptr && blockIdx.y == 0 && blockIdx.z == 0 && crank == 0;
     const bool no_fence = (a.flags & 1) != 0;
-    int mc[4] = {0, 0, 0, 0};
 #else
     constexpr bool mprof = false, no_fence = false;
 #endif
-    for (int s = 0; s < T; ++s) {
-      const int rb = (s & 1) ^ 1;
-      mbar_wait(gfull0 + 8 * slot, gph);
-      const uint64_t gd = gdesc0 + static_cast<uint64_t>(static_cast<uint32_t>(slot) * (g_stage >> 4));
+    // the whole time loop, instantiated for a compile-time k-step count (ksc > 0) or the run-time one (ksc = 0)
+    auto run = [&](auto ksc) {
+      constexpr int KSC = decltype(ksc)::value;
+      // W_hh . h for one tile and one K phase: phase 0 = k-steps 0,1 of every atom (units of the senders' first
+      // row tile), phase 1 = k-steps 2,3; without SPLIT phase 0 covers all four.  Tile after tile, not alternating
+      // (measured: alternating makes both tiles' epilogues start together instead of the first one overlapping the
+      // second tile's MMAs).  k-step k: A columns 8k of the tile, B = atom k/4, 32-byte slice k%4.
+      auto issue_h = [&](uint32_t d, int tile, int phase, uint32_t bd_lo) {
+        const uint32_t at = tmem_base + static_cast<uint32_t>(tile) * a_tile_cols;
+        const int k_lo = phase * 2, k_hi = SPLIT ? k_lo + 2 : 4;
+        if constexpr (KSC > 0) {
 #pragma unroll
-      for (int sb = 0; sb < SUBS; ++sb) {
-        int m0 = 0, m1 = 0, m2 = 0, m3 = 0;
-        if (mprof) m0 = clock();
-        const uint32_t dsub = d0 + static_cast<uint32_t>(sb * TILES) * NB;
-        // P . G_s: needs the accumulators of step s-1 drained -- long before h arrives
-        if (s > 0) {
-          mbar_wait(accempty0 + 8 * (sb * 2), (s - 1) & 1);
-          if constexpr (TILES == 2) mbar_wait(accempty0 + 8 * (sb * 2 + 1), (s - 1) & 1);
+          for (int k = 0; k < KSC; ++k)
+            if ((k & 3) >= k_lo && (k & 3) < k_hi)
+              tc_mma_bf16_ts2(d, at + 8 * k, bd_lo + (k >> 2) * (kAtomB >> 4) + 2 * (k & 3), desc_hi, idesc,
+                              (GEPI && k == 0) ? 0u : 1u);
+        } else {
+#pragma unroll 4
+          for (int k = 0; k < KS; ++k)
+            if ((k & 3) >= k_lo && (k & 3) < k_hi)
+              tc_mma_bf16_ts2(d, at + 8 * k, bd_lo + (k >> 2) * (kAtomB >> 4) + 2 * (k & 3), desc_hi, idesc,
+                              (GEPI && k == 0) ? 0u : 1u);
         }
-        tc_fence_after();
-        if (elect_one()) {
+      };
+      int mc[4] = {0, 0, 0, 0};
+      int slot = 0;
+      uint32_t gph = 0;
+      for (int s = 0; s < T; ++s) {
+        const int rb = (s & 1) ^ 1;
+        if constexpr (!GEPI) mbar_wait(gfull0 + 8 * slot, gph);
+        const uint32_t gd_lo = gdesc_lo0 + static_cast<uint32_t>(slot) * (g_stage >> 4);
 #pragma unroll
-          for (int tile = 0; tile < TILES; ++tile) {
-            const uint32_t hx = (crank * TILES + tile) & 1u;  // which 32 units of the 64-unit box
-#pragma unroll
-            for (int k = 0; k < 8; ++k)  // k-step k of P = gate k/2, half k%2 of the tile's 32 units; rows of sub-batch sb
-              tc_mma_bf16_ts(dsub + tile * NB, pt + k * 8,
-                             gd + static_cast<uint64_t>(static_cast<uint32_t>(k >> 1) * (kAtomG >> 4) +
-                                                        static_cast<uint32_t>(sb) * (NR * 8) + 2 * (2 * hx + (k & 1))),
-                             idesc, k > 0 ? 1u : 0u);
+        for (int sb = 0; sb < SUBS; ++sb) {
+          int m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+          if (mprof) m0 = clock();
+          const uint32_t dsub = d0 + static_cast<uint32_t>(sb * TILES) * NB;
+          // P . G_s: needs the accumulators of step s-1 drained -- long before h arrives
+          if (s > 0) {
+            mbar_wait(accempty0 + 8 * (sb * 2), (s - 1) & 1);
+            if constexpr (TILES == 2) mbar_wait(accempty0 + 8 * (sb * 2 + 1), (s - 1) & 1);
           }
-        }
-        __syncwarp();
-        if (mprof) m1 = clock();
-        const uint64_t bd = bdesc0 + static_cast<uint64_t>(static_cast<uint32_t>(sb * 2 + rb) * buf_step);
-        const uint32_t hbar = hfull0 + 8 * ((sb * 2 + rb) * 2);
-        if (s > 0) {
-          const uint32_t par = ((s - 1) >> 1) & 1;
-          mbar_wait(hbar, par);
-          if (mprof) m2 = clock();
-          if (lane == 0) mbar_arrive_expect_tx(hbar, tx_bytes);  // re-arm for the data of step s+1
-          // h arrived through st.async (generic proxy); the MMA reads it through the async proxy
-          if (!no_fence) ts_fence_proxy_async();
           tc_fence_after();
-          if (mprof) m3 = clock();
-          if constexpr (SPLIT) {
-            if (elect_one()) {
-              issue_h(dsub, 0, 0, bd);
-              issue_h(dsub + NB, 1, 0, bd);
+          if (!GEPI && elect_one()) {
+#pragma unroll
+            for (int tile = 0; tile < TILES; ++tile) {
+              // the tile's 32 units are one half (hx) of the 64-unit box: 64 bytes = 4 descriptor units into the row
+              const uint32_t gt_lo = gd_lo + static_cast<uint32_t>(sb) * (NR * 8) + 4u * ((crank * TILES + tile) & 1u);
+#pragma unroll
+              for (int k = 0; k < 8; ++k)  // k-step k of P = gate k/2, half k%2 of the tile's 32 units
+                tc_mma_bf16_ts2(dsub + tile * NB, pt + k * 8, gt_lo + (k >> 1) * (kAtomG >> 4) + 2 * (k & 1), desc_hi, idesc,
+                                k > 0 ? 1u : 0u);
             }
-            __syncwarp();
-            mbar_wait(hbar + 8, par);
-            if (lane == 0) mbar_arrive_expect_tx(hbar + 8, tx_bytes);
-            ts_fence_proxy_async();
+          }
+          __syncwarp();
+          if (mprof) m1 = clock();
+          const uint32_t bd_lo = bdesc_lo0 + static_cast<uint32_t>(sb * 2 + rb) * buf_step;
+          const uint32_t hbar = hfull0 + 8 * ((sb * 2 + rb) * 2);
+          if (s > 0) {
+            const uint32_t par = ((s - 1) >> 1) & 1;
+            mbar_wait(hbar, par);
+            if (mprof) m2 = clock();
+            if (lane == 0) mbar_arrive_expect_tx(hbar, tx_bytes);  // re-arm for the data of step s+1
+            // h arrived through st.async (generic proxy); the MMA reads it through the async proxy
+            if (!no_fence) ts_fence_proxy_async();
             tc_fence_after();
+            if (mprof) m3 = clock();
+            if constexpr (SPLIT) {
+              if (elect_one()) {
+                issue_h(dsub, 0, 0, bd_lo);
+                issue_h(dsub + NB, 1, 0, bd_lo);
+              }
+              __syncwarp();
+              mbar_wait(hbar + 8, par);
+              if (lane == 0) mbar_arrive_expect_tx(hbar + 8, tx_bytes);
+              ts_fence_proxy_async();
+              tc_fence_after();
+            }
+          }
+          if (elect_one()) {
+            if (GEPI && s == 0) {  // nothing to multiply at the first step: the epilogue takes G_0 alone
+              mbar_arrive(accfull0 + 8 * (sb * 2));
+              if constexpr (TILES == 2) mbar_arrive(accfull0 + 8 * (sb * 2 + 1));
+            } else {
+              if (s > 0) issue_h(dsub, 0, SPLIT ? 1 : 0, bd_lo);
+              tc_commit(accfull0 + 8 * (sb * 2));
+              if constexpr (TILES == 2) {
+                if (s > 0) issue_h(dsub + NB, 1, SPLIT ? 1 : 0, bd_lo);
+                tc_commit(accfull0 + 8 * (sb * 2 + 1));
+              }
+            }
+            if (!GEPI && sb == SUBS - 1) tc_commit(gempty0 + 8 * slot);  // the stage is free once the MMAs that read it are done
+          }
+          __syncwarp();
+          if (mprof && s > 0 && sb == 0) {
+            const int m4 = clock();
+            mc[0] += m1 - m0;  // accumulator-drained waits + P.G issue
+            mc[1] += m2 - m1;  // wait for h_{t-1}
+            mc[2] += m3 - m2;  // re-arm + proxy fence
+            mc[3] += m4 - m3;  // W_hh.h issue + commits
           }
         }
-        if (elect_one()) {
-          if (s > 0) issue_h(dsub, 0, SPLIT ? 1 : 0, bd);
-          tc_commit(accfull0 + 8 * (sb * 2));
-          if constexpr (TILES == 2) {
-            if (s > 0) issue_h(dsub + NB, 1, SPLIT ? 1 : 0, bd);
-            tc_commit(accfull0 + 8 * (sb * 2 + 1));
-          }
-          if (sb == SUBS - 1) tc_commit(gempty0 + 8 * slot);  // the stage is free once the MMAs that read it are done
+        if (++slot == GS) {
+          slot = 0;
+          gph ^= 1;
         }
-        __syncwarp();
-#ifdef TSSEP_DEBUG_KNOBS
-        if (mprof && s > 0 && sb == 0) {
-          const int m4 = clock();
-          mc[0] += m1 - m0;  // accumulator-drained waits + P.G issue
-          mc[1] += m2 - m1;  // wait for h_{t-1}
-          mc[2] += m3 - m2;  // re-arm + proxy fence
-          mc[3] += m4 - m3;  // W_hh.h issue + commits
-        }
-#endif
       }
-      if (++slot == GS) {
-        slot = 0;
-        gph ^= 1;
-      }
-    }
 #ifdef TSSEP_DEBUG_KNOBS
-    if (mprof && lane == 0)
-      for (int i = 0; i < 4; ++i) a.prof[8 + i] = mc[i];
+      if (mprof && lane == 0)
+        for (int i = 0; i < 4; ++i) a.prof[8 + i] = mc[i];
 #endif
+    };
+    if (KS == 19) run(std::integral_constant<int, 19>{});  // U = 300 (Up = 304)
+    else run(std::integral_constant<int, 0>{});
   } else {
     // ---- epilogue: gates, cell update, h exchange --------------------------------------------------
     const int wx = (warp - 2) >> 2;            // (tile, column group) of this warp
@@ -397,6 +434,13 @@ blstm_rec_ts_kernel(const RecTsArgs a, const __grid_constant__ CUtensorMap gmap)
     float cst[NQ];
 #pragma unroll
     for (int i = 0; i < NQ; ++i) cst[i] = 0.f;
+    // GEPI: this lane's G values of a step: gate plane `gate`, box rows sb*NR + half*NC + i, unit (gtile & 1)*32 + q*8 + ul
+    // of the 64-unit box; 128-byte rows, 16-byte chunks XOR-swizzled with the row (row base is a multiple of 8)
+    const uint32_t g_lane = sG + static_cast<uint32_t>(gate) * kAtomG + static_cast<uint32_t>(sb * NR + half * NC) * 128u +
+                            static_cast<uint32_t>(ul) * 2u;
+    const float g_scale = is_g ? 1.0f : 0.5f;  // the sigmoid gates work on x / 2 (W_hh rows are pre-scaled)
+    int gslot = 0;
+    uint32_t gph = 0;
 
 #ifdef TSSEP_DEBUG_KNOBS
     const bool do_prof = a.prof != nullptr && blockIdx.y == 0 && blockIdx.z == 0 && crank == 0 && (warp == 4 || warp == 8);
@@ -408,6 +452,25 @@ blstm_rec_ts_kernel(const RecTsArgs a, const __grid_constant__ CUtensorMap gmap)
       const int wb = s & 1;
       int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
       if (do_prof) c0 = clock();
+      uint32_t gv[GEPI ? NC / 2 : 1];  // bf16 pairs (rows 2j, 2j + 1)
+      if constexpr (GEPI) {
+        // G_s arrived steps ago (the ring runs ahead): fetch it while the accumulator is still being computed
+        mbar_wait(gfull0 + 8 * gslot, gph);
+        const uint32_t gs = g_lane + static_cast<uint32_t>(gslot) * g_stage;
+#pragma unroll
+        for (int j = 0; j < NC / 2; ++j) {
+          uint32_t lo, hi;
+          asm volatile("ld.shared.u16 %0, [%1];" : "=r"(lo) : "r"(gs + (2 * j) * 128u + ((static_cast<uint32_t>(oc) ^ ((2 * j) & 7u)) << 4)));
+          asm volatile("ld.shared.u16 %0, [%1];" : "=r"(hi) : "r"(gs + (2 * j + 1) * 128u + ((static_cast<uint32_t>(oc) ^ ((2 * j + 1) & 7u)) << 4)));
+          gv[j] = lo | (hi << 16);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(gempty0 + 8 * gslot);
+        if (++gslot == GS) {
+          gslot = 0;
+          gph ^= 1;
+        }
+      }
       mbar_wait(my_accfull, s & 1);
       if (do_prof) c1 = clock();
       tc_fence_after();
@@ -424,8 +487,17 @@ blstm_rec_ts_kernel(const RecTsArgs a, const __grid_constant__ CUtensorMap gmap)
 
       // gate non-linearity of this lane's row for the warp's NC batch rows
       float act[NC];
+      if constexpr (GEPI) {
 #pragma unroll
-      for (int i = 0; i < NC; ++i) act[i] = fmaf(ts_tanh<MATH>(__uint_as_float(v[i])), ka, kb);
+        for (int i = 0; i < NC; ++i) {
+          const float gx = __uint_as_float((i & 1) ? (gv[i / 2] & 0xFFFF0000u) : (gv[i / 2] << 16));
+          const float d = s > 0 ? __uint_as_float(v[i]) : 0.f;  // step 0: h_{-1} = 0, nothing was accumulated
+          act[i] = fmaf(ts_tanh<MATH>(fmaf(gx, g_scale, d)), ka, kb);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < NC; ++i) act[i] = fmaf(ts_tanh<MATH>(__uint_as_float(v[i])), ka, kb);
+      }
       // 4x4 transposes inside lane quads: afterwards act[4i + g] = gate g of batch row 4i + (lane & 3)
 #pragma unroll
       for (int i = 0; i < NQ; ++i) {
@@ -648,15 +720,15 @@ static int launch_ts(const RecTsArgs& a, const CUtensorMap& gmap, int C, int nsu
 
 // Relative cost of one dependent step per cluster shape (tiles per CTA, rows per cluster, sub-batches), measured at
 // U = 300 on B200 (profiles/r2_rec_ts_microbench.txt): ~us per step.  tssep_b200/dist.py::TS_STEP_COST mirrors the best
-// shape per rows-per-cluster.  32 rows per cluster run fastest as two sub-batches of 16 in anti-phase (1.83 us against
-// 2.03-2.36 us as one sub-batch: the step is then bound by the tensor pipe instead of the exchange + gate-math chain);
-// 16 rows as 2 x 8 are slower than one sub-batch (the MMAs of a step cost the same for 8 and 16 columns).
+// shape per rows-per-cluster.  16 and 32 rows per cluster run fastest as two sub-batches in anti-phase (1.0 against
+// 1.15-1.25 us and 1.5 against 2.0 us): while the h of one sub-batch travels through DSMEM and its gate math runs, the
+// tensor pipe works on the other.
 struct TsShape {
   int tiles, rows, subs;  // rows per cluster = subs sub-batches (advanced in anti-phase) of rows / subs
   double cost;
 };
-static const TsShape kTsShapes[] = {{1, 8, 1, 0.9},   {2, 8, 1, 1.0},  {1, 16, 1, 1.4},  {2, 16, 1, 1.37}, {2, 16, 2, 1.68},
-                                    {1, 32, 1, 2.6},  {2, 32, 1, 2.3}, {2, 32, 2, 1.86}, {2, 64, 2, 3.18}};
+static const TsShape kTsShapes[] = {{1, 8, 1, 0.78},  {2, 8, 1, 0.85}, {1, 16, 1, 1.07}, {2, 16, 1, 1.2},  {2, 16, 2, 1.0},
+                                    {1, 32, 1, 1.77}, {2, 32, 1, 2.0}, {2, 32, 2, 1.54}, {2, 64, 2, 3.06}};
 
 }  // namespace tssep
 

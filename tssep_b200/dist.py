@@ -111,7 +111,7 @@ def gather_segments(local_ids: Sequence[int], segments: torch.Tensor, counts: to
 # Relative cost of one dependent step of the tensor-memory recurrence at 8 / 16 / 32 / 64 rows per cluster, two row
 # tiles per CTA, the faster of one / two sub-batches (measured at U = 300 on B200, profiles/r2_rec_ts_microbench.txt);
 # the same ratios steer the kernel's own choice (csrc/lstm_ts.cu::kTsShapes).
-TS_STEP_COST: Dict[int, float] = {8: 1.0, 16: 1.37, 32: 1.86, 64: 3.18}
+TS_STEP_COST: Dict[int, float] = {8: 0.85, 16: 1.0, 32: 1.54, 64: 3.06}
 
 
 def plan_recurrence_waves(n_items: int, rows_per_item: int, capacity: Dict[int, int], max_items: Optional[int] = None,
