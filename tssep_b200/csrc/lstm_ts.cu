@@ -124,6 +124,9 @@ __device__ __forceinline__ float ts_tanh(float x) {
 // (profiles/r2_rec_ts_microbench.txt): 2 x 8 rows 0.96-1.00 us per step with GEPI against 1.14 without; 2 x 16 rows
 // 1.79-1.81 with against 1.48-1.54 without (16 conflicting 2-byte loads per lane cost the epilogue -- which bounds that
 // shape -- more than 16 MMAs cost the tensor pipe); 2 x 32 rows spill with it.
+// Also measured and dropped: a helper warp that takes the proxy fence of the h exchange (250 cycles under the st.async
+// traffic of a ping-pong step) off the MMA warp -- the MMA warp then waits that much longer for h: at 32 rows per cluster
+// the step is bound by the DSMEM egress of the exchange (16 KB per CTA and step at ~20 B/clk) plus its latency.
 template <int NR, int NC, int MATH, bool SPLIT, int TILES, int SUBS, bool SAVE = false, bool GEPI = (SUBS == 2 && NR == 8)>
 __global__ void __launch_bounds__(64 + 128 * TILES * SUBS * (NR / NC), 1)
 blstm_rec_ts_kernel(const RecTsArgs a, const __grid_constant__ CUtensorMap gmap) {
