@@ -33,7 +33,7 @@ typedef void* tssep_stream_t; /* cudaStream_t */
 
 /* Bumped whenever a signature or struct layout below changes; tssep_b200/_lib.py refuses a library that
  * reports another value. */
-#define TSSEP_ABI_VERSION 3
+#define TSSEP_ABI_VERSION 4
 
 const char* tssep_last_error(void);
 int tssep_abi_version(void);
@@ -135,7 +135,11 @@ int tssep_fold_embedding(int mode, const float* W, int64_t ldw, const float* b, 
  * mode TSSEP_EPI_F32 / TSSEP_EPI_BF16: out[m * ldo + n] (act: 0 none, 1 tanh).
  * mode TSSEP_EPI_HEAD (TS-VAD/TS-SEP output head, net.py:629-668, :928-986): column
  *   n = q * row_len + f of item z goes to plane p = plane_map[z * n_blocks + q]:
- *   logit[(p * M + m) * row_len + f] = v and mask[...] = sigmoid(v); either may be NULL.
+ *   logit[(p * M + m) * row_len + f] = v and mask[...] = sigmoid(v); either may be NULL.  Choose row_len % 8 == 0
+ *   (pad every block of B with zero rows: 513 -> 520): with 513-float rows the warp-wide 128-byte stores of the
+ *   epilogue start at arbitrary 4-byte offsets and half of the 32-byte sectors they touch are written in part; with
+ *   520 every store covers whole sectors (measured on B200: 1.9 -> 3.5 TB/s of output).  The consumers of the mask
+ *   take the row pitch (tssep_mask_istft, tssep_activity).
  *   The caller folds the speaker rotation / trial mean into B and bias (K = trials*projs)
  *   and the un-permutation into plane_map.
  * impl: 0 = tcgen05 (product path), 1 = plain SIMT kernel (debug / bisecting only). */
@@ -232,7 +236,8 @@ int tssep_pack_whh(const float* whh_fwd, const float* whh_bwd, int U, int Up, ui
  * ---------------------------------------------------------------------- */
 
 /* If mask != NULL:  Y[z,k] = X[z] * mask[z,k]  (X (Z,T,F) cfloat with item stride,
- * mask (Z,K,T,F) f32) else Y = X viewed as (Z*K, T, F) cfloat.
+ * mask (Z,K,T,F) f32, rows mask_pitch floats apart -- 0 = F; the head GEMM writes 513-float rows at a pitch of 520 so
+ * that every row starts on a 32-byte sector) else Y = X viewed as (Z*K, T, F) cfloat.
  * stft_estimate (Z,K,T,F) cfloat and time (Z,K,num_samples) f32 are optional outputs.
  * activity (Z,K,T) f32, optional (needs mask): activity[z,k,t] = mean_f mask[z,k,t,f], the frame activity of the
  * diarization stage (section 5), reduced from the mask rows this kernel reads anyway.
@@ -240,7 +245,7 @@ int tssep_pack_whh(const float* whh_fwd, const float* whh_bwd, int U, int Up, ui
  * size 1024 / shift 256 / window_length 1024 (every shipped config) takes a specialised kernel: 16 x 32
  * register FFT, two speakers per warp, overlap-add accumulator in registers; other geometries a generic
  * shared-memory kernel. */
-int tssep_mask_istft(const float* X, int64_t x_item_stride, const float* mask, int64_t Z, int n_spk,
+int tssep_mask_istft(const float* X, int64_t x_item_stride, const float* mask, int64_t mask_pitch, int64_t Z, int n_spk,
                      int64_t T, int size, int shift, int window_length, int fading,
                      const float* synwin, const float* twiddle, float* stft_estimate, float* time,
                      int64_t num_samples, float* activity, tssep_stream_t stream);
@@ -266,8 +271,9 @@ int tssep_bf_apply(const float* Y, const float* w, const float* mask, int64_t Z,
  *     tssep/util/utils.py:11-129, tssep/train/loss.py:343)
  * ---------------------------------------------------------------------- */
 
-/* activity[n,t] = mean_f mask[n,t,f]. */
-int tssep_activity(const float* mask, int64_t n, int64_t T, int F, float* activity, tssep_stream_t stream);
+/* activity[n,t] = mean_f mask[n,t,f]; mask rows mask_pitch floats apart (0 = F). */
+int tssep_activity(const float* mask, int64_t n, int64_t T, int F, int64_t mask_pitch, float* activity,
+                   tssep_stream_t stream);
 
 /* smooth = running median (odd width <= 63, edges replicated); active = smooth > thr. */
 int tssep_median_threshold(const float* activity, int64_t n, int64_t T, int width, float threshold,

@@ -29,8 +29,16 @@ def main():
         ("b1_in    bf16", 1, Bm * K8 * T, 8 * Up, P, ops.EPI_BF16),
         ("b2_in    bf16", Bm * 2, T, 8 * Up, K8 * P, ops.EPI_BF16),
         ("head     head", Bm, T, K8 * F, 2 * P, ops.EPI_HEAD),
+        # experiments on the output path of the head (not product shapes): 512-float rows (128-byte aligned), the
+        # same GEMM through the plain f32 epilogue, mask only
+        ("head512  head", Bm, T, K8 * 512, 2 * P, ops.EPI_HEAD),
+        ("headf32  f32 ", Bm, T, K8 * F, 2 * P, ops.EPI_F32),
+        ("headmask head", Bm, T, K8 * F, 2 * P, ops.EPI_HEAD),
     ]
     for name, batch, M, N, K, mode in shapes:
+        if not a.only and name.split()[0] in ("head512", "headf32", "headmask"):
+            continue
+        F = 512 if name.startswith("head512") else 513
         if a.only and a.only not in name:
             continue
         ld = ops.operand_ld(K)
@@ -42,8 +50,9 @@ def main():
             logit = torch.empty((batch * K8, M, F), device=dev)
             mask = torch.empty_like(logit)
             pm = torch.arange(batch * K8, dtype=torch.int32, device=dev)
-            run = lambda: ops.gemm(A, ld, B, ld, M, N, K, logit, mode=mode, mask=mask, plane_map=pm, n_blocks=K8, row_len=F, **kw)
-            out_bytes = 2 * logit.numel() * 4
+            lo = None if name.startswith("headmask") else logit
+            run = lambda: ops.gemm(A, ld, B, ld, M, N, K, lo, mode=mode, mask=mask, plane_map=pm, n_blocks=K8, row_len=F, **kw)
+            out_bytes = (1 if lo is None else 2) * logit.numel() * 4
         else:
             ldo = ops.round_up(N, 8)
             out = torch.empty((batch * M, ldo), dtype=torch.float32 if mode == ops.EPI_F32 else torch.bfloat16, device=dev)

@@ -242,3 +242,28 @@ def test_instance_norm_modules_mirror_the_reference_signatures():
     assert repr(InstanceNorm(dim=-1)) == "InstanceNorm(dim=-1, unbiased=False)"          # net.py:257-258
     assert repr(InstanceNorm_v2(-1, -2)) == "InstanceNorm_v2(mean_dim=-1, norm_dim=-2)"
     assert FACTORY_ALIASES["tssep.train.net.InstanceNorm_v2"] == "tssep_b200.net.InstanceNorm_v2"
+
+
+def test_row_pitch_view():
+    """The mask consumers read the head GEMM's padded buffers in place; anything else is made contiguous."""
+    import torch
+
+    from tssep_b200.ops import row_pitch_view
+
+    buf = torch.zeros((2, 3, 1, 7, 520))
+    v = buf[..., :513]
+    t, p = row_pitch_view(v)
+    assert p == 520 and t.data_ptr() == buf.data_ptr() and t.shape == v.shape
+    t, p = row_pitch_view(v[0])                      # un-batched view
+    assert p == 520 and t.data_ptr() == buf.data_ptr()
+    t, p = row_pitch_view(v[1, 1:])                  # sliced over a dense leading axis
+    assert p == 520 and t.data_ptr() == v[1, 1:].data_ptr()
+    c = torch.zeros((2, 3, 1, 7, 513))
+    t, p = row_pitch_view(c)
+    assert p == 513 and t.data_ptr() == c.data_ptr()
+    t, p = row_pitch_view(buf[:, :, :, ::2, :513])   # rows not equidistant with the leading axes -> copy
+    assert p == 513 and t.is_contiguous()
+    t, p = row_pitch_view(v.double())                # wrong dtype -> float32 copy
+    assert p == 513 and t.dtype == torch.float32 and t.is_contiguous()
+    t, p = row_pitch_view(buf[..., 1:514])           # offset start is fine as long as rows stay equidistant
+    assert p == 520 and t.data_ptr() == buf[..., 1:514].data_ptr()

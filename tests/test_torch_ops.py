@@ -59,7 +59,7 @@ def test_cpu_tensors_have_no_kernel():
     with pytest.raises(NotImplementedError, match="CPU"):
         torch.ops.tssep_b200.cast_bf16(torch.zeros(4, 4), 4, 4, 4, torch.zeros((4, 8), dtype=torch.bfloat16), 8)
     with pytest.raises(NotImplementedError, match="CPU"):
-        torch.ops.tssep_b200.activity(torch.zeros(1, 3, 5), 1, 3, 5, torch.zeros(1, 3))
+        torch.ops.tssep_b200.activity(torch.zeros(1, 3, 5), 1, 3, 5, 0, torch.zeros(1, 3))
 
 
 def test_dynamo_traces_a_layer_without_graph_breaks():

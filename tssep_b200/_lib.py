@@ -36,7 +36,7 @@ class GemmDesc(C.Structure):
 
 
 EPI_F32, EPI_BF16, EPI_HEAD = 0, 1, 2
-ABI_VERSION = 3  # TSSEP_ABI_VERSION of include/tssep_b200.h this binding was written against
+ABI_VERSION = 4  # TSSEP_ABI_VERSION of include/tssep_b200.h this binding was written against
 
 _SIGNATURES = {
     "tssep_abi_version": ([], C.c_int),
@@ -64,12 +64,12 @@ _SIGNATURES = {
     "tssep_blstm_recurrence_train": ([c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i32, c_i32, c_i32, c_vp], C.c_int),
     "tssep_blstm_recurrence_bwd": ([c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i32, c_vp], C.c_int),
     "tssep_pack_whh_bwd": ([c_vp, c_vp, c_i32, c_i32, c_vp, c_vp], C.c_int),
-    "tssep_mask_istft": ([c_vp, c_i64, c_vp, c_i64, c_i32, c_i64, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp,
+    "tssep_mask_istft": ([c_vp, c_i64, c_vp, c_i64, c_i64, c_i32, c_i64, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp,
                           c_i64, c_vp, c_vp], C.c_int),
     "tssep_bf_psd": ([c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i64, c_i32, c_vp, c_vp], C.c_int),
     "tssep_bf_mvdr_souden": ([c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, C.c_double, c_vp, c_vp], C.c_int),
     "tssep_bf_apply": ([c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i64, c_i32, c_f32, c_vp, c_vp], C.c_int),
-    "tssep_activity": ([c_vp, c_i64, c_i64, c_i32, c_vp, c_vp], C.c_int),
+    "tssep_activity": ([c_vp, c_i64, c_i64, c_i32, c_i64, c_vp, c_vp], C.c_int),
     "tssep_median_threshold": ([c_vp, c_i64, c_i64, c_i32, c_f32, c_vp, c_vp, c_vp], C.c_int),
     "tssep_segments": ([c_vp, c_i64, c_i64, c_i32, c_i32, c_i32, c_i64, c_vp, c_vp, c_i32, c_i32, c_vp], C.c_int),
     "tssep_stft_vad": ([c_vp, c_i64, c_i64, c_i32, c_i32, c_i32, c_i64, c_vp, c_vp], C.c_int),

@@ -83,7 +83,7 @@ constexpr int kEWarps = 8;
 constexpr int kEThreads = kEWarps * 32;
 
 __global__ void __launch_bounds__(kEThreads, 2)
-mask_istft_kernel(const float2* __restrict__ X, int64_t x_item_stride, const float* __restrict__ mask, int n_spk,
+mask_istft_kernel(const float2* __restrict__ X, int64_t x_item_stride, const float* __restrict__ mask, int64_t mp, int n_spk,
                   int64_t T, int S, int R, int wl, int trim, const float* __restrict__ synwin,
                   const float2* __restrict__ twiddle, float2* __restrict__ est, float* __restrict__ time_out,
                   int64_t num_samples, int hops) {
@@ -125,14 +125,14 @@ mask_istft_kernel(const float2* __restrict__ X, int64_t x_item_stride, const flo
         float2* scr = scratch + warp * PL;
         float2* first = odd_passes ? scr : slot;
         float2* other = odd_passes ? slot : scr;
-        const int64_t row = (sig * T + t) * F;
+        const int64_t row = (sig * T + t) * F, mrow = (sig * T + t) * mp;  // mask rows are mp floats apart
         const float2* xrow = mask ? X + z * x_item_stride + t * F : X + row;
         const bool own = est != nullptr && t >= j_begin;
 #pragma unroll 4
         for (int kk = lane; kk < M; kk += 32) {
           float2 yk = xrow[kk], ym = xrow[M - kk];
           if (mask) {
-            const float mk = mask[row + kk], mm = mask[row + M - kk];
+            const float mk = mask[mrow + kk], mm = mask[mrow + M - kk];
             yk = make_float2(yk.x * mk, yk.y * mk);
             ym = make_float2(ym.x * mm, ym.y * mm);
           }
@@ -238,7 +238,7 @@ __device__ __forceinline__ void idft_reg(float2 (&v)[N]) {
 
 template <bool ACT>
 __global__ void __launch_bounds__(32 * kFastWarps, 3)
-mask_istft_1024_kernel(const float2* __restrict__ X, int64_t x_item_stride, const float* __restrict__ mask, int n_spk,
+mask_istft_1024_kernel(const float2* __restrict__ X, int64_t x_item_stride, const float* __restrict__ mask, int64_t mp, int n_spk,
                        int groups, int64_t T, int trim, const float* __restrict__ synwin, const float2* __restrict__ twiddle,
                        float2* __restrict__ est, float* __restrict__ time_out, int64_t num_samples, int hops,
                        float* __restrict__ activity) {
@@ -287,6 +287,7 @@ mask_istft_1024_kernel(const float2* __restrict__ X, int64_t x_item_stride, cons
       // ---- pass A: both speakers, element k = 32 k1 + lane ------------------------------------------
       float2 va[16], vb[16];
       const int64_t row_a = (sig_a * T + t) * F, row_b = (sig_b * T + t) * F;
+      const int64_t mrow_a = (sig_a * T + t) * mp, mrow_b = (sig_b * T + t) * mp;  // mask rows are mp floats apart
       const float2* xrow_a = mask ? X + z * x_item_stride + t * F : X + row_a;
       const float2* xrow_b = mask ? xrow_a : X + row_b;
       const bool own = est != nullptr && t >= j_begin;
@@ -299,12 +300,12 @@ mask_istft_1024_kernel(const float2* __restrict__ X, int64_t x_item_stride, cons
           float sa = 0.f, sb = 0.f;
 #pragma unroll
           for (int k1 = 0; k1 < 16; ++k1) {
-            sa += mask[row_a + 32 * k1 + lane];
-            sb += mask[row_b + 32 * k1 + lane];
+            sa += mask[mrow_a + 32 * k1 + lane];
+            sb += mask[mrow_b + 32 * k1 + lane];
           }
           if (lane == 0) {
-            sa += mask[row_a + M];
-            sb += mask[row_b + M];
+            sa += mask[mrow_a + M];
+            sb += mask[mrow_b + M];
           }
           sa = warp_sum(sa);
           sb = warp_sum(sb);
@@ -320,8 +321,8 @@ mask_istft_1024_kernel(const float2* __restrict__ X, int64_t x_item_stride, cons
         float2 yk = xrow_a[kk], ym = xrow_a[M - kk];
         float2 yk2 = yk, ym2 = ym;
         if (mask) {
-          const float mk = mask[row_a + kk], mm = mask[row_a + M - kk];
-          const float mk2 = mask[row_b + kk], mm2 = mask[row_b + M - kk];
+          const float mk = mask[mrow_a + kk], mm = mask[mrow_a + M - kk];
+          const float mk2 = mask[mrow_b + kk], mm2 = mask[mrow_b + M - kk];
           yk = make_float2(yk.x * mk, yk.y * mk);
           ym = make_float2(ym.x * mm, ym.y * mm);
           yk2 = make_float2(yk2.x * mk2, yk2.y * mk2);
@@ -434,7 +435,7 @@ int tssep_head_expand_t(const float* small, int64_t Z, int64_t T, int n_spk, int
   return check_launch("tssep_head_expand_t");
 }
 
-int tssep_mask_istft(const float* X, int64_t x_item_stride, const float* mask, int64_t Z, int n_spk, int64_t T,
+int tssep_mask_istft(const float* X, int64_t x_item_stride, const float* mask, int64_t mask_pitch, int64_t Z, int n_spk, int64_t T,
                      int size, int shift, int window_length, int fading, const float* synwin, const float* twiddle,
                      float* stft_estimate, float* time, int64_t num_samples, float* activity, tssep_stream_t stream) {
   TSSEP_REQUIRE(X && synwin && twiddle, "tssep_mask_istft: null pointer");
@@ -445,6 +446,8 @@ int tssep_mask_istft(const float* X, int64_t x_item_stride, const float* mask, i
   TSSEP_REQUIRE(window_length <= size && shift >= 1 && window_length % shift == 0,
                 "tssep_mask_istft: need window_length <= size and window_length %% shift == 0");
   TSSEP_REQUIRE(Z >= 0 && Z < 65536 && n_spk >= 1 && T >= 0, "tssep_mask_istft: bad extent");
+  TSSEP_REQUIRE(mask_pitch == 0 || mask_pitch >= size / 2 + 1, "tssep_mask_istft: mask_pitch must be 0 or >= size / 2 + 1");
+  const int64_t mp = mask_pitch > 0 ? mask_pitch : size / 2 + 1;
   if (Z == 0 || T == 0) return 0;
   if (size == 1024 && shift == 256 && window_length == 1024 && debug_env("TSSEP_ISTFT_GENERIC") == nullptr) {
     // (the fast kernel loses nothing by also reducing the mask rows it reads to the frame activity)
@@ -455,19 +458,19 @@ int tssep_mask_istft(const float* X, int64_t x_item_stride, const float* mask, i
     dim3 grid(static_cast<unsigned>((J + hops - 1) / hops), static_cast<unsigned>(Z * groups));
     if (activity != nullptr)
       mask_istft_1024_kernel<true><<<grid, 32 * kFastWarps, 0, static_cast<cudaStream_t>(stream)>>>(
-          reinterpret_cast<const float2*>(X), x_item_stride, mask, n_spk, groups, T, fading ? window_length - shift : 0, synwin,
+          reinterpret_cast<const float2*>(X), x_item_stride, mask, mp, n_spk, groups, T, fading ? window_length - shift : 0, synwin,
           reinterpret_cast<const float2*>(twiddle), reinterpret_cast<float2*>(stft_estimate), time, num_samples, hops,
           activity);
     else
       mask_istft_1024_kernel<false><<<grid, 32 * kFastWarps, 0, static_cast<cudaStream_t>(stream)>>>(
-          reinterpret_cast<const float2*>(X), x_item_stride, mask, n_spk, groups, T, fading ? window_length - shift : 0, synwin,
+          reinterpret_cast<const float2*>(X), x_item_stride, mask, mp, n_spk, groups, T, fading ? window_length - shift : 0, synwin,
           reinterpret_cast<const float2*>(twiddle), reinterpret_cast<float2*>(stft_estimate), time, num_samples, hops,
           activity);
     return check_launch("tssep_mask_istft");
   }
   // generic geometries: the frame activity comes from the stand-alone reduction
   if (activity != nullptr) {
-    if (int r = tssep_activity(mask, Z * n_spk, T, size / 2 + 1, activity, stream)) return r;
+    if (int r = tssep_activity(mask, Z * n_spk, T, size / 2 + 1, mp, activity, stream)) return r;
   }
   const int M = size / 2, OV = window_length / shift;
   const size_t smem = sizeof(float2) * (M + (2 * kEWarps + OV - 1) * padded_len(M)) + sizeof(float) * window_length;
@@ -480,7 +483,7 @@ int tssep_mask_istft(const float* X, int64_t x_item_stride, const float* mask, i
   while (hops > 8 && ((J + hops - 1) / hops) * n_sig < 4 * 148) hops /= 2;
   dim3 grid(static_cast<unsigned>(((J + hops - 1) / hops) * n_spk), static_cast<unsigned>(Z));
   mask_istft_kernel<<<grid, kEThreads, smem, static_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const float2*>(X), x_item_stride, mask, n_spk, T, size, shift, window_length,
+      reinterpret_cast<const float2*>(X), x_item_stride, mask, mp, n_spk, T, size, shift, window_length,
       fading ? window_length - shift : 0, synwin, reinterpret_cast<const float2*>(twiddle),
       reinterpret_cast<float2*>(stft_estimate), time, num_samples, hops);
   return check_launch("tssep_mask_istft");

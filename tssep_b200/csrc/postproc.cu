@@ -11,12 +11,12 @@
 
 namespace tssep {
 
-__global__ void activity_kernel(const float* __restrict__ mask, int64_t rows, int F, float* __restrict__ act) {
+__global__ void activity_kernel(const float* __restrict__ mask, int64_t rows, int F, int64_t pitch, float* __restrict__ act) {
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   for (int64_t r = blockIdx.x * static_cast<int64_t>(wpb) + (threadIdx.x >> 5); r < rows;
        r += static_cast<int64_t>(gridDim.x) * wpb) {
-    const float* m = mask + r * F;
+    const float* m = mask + r * pitch;
     float s = 0.f;
     for (int f = lane; f < F; f += 32) s += m[f];
     s = warp_sum(s);
@@ -155,12 +155,12 @@ using namespace tssep;
 
 extern "C" {
 
-int tssep_activity(const float* mask, int64_t n, int64_t T, int F, float* activity, tssep_stream_t stream) {
-  TSSEP_REQUIRE(mask && activity && F >= 1, "tssep_activity: bad arguments");
+int tssep_activity(const float* mask, int64_t n, int64_t T, int F, int64_t mask_pitch, float* activity, tssep_stream_t stream) {
+  TSSEP_REQUIRE(mask && activity && F >= 1 && (mask_pitch == 0 || mask_pitch >= F), "tssep_activity: bad arguments");
   const int64_t rows = n * T;
   if (rows == 0) return 0;
   const int blocks = static_cast<int>(imin64((rows + 7) / 8, 148 * 32));
-  activity_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(mask, rows, F, activity);
+  activity_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(mask, rows, F, mask_pitch > 0 ? mask_pitch : F, activity);
   return check_launch("tssep_activity");
 }
 

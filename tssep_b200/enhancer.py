@@ -48,7 +48,9 @@ class Masking(ABC):
         if masks.shape[-3] != 1:
             raise ValueError(f"Masking needs nmask == 1, got mask shape {tuple(masks.shape)}")
         obs = obs.to(torch.complex64).contiguous()
-        m = masks.float().contiguous()
+        from .ops import row_pitch_view
+
+        m, mask_pitch = row_pitch_view(masks)   # the head GEMM's padded rows are read in place
         T, F = m.shape[-2:]
         K = m.shape[-4]
         Z = m.shape[0] if batched else 1
@@ -72,7 +74,7 @@ class Masking(ABC):
                     or not activity_out.is_contiguous()):
                 raise ValueError(f"activity_out must be a contiguous float32 tensor of shape {(*lead, T)}")
         tab = fe._device_tables(m.device)
-        torch_ops.op.mask_istft(obs, T * F, m, Z, K, T, fe.size, fe.shift, fe.window_length, int(bool(fe.fading)),
+        torch_ops.op.mask_istft(obs, T * F, m, mask_pitch, Z, K, T, fe.size, fe.shift, fe.window_length, int(bool(fe.fading)),
                                 tab["synwin"], tab["twiddle"], est, time, time.shape[-1] if time is not None else 0,
                                 activity_out)
         return est, time

@@ -144,7 +144,7 @@ class STFT(Configurable):
         tab = self._device_tables(Xc.device)
         out = torch.empty((*lead, n), dtype=torch.float32, device=Xc.device)
         n_sig = int(np.prod(lead)) if lead else 1
-        torch_ops.op.mask_istft(Xc, 0, None, n_sig, 1, t, self.size, self.shift, self.window_length,
+        torch_ops.op.mask_istft(Xc, 0, None, 0, n_sig, 1, t, self.size, self.shift, self.window_length,
                                 int(bool(fading)), tab["synwin"], tab["twiddle"], None, out, n, None)
         return out.cpu().numpy() if was_np else out
 

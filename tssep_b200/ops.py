@@ -49,6 +49,27 @@ def gemm(A, lda, B, ldb, M, N, K, out, *, mode, ldo=0, batch=1, a_stride=0, a_di
                       out_stride_hi, mask, plane_map, n_blocks, row_len, _gemm_impl() if impl is None else impl, max_ctas)
 
 
+def row_pitch_view(t: torch.Tensor):
+    """(tensor, pitch) of t (..., T, F) float32 for the kernels that take a row pitch: t itself when its rows are
+    ``pitch >= F`` floats apart and everything in front of them is dense (the padded mask / logit buffers of the head
+    GEMM, and every contiguous tensor), else a contiguous copy."""
+    F = t.shape[-1]
+    if t.dtype == torch.float32 and t.dim() >= 2 and (F == 1 or t.stride(-1) == 1):
+        if t.is_contiguous():
+            return t, F
+        pitch = t.stride(-2)
+        if pitch >= F:
+            expect, ok = pitch * t.shape[-2], True
+            for size, stride in zip(reversed(t.shape[:-2]), reversed(t.stride()[:-2])):
+                if size != 1 and stride != expect:
+                    ok = False
+                    break
+                expect *= size
+            if ok:
+                return t, pitch
+    return t.float().contiguous(), F
+
+
 def cast_bf16(src: torch.Tensor, ld_dst: int = None) -> torch.Tensor:
     """(rows, cols) f32 -> (rows, ld_dst) bf16 with zero padded columns."""
     _lib.require_cuda(src)

@@ -41,9 +41,11 @@ def diarize(mask: torch.Tensor, fe, *, num_samples=None, threshold=0.5, median_w
     n = mask.numel() // (T * F)
     dev = mask.device
     if activity is None:
-        m = mask.float().contiguous()
+        from .ops import row_pitch_view
+
+        m, mask_pitch = row_pitch_view(mask)
         act = torch.empty((*lead, T), dtype=torch.float32, device=dev)
-        torch_ops.op.activity(m, n, T, F, act)
+        torch_ops.op.activity(m, n, T, F, mask_pitch, act)
     else:
         if tuple(activity.shape) != (*lead, T) or activity.dtype != torch.float32 or not activity.is_contiguous():
             raise ValueError(f"activity must be a contiguous float32 tensor of shape {(*lead, T)}")

@@ -81,7 +81,7 @@ _OPS = {
         "(Tensor whh_fwd, Tensor whh_bwd, int U, int Up, Tensor(a!) WTimg) -> ()",
         "tssep_pack_whh_bwd"),
     "mask_istft": (
-        "(Tensor X, int x_item_stride, Tensor? mask, int Z, int n_spk, int T, int size, int shift, int window_length, "
+        "(Tensor X, int x_item_stride, Tensor? mask, int mask_pitch, int Z, int n_spk, int T, int size, int shift, int window_length, "
         "int fading, Tensor synwin, Tensor twiddle, Tensor(a!)? stft_estimate, Tensor(b!)? time, int num_samples, "
         "Tensor(c!)? activity) -> ()",
         "tssep_mask_istft"),
@@ -96,7 +96,7 @@ _OPS = {
         "Tensor(a!) out) -> ()",
         "tssep_bf_apply"),
     "activity": (
-        "(Tensor mask, int n, int T, int F, Tensor(a!) activity) -> ()",
+        "(Tensor mask, int n, int T, int F, int mask_pitch, Tensor(a!) activity) -> ()",
         "tssep_activity"),
     "median_threshold": (
         "(Tensor activity, int n, int T, int width, float threshold, Tensor(a!)? smooth, Tensor(b!)? active) -> ()",
