@@ -28,17 +28,18 @@ def main():
         ("b0_proj  bf16", 1, Bm * K8 * T, P, 2 * Up, ops.EPI_BF16),
         ("b1_in    bf16", 1, Bm * K8 * T, 8 * Up, P, ops.EPI_BF16),
         ("b2_in    bf16", Bm * 2, T, 8 * Up, K8 * P, ops.EPI_BF16),
-        ("head     head", Bm, T, K8 * F, 2 * P, ops.EPI_HEAD),
-        # experiments on the output path of the head (not product shapes): 512-float rows (128-byte aligned), the
-        # same GEMM through the plain f32 epilogue, mask only
+        ("head     head", Bm, T, K8 * 520, 2 * P, ops.EPI_HEAD),   # product: 513-float rows padded to 520 (net.py)
+        # experiments on the output path of the head (not product shapes): dense 513-float rows, 512-float rows
+        # (128-byte aligned), the same GEMM through the plain f32 epilogue, mask only
+        ("head513  head", Bm, T, K8 * F, 2 * P, ops.EPI_HEAD),
         ("head512  head", Bm, T, K8 * 512, 2 * P, ops.EPI_HEAD),
         ("headf32  f32 ", Bm, T, K8 * F, 2 * P, ops.EPI_F32),
         ("headmask head", Bm, T, K8 * F, 2 * P, ops.EPI_HEAD),
     ]
     for name, batch, M, N, K, mode in shapes:
-        if not a.only and name.split()[0] in ("head512", "headf32", "headmask"):
+        if not a.only and name.split()[0] in ("head513", "head512", "headf32", "headmask"):
             continue
-        F = 512 if name.startswith("head512") else 513
+        F = 512 if name.startswith("head512") else (520 if name.startswith("head ") else 513)
         if a.only and a.only not in name:
             continue
         ld = ops.operand_ld(K)
