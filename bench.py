@@ -361,12 +361,25 @@ def run_b200(args):
     aux_host = torch.tensor(np.stack([m[1] for m in meetings])).pin_memory()
     obs_dev, aux_dev = obs_host.to(dev), aux_host.to(dev)
     diar = dict(threshold=0.5, median_width=11, max_segments=256)
-    gather = tdist.SegmentGather(plan, rank, K, diar["max_segments"], dev)
+    # Steps in flight.  With few meetings per GPU a step is a chain of latency-bound recurrence launches that occupy
+    # 20-80 of the 148 SMs, so a serving loop keeps two or three steps (independent batches) in flight on as many
+    # streams (measured per-rank step at 8 meetings: 149 / 101 / 86 / 84 ms with 1 / 2 / 3 / 4 in flight; at 16 meetings
+    # 194 / 151 / 145 ms with 1 / 2 / 3 and a collapse with 4 -- profiles/r2_steps_in_flight.txt), each
+    # confined to two thirds of the SMs (rnnp.set_cta_budget; measured: 1/2, 2/3 and no bound are within 6 % of each
+    # other): the recurrences of both run side by side.  With many meetings
+    # per GPU the launches fill the device (and the memory), and steps run back to back.
+    in_flight = int(os.environ.get("TSSEP_BENCH_IN_FLIGHT", 0)) or (3 if M <= 8 else (2 if M <= 16 else 1))
+    if in_flight >= 2:
+        from tssep_b200 import rnnp as _rnnp
+        _rnnp.set_cta_budget(int(os.environ.get("TSSEP_BENCH_CTA_BUDGET", 0)) or
+                             (2 * torch.cuda.get_device_properties(dev).multi_processor_count) // 3)
+    step_streams = [torch.cuda.Stream(device=dev) for _ in range(in_flight)] if in_flight > 1 else [None]
+    gathers = [tdist.SegmentGather(plan, rank, K, diar["max_segments"], dev) for _ in range(in_flight)]
 
     class StepOut:
         pass
 
-    def step(obs, aux, on_wave=None, time_out=None, wave_plan=None, do_gather=True):
+    def step(obs, aux, on_wave=None, time_out=None, wave_plan=None, do_gather=True, slot=0):
         """One pass over the rank's meetings (Model.separate_waves).  The big per-wave outputs (mask, logit,
         stft_estimate) are fully written to HBM and released when the next output wave starts; time_estimate and the
         segment tables of all waves stay.  Speaker permutations are drawn on the host in meeting order."""
@@ -383,7 +396,7 @@ def run_b200(args):
         out.segments = torch.cat(segs) if len(segs) > 1 else segs[0]
         out.counts = torch.cat(cnts) if len(cnts) > 1 else cnts[0]
         if do_gather and world > 1:
-            out.all_segments, out.all_counts = gather.start(out.segments, out.counts).result()
+            out.all_segments, out.all_counts = gathers[slot].start(out.segments, out.counts).result()
         return out
 
     def barrier():
@@ -391,9 +404,26 @@ def run_b200(args):
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        out = step(obs_dev, aux_dev)
-        del out
+    main0 = torch.cuda.current_stream(dev)
+
+    def run_steps(k):
+        """k device-resident steps, at most `in_flight` of them overlapping: step i runs on stream i % in_flight (every
+        stream runs its steps in order); returns after making the main stream wait for all of them."""
+        for i in range(k):
+            if in_flight == 1:
+                out = step(obs_dev, aux_dev)
+            else:
+                st = step_streams[i % in_flight]
+                if i < in_flight:
+                    st.wait_stream(main0)
+                with torch.cuda.stream(st):
+                    out = step(obs_dev, aux_dev, slot=i % in_flight)
+            del out
+        for st in step_streams:
+            if st is not None:
+                main0.wait_stream(st)
+
+    run_steps(max(args.warmup, in_flight))  # also grows every stream's memory pool to its steady state
     barrier()
 
     # ---- device-resident timed region -----------------------------------------------------
@@ -404,9 +434,7 @@ def run_b200(args):
     with ClockSampler(local, enabled=rank == 0) as clocks:
         barrier()
         ev0.record()
-        for _ in range(args.steps):
-            out = step(obs_dev, aux_dev)
-            del out
+        run_steps(args.steps)
         ev1.record()
         barrier()
     _lib.set_timeline(None)
@@ -430,19 +458,23 @@ def run_b200(args):
     # step produces output (its output stages come last), and the copy stream is ordered anyway.
     copy_stream = torch.cuda.Stream(device=dev)   # device -> host
     in_stream = torch.cuda.Stream(device=dev)     # host -> device (separate, or it would queue behind the D2H)
-    main_stream = torch.cuda.current_stream(dev)
 
     # Persistent device buffers of the serving loop (two of each input, used alternately): the inputs land in them by
     # H2D copy, the separated audio is written into time_buf by the enhancement kernel and read back by D2H copy.
     torch.cuda.empty_cache()
-    obs_bufs = [torch.empty_like(obs_dev) for _ in range(2)]
-    aux_bufs = [torch.empty_like(aux_dev) for _ in range(2)]
-    time_buf = torch.empty((M, K, n), dtype=torch.float32, device=dev)  # one: it is written only at the end of a step
-    copied = [None]         # event: the D2H copies of the previous step out of time_buf are done
-    in_free = [None, None]  # event: the step that read obs_bufs[j] / aux_bufs[j] is done
+    n_in = max(2, in_flight)
+    obs_bufs = [torch.empty_like(obs_dev) for _ in range(n_in)]
+    aux_bufs = [torch.empty_like(aux_dev) for _ in range(n_in)]
+    # one time buffer per step in flight (with one step in flight it is written only at the end of a step, after the
+    # previous step's audio has left it)
+    time_bufs = [torch.empty((M, K, n), dtype=torch.float32, device=dev) for _ in range(in_flight)]
+    copied = [None] * in_flight  # event: the D2H copies of the previous step out of time_bufs[slot] are done
+    in_free = [None] * n_in  # event: the step that read obs_bufs[j] / aux_bufs[j] is done
 
     def e2e_step(i):
-        j = i % 2
+        j = i % n_in
+        slot = i % in_flight
+        main_stream = step_streams[slot] if in_flight > 1 else main0   # the stream this step computes on
         ev_in = torch.cuda.Event()
         with torch.cuda.stream(in_stream):
             if in_free[j] is not None:
@@ -453,9 +485,9 @@ def run_b200(args):
         main_stream.wait_event(ev_in)
 
         def time_out():  # called right before the first output wave of this step is written
-            if copied[0] is not None:
-                main_stream.wait_event(copied[0])  # the previous step's audio has left time_buf
-            return time_buf
+            if copied[slot] is not None:
+                main_stream.wait_event(copied[slot])  # the previous step's audio has left this time buffer
+            return time_bufs[slot]
 
         def ship(lo, hi, time_estimate):  # D2H of a wave's separated audio as soon as it exists
             ev = torch.cuda.Event()
@@ -464,18 +496,19 @@ def run_b200(args):
             with torch.cuda.stream(copy_stream):
                 time_host[lo:hi].copy_(time_estimate, non_blocking=True)
 
-        out = step(obs_bufs[j], aux_bufs[j], on_wave=ship, time_out=time_out)
+        with torch.cuda.stream(main_stream):
+            out = step(obs_bufs[j], aux_bufs[j], on_wave=ship, time_out=time_out, slot=slot)
         ev_done = torch.cuda.Event()
         ev_done.record(main_stream)
-        in_free[j] = ev_done  # the inputs of step i+2 may overwrite obs_bufs[j] only after this step
+        in_free[j] = ev_done  # the inputs of step i + n_in may overwrite obs_bufs[j] only after this step
         copy_stream.wait_event(ev_done)
         with torch.cuda.stream(copy_stream):
             out.segments.record_stream(copy_stream)
             out.counts.record_stream(copy_stream)
             seg_host.copy_(out.segments, non_blocking=True)
             cnt_host.copy_(out.counts, non_blocking=True)
-            copied[0] = torch.cuda.Event()
-            copied[0].record(copy_stream)
+            copied[slot] = torch.cuda.Event()
+            copied[slot].record(copy_stream)
 
     # plain D2H bandwidth of this rank with every rank copying at once (what bounds the end-to-end number: 512 KB of
     # separated audio per audio-second)
@@ -495,16 +528,22 @@ def run_b200(args):
     copy_stream.synchronize()
     barrier()
     ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ee0.record(main_stream)
+    ee0.record(main0)
     copy_stream.wait_event(ee0)
     in_stream.wait_event(ee0)
+    for st in step_streams:
+        if st is not None:
+            st.wait_event(ee0)
     for i in range(args.steps):
         e2e_step(i)
-    main_stream.wait_stream(copy_stream)
-    ee1.record(main_stream)
+    main0.wait_stream(copy_stream)
+    for st in step_streams:
+        if st is not None:
+            main0.wait_stream(st)
+    ee1.record(main0)
     barrier()
     e2e_ms = ee0.elapsed_time(ee1)
-    del obs_bufs, aux_bufs, time_buf, time_host
+    del obs_bufs, aux_bufs, time_bufs, time_host
 
     d2h_all = d2h_gbs
     if world > 1:
@@ -653,6 +692,11 @@ def run_b200(args):
                                f"reused from one output wave of {out_wave} meetings to the next)",
                    "precision": "bf16 GEMM / recurrence operands, f32 accumulation, f32 cell state, f32 STFT / iSTFT",
                    "meetings_total": args.meetings, "meetings_per_gpu": M, "recurrence_waves": waves,
+                   "steps_in_flight": in_flight,
+                   "steps_in_flight_note": ("consecutive steps (independent batches of the same 64 meetings) overlap on "
+                                            "as many streams, every recurrence launch confined to 2/3 of the SMs; ms_per_step = "
+                                            "timed region / steps; the per-kernel times below overlap and add up to more "
+                                            "than that" if in_flight > 1 else "steps run back to back on one stream"),
                    "recurrence_capacity_rows": cap, "meetings_per_output_wave": out_wave,
                    "meeting_seconds": args.seconds, "frames": T,
                    "l2": "inputs and intermediates (GBs per step) far exceed the 126 MB L2; no explicit flush",

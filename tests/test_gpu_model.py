@@ -234,3 +234,42 @@ def test_runs_on_a_device_that_is_not_current(lib):
     assert (got.mask.cpu() - want.mask).abs().max().item() < MASK_TOL
     with pytest.raises(RuntimeError, match="different devices|same device"):
         me(torch.zeros((10, 553), device="cuda:0"), [a for a in aux.to(dev)])
+
+
+def test_steps_in_flight_on_several_streams_match_sequential_runs(cuda):
+    """A serving loop keeps several steps in flight on as many streams (bench.py at <= 16 meetings per GPU), with the
+    recurrence launches confined to a share of the SMs (rnnp.set_cta_budget): same results as one step at a time
+    (bit for bit while the budget leaves the cluster shapes unchanged, as here; the shape with the epilogue-side G add
+    rounds differently, hence the tolerance)."""
+    from tssep_b200 import rnnp
+
+    ref, me = make_pair(_me_kwargs(units=300, projs=320))
+    model = _product_model(me)
+    exs = [_ex(s, 513, num_samples=48_000) for s in range(3)]
+    obs = [torch.tensor(np.stack([e["observation"]] * 2)).to(cuda) for e in exs]    # 2 meetings per step
+    aux = [torch.tensor(np.stack([e["auxInput"]] * 2)).to(cuda) for e in exs]
+
+    def run(i):
+        np.random.seed(i)
+        return [(o.mask.clone(), o.time_estimate.clone(), o.segments.segments.clone())
+                for _, _, o in model.separate_waves(obs[i], aux[i], diarize=dict(threshold=0.5, median_width=5))]
+
+    want = [run(i) for i in range(3)]
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(device=cuda) for _ in range(3)]
+    rnnp.set_cta_budget(98)
+    try:
+        got = [None] * 3
+        for rep in range(2):      # second round: every stream's allocator pool is warm, kernels really overlap
+            for i, st in enumerate(streams):
+                st.wait_stream(torch.cuda.current_stream(cuda))
+                with torch.cuda.stream(st):
+                    got[i] = run(i)
+        torch.cuda.synchronize()
+    finally:
+        rnnp.set_cta_budget(None)
+    for w, g in zip(want, got):
+        for (wm, wt, ws), (gm, gt, gs) in zip(w, g):
+            assert (wm - gm).abs().max().item() <= 2e-5 and (wt - gt).abs().max().item() <= 2e-4
+            if torch.equal(wm, gm):
+                assert torch.equal(wt, gt) and torch.equal(ws, gs)

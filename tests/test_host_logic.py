@@ -267,3 +267,19 @@ def test_row_pitch_view():
     assert p == 513 and t.dtype == torch.float32 and t.is_contiguous()
     t, p = row_pitch_view(buf[..., 1:514])           # offset start is fine as long as rows stay equidistant
     assert p == 520 and t.data_ptr() == buf[..., 1:514].data_ptr()
+
+
+def test_choose_ts_shape_respects_the_cta_budget():
+    """Two steps in flight: every recurrence launch gets half of the 148 SMs."""
+    from tssep_b200.rnnp import choose_ts_shape
+
+    cap = {(8, 1, 1): 56, (8, 2, 1): 104, (16, 2, 2): 208, (32, 2, 2): 416, (64, 2, 2): 832}
+    capacity = lambda Up, rpc, tiles, subs: cap.get((rpc, tiles, subs), 0)
+    # (rows per cluster, tiles, subs)
+    assert choose_ts_shape(8, 304, 74, capacity) == (8, 1, 1)        # 20 CTAs, the latency shape
+    assert choose_ts_shape(16, 304, 74, capacity) == (8, 1, 1)       # 40 CTAs
+    assert choose_ts_shape(64, 304, 74, capacity) == (16, 2, 2)      # (8, 2, 1) would need 80 CTAs
+    assert choose_ts_shape(64, 304, 148, capacity) == (8, 2, 1)
+    assert choose_ts_shape(128, 304, 74, capacity) == (32, 2, 2)     # 4 clusters of 5 per direction = 40 CTAs
+    assert choose_ts_shape(416, 304, 74, capacity) == (64, 2, 2)     # 7 clusters x 5 x 2 = 70 CTAs
+    assert choose_ts_shape(832, 304, 74, capacity) == (0, 0, 0)      # nothing fits half the device: library's choice

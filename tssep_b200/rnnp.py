@@ -33,6 +33,42 @@ def rec_kernel(g_dtype: torch.dtype = torch.bfloat16, Up: int = 0) -> str:
     return choice
 
 
+# Cluster shapes of the tensor-memory recurrence as (row tiles per CTA, rows per cluster, sub-batches, us per dependent
+# step at U = 300 on B200): the best shape per cluster width of csrc/lstm_ts.cu::kTsShapes.
+TS_SHAPES = ((1, 8, 1, 0.78), (2, 8, 1, 0.85), (2, 16, 2, 1.0), (2, 32, 2, 1.54), (2, 64, 2, 3.06))
+
+_cta_budget = None
+
+
+def set_cta_budget(n):
+    """Upper bound on the CTAs (= SMs: one CTA per SM) a recurrence launch may occupy; ``None`` = the library's choice
+    (the fastest shape that fits the device).  A serving loop that keeps two steps in flight on two streams gives
+    every step half of the SMs, so that the latency-bound recurrences of both run side by side instead of one waiting
+    for the clusters of the other to drain (bench.py at <= 16 meetings per GPU)."""
+    global _cta_budget
+    _cta_budget = None if n is None else int(n)
+
+
+def choose_ts_shape(rows: int, Up: int, cta_budget: int, capacity=None):
+    """(rows_per_cluster, tiles_per_cta, sub_batches) of the cheapest shape whose launch needs at most ``cta_budget``
+    CTAs, or (0, 0, 0) -- let the library choose -- when none does.  ``capacity(Up, rows_per_cluster, tiles, subs)``:
+    rows one wave of co-resident clusters holds (default: the device query)."""
+    capacity = ops.recurrence_ts_capacity if capacity is None else capacity
+    best, pick = None, (0, 0, 0)
+    for tiles, rpc, subs, cost in TS_SHAPES:
+        ctas_per_cluster = 2 * ((Up + 63) // 64) // tiles
+        if ctas_per_cluster > 16:
+            continue
+        ctas = 2 * (-(-rows // rpc)) * ctas_per_cluster           # both directions
+        cap = capacity(Up, rpc, tiles, subs)
+        if cap <= 0 or ctas > cta_budget:
+            continue
+        total = cost * (-(-rows // cap))
+        if best is None or total < best:
+            best, pick = total, (rpc, tiles, subs)
+    return pick
+
+
 class LayerPack:
     """Device-resident, kernel-ready copies of one BLSTM + projection layer (a derived cache)."""
 
@@ -113,11 +149,13 @@ class LayerPack:
         if rec_kernel(G.dtype, self.Up) == "ts":
             self.whh_ts_image()
             # host-side tuning knobs, handed to the library as explicit arguments (0 / -1 = let it choose)
-            return ops.blstm_recurrence_ts(G, self.whh_ts, rows, T, self.Up,
-                                           rows_per_cluster=int(os.environ.get("TSSEP_TS_ROWS", "0")),
+            rpc, tiles = int(os.environ.get("TSSEP_TS_ROWS", "0")), int(os.environ.get("TSSEP_TS_TILES", "0"))
+            subs = int(os.environ.get("TSSEP_TS_SUBS", "0"))
+            if _cta_budget is not None and (rpc, tiles, subs) == (0, 0, 0):
+                rpc, tiles, subs = choose_ts_shape(rows, self.Up, _cta_budget)
+            return ops.blstm_recurrence_ts(G, self.whh_ts, rows, T, self.Up, rows_per_cluster=rpc,
                                            k_split=int(os.environ.get("TSSEP_TS_KSPLIT", "-1")),
-                                           tiles_per_cta=int(os.environ.get("TSSEP_TS_TILES", "0")),
-                                           sub_batches=int(os.environ.get("TSSEP_TS_SUBS", "0")))
+                                           tiles_per_cta=tiles, sub_batches=subs)
         if self.whh_regs is None:
             self.whh_regs = ops.pack_whh(self._whh_f32[0], self._whh_f32[1], self.U, self.Up)
         return ops.blstm_recurrence(G, self.whh_regs, rows, T, self.Up)
