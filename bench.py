@@ -471,6 +471,10 @@ def run_b200(args):
     copied = [None] * in_flight  # event: the D2H copies of the previous step out of time_bufs[slot] are done
     in_free = [None] * n_in  # event: the step that read obs_bufs[j] / aux_bufs[j] is done
 
+    pcm = {"on": False}
+    pcm_host = None
+    pcm_bufs = None
+
     def e2e_step(i):
         j = i % n_in
         slot = i % in_flight
@@ -492,9 +496,16 @@ def run_b200(args):
         def ship(lo, hi, time_estimate):  # D2H of a wave's separated audio as soon as it exists
             ev = torch.cuda.Event()
             ev.record(main_stream)
+            if pcm["on"]:  # 16-bit PCM: converted on the device (tssep_pcm16), half the bytes over PCIe and into host memory
+                with torch.cuda.stream(main_stream):
+                    _ops.pcm16(time_estimate, 32767.0 / 8.0, out=pcm_bufs[slot][lo:hi])
+                ev.record(main_stream)
             copy_stream.wait_event(ev)
             with torch.cuda.stream(copy_stream):
-                time_host[lo:hi].copy_(time_estimate, non_blocking=True)
+                if pcm["on"]:
+                    pcm_host[lo:hi].copy_(pcm_bufs[slot][lo:hi], non_blocking=True)
+                else:
+                    time_host[lo:hi].copy_(time_estimate, non_blocking=True)
 
         with torch.cuda.stream(main_stream):
             out = step(obs_bufs[j], aux_bufs[j], on_wave=ship, time_out=time_out, slot=slot)
@@ -543,13 +554,44 @@ def run_b200(args):
     ee1.record(main0)
     barrier()
     e2e_ms = ee0.elapsed_time(ee1)
+
+    # The same loop shipping the separated audio as 16-bit PCM (the format the evaluation driver writes to disk) instead
+    # of float32: a clearly separate line -- the headline e2e above keeps the reference's float32 output.  Measured where
+    # the host side of the device-to-host copies bounds the end-to-end number (several ranks copying at once).
+    e2e_pcm_ms = None
+    if world > 1:
+        try:
+            pcm_host = torch.empty((M, K, n), dtype=torch.int16).pin_memory()
+        except RuntimeError:
+            pcm_host = torch.empty((M, K, n), dtype=torch.int16)
+        pcm_bufs = [torch.empty((M, K, n), dtype=torch.int16, device=dev) for _ in range(in_flight)]
+        pcm["on"] = True
+        for i in range(max(2, in_flight)):
+            e2e_step(i)
+        copy_stream.synchronize()
+        barrier()
+        pp0, pp1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        pp0.record(main0)
+        for st in [copy_stream, in_stream] + [st for st in step_streams if st is not None]:
+            st.wait_event(pp0)
+        for i in range(args.steps):
+            e2e_step(i)
+        main0.wait_stream(copy_stream)
+        for st in step_streams:
+            if st is not None:
+                main0.wait_stream(st)
+        pp1.record(main0)
+        barrier()
+        e2e_pcm_ms = pp0.elapsed_time(pp1)
+        pcm["on"] = False
+        del pcm_bufs, pcm_host
     del obs_bufs, aux_bufs, time_bufs, time_host
 
     d2h_all = d2h_gbs
     if world > 1:
-        t = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
+        t = torch.tensor([ms, e2e_ms, e2e_pcm_ms], device=dev, dtype=torch.float64)
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-        ms, e2e_ms = float(t[0]), float(t[1])
+        ms, e2e_ms, e2e_pcm_ms = float(t[0]), float(t[1]), float(t[2])
         s = torch.tensor([d2h_gbs, float(pinned)], device=dev, dtype=torch.float64)
         torch.distributed.all_reduce(s, op=torch.distributed.ReduceOp.SUM)
         d2h_all, pinned_ranks = float(s[0]), int(round(float(s[1])))
@@ -710,6 +752,12 @@ def run_b200(args):
                 "note": "per-rank byte counts; bounded by the device-to-host copy of the separated audio (8 speakers x f32 = "
                         "512 KB per audio-second); copies overlap the next step, the last step's copy tail is inside the "
                         "timed region"},
+        "e2e_pcm16": (None if e2e_pcm_ms is None else {
+            "value": audio_s / (e2e_pcm_ms / 1e3), "unit": "audio-s/s", "ms_per_step": e2e_pcm_ms / args.steps,
+            "d2h_bytes_per_step": int(M * K * n * 2),
+            "note": "NOT the headline: the same end-to-end loop with the separated audio converted to 16-bit PCM on the device "
+                    "(tssep_pcm16; what the evaluation driver writes to disk) before it is copied to the host -- half the "
+                    "device-to-host bytes, which is what bounds e2e when several ranks copy into host memory at once"}),
         "gpu_launches": launches,
         "roofline": roofline, "roofline_gemm": roofline_gemm, "hbm_kernels": hbm,
         "cpu_baseline": cpu,

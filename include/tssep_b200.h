@@ -250,6 +250,10 @@ int tssep_mask_istft(const float* X, int64_t x_item_stride, const float* mask, i
                      const float* synwin, const float* twiddle, float* stft_estimate, float* time,
                      int64_t num_samples, float* activity, tssep_stream_t stream);
 
+/* out[i] = saturate_int16(round_to_nearest_even(x[i] * scale)): separated audio as 16-bit PCM, the format the evaluation
+ * driver writes (tssep_b200/eval.py::write_wav); scale = 32767 / peak. */
+int tssep_pcm16(const float* x, int64_t n, float scale, int16_t* out, tssep_stream_t stream);
+
 /* Mask-based MVDR beamformer, Souden formulation: TorchBF.__call__ (tssep/train/enhancer.py:140-283).
  * Y (Z, D, T, F) cfloat multi-channel STFT, D <= 8 channels; mask (Z, K, nmask, T, F) f32, nmask 1 (interference
  * weight = 1 - mask) or 2 (target, interference); K * nmask (+1) <= 17.

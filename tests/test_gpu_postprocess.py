@@ -71,3 +71,15 @@ def test_activity_from_the_enhancement_kernel(cuda, size, shift):
     a = diarize(mask, fe, threshold=0.5, median_width=5)
     b = diarize(mask, fe, threshold=0.5, median_width=5, activity=act)
     assert (a.activity - b.activity).abs().max().item() < 1e-6
+
+
+def test_pcm16_matches_numpy(cuda):
+    """tssep_pcm16: round to nearest even, saturate (the conversion of eval.write_wav, on the device)."""
+    from tssep_b200 import ops
+
+    rng = np.random.RandomState(0)
+    x = np.concatenate([rng.randn(100_003).astype(np.float32) * 0.4, np.array([1.5, -1.5, 0.5 / 32767, 1.5 / 32767, -2.5 / 32767, 0.0], np.float32)])
+    want = np.clip(np.rint(x * np.float32(32767.0)), -32768, 32767).astype(np.int16)
+    got = ops.pcm16(torch.as_tensor(x).to(cuda), 32767.0).cpu().numpy()
+    assert got.dtype == np.int16 and np.array_equal(got, want)
+    assert ops.pcm16(torch.zeros(0, device=cuda)).numel() == 0

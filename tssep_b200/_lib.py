@@ -48,6 +48,7 @@ _SIGNATURES = {
                              c_i32, c_vp, c_vp, c_i64, c_vp], C.c_int),
     "tssep_wpe_workspace_bytes": ([c_i32, c_i64, c_i32, c_i32], c_i64),
     "tssep_wpe": ([c_vp, c_i32, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_i64, c_vp], C.c_int),
+    "tssep_pcm16": ([c_vp, c_i64, c_f32, c_vp, c_vp], C.c_int),
     "tssep_log1p_abs": ([c_vp, c_i64, c_vp, c_vp], C.c_int),
     "tssep_ipd": ([c_vp, c_i64, c_i32, c_i64, c_vp, c_vp, c_vp, c_vp], C.c_int),
     "tssep_cast_bf16": ([c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp], C.c_int),

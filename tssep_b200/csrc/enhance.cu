@@ -399,6 +399,13 @@ static int ilog2_exact(int v) {
   return (1 << l) == v ? l : -1;
 }
 
+// separated audio -> 16-bit PCM (what the evaluation writes to disk, tssep_b200/eval.py::write_wav): round to nearest,
+// saturate.  Halves the device-to-host bytes of a serving loop that ships audio (bench.py, e2e_pcm16).
+__global__ void pcm16_kernel(const float* __restrict__ x, int64_t n, float scale, int16_t* __restrict__ out) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    out[i] = static_cast<int16_t>(fminf(fmaxf(rintf(x[i] * scale), -32768.f), 32767.f));
+}
+
 }  // namespace tssep
 
 using namespace tssep;
@@ -433,6 +440,15 @@ int tssep_head_expand_t(const float* small, int64_t Z, int64_t T, int n_spk, int
   const int blocks = static_cast<int>(imin64((rows + 7) / 8, 148 * 16));
   head_expand_t_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(small, Z, T, n_spk, F, perm, logit, mask);
   return check_launch("tssep_head_expand_t");
+}
+
+int tssep_pcm16(const float* x, int64_t n, float scale, int16_t* out, tssep_stream_t stream) {
+  TSSEP_REQUIRE(n >= 0, "tssep_pcm16: bad extent");
+  if (n == 0) return 0;
+  TSSEP_REQUIRE(x && out, "tssep_pcm16: null pointer");
+  const int blocks = static_cast<int>(imin64((n + 1023) / 1024, 148 * 16));
+  pcm16_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, n, scale, out);
+  return check_launch("tssep_pcm16");
 }
 
 int tssep_mask_istft(const float* X, int64_t x_item_stride, const float* mask, int64_t mask_pitch, int64_t Z, int n_spk, int64_t T,

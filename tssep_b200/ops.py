@@ -163,3 +163,13 @@ def instance_norm(x: torch.Tensor, unbiased=False, dim: int = -1, mode: int = 0)
 
 __all__ = ["gemm", "cast_bf16", "operand_ld", "pack_whh", "blstm_recurrence", "pack_whh_ts", "blstm_recurrence_ts",
            "recurrence_ts_capacity", "instance_norm", "round_up", "fast_math_default", "EPI_F32", "EPI_BF16", "EPI_HEAD"]
+
+
+def pcm16(x: torch.Tensor, scale: float = 32767.0, out: torch.Tensor = None) -> torch.Tensor:
+    """float32 audio -> int16 PCM on the device (round to nearest, saturate); ``scale`` = 32767 / peak."""
+    _lib.require_cuda(x)
+    x = x.contiguous()
+    if out is None:
+        out = torch.empty(x.shape, dtype=torch.int16, device=x.device)
+    torch_ops.op.pcm16(x, x.numel(), float(scale), out)
+    return out

@@ -40,6 +40,7 @@ _OPS = {
         "(Tensor Y, int D, int T, int F, int taps, int delay, int iterations, int psd_context, int statistics_mode, "
         "Tensor(a!) X, Tensor(b!) workspace, int workspace_bytes) -> ()",
         "tssep_wpe"),
+    "pcm16": ("(Tensor x, int n, float scale, Tensor(a!) out) -> ()", "tssep_pcm16"),
     "log1p_abs": ("(Tensor X, int n, Tensor(a!) out) -> ()", "tssep_log1p_abs"),
     "ipd": (
         "(Tensor X, int lead, int D, int TF, Tensor second_channel, Tensor(a!) cos_out, Tensor(b!) sin_out) -> ()",
