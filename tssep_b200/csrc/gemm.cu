@@ -407,6 +407,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                            (static_cast<uint32_t>(BM >> 4) << 24);
     const uint64_t adesc0 = make_smem_desc(sA), bdesc0 = make_smem_desc(sB);
     const uint32_t a_step = a_bytes >> 4, b_step = b_bytes >> 4;  // encoded distance of two pipeline stages
+    const int tail_ksteps = (g.K - (g.k_blocks - 1) * BK + 15) / 16;  // k-steps of the last k-block that hold data
     int s = 0;
     uint32_t ph = 0;
     uint32_t it = 0;
@@ -420,8 +421,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc_fence_after();
         if (elect_one()) {
           const uint64_t ad = adesc0 + static_cast<uint64_t>(s * a_step), bd = bdesc0 + static_cast<uint64_t>(s * b_step);
+          // the last k-block may hold fewer than four k-steps of data (K = 513: one): the rest is zero padding of the
+          // operand rows and is not multiplied (3 of 36 MMAs at K = 513, 2 of 40 at K = 608)
+          const int ksteps = kb == g.k_blocks - 1 ? tail_ksteps : BK / 16;
 #pragma unroll
-          for (int k4 = 0; k4 < BK / 16; ++k4) tc_mma_bf16(d_tmem, ad + 2 * k4, bd + 2 * k4, idesc, (kb | k4) != 0 ? 1u : 0u);
+          for (int k4 = 0; k4 < BK / 16; ++k4)
+            if (k4 < ksteps) tc_mma_bf16(d_tmem, ad + 2 * k4, bd + 2 * k4, idesc, (kb | k4) != 0 ? 1u : 0u);
           tc_commit(empty0 + 8 * s);
           if (kb == g.k_blocks - 1) tc_commit(tfull0 + 8 * as);
         }
