@@ -409,6 +409,11 @@ int tssep_wpe(const float* Y, int D, int64_t T, int F, int taps, int delay, int 
   const dim3 cgrid((Ti + kWpeChunk - 1) / kWpeChunk, F);
   TSSEP_CUDA(cudaFuncSetAttribute(wpe_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(stats_smem)));
   TSSEP_CUDA(cudaFuncSetAttribute(wpe_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(solve_smem)));
+  // one thread per 4x4 tile of the statistics / per element of a solver row: small problems (ChannelWiseWPE: D = 1,
+  // 10 x 10 matrices, thousands of frequencies) get small CTAs, so that many of them share an SM
+  const int nt4 = (DK + 3) / 4;
+  const int stats_threads = static_cast<int>(imin64(256, ((nt4 * (nt4 + 1) / 2 + nt4 * ((D + 3) / 4) + 31) / 32) * 32));
+  const int solve_threads = static_cast<int>(imin64(256, ((static_cast<int64_t>(DK) * NCOL / 4 + 31) / 32) * 32));
   for (int it = 0; it < iterations; ++it) {
     const bool last = it + 1 == iterations;
     if (it == 0) {
@@ -421,8 +426,8 @@ int tssep_wpe(const float* Y, int D, int64_t T, int F, int taps, int delay, int 
       lam = power2;
     }
     TSSEP_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * 2 * F * (static_cast<size_t>(DK) * DK + static_cast<size_t>(DK) * D), s));
-    wpe_stats_kernel<<<cgrid, 256, stats_smem, s>>>(Yt, lam, pmax, g, acc);
-    wpe_solve_kernel<<<F, 256, solve_smem, s>>>(acc, DK, D, G);
+    wpe_stats_kernel<<<cgrid, stats_threads, stats_smem, s>>>(Yt, lam, pmax, g, acc);
+    wpe_solve_kernel<<<F, solve_threads, solve_smem, s>>>(acc, DK, D, G);
     if (!last) TSSEP_CUDA(cudaMemsetAsync(pmax, 0, sizeof(unsigned int) * F, s));  // read by the kernels above, rewritten below
     float* pw = last ? nullptr : power;
     unsigned int* pm = (last || psd_context > 0) ? nullptr : pmax;
