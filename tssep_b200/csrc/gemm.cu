@@ -20,8 +20,12 @@ namespace tssep {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int kMaxStages = 4;
-constexpr int kEpiWarps = 8;  // two sets of four: each set covers the 128 TMEM lanes, the sets split the column chunks
-constexpr int kGemmThreads = 64 + 32 * kEpiWarps;
+// Epilogue warps (template parameter EPIW of the kernel): sets of four, each set covers the 128 TMEM lanes, the sets
+// split the 32-column chunks of a tile.  8 warps leave room for a 4-stage operand ring (what the K = 2560 projection
+// wants: 1.38 vs 1.22 PFLOP/s); 16 warps (3 stages) are for the GEMMs whose tile time is epilogue time: the head
+// (two f32 outputs + sigmoid per accumulator: 1.97 -> 3.49 TB/s of output), the K <= 384 input projections (+7 %) and the
+// narrow output projections (N <= 512, +5 %).
+constexpr int gemm_threads(int epiw) { return 64 + 32 * epiw; }
 constexpr int kTmemCols = 512;
 constexpr int kAccCols = 256;
 
@@ -330,8 +334,8 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   return static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
 
-template <int MODE, int ACT>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+template <int MODE, int ACT, int EPIW>
+__global__ void __launch_bounds__(gemm_threads(EPIW), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -344,7 +348,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t sBar = sB + kStages * b_bytes;  // 8-byte aligned (multiples of 1024 before it)
   const uint32_t full0 = sBar, empty0 = sBar + 8 * kMaxStages, tfull0 = sBar + 16 * kMaxStages,
                  tempty0 = tfull0 + 16, tptr = tempty0 + 16;
-  const uint32_t sStage = sBar + 128;  // kEpiWarps x 32 rows x kStageLd words
+  const uint32_t sStage = sBar + 128;  // EPIW x 32 rows x kStageLd words
+  constexpr int kEpiSets = EPIW / 4;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -360,7 +365,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       for (int s = 0; s < 2; ++s) {
         mbar_init(tfull0 + 8 * s, 1);
-        mbar_init(tempty0 + 8 * s, kEpiWarps);
+        mbar_init(tempty0 + 8 * s, EPIW);
       }
       mbar_fence_init();
     }
@@ -440,7 +445,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else {
     const int q = warp & 3;  // TMEM lane quarter this warp may touch
     const uint32_t stage = sStage + static_cast<uint32_t>(warp - 2) * (32 * kStageLd * 4);
-    const int cset = (warp - 2) >> 2;  // column chunks are dealt alternately to the two warp sets
+    const int cset = (warp - 2) >> 2;  // column chunks are dealt in turn to the warp sets
     uint32_t it = 0;
     for (int64_t tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++it) {
       const uint32_t as = it & 1, aph = (it >> 1) & 1;
@@ -456,10 +461,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(tfull0 + 8 * as, aph);
       tc_fence_after();
       const uint32_t t0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kAccCols;
-      for (int c0 = cset * 32; c0 < g.bn; c0 += 64) {
+      for (int c0 = cset * 32; c0 < g.bn; c0 += 32 * kEpiSets) {
         uint32_t v[32];
         tc_ld32(t0 + c0, v);
-        const ChunkBias cb_next = load_chunk_bias<MODE>(g, bias, plane_row, nbase + c0 + 64, lane);  // for the next chunk
+        const ChunkBias cb_next = load_chunk_bias<MODE>(g, bias, plane_row, nbase + c0 + 32 * kEpiSets, lane);  // for the next chunk
         tc_wait_ld();
         if (m0 < g.M) {
           if (MODE == EPI_HEAD) epilogue_head(g, et, m0, nbase + c0, min(32, g.bn - c0), v, cb, stage, lane);
@@ -584,7 +589,8 @@ static int launch_gemm(GemmArgs g, const uint16_t* A, int64_t lda, int64_t a_str
   TSSEP_CUDA(cudaGetDevice(&dev));
   TSSEP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const size_t stage_bytes = BM * BK * 2 + static_cast<size_t>(g.bn) * BK * 2;
-  const size_t fixed = 1024 + 128 + kEpiWarps * 32 * kStageLd * 4;
+  const int epiw = (g.mode == EPI_HEAD || g.K <= 384 || g.N <= 512) ? 16 : 8;  // measured per shape, profiles/r2_gemm_microbench.txt
+  const size_t fixed = 1024 + 128 + static_cast<size_t>(epiw) * 32 * kStageLd * 4;
   g.stages = static_cast<int>(imin64(kMaxStages, (227 * 1024 - fixed) / stage_bytes));
   TSSEP_REQUIRE(g.stages >= 2, "gemm: tile does not fit shared memory");
   const size_t smem = fixed + g.stages * stage_bytes;
@@ -593,19 +599,21 @@ static int launch_gemm(GemmArgs g, const uint16_t* A, int64_t lda, int64_t a_str
   // clocks it leaves behind decide the speed of the latency-bound recurrence that follows
   // (profiles/r1_power_cap_probe.txt).
   if (max_ctas >= 1 && max_ctas < grid) grid = max_ctas;
-#define TSSEP_GEMM_CASE(MODE_, ACT_)                                                                                     \
-  if (g.mode == MODE_ && g.act == ACT_) {                                                                                \
-    TSSEP_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<MODE_, ACT_>, cudaFuncAttributeMaxDynamicSharedMemorySize,           \
+#define TSSEP_GEMM_CASE_W(MODE_, ACT_, EPIW_)                                                                            \
+  if (g.mode == MODE_ && g.act == ACT_ && epiw == EPIW_) {                                                               \
+    TSSEP_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<MODE_, ACT_, EPIW_>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
                                     static_cast<int>(smem)));                                                           \
-    gemm_tc_kernel<MODE_, ACT_><<<grid, kGemmThreads, smem, stream>>>(tmA, tmB, g);                                      \
+    gemm_tc_kernel<MODE_, ACT_, EPIW_><<<grid, gemm_threads(EPIW_), smem, stream>>>(tmA, tmB, g);                        \
     return check_launch("gemm_tc");                                                                                      \
   }
+#define TSSEP_GEMM_CASE(MODE_, ACT_) TSSEP_GEMM_CASE_W(MODE_, ACT_, 8) TSSEP_GEMM_CASE_W(MODE_, ACT_, 16)
   TSSEP_GEMM_CASE(EPI_F32, 0)
   TSSEP_GEMM_CASE(EPI_F32, 1)
   TSSEP_GEMM_CASE(EPI_BF16, 0)
   TSSEP_GEMM_CASE(EPI_BF16, 1)
   TSSEP_GEMM_CASE(EPI_HEAD, 0)
 #undef TSSEP_GEMM_CASE
+#undef TSSEP_GEMM_CASE_W
   set_error("gemm: no tensor-core instantiation for mode %d act %d", g.mode, g.act);
   return -1;
 }
