@@ -24,7 +24,7 @@ def main():
     x = torch.randn((a.meetings, 1, n), device=dev)
     X = fe.stft(x)
     T, F = X.shape[-2:]
-    mask = torch.rand((a.meetings, a.speakers, 1, T, F), device=dev)
+    mask = torch.rand((a.meetings, a.speakers, 1, T, 520), device=dev)[..., :F]   # rows at the head GEMM's pitch (net.py)
     act = torch.empty((a.meetings, a.speakers, T), device=dev)
     for label, act_out in (("without activity", None), ("with fused activity", act), ("without activity", None),
                            ("with fused activity", act)):
