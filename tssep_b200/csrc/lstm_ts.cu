@@ -6,8 +6,8 @@
 // One cluster per (NR batch rows, direction), NR = 8, 16 or 32.  Each CTA owns TILES row tiles of 32 hidden units =
 // 128 gate rows (row = 4*unit + gate), each an M=128 A tile of Up/2 TMEM columns (two bf16 per 32-bit column),
 // written ONCE.  TILES = 2: clusters of ceil(Up/64) CTAs (5 at U = 300), the throughput shape; TILES = 1: clusters
-// of 2*ceil(Up/64) CTAs (10 at U = 300, a non-portable cluster size), the latency shape -- a step is bound by the
-// tensor pipe (27 cycles per M=128,K=16 MMA whatever N, measured), and one tile per CTA halves the MMAs of a step.
+// of 2*ceil(Up/64) CTAs (10 at U = 300, a non-portable cluster size), the latency shape -- one tile per CTA halves
+// the MMAs (13-17 cycles each to issue) and the gate math on the dependent chain of a step.
 // Per step the pre-activations of a tile are
 //
 //     D[gate row, batch row] = P . G_t  +  W_hh . h_{t-1}
@@ -116,8 +116,7 @@ __device__ __forceinline__ float ts_tanh(float x) {
 // NR batch rows per sub-batch, NC of them per epilogue warp; MATH: gate arithmetic; SPLIT: two K phases per step (see
 // the header); TILES: row tiles per CTA; SUBS: independent sub-batches of NR rows per cluster.  SUBS = 2 is the
 // throughput shape: the cluster advances two recurrences in anti-phase -- while one sub-batch's h travels through
-// DSMEM and its epilogue warps run, the tensor pipe works on the other (an MMA costs ~27 cycles whatever its N, so 64
-// rows per cluster at N = 32 halve the tensor-pipe time per row, and the ping-pong hides the exchange).
+// DSMEM and its epilogue warps run, the MMA warp and the tensor pipe work on the other.
 // Everything the per-step loops branch on is a template parameter.
 // GEPI (the default for two sub-batches of 8 rows): the epilogue adds G_t from shared memory instead of the P . G MMAs;
 // the loads are issued while the warp waits for the accumulator anyway.  Measured after the MMA issue was unrolled
