@@ -6,6 +6,6 @@ echo "bench n8 rc=$?"; tail -3 gpurun_out/r2_bench_c4_n8.err
 python - <<'PY'
 import json
 d = json.loads(open("gpurun_out/r2_bench_c4_n8.json").read().strip().splitlines()[-1])
-print({k: d[k] for k in ("value", "ms_per_step", "n_gpus", "scaling")}); print(d["e2e"]); print(d["config"].get("recurrence_waves"), d["clocks"])
+print({k: d[k] for k in ("value", "ms_per_step", "n_gpus", "scaling")}); print(d["e2e"]); print(d["config"].get("recurrence_waves"), d["config"]["steps_in_flight"], d["clocks"]); print({k: v for k, v in (d.get("e2e_pcm16") or {}).items() if k != "note"})
 for k, v in d["roofline"]["launches"].items(): print("  ", k, round(v["ms_per_step"], 2), round(v["us_per_dependent_step"], 3))
 PY
