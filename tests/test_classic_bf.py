@@ -16,17 +16,35 @@ SUM_DOC = np.array([[[0., 0.2, 0.8, 1., 0.], [0.1, 0., 0.5, 1., 0.], [1., 0.1, 1
                     [[1.1, 0.1, 1.5, 1.5, 0.01], [1., 0.3, 1.8, 1.5, 0.01], [0.1, 0.2, 1.3, 2., 0.01]]])
 
 
-def test_distortion_masks_match_reference_doctests():
-    from tssep_b200.enhancer_distortion_mask import OneMinus, SumCrossTalker
-
+def test_oracle_distortion_masks_match_reference_doctests():
     np.testing.assert_allclose(np.squeeze(O.sum_cross_talker(M_DOC, eps=0.01)), SUM_DOC, atol=1e-12)
-    np.testing.assert_allclose(np.squeeze(SumCrossTalker(eps=0.01)(M_DOC)), SUM_DOC, atol=1e-12)
     m = np.array([0, 0.5, 1])[None]
     np.testing.assert_array_equal(O.one_minus(m), [[0., 0.5, 1.], [1., 0.5, 0.]])
+
+
+def test_product_distortion_masks_have_no_cpu_path():
+    from tssep_b200.enhancer_distortion_mask import SumCrossTalker
+
+    with pytest.raises(RuntimeError, match="CUDA"):
+        SumCrossTalker()(torch.zeros((1, 3, 4, 2)))
+
+
+@pytest.mark.gpu
+def test_distortion_masks_match_reference_doctests(cuda):
+    from tssep_b200.enhancer_distortion_mask import OneMinus, SumCrossTalker
+
+    got = SumCrossTalker(eps=0.01)(M_DOC)                      # numpy in -> numpy out, computed on the device
+    assert isinstance(got, np.ndarray)
+    np.testing.assert_allclose(np.squeeze(got), SUM_DOC, atol=1e-12)
+    m = np.array([0, 0.5, 1])[None]
     np.testing.assert_array_equal(OneMinus()(m), [[0., 0.5, 1.], [1., 0.5, 0.]])
-    # torch path of the product classes (device agnostic arithmetic)
-    np.testing.assert_allclose(np.squeeze(SumCrossTalker(eps=0.01)(torch.tensor(M_DOC)).numpy()), SUM_DOC, atol=1e-12)
-    np.testing.assert_array_equal(OneMinus()(torch.tensor(m)).numpy(), [[0., 0.5, 1.], [1., 0.5, 0.]])
+    got = SumCrossTalker(eps=0.01)(torch.tensor(M_DOC).to(cuda))
+    assert got.is_cuda
+    np.testing.assert_allclose(np.squeeze(got.cpu().numpy()), SUM_DOC, atol=1e-12)
+    rng = np.random.RandomState(0)
+    big = rng.rand(1, 8, 33, 50)
+    np.testing.assert_allclose(SumCrossTalker()(big), O.sum_cross_talker(big), rtol=0, atol=1e-13)   # summation order
+    np.testing.assert_array_equal(OneMinus()(big), O.one_minus(big))
 
 
 def toy_scene(seed=0, F=17, T=79, D=6):

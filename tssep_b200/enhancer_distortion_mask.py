@@ -1,7 +1,7 @@
 """Distortion masks for the segment-wise beamformer (tssep/train/enhancer_distortion_mask.py:9-55).
 
 ``masks`` (1, speakers, ...) -> (2, speakers, ...): the second plane is the weight of everything that is NOT the
-speaker.  numpy in -> numpy out (host arithmetic on a mask-sized array, as the reference); CUDA tensor in -> CUDA tensor.
+speaker.  CUDA tensor in -> CUDA tensor out; numpy in -> moved to the current CUDA device, numpy out (no CPU path).
 """
 from __future__ import annotations
 
@@ -9,14 +9,24 @@ import numpy as np
 import torch
 
 
+def _to_cuda(masks):
+    if isinstance(masks, np.ndarray):
+        if not torch.cuda.is_available():
+            raise RuntimeError("tssep_b200 needs a CUDA device (no CPU fallback)")
+        return torch.as_tensor(masks).cuda(), True
+    if not masks.is_cuda:
+        raise RuntimeError(f"tssep_b200 operators run on CUDA tensors only (no CPU fallback); got a tensor on {masks.device}")
+    return masks, False
+
+
 class OneMinus:
     """noise mask = max(1 - mask, 0) (enhancer_distortion_mask.py:9-21)."""
 
     def __call__(self, masks):
         assert masks.shape[0] == 1, masks.shape
-        if isinstance(masks, torch.Tensor):
-            return torch.cat([masks, torch.clamp(1 - masks, min=0)], dim=0)
-        return np.concatenate([masks, np.maximum(1 - masks, 0)], axis=0)
+        m, was_np = _to_cuda(masks)
+        out = torch.cat([m, torch.clamp(1 - m, min=0)], dim=0)
+        return out.cpu().numpy() if was_np else out
 
 
 class SumCrossTalker:
@@ -28,10 +38,9 @@ class SumCrossTalker:
 
     def __call__(self, masks):
         assert masks.shape[0] == 1, masks.shape
-        if isinstance(masks, torch.Tensor):
-            total = masks.sum(dim=1, keepdim=True)
-            return torch.cat([masks, torch.clamp(total - masks, min=self.eps)], dim=0)
-        speakers = masks.shape[1]
-        # summed speaker by speaker like the reference (total - own would round differently)
-        noise = np.stack([np.sum(np.delete(masks, spk, axis=1), axis=1) for spk in range(speakers)], axis=1)
-        return np.concatenate([masks, np.maximum(noise, self.eps)], axis=0)
+        m, was_np = _to_cuda(masks)
+        speakers = m.shape[1]
+        # summed speaker by speaker in the reference's order (total - own would round differently)
+        noise = torch.stack([m[:, [j for j in range(speakers) if j != spk]].sum(dim=1) for spk in range(speakers)], dim=1)
+        out = torch.cat([m, torch.clamp(noise, min=self.eps)], dim=0)
+        return out.cpu().numpy() if was_np else out
