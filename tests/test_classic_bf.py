@@ -147,6 +147,28 @@ def test_classic_bf_against_oracle(kw, cuda):
 
 
 @pytest.mark.gpu
+def test_classic_bf_edge_cases(cuda):
+    """A speaker without any interval stays silent; one-frame and whole-signal intervals work; segment_wpe is applied
+    to the interval only."""
+    from tssep_b200.enhancer import WPE, ClassicBF_np
+
+    obs, src, mask, _ = toy_scene(seed=5, F=9, T=120, D=6)
+    dia = [[], [(0, 1), (10, 120)]]
+    want = O.classic_bf_np(mask[:-1, None], obs, dia)
+    got = ClassicBF_np()(mask[:-1, None], obs, dia, numpy_out=True)
+    assert np.all(got[0] == 0) and np.abs(got - want).max() < 2e-5 * np.abs(obs).max()
+    ret = ClassicBF_np()(mask[:-1, None], obs, dia)
+    assert ret[0] == {} and sorted(ret[1]) == [(0, 1), (10, 120)] and ret[1][(0, 1)].shape == (1, 9)
+    wpe_kw = dict(taps=2, delay=1, iterations=1)
+    got = ClassicBF_np(segment_wpe=WPE(**wpe_kw))(mask[:-1, None], obs, [[(20, 100)], []], numpy_out=True)
+    seg = O.wpe(obs[:, 20:100].astype(np.complex64), **wpe_kw)
+    pad = np.zeros_like(obs)
+    pad[:, 20:100] = seg
+    want = O.classic_bf_np(mask[:-1, None], pad, [[(20, 100)], []])
+    assert np.abs(got - want).max() < 5e-4 * np.abs(obs).max()
+
+
+@pytest.mark.gpu
 def test_classic_bf_whole_signal_and_wpe_hooks(cuda):
     from tssep_b200.enhancer import WPE, ClassicBF_np
 

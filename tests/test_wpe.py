@@ -94,6 +94,8 @@ def _rel(got, want, scale=None):
     (4, 700, 9, dict(taps=6, delay=1, iterations=2, psd_context=2), 2e-4),
     (2, 513, 4, dict(taps=3, delay=2, iterations=1, statistics_mode="valid"), 2e-4),
     (8, 600, 3, dict(taps=8, delay=0, iterations=2), 2e-4),            # delay 0 predicts the frame from itself: X ~ 0
+    (2, 12, 3, dict(taps=3, delay=2, iterations=1), 2e-4),             # barely more frames than unknowns, one chunk
+    (3, 257, 2, dict(taps=2, delay=1, iterations=2, psd_context=400), 2e-4),   # context wider than the signal; chunk edge + 1
 ])
 def test_wpe_against_oracle(D, T, F, kw, tol, cuda):
     from tssep_b200.enhancer import WPE
