@@ -283,3 +283,21 @@ def test_choose_ts_shape_respects_the_cta_budget():
     assert choose_ts_shape(128, 304, 74, capacity) == (32, 2, 2)     # 4 clusters of 5 per direction = 40 CTAs
     assert choose_ts_shape(416, 304, 74, capacity) == (64, 2, 2)     # 7 clusters x 5 x 2 = 70 CTAs
     assert choose_ts_shape(832, 304, 74, capacity) == (0, 0, 0)      # nothing fits half the device: library's choice
+
+
+def test_classic_bf_config_protocol():
+    """``ClassicBF_np.get_config()`` / ``new()`` as the reference's doctest shows them (enhancer.py:386-398), and
+    reference factory strings inside a config resolve to this package's classes."""
+    from tssep_b200.enhancer import WPE, ClassicBF_np
+    from tssep_b200.enhancer_distortion_mask import SumCrossTalker
+
+    cfg = ClassicBF_np.get_config()
+    assert cfg == {"factory": "tssep_b200.enhancer.ClassicBF_np", "bf": "mvdr_souden", "masking": False, "masking_eps": 0,
+                   "distortion_mask": {"factory": "tssep_b200.enhancer_distortion_mask.SumCrossTalker", "eps": 0.0001},
+                   "pre_wpe": None, "segment_wpe": None, "mask_power": 1}
+    enh = ClassicBF_np.new()
+    assert isinstance(enh.distortion_mask, SumCrossTalker) and enh.distortion_mask.eps == 0.0001
+    enh = ClassicBF_np.new({"pre_wpe": {"factory": "tssep.train.enhancer.WPE", "taps": 5}, "bf": "ch0",
+                            "distortion_mask": {"eps": 0.01}})
+    assert isinstance(enh.pre_wpe, WPE) and enh.pre_wpe.taps == 5 and enh.pre_wpe.delay == 2
+    assert enh.bf == "ch0" and enh.distortion_mask.eps == 0.01

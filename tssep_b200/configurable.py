@@ -61,6 +61,7 @@ def class_to_str(cls) -> str:
 def import_class(name):
     if not isinstance(name, str):
         return name
+    name = FACTORY_ALIASES.get(name, name)  # a reference factory string names this package's drop-in class
     module, _, attr = name.rpartition(".")
     if not module:
         raise ImportError(f"factory {name!r} is not a dotted path")

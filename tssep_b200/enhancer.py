@@ -214,6 +214,11 @@ class ClassicBF_np(ABC):
     beamformers (``scaled_gev_atf+mvdr``, ``rank1_gev+mvdr_souden``, ``wmwf``) raise ``NotImplementedError``.
     """
 
+    @classmethod
+    def finalize_dogmatic_config(cls, config):
+        # as the reference (enhancer.py:420-427); WPE is activated by a {'factory': WPE} entry for pre_wpe / segment_wpe
+        config["distortion_mask"] = {"factory": "tssep_b200.enhancer_distortion_mask.SumCrossTalker"}
+
     def __init__(self, bf="mvdr_souden", masking=False, masking_eps=0, distortion_mask=None, pre_wpe: "WPE" = None,
                  segment_wpe: "WPE" = None, mask_power=1):
         super().__init__()
