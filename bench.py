@@ -759,6 +759,10 @@ def run_b200(args):
                     "(tssep_pcm16; what the evaluation driver writes to disk) before it is copied to the host -- half the "
                     "device-to-host bytes, which is what bounds e2e when several ranks copy into host memory at once"}),
         "gpu_launches": launches,
+        "memory": {"max_reserved_GB": torch.cuda.max_memory_reserved(dev) / 1e9,
+                   "max_allocated_GB": torch.cuda.max_memory_allocated(dev) / 1e9,
+                   "device_total_GB": torch.cuda.get_device_properties(dev).total_memory / 1e9,
+                   "note": "rank 0, whole run (device-resident loop, end-to-end loops with their staging buffers, config 3)"},
         "roofline": roofline, "roofline_gemm": roofline_gemm, "hbm_kernels": hbm,
         "cpu_baseline": cpu,
         "config3": config3,
